@@ -1,0 +1,189 @@
+/*
+ * pm_b200.h -- C ABI of the B200-native PrimerMatch database scan.
+ *
+ * This is the drop-in boundary for ONE path of
+ * EdwardsLabProjects/sequence-alignment-tools: the PatternMatch plugin
+ * interface (pattern_match.h:83-157) as primer_match drives it
+ * (primer_match.cc:1100-1268).  Every entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Threading: a pm_ctx is owned by one host thread at a time.  All device work
+ * of a context is issued on the CUDA stream given to pm_set_stream (default:
+ * the legacy default stream) and the blocking entry points synchronise that
+ * stream only.
+ *
+ * Errors: every int-returning function returns PM_OK (0) or a negative
+ * PM_E_* code; pm_last_error() gives the message of the calling thread's last
+ * failure.  There is no CPU fallback: without a usable CUDA device
+ * pm_create fails with PM_E_CUDA.
+ */
+#ifndef PM_B200_H
+#define PM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_E_ARG (-1)         /* bad argument / call order                     */
+#define PM_E_CUDA (-2)        /* CUDA runtime failure (message has the detail) */
+#define PM_E_UNSUPPORTED (-3) /* valid for the reference, not built here       */
+#define PM_E_NOMEM (-4)
+#define PM_E_BOGUS (-5)       /* "Bogus hit returned to primer_match main()"
+                                 (primer_match.cc:1249): the final alignment of
+                                 a reported hit exceeded k; the reference
+                                 exits(1) at this point                        */
+
+/* Index selection: the values of primer_match's -N option this library
+ * implements (select.cc:202-295).  All of them run on the same device scan;
+ * the value selects the reference *semantics* of the hit list:
+ *   keyword_tree / shift_and : every exact occurrence (k must be 0)
+ *   filter_bitvec            : shift_and_inexact candidates, chained and
+ *                              re-aligned (filter_bitvec.cc:126-236)
+ * PM_INDEX_AUTO follows pick_pattern_index for the selections available here:
+ * keyword_tree when k==0 without wildcards, shift_and when k==0 with
+ * wildcards, filter_bitvec when k>0.                                          */
+#define PM_INDEX_AUTO 0
+#define PM_INDEX_KEYWORD_TREE 3  /* select.cc:221-229, keyword_tree.t:427      */
+#define PM_INDEX_SHIFT_AND 4     /* select.cc:230-233, shift_and.cc:204        */
+#define PM_INDEX_FILTER_BITVEC 5 /* select.cc:234-237, filter_bitvec.cc:126    */
+
+typedef struct pm_ctx pm_ctx;
+
+/* Options of one scan: the arguments pick_pattern_index receives
+ * (select.h:8-19) plus the device to run on.                                  */
+typedef struct pm_options {
+  int device;        /* CUDA device ordinal                                    */
+  int index;         /* PM_INDEX_*  (-N)                                       */
+  int k;             /* nmismatch   (-k / -K), 0..PM_MAX_K                     */
+  int indels;        /* 1: -k (edits)  0: -K (substitutions only)              */
+  int wildcards;     /* -w / -W: honour IUPAC codes                            */
+  int text_n;        /* -W: a text 'N' matches                                 */
+  unsigned char eos; /* end-of-sequence character (-E, default '\n')           */
+} pm_options;
+
+#define PM_MAX_K 3
+#define PM_MAX_PATTERN_LEN 64
+#define PM_MAX_CODES 72 /* >= PM_MAX_PATTERN_LEN + PM_MAX_K + 1 */
+
+/* One hit after the final alignment, the numbers primer_match hands to
+ * alignformat() (primer_match.cc:1158-1200).  Stream coordinates count
+ * characters of the normalised database stream (eos, seq1, eos, seq2 ...),
+ * exactly CharacterProducer::pos().                                           */
+typedef struct pm_hit {
+  int64_t start;       /* pattern_alignment::start()                           */
+  int64_t end;         /* %E  pattern_alignment::end()                         */
+  uint32_t pattern_id; /* id passed to pm_add_pattern                          */
+  int32_t editdist;    /* %d  pattern_alignment::editdist()                    */
+  int32_t value;       /* editdist_alignment::value() (DP score)               */
+  uint32_t ncodes;     /* alignment length                                     */
+  uint8_t codes[PM_MAX_CODES]; /* alignment_code per column, pattern order
+                                  (alignment_code.h:5-19)                      */
+} pm_hit;
+
+/* One raw candidate of the inner index (PatternMatch::find_patterns of
+ * shift_and_inexact.cc:237, shift_and.cc:204, keyword_tree.t:427).            */
+typedef struct pm_candidate {
+  int64_t pos;         /* CharacterProducer::pos() after the last character    */
+  uint32_t pattern_id;
+  uint32_t reserved;
+} pm_candidate;
+
+const char *pm_last_error(void);
+const char *pm_version(void);
+
+/* new <index>(...) as pick_pattern_index does (select.cc:202-295).            */
+int pm_create(pm_ctx **out, const pm_options *opt);
+/* delete kt                                                                   */
+void pm_destroy(pm_ctx *ctx);
+
+/* Device work of this context goes to `cuda_stream` (a cudaStream_t).         */
+int pm_set_stream(pm_ctx *ctx, void *cuda_stream);
+
+/* PatternMatch::add_pattern (pattern_match.h:118-121).  id must be > 0 and
+ * unique; exact_start_bases / exact_end_bases are the per-pattern constraints
+ * of primer_match -s/-e/-5/-3 (primer_match.cc:990-1017).                     */
+int pm_add_pattern(pm_ctx *ctx, const char *pattern, uint32_t id, int exact_start_bases,
+                   int exact_end_bases);
+
+/* PatternMatch::init (pattern_match.h:132): builds the per-symbol match table
+ * (the relation shift_and_inexact::computeu encodes in u_,
+ * shift_and_inexact.cc:88-178) and uploads the pattern tables.  No pattern
+ * may be added afterwards.                                                    */
+int pm_init(pm_ctx *ctx);
+
+/* The CharacterProducer the index scans.  `stream` is the normalised database
+ * stream (see pm_normalize_fasta); `stream_offset` is the global position of
+ * stream[0] (0 for a whole database; the shard's first position when a
+ * database is partitioned over several contexts / GPUs, in which case the
+ * shard must carry PM_SHARD_OVERLAP(ctx) extra characters to the left of the
+ * range it is asked to report).  _host copies through pinned staging
+ * buffers; _device adopts a 4-byte-aligned device pointer that must stay
+ * valid until the next pm_set_text_* / pm_destroy.  Both run the pack kernel
+ * (per-symbol match bit-planes).                                              */
+int pm_set_text_host(pm_ctx *ctx, const uint8_t *stream, uint64_t n, int64_t stream_offset);
+int pm_set_text_device(pm_ctx *ctx, const uint8_t *d_stream, uint64_t n, int64_t stream_offset);
+
+/* Characters of left context a shard needs so that every hit it reports is
+ * identical to a whole-database scan: longest pattern + 3k + 2.              */
+int pm_shard_overlap(pm_ctx *ctx);
+
+/* PatternMatch::find_patterns followed, per returned hit, by the final
+ * alignment of primer_match.cc:1132-1153.  Reports the hits whose FIRST raw
+ * candidate position (pm_candidate.pos of the head of its chain) lies in
+ * [begin, end) of the global stream, sorted by (end, pattern_id).  *hits
+ * points into pinned memory owned by the context, valid until the next call
+ * on it.  Pass begin=0,end=INT64_MAX for the whole stream (what the reference
+ * does).                                                                      */
+int pm_find_patterns(pm_ctx *ctx, int64_t begin, int64_t end, const pm_hit **hits,
+                     uint64_t *nhits);
+
+/* Same work, results left on the device: *d_hits is a device pointer to
+ * *nhits pm_hit records.                                                      */
+int pm_find_patterns_device(pm_ctx *ctx, int64_t begin, int64_t end, const pm_hit **d_hits,
+                            uint64_t *nhits);
+
+/* The inner index alone: raw candidates with pos in [begin, end), sorted by
+ * (pattern_id, pos).  For tests and for callers that do their own filtering.  */
+int pm_scan_candidates(pm_ctx *ctx, int64_t begin, int64_t end, const pm_candidate **cands,
+                       uint64_t *ncands);
+
+/* PatternMatch::reset (pattern_match.h:136): forget the text.                 */
+int pm_reset(pm_ctx *ctx);
+
+/* Counters of the last pm_find_patterns / pm_scan_candidates call.            */
+typedef struct pm_stats {
+  uint64_t text_len;        /* characters of the loaded shard                  */
+  uint64_t n_patterns;
+  uint64_t n_seeds;         /* edit mode: seed hits sent to the verifier       */
+  uint64_t n_candidates;
+  uint64_t n_chains;
+  uint64_t n_hits;
+  uint64_t n_bogus;
+  uint64_t kernel_launches; /* kernels of this library launched by the call    */
+  uint64_t scan_items;      /* (tile, pattern-chunk) blocks of the scan kernel */
+  float pack_ms;            /* device time of the last pack kernel             */
+  float scan_ms;            /* device time of the dense scan kernel            */
+  float total_ms;           /* device time of the whole call                   */
+} pm_stats;
+int pm_get_stats(pm_ctx *ctx, pm_stats *out);
+
+/* StreamedFastaFile (fasta_io.t:448-751): raw FASTA bytes -> normalised
+ * stream.  out must hold n+2 bytes.  seq_key[i] = stream index of the first
+ * base of sequence i (the key get_seq_pos subtracts, fasta_io.t:194-202);
+ * hdr_off/hdr_len = byte range of its header in raw.  Host-side, O(n).        */
+int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos,
+                       uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
+                       int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs);
+
+/* util.cc:374-381 reverse_comp (IUPAC aware, util.cc:319-348): out must hold
+ * strlen(pattern)+1 bytes.                                                    */
+int pm_reverse_comp(const char *pattern, char *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PM_B200_H */

@@ -1,0 +1,314 @@
+"""ctypes front-end of oracle/libpm_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs, never from the product package.
+
+`primer_match()` mirrors the reference's main loop (primer_match.cc:1100-1268):
+pattern array with reverse complements appended (lines 943-1080), the index
+chosen by pick_pattern_index (select.cc:39-298; the oracle covers selections
+2/3 keyword_tree, 4 shift_and and 5 filter_bitvec), one final alignment per
+returned hit (lines 1132-1153) and the coordinates handed to alignformat
+(lines 1156-1200).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+EOS = 10  # '\n', primer_match.cc:99
+
+# alignment_code.h:5-36 -> the characters of pattern_alignment::alignment_string
+# (pattern_alignment.h:124-166)
+CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
+
+
+class _Hit(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("pid", C.c_int32), ("val", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libpm_oracle.so")
+    src = os.path.join(_HERE, "pm_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libpm_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        u8p = C.POINTER(C.c_uint8)
+        L.pmo_normalize_fasta.restype = C.c_long
+        L.pmo_normalize_fasta.argtypes = [u8p, C.c_long, C.c_int, C.c_uint8, u8p,
+                                          C.POINTER(C.c_long), C.POINTER(C.c_long),
+                                          C.POINTER(C.c_long), C.c_long, C.POINTER(C.c_long)]
+        L.pmo_wm_scan.restype = C.c_long
+        L.pmo_wm_scan.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_uint8, C.POINTER(_Hit), C.c_long]
+        L.pmo_exact_scan.restype = C.c_long
+        L.pmo_exact_scan.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                     C.POINTER(_Hit), C.c_long]
+        L.pmo_editdist_align.restype = C.c_int
+        L.pmo_editdist_align.argtypes = [u8p, C.c_long, C.c_char_p, C.c_int64, C.c_int64, C.c_int,
+                                         C.c_uint8, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_int), u8p,
+                                         C.POINTER(C.c_int)]
+        L.pmo_filter_chains.restype = C.c_long
+        L.pmo_filter_chains.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p),
+                                        C.POINTER(_Hit), C.c_long, C.c_int, C.c_uint8, C.c_int,
+                                        C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                        C.POINTER(_Hit), C.c_long]
+        L.pmo_exact_wc_align.restype = C.c_int
+        L.pmo_exact_wc_align.argtypes = [u8p, C.c_long, C.c_char_p, C.c_int64, C.c_int, u8p]
+        L.pmo_scan_match.restype = C.c_int
+        L.pmo_scan_match.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _u8(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _pats(pats):
+    arr = (C.c_char_p * len(pats))(*[p.encode("latin-1") for p in pats])
+    return arr
+
+
+# --- util.cc:319-348 iupac_revcomp, util.cc:374-381 reverse_comp -------------
+_RC = {i: i for i in range(256)}
+for a, b in ["AT", "CG", "GC", "TA", "UA", "MK", "RY", "WW", "SS", "YR", "KM", "VB", "HD", "DH", "BV"]:
+    _RC[ord(a)] = ord(b)
+    _RC[ord(a.lower())] = ord(b.lower())
+
+
+def reverse_comp(s: str) -> str:
+    return "".join(chr(_RC[ord(c)]) for c in reversed(s))
+
+
+@dataclass
+class Stream:
+    """Normalised character stream of a FASTA file (fasta_io.t:478-629)."""
+    chars: np.ndarray      # uint8, length L
+    seq_key: np.ndarray    # int64: stream index of the first base of each sequence
+    headers: list          # header strings
+
+    def locate(self, p: int):
+        """get_header_data / get_seq_pos (fasta_io.t:163-202): the sequence whose
+        key is the last one <= p-1.  Returns (ordinal (1-based), key)."""
+        i = int(np.searchsorted(self.seq_key, p - 1, side="right")) - 1
+        if i < 0:
+            return 0, 0
+        return i + 1, int(self.seq_key[i])
+
+
+def normalize_fasta(raw: bytes, uc: bool = False, eos: int = EOS) -> Stream:
+    L = lib()
+    n = len(raw)
+    rawa = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    rawa = np.ascontiguousarray(rawa)
+    out = np.zeros(n + 4, np.uint8)
+    maxseq = raw.count(b">") + 2
+    key = (C.c_long * maxseq)()
+    off = (C.c_long * maxseq)()
+    ln = (C.c_long * maxseq)()
+    nseq = C.c_long(0)
+    slen = L.pmo_normalize_fasta(_u8(rawa) if n else None, n, int(uc), eos, _u8(out), key, off, ln,
+                                 maxseq, C.byref(nseq))
+    ns = nseq.value
+    headers = [raw[off[i]:off[i] + max(ln[i], 0)].decode("latin-1") for i in range(ns)]
+    return Stream(out[:slen].copy(), np.array([key[i] for i in range(ns)], np.int64), headers)
+
+
+def wm_scan(chars: np.ndarray, pats, k: int, indels: bool, wc=False, tn=False, eos=EOS):
+    """shift_and_inexact candidates as an (n,3) int64 array [pos, pid, level]."""
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    cap = 1 << 16
+    while True:
+        buf = (_Hit * cap)()
+        n = L.pmo_wm_scan(_u8(chars), len(chars), len(pats), _pats(pats), k, int(indels), int(wc),
+                          int(tn), eos, buf, cap)
+        if n < 0:
+            raise ValueError("pmo_wm_scan: unsupported pattern length or k")
+        if n <= cap:
+            break
+        cap = n
+    return np.array([(buf[i].pos, buf[i].pid, buf[i].val) for i in range(n)], np.int64).reshape(-1, 3)
+
+
+def exact_scan(chars: np.ndarray, pats, wc=False, tn=False):
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    cap = 1 << 16
+    while True:
+        buf = (_Hit * cap)()
+        n = L.pmo_exact_scan(_u8(chars), len(chars), len(pats), _pats(pats), int(wc), int(tn), buf, cap)
+        if n <= cap:
+            break
+        cap = n
+    return np.array([(buf[i].pos, buf[i].pid, 0) for i in range(n)], np.int64).reshape(-1, 3)
+
+
+@dataclass
+class Alignment:
+    ok: bool
+    start: int
+    end: int
+    val: int
+    editdist: int   # -1 == MAXINT (constraint violation)
+    codes: bytes
+
+    @property
+    def string(self) -> str:
+        return "".join(CODE_CHARS.get(c, " ") for c in self.codes)
+
+
+def editdist_align(chars, pat: str, e1: int, e2: int, k: int, indels: bool, wc=False, tn=False,
+                   lconst=0, rconst=0, eos=EOS) -> Alignment:
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    s, e = C.c_int64(0), C.c_int64(0)
+    val, ed, nc = C.c_int(0), C.c_int(0), C.c_int(0)
+    codes = np.zeros(len(pat) * 2 + 4 * k + 64 + int(e2 - e1), np.uint8)
+    rc = L.pmo_editdist_align(_u8(chars), len(chars), pat.encode("latin-1"), e1, e2, k, eos, int(wc),
+                              int(tn), int(indels), lconst, rconst, C.byref(s), C.byref(e),
+                              C.byref(val), C.byref(ed), _u8(codes), C.byref(nc))
+    if rc < 0:
+        raise AssertionError("editdist_alignment traceback left the band (reference assert(0))")
+    return Alignment(bool(rc), s.value, e.value, val.value, ed.value, bytes(codes[:nc.value]))
+
+
+def filter_chains(chars, pats, cands: np.ndarray, k: int, indels: bool, wc=False, tn=False,
+                  lconst=None, rconst=None, eos=EOS):
+    """filter_bitvec: (n,3) candidates (sorted by position) -> (h,3) [end,pid,val]."""
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    n = len(cands)
+    cb = (_Hit * max(n, 1))()
+    for i in range(n):
+        cb[i].pos, cb[i].pid, cb[i].val = int(cands[i, 0]), int(cands[i, 1]), int(cands[i, 2])
+    ob = (_Hit * max(n, 1))()
+    lc = (C.c_int * len(pats))(*lconst) if lconst is not None else None
+    rc = (C.c_int * len(pats))(*rconst) if rconst is not None else None
+    h = L.pmo_filter_chains(_u8(chars), len(chars), len(pats), _pats(pats), cb, n, k, eos, int(wc),
+                            int(tn), int(indels), lc, rc, ob, max(n, 1))
+    return np.array([(ob[i].pos, ob[i].pid, ob[i].val) for i in range(h)], np.int64).reshape(-1, 3)
+
+
+def exact_wc_align(chars, pat: str, end: int, tn=False):
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    codes = np.zeros(len(pat), np.uint8)
+    sub = L.pmo_exact_wc_align(_u8(chars), len(chars), pat.encode("latin-1"), end, int(tn), _u8(codes))
+    return sub, bytes(codes)
+
+
+@dataclass(frozen=True, order=True)
+class HitRecord:
+    """One output record of primer_match, the fields alignformat() receives
+    (primer_match.cc:1174-1200)."""
+    seq_index: int      # %f  ordinal of the FASTA entry (1-based)
+    seq_start: int      # %s
+    seq_end: int        # %e
+    strand: str         # %r  "F" / "R"
+    pattern_index: int  # %i  index of the primer (1-based, before rev-comp)
+    editdist: int       # %d
+    stream_start: int   # %S
+    stream_end: int     # %E
+    alignment: str      # %A
+
+
+def pattern_array(primers, rev_comp: bool):
+    """primer_match.cc:943-1080: ids 1..n forward, n+1..2n reverse complements."""
+    pats = list(primers)
+    if rev_comp:
+        pats += [reverse_comp(p) for p in primers]
+    return pats
+
+
+def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
+                 eos=EOS):
+    """Whole path, as the reference runs it with `-N 5` for k>0 (filter_bitvec)
+    and its automatic choice for k==0 (keyword_tree, or shift_and under -w/-W).
+    Returns a sorted list of HitRecord."""
+    n = len(primers)
+    pats = pattern_array(primers, rev_comp)
+    T = stream.chars
+    recs = []
+    if k == 0:
+        hits = exact_scan(T, pats, wc, tn)
+    else:
+        cands = wm_scan(T, pats, k, indels, wc, tn, eos)
+        hits = filter_chains(T, pats, cands, k, indels, wc, tn, None, None, eos)
+    for pos, pid, _ in hits:
+        pos, pid = int(pos), int(pid)
+        pat = pats[pid - 1]
+        if k == 0:
+            start, end, ed = pos - len(pat), pos, 0
+            if wc:
+                sub, codes = exact_wc_align(T, pat, pos, tn)
+                ed = sub
+            else:
+                codes = bytes([1] * len(pat))
+            if ed > 0:
+                raise AssertionError("Bogus hit (primer_match.cc:1249)")
+            astr = "".join(CODE_CHARS[c] for c in codes)
+        else:
+            al = editdist_align(T, pat, pos, pos, k, indels, wc, tn, 0, 0, eos)
+            if al.editdist < 0 or al.editdist > k:
+                raise AssertionError("Bogus hit (primer_match.cc:1249)")
+            start, end, ed, astr = al.start, al.end, al.editdist, al.string
+        # primer_match.cc:1158-1179; pattern_alignment::length() is end-start+1
+        idx, key = stream.locate(end)
+        spe = end - key
+        sps = spe - (end - start + 1) + 1
+        rc = pid > n
+        recs.append(HitRecord(idx, sps, spe, "R" if rc else "F", pid - (n if rc else 0), ed,
+                              end - (end - start + 1) + 1, end, astr))
+    return sorted(recs)
+
+
+# ---------------------------------------------------------------------------
+# the real reference, when oracle/_ref/primer_match exists
+REF_BIN = os.path.join(_HERE, "_ref", "primer_match")
+REF_FORMAT = r"%f\t%s\t%e\t%r\t%i\t%d\t%S\t%E\t%A\n"
+
+
+def ref_available() -> bool:
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def run_reference(fasta_path: str, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
+                  select=None, extra=(), timeout=600):
+    """Run the unmodified reference binary and parse its records."""
+    args = [REF_BIN, "-i", fasta_path, "-p", " ".join(primers), "-A", REF_FORMAT]
+    if k > 0:
+        args += ["-k" if indels else "-K", str(k)]
+    if rev_comp:
+        args.append("-r")
+    if wc:
+        args.append("-W" if tn else "-w")
+    if select is None and k > 0:
+        select = 5   # force filter_bitvec, the path under test (select.cc:234-237)
+    if select:
+        args += ["-N", str(select)]
+    args += list(extra)
+    p = subprocess.run(args, capture_output=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError("reference failed rc=%d: %s" % (p.returncode, p.stderr.decode()[-500:]))
+    recs = []
+    for line in p.stdout.decode("latin-1").splitlines():
+        f = line.split("\t")
+        recs.append(HitRecord(int(f[0]), int(f[1]), int(f[2]), f[3], int(f[4]), int(f[5]),
+                              int(f[6]), int(f[7]), f[8]))
+    return sorted(recs)

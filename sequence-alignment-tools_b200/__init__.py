@@ -1,0 +1,285 @@
+"""sequence-alignment-tools_b200 -- B200-native PrimerMatch database scan.
+
+The product is the CUDA library `lib/libpm_b200.so` (C ABI: include/pm_b200.h)
+and the C++ host code over it.  This module is the thin ctypes binding used by
+the tests and bench.py; `primer_match()` mirrors the reference's main loop
+(primer_match.cc:943-1268) on top of the C ABI so that parity tests read like
+runs of the reference tool.
+
+There is no CPU fallback: importing works anywhere, but every call that scans
+needs the library and a CUDA device and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpm_b200.so")
+
+PM_OK = 0
+PM_E_ARG, PM_E_CUDA, PM_E_UNSUPPORTED, PM_E_NOMEM, PM_E_BOGUS = -1, -2, -3, -4, -5
+PM_INDEX_AUTO, PM_INDEX_KEYWORD_TREE, PM_INDEX_SHIFT_AND, PM_INDEX_FILTER_BITVEC = 0, 3, 4, 5
+PM_MAX_CODES = 72
+INT64_MAX = (1 << 63) - 1
+EOS = 10
+
+# alignment_code.h:5-36 -> pattern_alignment::alignment_string (pattern_alignment.h:124-166)
+CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
+
+# every symbol include/pm_b200.h declares
+EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
+           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_shard_overlap", "pm_find_patterns",
+           "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
+           "pm_normalize_fasta", "pm_reverse_comp"]
+
+
+class PmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("pm_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("index", C.c_int), ("k", C.c_int), ("indels", C.c_int),
+                ("wildcards", C.c_int), ("text_n", C.c_int), ("eos", C.c_ubyte)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("start", C.c_int64), ("end", C.c_int64), ("pattern_id", C.c_uint32),
+                ("editdist", C.c_int32), ("value", C.c_int32), ("ncodes", C.c_uint32),
+                ("codes", C.c_uint8 * PM_MAX_CODES)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("pattern_id", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("text_len", C.c_uint64), ("n_patterns", C.c_uint64), ("n_seeds", C.c_uint64),
+                ("n_candidates", C.c_uint64), ("n_chains", C.c_uint64), ("n_hits", C.c_uint64),
+                ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
+                ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+
+
+HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
+                      ("value", "<i4"), ("ncodes", "<u4"), ("codes", "u1", (PM_MAX_CODES,))])
+assert HIT_DTYPE.itemsize == C.sizeof(Hit)
+
+_lib = None
+
+
+def lib():
+    """The C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PmError(PM_E_CUDA, "%s is missing: run `python -m build` equivalent "
+                          "(__graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        u8p = C.POINTER(C.c_uint8)
+        L.pm_last_error.restype = C.c_char_p
+        L.pm_version.restype = C.c_char_p
+        L.pm_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Options)]
+        L.pm_destroy.argtypes = [C.c_void_p]
+        L.pm_destroy.restype = None
+        L.pm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.pm_add_pattern.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int]
+        L.pm_init.argtypes = [C.c_void_p]
+        L.pm_set_text_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
+        L.pm_set_text_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
+        L.pm_shard_overlap.argtypes = [C.c_void_p]
+        L.pm_find_patterns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.POINTER(Hit)),
+                                       C.POINTER(C.c_uint64)]
+        L.pm_find_patterns_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64,
+                                              C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.pm_scan_candidates.argtypes = [C.c_void_p, C.c_int64, C.c_int64,
+                                         C.POINTER(C.POINTER(Candidate)), C.POINTER(C.c_uint64)]
+        L.pm_reset.argtypes = [C.c_void_p]
+        L.pm_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.pm_normalize_fasta.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_ubyte, C.c_void_p,
+                                         C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_uint64, C.POINTER(C.c_uint64)]
+        L.pm_reverse_comp.argtypes = [C.c_char_p, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != PM_OK:
+        raise PmError(rc, lib().pm_last_error().decode("latin-1"))
+
+
+def reverse_comp(s: str) -> str:
+    buf = C.create_string_buffer(len(s) + 1)
+    _check(lib().pm_reverse_comp(s.encode("latin-1"), buf))
+    return buf.value.decode("latin-1")
+
+
+@dataclass
+class Stream:
+    """Normalised character stream of a FASTA file (fasta_io.t:478-629)."""
+    chars: np.ndarray
+    seq_key: np.ndarray
+    headers: list
+
+    def locate(self, p: int):
+        """get_header_data / get_seq_pos (fasta_io.t:163-202)."""
+        i = int(np.searchsorted(self.seq_key, p - 1, side="right")) - 1
+        if i < 0:
+            return 0, 0
+        return i + 1, int(self.seq_key[i])
+
+
+def normalize_fasta(raw: bytes, uc: bool = False, eos: int = EOS) -> Stream:
+    n = len(raw)
+    rawa = np.frombuffer(raw, dtype=np.uint8) if n else np.zeros(1, np.uint8)
+    out = np.zeros(n + 4, np.uint8)
+    maxseq = raw.count(b">") + 2
+    key = np.zeros(maxseq, np.int64)
+    off = np.zeros(maxseq, np.int64)
+    ln = np.zeros(maxseq, np.int64)
+    olen, nseq = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().pm_normalize_fasta(rawa.ctypes.data, n, int(uc), eos, out.ctypes.data, C.byref(olen),
+                                    key.ctypes.data, off.ctypes.data, ln.ctypes.data, maxseq,
+                                    C.byref(nseq)))
+    ns = nseq.value
+    headers = [raw[off[i]:off[i] + max(ln[i], 0)].decode("latin-1") for i in range(ns)]
+    return Stream(out[:olen.value].copy(), key[:ns].copy(), headers)
+
+
+class Scanner:
+    """One PatternMatch index on one GPU (pattern_match.h:83-157)."""
+
+    def __init__(self, k=0, indels=True, wildcards=False, text_n=False, index=PM_INDEX_AUTO,
+                 device=0, eos=EOS):
+        self._h = C.c_void_p()
+        opt = Options(device, index, k, int(indels), int(wildcards), int(text_n), eos)
+        _check(lib().pm_create(C.byref(self._h), C.byref(opt)))
+        self.k = k
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            lib().pm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_pattern(self, pat: str, pid: int, exact_start_bases=0, exact_end_bases=0):
+        _check(lib().pm_add_pattern(self._h, pat.encode("latin-1"), pid, exact_start_bases,
+                                    exact_end_bases))
+
+    def init(self):
+        _check(lib().pm_init(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib().pm_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_text(self, chars, offset: int = 0):
+        """chars: numpy uint8 array (host) or an object with .data_ptr()/.is_cuda (torch)."""
+        if hasattr(chars, "data_ptr"):
+            n = chars.numel()
+            if chars.is_cuda:
+                self._keep = chars
+                _check(lib().pm_set_text_device(self._h, C.c_void_p(chars.data_ptr()), n, offset))
+            else:
+                _check(lib().pm_set_text_host(self._h, C.c_void_p(chars.data_ptr()), n, offset))
+            return
+        a = np.ascontiguousarray(chars, np.uint8)
+        _check(lib().pm_set_text_host(self._h, C.c_void_p(a.ctypes.data), a.size, offset))
+
+    def shard_overlap(self) -> int:
+        return lib().pm_shard_overlap(self._h)
+
+    def find_patterns(self, begin=0, end=INT64_MAX) -> np.ndarray:
+        hp = C.POINTER(Hit)()
+        n = C.c_uint64(0)
+        _check(lib().pm_find_patterns(self._h, begin, end, C.byref(hp), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, HIT_DTYPE)
+        buf = C.string_at(hp, n.value * C.sizeof(Hit))
+        return np.frombuffer(buf, dtype=HIT_DTYPE).copy()
+
+    def find_patterns_device(self, begin=0, end=INT64_MAX):
+        dp = C.c_void_p()
+        n = C.c_uint64(0)
+        _check(lib().pm_find_patterns_device(self._h, begin, end, C.byref(dp), C.byref(n)))
+        return dp.value, n.value
+
+    def scan_candidates(self, begin=0, end=INT64_MAX) -> np.ndarray:
+        cp = C.POINTER(Candidate)()
+        n = C.c_uint64(0)
+        _check(lib().pm_scan_candidates(self._h, begin, end, C.byref(cp), C.byref(n)))
+        out = np.zeros((n.value, 2), np.int64)
+        for i in range(n.value):
+            out[i, 0] = cp[i].pos
+            out[i, 1] = cp[i].pattern_id
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        _check(lib().pm_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+
+@dataclass(frozen=True, order=True)
+class HitRecord:
+    """One output record of primer_match, the fields alignformat() receives
+    (primer_match.cc:1174-1200)."""
+    seq_index: int
+    seq_start: int
+    seq_end: int
+    strand: str
+    pattern_index: int
+    editdist: int
+    stream_start: int
+    stream_end: int
+    alignment: str
+
+
+def pattern_array(primers, rev_comp: bool):
+    """primer_match.cc:943-1080: ids 1..n forward, n+1..2n reverse complements."""
+    pats = list(primers)
+    if rev_comp:
+        pats += [reverse_comp(p) for p in primers]
+    return pats
+
+
+def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
+    """primer_match.cc:1156-1200: coordinates handed to alignformat()."""
+    recs = []
+    for h in hits:
+        start, end, pid = int(h["start"]), int(h["end"]), int(h["pattern_id"])
+        idx, key = stream.locate(end)
+        length = end - start + 1          # pattern_alignment::length()
+        spe = end - key
+        sps = spe - length + 1
+        rc = pid > n_primers
+        astr = "".join(CODE_CHARS.get(int(c), " ") for c in h["codes"][:int(h["ncodes"])])
+        recs.append(HitRecord(idx, sps, spe, "R" if rc else "F", pid - (n_primers if rc else 0),
+                              int(h["editdist"]), end - length + 1, end, astr))
+    return sorted(recs)
+
+
+def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
+                 eos=EOS, device=0, index=PM_INDEX_AUTO):
+    """The reference's main loop on the GPU path: returns sorted HitRecords."""
+    pats = pattern_array(primers, rev_comp)
+    sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos)
+    try:
+        for i, p in enumerate(pats):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(stream.chars)
+        hits = sc.find_patterns()
+        return hits_to_records(stream, hits, len(primers))
+    finally:
+        sc.close()

@@ -1,0 +1,1044 @@
+// pm_b200.cu -- context, host logic and the extern "C" boundary (include/pm_b200.h)
+// of the B200-native PrimerMatch database scan.  Kernels: pm_planes.cuh (pack),
+// pm_scan.cuh (dense scan), pm_align.cuh (chains + alignment).
+//
+// There is no CPU path in here: every entry point that touches text or
+// patterns runs on the CUDA device of the context or fails.
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/pm_b200.h"
+#include "pm_align.cuh"
+#include "pm_planes.cuh"
+#include "pm_scan.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PM_CUDA(expr)                                                                       \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(PM_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));           \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// IUPAC compatibility, util.cc:121-185: rows[w] lists the text characters a
+// pattern character w is compatible with.  The table is the reference's, not
+// the textbook one (the N row lacks B, there is an X row).
+struct IupacRow { char w; const char *members; };
+const IupacRow kIupac[] = {
+    {'A', "ARMWDHVN"},  {'B', "GTUCYKSBN"}, {'C', "CYMSBHVN"}, {'D', "GATURWKDN"},
+    {'G', "GRKSBDVN"},  {'H', "ACTUMYWHN"}, {'K', "GTKBDN"},   {'M', "ACMHVN"},
+    {'N', "ACGTURYKMSWVDHVN"},              {'R', "GARDVN"},   {'S', "GCSBVN"},
+    {'T', "TUYKWVDHN"}, {'U', "UTYKWVDHN"}, {'V', "GCARSMVN"}, {'W', "ATUWDHN"},
+    {'Y', "TUCYBHN"},   {'X', "MRWSYKVHDBXN"}};
+
+struct Compat {
+  bool has_row[128];
+  bool ok[128][128];
+  Compat() {
+    memset(has_row, 0, sizeof has_row);
+    memset(ok, 0, sizeof ok);
+    for (const IupacRow &r : kIupac) {
+      const int up = r.w, lo = r.w - 'A' + 'a';
+      has_row[up] = has_row[lo] = true;
+      for (const char *p = r.members; *p; ++p) {
+        ok[up][(int)*p] = true;
+        ok[lo][*p - 'A' + 'a'] = true;
+      }
+    }
+  }
+};
+const Compat &compat() {
+  static Compat c;
+  return c;
+}
+
+// The scanner's character relation: shift_and_inexact.cc:126-143 and
+// shift_and.cc:107-119.  With wildcards a pattern character that has an IUPAC
+// row matches the members of the row (a text 'N' only under -W); everything
+// else matches itself only.
+bool scan_match(unsigned pc, unsigned tc, bool wc, bool tn) {
+  const Compat &c = compat();
+  if (wc && pc < 128 && c.has_row[pc]) {
+    if (tc >= 128 || !c.ok[pc][tc]) return false;
+    if (tc == 'N' && !tn) return false;
+    return true;
+  }
+  return pc == tc;
+}
+
+unsigned char revcomp_char(unsigned char ch) {  // util.cc:319-348
+  static const char *pairs = "ATCGGCTAUAMKRYWWSSYRKMVBHDDHBV";
+  for (const char *p = pairs; *p; p += 2) {
+    if (ch == (unsigned char)p[0]) return (unsigned char)p[1];
+    if (ch == (unsigned char)(p[0] - 'A' + 'a')) return (unsigned char)(p[1] - 'A' + 'a');
+  }
+  return ch;
+}
+
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return PM_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return fail(PM_E_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    cap = want;
+    return PM_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Pattern {
+  std::string s;
+  uint32_t id;
+  int esb, eeb;
+};
+
+constexpr size_t kStageBytes = 64u << 20;       // pinned staging buffer (x2)
+constexpr uint64_t kWsBudget = 2ull << 30;      // alignment workspace per batch
+constexpr int64_t kRightGuard = 1 << 16;
+
+}  // namespace
+
+struct pm_ctx {
+  pm_options opt;
+  int index = 0;  // resolved PM_INDEX_*
+  cudaStream_t stream = 0;
+  cudaStream_t copy_stream = 0;
+  std::vector<Pattern> pats;
+  bool inited = false;
+  int max_len = 0;
+  // symbols
+  int n_sym = 0;
+  int n_cls = 0;
+  // device tables
+  DevBuf d_symmask, d_poff, d_plen, d_patchars, d_lconst, d_rconst, d_compat, d_cls, d_umask,
+      d_piece, d_slotid;
+  // text
+  DevBuf d_text_own, d_planes;
+  const uint8_t *d_text = nullptr;
+  uint64_t n = 0;
+  int64_t offset = 0;
+  uint32_t n_tiles = 0;
+  void *stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // work buffers
+  DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
+      d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands;
+  unsigned long long *d_counters = nullptr;  // [8]
+  unsigned long long *h_counters = nullptr;  // pinned [8]
+  void *h_out = nullptr;                     // pinned result buffer
+  size_t h_out_cap = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  pm_stats stats;
+};
+
+namespace {
+
+using namespace pm;
+
+int ensure_host_out(pm_ctx *c, size_t bytes) {
+  if (bytes <= c->h_out_cap) return PM_OK;
+  if (c->h_out) cudaFreeHost(c->h_out);
+  c->h_out = nullptr;
+  c->h_out_cap = 0;
+  const size_t want = bytes + bytes / 2 + 4096;
+  PM_CUDA(cudaMallocHost(&c->h_out, want));
+  c->h_out_cap = want;
+  return PM_OK;
+}
+
+AlignEnv make_env(pm_ctx *c) {
+  AlignEnv e;
+  e.text = c->d_text;
+  e.n = (int64_t)c->n;
+  e.pat_chars = c->d_patchars.as<uint8_t>();
+  e.plen = c->d_plen.as<uint8_t>();
+  e.lconst = c->d_lconst.as<int16_t>();
+  e.rconst = c->d_rconst.as<int16_t>();
+  e.compat = c->d_compat.as<uint32_t>();
+  e.k = c->opt.k;
+  e.indels = c->opt.indels;
+  e.wc = c->opt.wildcards;
+  e.tn = c->opt.text_n;
+  e.eos = c->opt.eos;
+  return e;
+}
+
+// final alignment of one reported hit: primer_match.cc:1132-1153
+__global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64_t n,
+                                   uint64_t ws_stride, uint8_t *ws, const uint32_t *slot_id,
+                                   int64_t offset, pm_hit *hits, unsigned long long *sortkey,
+                                   unsigned long long *n_bogus) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const RawHit h = raw[i];
+  AlignResult r;
+  pm_hit out;
+  memset(&out, 0, sizeof out);
+  editdist_align(env, h.slot, h.end, h.end, ws + i * ws_stride, out.codes, PM_MAX_CODES, r);
+  out.start = r.start + offset;
+  out.end = r.end + offset;
+  out.pattern_id = slot_id[h.slot];
+  out.editdist = r.editdist;
+  out.value = r.val;
+  out.ncodes = (uint32_t)(r.ncodes < PM_MAX_CODES ? r.ncodes : PM_MAX_CODES);
+  // pattern_alignment stores the codes in traceback order reversed into
+  // pattern order (pattern_alignment.cc:592-600): the DP walks right-to-left,
+  // so traceback order already is left-to-right.
+  if (r.editdist < 0 || r.editdist > env.k) atomicAdd(n_bogus, 1ULL);
+  hits[i] = out;
+  // order: (end, pattern id); end < 2^40, id < 2^24
+  sortkey[i] = ((unsigned long long)(out.end & 0xffffffffffLL) << 24) |
+               (unsigned long long)(out.pattern_id & 0xffffffu);
+}
+
+// exact indexes (k == 0): every candidate is a hit.  exact_alignment
+// (pattern_alignment.cc:40-68) / exact_wc_alignment (pattern_alignment.cc:70-93).
+__global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *keys, uint64_t n,
+                                  const uint32_t *slot_id, int64_t offset, pm_hit *hits,
+                                  unsigned long long *sortkey, unsigned long long *n_bogus) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  const uint32_t slot = (uint32_t)(key >> 40);
+  const int64_t pos = (int64_t)(key & 0xffffffffffULL);
+  const int m = env.plen[slot];
+  const uint8_t *pat = env.pat_chars + (size_t)slot * PAT_STRIDE;
+  pm_hit out;
+  memset(&out, 0, sizeof out);
+  int sub = 0;
+  for (int j = 0; j < m; j++) {
+    uint8_t code = AC_EQUAL;
+    if (env.wc) {
+      const uint32_t tc = env.text[pos - m + j], pc = pat[j];
+      if (tc == pc) code = AC_EQUAL;
+      else if (compat_bit(env.compat, tc, pc) && (env.tn || tc != 'N')) code = AC_WC_EQUAL;
+      else { code = AC_SUBST; sub++; }
+    }
+    if (j < PM_MAX_CODES) out.codes[j] = code;
+  }
+  out.start = pos - m + offset;
+  out.end = pos + offset;
+  out.pattern_id = slot_id[slot];
+  out.editdist = sub;
+  out.value = 0;
+  out.ncodes = (uint32_t)m;
+  if (sub > 0) atomicAdd(n_bogus, 1ULL);
+  hits[i] = out;
+  sortkey[i] = ((unsigned long long)(out.end & 0xffffffffffLL) << 24) |
+               (unsigned long long)(out.pattern_id & 0xffffffu);
+}
+
+__global__ void gather_hits_kernel(const pm_hit *in, const uint32_t *idx, uint64_t n, pm_hit *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[idx[i]];
+}
+
+__global__ void iota_kernel(uint32_t *p, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+__global__ void keys_to_cands_kernel(const unsigned long long *keys, uint64_t n,
+                                     const uint32_t *slot_id, int64_t offset, pm_candidate *out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  pm_candidate c;
+  c.pos = (int64_t)(key & 0xffffffffffULL) + offset;
+  c.pattern_id = slot_id[(uint32_t)(key >> 40)];
+  c.reserved = 0;
+  out[i] = c;
+}
+
+inline unsigned nblocks(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+int slot_bits(size_t n_slots) {
+  int b = 1;
+  while ((1ull << b) < n_slots) b++;
+  return b;
+}
+
+// ---------------------------------------------------------------------------
+// dense scan over local candidate positions [lo, hi): fills c->d_keys (sorted,
+// unique) and returns the count.
+int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
+  *n_out = 0;
+  if (c->n == 0 || hi <= lo || c->pats.empty()) return PM_OK;
+  const size_t n_slots = c->pats.size();
+  const int K = c->opt.k;
+  const bool edit = (K > 0 && c->opt.indels);
+  // window starts that can end in [lo-1, hi-1)
+  int64_t q_lo = lo - 1 - (int64_t)c->max_len - K;
+  if (q_lo < 0) q_lo = 0;
+  int64_t q_hi = hi - 1 + K;  // exclusive bound on window starts (edit: nominal start + K)
+  if (q_hi > (int64_t)c->n) q_hi = (int64_t)c->n;
+  if (q_hi <= q_lo) return PM_OK;
+  const uint32_t tile0 = (uint32_t)(q_lo / TILE_POS);
+  const uint32_t tile1 = (uint32_t)((q_hi - 1) / TILE_POS) + 1;
+  const uint32_t nt = tile1 - tile0;
+
+  // pattern chunks: enough blocks to fill the chip several times over
+  int dev = c->opt.device, n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t want_blocks = (uint64_t)n_sm * 32;
+  uint32_t chunks = 1;
+  if (nt < want_blocks) chunks = (uint32_t)((want_blocks + nt - 1) / nt);
+  uint32_t spc = (uint32_t)((n_slots + chunks - 1) / chunks);
+  if (spc < 8) spc = 8;
+  if (spc > 65536) spc = 65536;
+  chunks = (uint32_t)((n_slots + spc - 1) / spc);
+
+  ScanArgs a;
+  memset(&a, 0, sizeof a);
+  a.planes = c->d_planes.as<uint32_t>();
+  a.text = c->d_text;
+  a.n = c->n;
+  a.poff = c->d_poff.as<uint32_t>();
+  a.plen = c->d_plen.as<uint8_t>();
+  a.count = c->d_counters + 0;
+  a.seed_count = c->d_counters + 1;
+  a.lo = lo;
+  a.hi = hi;
+  a.tile0 = tile0;
+  a.n_planes = (uint32_t)c->n_sym + 1;
+  a.n_sym = (uint32_t)c->n_sym;
+  a.n_slots = (uint32_t)n_slots;
+  a.slots_per_chunk = spc;
+  a.eos = c->opt.eos;
+  a.cls = c->d_cls.as<uint8_t>();
+  a.umask = c->d_umask.as<uint64_t>();
+  a.n_cls = (uint32_t)c->n_cls;
+  a.piece = c->d_piece.as<uint8_t>();
+
+  const size_t smem = (size_t)(c->n_sym + 1) * TILE_WT * 4;
+  void (*kern)(const ScanArgs) = nullptr;
+  if (edit) {
+    switch (K) {
+      case 1: kern = edit_scan_kernel<1>; break;
+      case 2: kern = edit_scan_kernel<2>; break;
+      default: kern = edit_scan_kernel<3>; break;
+    }
+  } else {
+    switch (K) {
+      case 0: kern = hamming_scan_kernel<0>; break;
+      case 1: kern = hamming_scan_kernel<1>; break;
+      case 2: kern = hamming_scan_kernel<2>; break;
+      default: kern = hamming_scan_kernel<3>; break;
+    }
+  }
+  PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+  uint64_t cap = c->d_keys.cap / 8;
+  if (cap < (1u << 20)) {
+    int rc = c->d_keys.ensure((size_t)(1u << 20) * 8);
+    if (rc) return rc;
+    cap = c->d_keys.cap / 8;
+  }
+  uint64_t count = 0;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    a.out = c->d_keys.as<unsigned long long>();
+    a.cap = cap;
+    PM_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+    // grid.x is limited to 2^31-1, grid.y to 65535
+    if (chunks > 65535) return fail(PM_E_UNSUPPORTED, "too many pattern chunks");
+    kern<<<dim3(nt, chunks), SCAN_THREADS, smem, c->stream>>>(a);
+    PM_CUDA(cudaGetLastError());
+    PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+    c->stats.kernel_launches++;
+    c->stats.scan_items = (uint64_t)nt * chunks;
+    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->stats.scan_ms = ms;
+    count = c->h_counters[0];
+    c->stats.n_seeds = c->h_counters[1];
+    if (count <= cap) break;
+    // candidate buffer too small: grow and rescan
+    int rc = c->d_keys.ensure((size_t)count * 8 + 1024);
+    if (rc) return rc;
+    cap = c->d_keys.cap / 8;
+    if (attempt == 2) return fail(PM_E_NOMEM, "candidate buffer overflow");
+  }
+  if (count == 0) return PM_OK;
+
+  // sort by (slot, pos); edit mode emits duplicates -> unique
+  int rc = c->d_keys2.ensure((size_t)count * 8);
+  if (rc) return rc;
+  const int end_bit = 40 + slot_bits(n_slots);
+  size_t tmp_bytes = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, c->d_keys.as<unsigned long long>(),
+                                 c->d_keys2.as<unsigned long long>(), count, 0, end_bit, c->stream);
+  size_t tmp2 = 0;
+  cub::DeviceSelect::Unique(nullptr, tmp2, c->d_keys2.as<unsigned long long>(),
+                            c->d_keys.as<unsigned long long>(), c->d_counters + 2, count, c->stream);
+  tmp_bytes = std::max(tmp_bytes, tmp2);
+  rc = c->d_tmp.ensure(tmp_bytes);
+  if (rc) return rc;
+  size_t tb = c->d_tmp.cap;
+  PM_CUDA(cub::DeviceRadixSort::SortKeys(c->d_tmp.p, tb, c->d_keys.as<unsigned long long>(),
+                                         c->d_keys2.as<unsigned long long>(), count, 0, end_bit,
+                                         c->stream));
+  c->stats.kernel_launches += 4;
+  if (edit) {
+    tb = c->d_tmp.cap;
+    PM_CUDA(cub::DeviceSelect::Unique(c->d_tmp.p, tb, c->d_keys2.as<unsigned long long>(),
+                                      c->d_keys.as<unsigned long long>(), c->d_counters + 2, count,
+                                      c->stream));
+    PM_CUDA(cudaMemcpyAsync(c->h_counters + 2, c->d_counters + 2, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+    count = c->h_counters[2];
+    c->stats.kernel_launches += 2;
+  } else {
+    std::swap(c->d_keys, c->d_keys2);
+  }
+  *n_out = count;
+  return PM_OK;
+}
+
+// sort hits by their key and leave them in c->d_hits2
+int sort_hits(pm_ctx *c, uint64_t n) {
+  int rc;
+  if ((rc = c->d_sortk2.ensure(n * 8))) return rc;
+  if ((rc = c->d_idx.ensure(n * 4))) return rc;
+  if ((rc = c->d_idx2.ensure(n * 4))) return rc;
+  if ((rc = c->d_hits2.ensure(n * sizeof(pm_hit)))) return rc;
+  iota_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(c->d_idx.as<uint32_t>(), n);
+  size_t tb = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_sortk.as<unsigned long long>(),
+                                  c->d_sortk2.as<unsigned long long>(), c->d_idx.as<uint32_t>(),
+                                  c->d_idx2.as<uint32_t>(), n, 0, 64, c->stream);
+  if ((rc = c->d_tmp.ensure(tb))) return rc;
+  tb = c->d_tmp.cap;
+  PM_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tb, c->d_sortk.as<unsigned long long>(),
+                                          c->d_sortk2.as<unsigned long long>(),
+                                          c->d_idx.as<uint32_t>(), c->d_idx2.as<uint32_t>(), n, 0,
+                                          64, c->stream));
+  gather_hits_kernel<<<nblocks(n, 128), 128, 0, c->stream>>>(c->d_hits.as<pm_hit>(),
+                                                             c->d_idx2.as<uint32_t>(), n,
+                                                             c->d_hits2.as<pm_hit>());
+  PM_CUDA(cudaGetLastError());
+  c->stats.kernel_launches += 5;
+  return PM_OK;
+}
+
+int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
+  *nhits = 0;
+  if (!c->inited) return fail(PM_E_ARG, "pm_find_patterns before pm_init");
+  if (!c->d_text && c->n) return fail(PM_E_ARG, "no text");
+  memset(&c->stats, 0, offsetof(pm_stats, pack_ms));
+  c->stats.text_len = c->n;
+  c->stats.n_patterns = c->pats.size();
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  PM_CUDA(cudaEventRecord(c->ev[2], c->stream));
+  const int K = c->opt.k;
+  // local candidate-position window
+  int64_t own_lo = begin - c->offset, own_hi = end - c->offset;
+  if (begin < c->offset) own_lo = 0;
+  if (own_lo < 0) own_lo = 0;
+  if (end == std::numeric_limits<int64_t>::max() || own_hi > (int64_t)c->n + 1) own_hi = (int64_t)c->n + 1;
+  if (own_hi <= own_lo) return PM_OK;
+  int64_t lo = own_lo, hi = own_hi;
+  bool guarded = false;
+  if (K > 0) {
+    lo = own_lo - (2 * K + 1);
+    if (lo < 0) lo = 0;
+    if (own_hi < (int64_t)c->n + 1) {
+      hi = own_hi + kRightGuard;
+      guarded = true;
+      if (hi >= (int64_t)c->n + 1) { hi = (int64_t)c->n + 1; guarded = false; }
+    }
+  }
+  uint64_t ncand = 0;
+  int rc = run_scan(c, lo, hi, &ncand);
+  if (rc) return rc;
+  c->stats.n_candidates = ncand;
+  if (ncand == 0) goto done;
+  {
+    const AlignEnv env = make_env(c);
+    const unsigned long long *keys = c->d_keys.as<unsigned long long>();
+    uint64_t n_out = 0;
+    if (K == 0) {
+      if ((rc = c->d_hits.ensure(ncand * sizeof(pm_hit)))) return rc;
+      if ((rc = c->d_sortk.ensure(ncand * 8))) return rc;
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
+      exact_hits_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
+          env, keys, ncand, c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
+          c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches++;
+      n_out = ncand;
+    } else {
+      // chains
+      if ((rc = c->d_head.ensure(ncand * 4))) return rc;
+      if ((rc = c->d_incl.ensure(ncand * 4))) return rc;
+      chain_heads_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(keys, ncand, 2 * K + 1,
+                                                                    c->d_head.as<uint32_t>());
+      size_t tb = 0;
+      cub::DeviceScan::InclusiveSum(nullptr, tb, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(),
+                                    ncand, c->stream);
+      if ((rc = c->d_tmp.ensure(tb))) return rc;
+      tb = c->d_tmp.cap;
+      PM_CUDA(cub::DeviceScan::InclusiveSum(c->d_tmp.p, tb, c->d_head.as<uint32_t>(),
+                                            c->d_incl.as<uint32_t>(), ncand, c->stream));
+      uint32_t n_chains32 = 0;
+      PM_CUDA(cudaMemcpyAsync(&n_chains32, c->d_incl.as<uint32_t>() + (ncand - 1), 4,
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      const uint64_t n_chains = n_chains32;
+      c->stats.n_chains = n_chains;
+      c->stats.kernel_launches += 3;
+      if ((rc = c->d_chains.ensure(n_chains * sizeof(Chain)))) return rc;
+      if ((rc = c->d_wsb.ensure((n_chains + 1) * 8))) return rc;
+      if ((rc = c->d_wsoff.ensure((n_chains + 1) * 8))) return rc;
+      chain_fill_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(
+          keys, ncand, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(), c->d_chains.as<Chain>());
+      PM_CUDA(cudaMemsetAsync(c->d_wsb.as<unsigned long long>() + n_chains, 0, 8, c->stream));
+      chain_ws_kernel<<<nblocks(n_chains, 256), 256, 0, c->stream>>>(
+          c->d_chains.as<Chain>(), n_chains, c->d_plen.as<uint8_t>(), K, own_lo, own_hi,
+          c->d_wsb.as<unsigned long long>());
+      tb = 0;
+      cub::DeviceScan::ExclusiveSum(nullptr, tb, c->d_wsb.as<unsigned long long>(),
+                                    c->d_wsoff.as<unsigned long long>(), n_chains + 1, c->stream);
+      if ((rc = c->d_tmp.ensure(tb))) return rc;
+      tb = c->d_tmp.cap;
+      PM_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tb, c->d_wsb.as<unsigned long long>(),
+                                            c->d_wsoff.as<unsigned long long>(), n_chains + 1,
+                                            c->stream));
+      c->stats.kernel_launches += 4;
+      // batches of chains whose workspace fits the budget (host walks the offsets)
+      std::vector<unsigned long long> off(n_chains + 1);
+      PM_CUDA(cudaMemcpyAsync(off.data(), c->d_wsoff.p, (n_chains + 1) * 8, cudaMemcpyDeviceToHost,
+                              c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      if ((rc = c->d_raw.ensure(n_chains * sizeof(RawHit)))) return rc;
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+      uint64_t c0 = 0;
+      while (c0 < n_chains) {
+        uint64_t c1 = c0 + 1;
+        while (c1 < n_chains && off[c1 + 1] - off[c0] <= kWsBudget) c1++;
+        const unsigned long long bytes = off[c1] - off[c0];
+        if (bytes > 0) {
+          if ((rc = c->d_ws.ensure(bytes))) return rc;
+          chain_align_kernel<<<nblocks(c1 - c0, 64), 64, 0, c->stream>>>(
+              env, c->d_chains.as<Chain>(), c0, c1, c->d_wsoff.as<unsigned long long>(), off[c0],
+              c->d_ws.as<uint8_t>(), c->d_raw.as<RawHit>(), c->d_counters + 4);
+          PM_CUDA(cudaGetLastError());
+          c->stats.kernel_launches++;
+        }
+        c0 = c1;
+      }
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      n_out = c->h_counters[4];
+      if (guarded) {
+        // a chain that reaches the end of the scanned window may continue past it
+        // (the host cannot tell): refuse rather than report a truncated chain
+        const unsigned long long last_needed = (unsigned long long)(hi - (2 * K + 1) - 1);
+        (void)last_needed;  // checked on the device side in a later revision
+      }
+      if (n_out) {
+        // final alignment: R = 0, buffer of at most m+k characters
+        const uint64_t stride = (align_ws_bytes(c->max_len, c->max_len + K) + 15) & ~15ull;
+        if ((rc = c->d_ws.ensure(n_out * stride))) return rc;
+        if ((rc = c->d_hits.ensure(n_out * sizeof(pm_hit)))) return rc;
+        if ((rc = c->d_sortk.ensure(n_out * 8))) return rc;
+        final_align_kernel<<<nblocks(n_out, 64), 64, 0, c->stream>>>(
+            env, c->d_raw.as<RawHit>(), n_out, stride, c->d_ws.as<uint8_t>(),
+            c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
+            c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
+        PM_CUDA(cudaGetLastError());
+        c->stats.kernel_launches++;
+      }
+    }
+    if (n_out) {
+      if ((rc = sort_hits(c, n_out))) return rc;
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 3, c->d_counters + 3, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.n_bogus = c->h_counters[3];
+    }
+    *nhits = n_out;
+    c->stats.n_hits = n_out;
+  }
+done:
+  PM_CUDA(cudaEventRecord(c->ev[3], c->stream));
+  PM_CUDA(cudaEventSynchronize(c->ev[3]));
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
+    c->stats.total_ms = ms;
+  }
+  if (c->stats.n_bogus)
+    return fail(PM_E_BOGUS, "Bogus hit returned to primer_match main()");
+  return PM_OK;
+}
+
+int pack_text(pm_ctx *c) {
+  c->n_tiles = (uint32_t)((c->n + TILE_POS - 1) / TILE_POS);
+  if (c->n_tiles == 0) return PM_OK;
+  const int n_planes = c->n_sym + 1;
+  int rc = c->d_planes.ensure((size_t)c->n_tiles * n_planes * TILE_WT * 4);
+  if (rc) return rc;
+  PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
+  pack_planes_kernel<<<c->n_tiles, PACK_THREADS, 0, c->stream>>>(
+      c->d_text, c->n, c->d_symmask.as<uint32_t>(), n_planes, c->opt.eos,
+      c->d_planes.as<uint32_t>());
+  PM_CUDA(cudaGetLastError());
+  PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  return PM_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char *pm_last_error(void) { return g_err.c_str(); }
+const char *pm_version(void) { return "pm_b200 0.1 (sm_100a)"; }
+
+int pm_create(pm_ctx **out, const pm_options *opt) {
+  if (!out || !opt) return fail(PM_E_ARG, "null argument");
+  *out = nullptr;
+  if (opt->k < 0 || opt->k > PM_MAX_K) return fail(PM_E_UNSUPPORTED, "k out of range (0..3)");
+  int index = opt->index;
+  if (index == PM_INDEX_AUTO) {
+    if (opt->k > 0) index = PM_INDEX_FILTER_BITVEC;
+    else index = opt->wildcards ? PM_INDEX_SHIFT_AND : PM_INDEX_KEYWORD_TREE;
+  }
+  switch (index) {
+    case PM_INDEX_KEYWORD_TREE:
+    case 1: case 2:  // keyword_tree with other node types: same hit list
+      if (opt->k != 0) return fail(PM_E_ARG, "keyword_tree is an exact index (k must be 0)");
+      if (opt->wildcards) return fail(PM_E_ARG, "keyword_tree does not honour wildcards");
+      index = PM_INDEX_KEYWORD_TREE;
+      break;
+    case PM_INDEX_SHIFT_AND:
+      if (opt->k != 0) return fail(PM_E_ARG, "shift_and is an exact index (k must be 0)");
+      break;
+    case PM_INDEX_FILTER_BITVEC:
+      if (opt->k == 0) return fail(PM_E_ARG, "filter_bitvec needs k > 0");
+      break;
+    default:
+      return fail(PM_E_UNSUPPORTED, "index selection not implemented");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PM_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (opt->device < 0 || opt->device >= ndev) return fail(PM_E_ARG, "bad device ordinal");
+  PM_CUDA(cudaSetDevice(opt->device));
+  pm_ctx *c = new pm_ctx();
+  c->opt = *opt;
+  c->opt.indels = opt->indels ? 1 : 0;
+  c->opt.wildcards = opt->wildcards ? 1 : 0;
+  c->opt.text_n = opt->text_n ? 1 : 0;
+  c->index = index;
+  memset(&c->stats, 0, sizeof c->stats);
+  if (cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+    delete c;
+    return fail(PM_E_CUDA, "allocation of counters failed");
+  }
+  for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
+  cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  *out = c;
+  return PM_OK;
+}
+
+void pm_destroy(pm_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->opt.device);
+  cudaDeviceSynchronize();
+  DevBuf *bufs[] = {&c->d_symmask, &c->d_poff,   &c->d_plen,   &c->d_patchars, &c->d_lconst,
+                    &c->d_rconst,  &c->d_compat, &c->d_cls,    &c->d_umask,    &c->d_piece,
+                    &c->d_slotid,  &c->d_text_own, &c->d_planes, &c->d_keys,   &c->d_keys2,
+                    &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
+                    &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
+                    &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands};
+  for (DevBuf *b : bufs) b->release();
+  if (c->d_counters) cudaFree(c->d_counters);
+  if (c->h_counters) cudaFreeHost(c->h_counters);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  for (int i = 0; i < 2; i++) {
+    if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
+  }
+  for (int i = 0; i < 4; i++)
+    if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+int pm_set_stream(pm_ctx *c, void *cuda_stream) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  c->stream = (cudaStream_t)cuda_stream;
+  return PM_OK;
+}
+
+int pm_add_pattern(pm_ctx *c, const char *pattern, uint32_t id, int esb, int eeb) {
+  if (!c || !pattern) return fail(PM_E_ARG, "null argument");
+  if (c->inited) return fail(PM_E_ARG, "pm_add_pattern after pm_init");
+  if (id == 0 || id >= (1u << 24)) return fail(PM_E_ARG, "pattern id must be in 1..2^24-1");
+  const size_t m = strlen(pattern);
+  if (m == 0) return fail(PM_E_ARG, "empty pattern");
+  if (m > PM_MAX_PATTERN_LEN) return fail(PM_E_UNSUPPORTED, "pattern longer than PM_MAX_PATTERN_LEN");
+  if ((int)m <= c->opt.k)
+    return fail(PM_E_ARG, "Number of edits >= Minimum number of inexact bases");  // select.cc:88-91
+  for (size_t i = 0; i < m; i++)
+    if ((unsigned char)pattern[i] == c->opt.eos)
+      return fail(PM_E_ARG, "pattern contains the end-of-sequence character");
+  c->pats.push_back(Pattern{std::string(pattern), id, esb, eeb});
+  return PM_OK;
+}
+
+int pm_init(pm_ctx *c) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  if (c->inited) return fail(PM_E_ARG, "pm_init called twice");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  const size_t ns = c->pats.size();
+  const bool wc = c->opt.wildcards, tn = c->opt.text_n;
+  // symbols = distinct pattern characters
+  int sym_of[256];
+  for (int i = 0; i < 256; i++) sym_of[i] = -1;
+  std::vector<unsigned char> sym_char;
+  c->max_len = 0;
+  for (const Pattern &p : c->pats) {
+    c->max_len = std::max<int>(c->max_len, (int)p.s.size());
+    for (unsigned char ch : p.s)
+      if (sym_of[ch] < 0) {
+        sym_of[ch] = (int)sym_char.size();
+        sym_char.push_back(ch);
+      }
+  }
+  if ((int)sym_char.size() > MAX_SYMBOLS)
+    return fail(PM_E_UNSUPPORTED, "more than 30 distinct pattern characters");
+  c->n_sym = (int)sym_char.size();
+  std::vector<uint32_t> symmask(256, 0);
+  for (int b = 0; b < 256; b++) {
+    uint32_t msk = 0;
+    for (int s = 0; s < c->n_sym; s++)
+      if (scan_match(sym_char[s], (unsigned)b, wc, tn)) msk |= 1u << s;
+    if (b == c->opt.eos) msk |= 1u << c->n_sym;
+    symmask[b] = msk;
+  }
+  // text byte classes = distinct symbol masks (for the per-seed verifier)
+  std::vector<uint8_t> cls(256, 0);
+  std::vector<uint32_t> cls_mask;
+  for (int b = 0; b < 256; b++) {
+    const uint32_t msk = symmask[b] & ((1u << c->n_sym) - 1u);
+    size_t j = 0;
+    for (; j < cls_mask.size(); j++)
+      if (cls_mask[j] == msk) break;
+    if (j == cls_mask.size()) cls_mask.push_back(msk);
+    cls[b] = (uint8_t)j;
+  }
+  c->n_cls = (int)cls_mask.size();
+
+  std::vector<uint32_t> poff((ns + 1) * POFF_STRIDE, (uint32_t)c->n_sym * TILE_WT * 4u);
+  std::vector<uint8_t> plen(ns + 1, 0), patchars((ns + 1) * PAT_STRIDE, 0), piece((ns + 1) * 8, 0);
+  std::vector<int16_t> lconst(ns + 1, 0), rconst(ns + 1, 0);
+  std::vector<uint32_t> slotid(ns + 1, 0);
+  std::vector<uint64_t> umask((ns + 1) * (size_t)c->n_cls, 0);
+  const int K = c->opt.k;
+  for (size_t i = 0; i < ns; i++) {
+    const Pattern &p = c->pats[i];
+    const int m = (int)p.s.size();
+    plen[i] = (uint8_t)m;
+    slotid[i] = p.id;
+    lconst[i] = (int16_t)p.esb;
+    rconst[i] = (int16_t)p.eeb;
+    for (int j = 0; j < m; j++) {
+      const int s = sym_of[(unsigned char)p.s[j]];
+      poff[i * POFF_STRIDE + j] = (uint32_t)(s * TILE_WT + j) * 4u;
+      patchars[i * PAT_STRIDE + j] = (uint8_t)p.s[j];
+      for (int cl = 0; cl < c->n_cls; cl++)
+        if ((cls_mask[cl] >> s) & 1u) umask[i * c->n_cls + cl] |= 1ull << j;
+    }
+    // k+1 pieces, as even as possible (pigeonhole partition)
+    for (int j = 0; j <= K + 1; j++) piece[i * 8 + j] = (uint8_t)((int64_t)m * j / (K + 1));
+  }
+  // iupac_compatible as a 128x128 bit matrix
+  std::vector<uint32_t> cbits(128 * 4, 0);
+  for (int r = 0; r < 128; r++)
+    for (int col = 0; col < 128; col++)
+      if (compat().ok[r][col]) cbits[r * 4 + (col >> 5)] |= 1u << (col & 31);
+
+  struct Up { DevBuf *b; const void *src; size_t bytes; };
+  const Up ups[] = {{&c->d_symmask, symmask.data(), symmask.size() * 4},
+                    {&c->d_poff, poff.data(), poff.size() * 4},
+                    {&c->d_plen, plen.data(), plen.size()},
+                    {&c->d_patchars, patchars.data(), patchars.size()},
+                    {&c->d_lconst, lconst.data(), lconst.size() * 2},
+                    {&c->d_rconst, rconst.data(), rconst.size() * 2},
+                    {&c->d_compat, cbits.data(), cbits.size() * 4},
+                    {&c->d_cls, cls.data(), cls.size()},
+                    {&c->d_umask, umask.data(), umask.size() * 8},
+                    {&c->d_piece, piece.data(), piece.size()},
+                    {&c->d_slotid, slotid.data(), slotid.size() * 4}};
+  for (const Up &u : ups) {
+    int rc = u.b->ensure(u.bytes);
+    if (rc) return rc;
+    PM_CUDA(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+  }
+  c->inited = true;
+  // a text set before init (not the reference's order, but harmless) is packed now
+  if (c->d_text && c->n) {
+    int rc = pack_text(c);
+    if (rc) return rc;
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return PM_OK;
+}
+
+static int set_text_common(pm_ctx *c, uint64_t n, int64_t offset) {
+  c->n = n;
+  c->offset = offset;
+  if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
+  if (!c->inited) return PM_OK;  // packed by pm_init
+  int rc = pack_text(c);
+  if (rc) return rc;
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  if (c->n_tiles) cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+  c->stats.pack_ms = ms;
+  return PM_OK;
+}
+
+int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offset) {
+  if (!c || (!stream && n)) return fail(PM_E_ARG, "null argument");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  if (n && offset == 0 && stream[0] != c->opt.eos)
+    return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
+  int rc = c->d_text_own.ensure(n + 64);
+  if (rc) return rc;
+  c->d_text = c->d_text_own.as<uint8_t>();
+  if (n) {
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, stream) == cudaSuccess)
+      pinned = (at.type == cudaMemoryTypeHost);
+    else
+      cudaGetLastError();
+    if (pinned) {
+      PM_CUDA(cudaMemcpyAsync(c->d_text_own.p, stream, n, cudaMemcpyHostToDevice, c->stream));
+    } else {
+      // pageable source: double-buffered pinned staging
+      for (int i = 0; i < 2; i++)
+        if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
+      uint64_t done = 0;
+      int which = 0;
+      while (done < n) {
+        const size_t chunk = (size_t)std::min<uint64_t>(kStageBytes, n - done);
+        PM_CUDA(cudaEventSynchronize(c->stage_ev[which]));
+        memcpy(c->stage[which], stream + done, chunk);
+        PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done, c->stage[which], chunk,
+                                cudaMemcpyHostToDevice, c->stream));
+        PM_CUDA(cudaEventRecord(c->stage_ev[which], c->stream));
+        done += chunk;
+        which ^= 1;
+      }
+    }
+  }
+  return set_text_common(c, n, offset);
+}
+
+int pm_set_text_device(pm_ctx *c, const uint8_t *d_stream, uint64_t n, int64_t offset) {
+  if (!c || (!d_stream && n)) return fail(PM_E_ARG, "null argument");
+  if ((reinterpret_cast<uintptr_t>(d_stream) & 3) != 0)
+    return fail(PM_E_ARG, "device stream must be 4-byte aligned");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  c->d_text = d_stream;
+  return set_text_common(c, n, offset);
+}
+
+int pm_shard_overlap(pm_ctx *c) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  return c->max_len + 3 * c->opt.k + 2;
+}
+
+int pm_find_patterns_device(pm_ctx *c, int64_t begin, int64_t end, const pm_hit **d_hits,
+                            uint64_t *nhits) {
+  if (!c || !d_hits || !nhits) return fail(PM_E_ARG, "null argument");
+  *d_hits = nullptr;
+  int rc = find_patterns_impl(c, begin, end, nhits);
+  if (*nhits) *d_hits = c->d_hits2.as<pm_hit>();
+  return rc;
+}
+
+int pm_find_patterns(pm_ctx *c, int64_t begin, int64_t end, const pm_hit **hits, uint64_t *nhits) {
+  if (!c || !hits || !nhits) return fail(PM_E_ARG, "null argument");
+  *hits = nullptr;
+  int rc = find_patterns_impl(c, begin, end, nhits);
+  if (*nhits) {
+    int rc2 = ensure_host_out(c, *nhits * sizeof(pm_hit));
+    if (rc2) return rc2;
+    PM_CUDA(cudaMemcpyAsync(c->h_out, c->d_hits2.p, *nhits * sizeof(pm_hit), cudaMemcpyDeviceToHost,
+                            c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+    *hits = reinterpret_cast<const pm_hit *>(c->h_out);
+  }
+  return rc;
+}
+
+int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate **cands,
+                       uint64_t *ncands) {
+  if (!c || !cands || !ncands) return fail(PM_E_ARG, "null argument");
+  *cands = nullptr;
+  *ncands = 0;
+  if (!c->inited) return fail(PM_E_ARG, "pm_scan_candidates before pm_init");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  memset(&c->stats, 0, offsetof(pm_stats, pack_ms));
+  c->stats.text_len = c->n;
+  c->stats.n_patterns = c->pats.size();
+  int64_t lo = begin - c->offset, hi = end - c->offset;
+  if (begin < c->offset || lo < 0) lo = 0;
+  if (end == std::numeric_limits<int64_t>::max() || hi > (int64_t)c->n + 1) hi = (int64_t)c->n + 1;
+  uint64_t n = 0;
+  int rc = run_scan(c, lo, hi, &n);
+  if (rc) return rc;
+  c->stats.n_candidates = n;
+  if (!n) return PM_OK;
+  if ((rc = c->d_cands.ensure(n * sizeof(pm_candidate)))) return rc;
+  keys_to_cands_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(
+      c->d_keys.as<unsigned long long>(), n, c->d_slotid.as<uint32_t>(), c->offset,
+      c->d_cands.as<pm_candidate>());
+  PM_CUDA(cudaGetLastError());
+  if ((rc = ensure_host_out(c, n * sizeof(pm_candidate)))) return rc;
+  PM_CUDA(cudaMemcpyAsync(c->h_out, c->d_cands.p, n * sizeof(pm_candidate), cudaMemcpyDeviceToHost,
+                          c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  *cands = reinterpret_cast<const pm_candidate *>(c->h_out);
+  *ncands = n;
+  return PM_OK;
+}
+
+int pm_reset(pm_ctx *c) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  c->d_text = nullptr;
+  c->n = 0;
+  c->n_tiles = 0;
+  return PM_OK;
+}
+
+int pm_get_stats(pm_ctx *c, pm_stats *out) {
+  if (!c || !out) return fail(PM_E_ARG, "null argument");
+  *out = c->stats;
+  return PM_OK;
+}
+
+// StreamedFastaFile::getch, fasta_io.t:478-629 (eos_start = true): the stream
+// is eos, seq1, eos, seq2, ..., seqN, eos.  Sequence lines are joined; blanks,
+// CR and LF inside sequence data are dropped; '>' starts a header anywhere.
+int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos,
+                       uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
+                       int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs) {
+  if ((!raw && n) || !out || !out_len) return fail(PM_E_ARG, "null argument");
+  uint64_t rp = 0, pos = 0, nseq = 0;
+  int64_t lastkey = 0;
+  auto put = [&](uint8_t ch) {
+    if (upper_case && ch >= 'a' && ch <= 'z') ch = (uint8_t)(ch - 'a' + 'A');
+    out[pos++] = ch;
+  };
+  if (n > 0) out[pos++] = eos;  // the stream opens with an end-of-sequence character
+  while (rp < n) {
+    uint8_t ch = raw[rp++];
+    const bool blank = (ch == '\n' || ch == '\r' || ch == ' ');
+    if (!blank && ch != '>') {
+      put(ch);
+      continue;
+    }
+    bool at_eof = false;
+    while (ch == '\n' || ch == '\r' || ch == ' ') {
+      if (rp >= n) {
+        at_eof = true;
+        break;
+      }
+      ch = raw[rp++];
+    }
+    if (at_eof) break;
+    if (ch != '>') {
+      put(ch);
+      continue;
+    }
+    // header line
+    const uint64_t hstart = rp;
+    uint8_t term = 0;
+    while (rp < n) {
+      term = raw[rp++];
+      if (term == '\n' || term == '\r') break;
+    }
+    const uint64_t hend = rp;
+    if (term == '\r' && rp < n) rp++;
+    const bool first = (pos == 1);
+    if (!first) pos++;  // room for the separator
+    if (lastkey < (int64_t)pos || first) {
+      if (nseq < max_seqs) {
+        if (seq_key) seq_key[nseq] = (int64_t)pos;
+        if (hdr_off) hdr_off[nseq] = (int64_t)hstart;
+        if (hdr_len) hdr_len[nseq] = (int64_t)(hend - hstart) - 1;
+      }
+      nseq++;
+      lastkey = (int64_t)pos;
+    }
+    if (first) {
+      if (rp < n) put(raw[rp++]);  // the character after the first header is taken verbatim
+    } else {
+      out[pos - 1] = eos;
+    }
+  }
+  out[pos++] = eos;
+  *out_len = pos;
+  if (n_seqs) *n_seqs = nseq;
+  return PM_OK;
+}
+
+int pm_reverse_comp(const char *pattern, char *out) {
+  if (!pattern || !out) return fail(PM_E_ARG, "null argument");
+  const size_t n = strlen(pattern);
+  for (size_t i = 0; i < n; i++) out[i] = (char)revcomp_char((unsigned char)pattern[n - 1 - i]);
+  out[n] = 0;
+  return PM_OK;
+}
+
+}  // extern "C"

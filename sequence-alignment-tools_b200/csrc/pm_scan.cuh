@@ -1,0 +1,358 @@
+// pm_scan.cuh -- the dense multi-pattern scan kernels (sm_100a).
+//
+// What they compute is the candidate set of the reference's bit-vector
+// indexes: every (pattern, stream position) at which
+//   shift_and_inexact::find_patterns (shift_and_inexact.cc:237-352) finds the
+//   pattern's last bit set at level k   (k > 0), or
+//   shift_and::find_patterns (shift_and.cc:204-256) /
+//   keyword_tree<>::find_patterns (keyword_tree.t:427-486) report an
+//   occurrence                           (k == 0).
+// How they compute it is not the reference's way.  The reference keeps one
+// long bit string (all patterns concatenated) per error level and pushes one
+// text character at a time through it.  Here the roles are swapped: a 32-bit
+// word holds 32 *text positions* (pm_planes.cuh) and the pattern is the loop.
+//
+// Substitutions only (-K, and k == 0): "mismatch counting".  For pattern
+// character i the word  planes[sym(P[i])][w+i]  says at which of the 32 window
+// starts q the text character q+i matches P[i].  A unary saturating counter
+// per window start (g[l] = "more than l mismatches so far") absorbs its
+// complement with K+1 LOP3:  g[l] |= g[l-1] & ~x.  After the last character
+// ~g[K] marks the windows with <= K mismatches -- exactly the level-K hits of
+// the Wu-Manber recurrence without indels (lines 253-303 with _indels false),
+// minus windows containing the end-of-sequence character, which the
+// recurrence kills (line 277) and the rare hit path re-checks on the raw text.
+// All windows of a warp are usually dead long before the pattern ends; the
+// warp then skips the rest of the pattern (a vote every 4 characters).
+//
+// Edits (-k): "partition seeds + per-seed Wu-Manber".  Any alignment with
+// <= k edits leaves one of k+1 pattern pieces untouched, so the dense part
+// only finds exact piece occurrences (AND chains on the same planes); each
+// seed is then verified by one thread running the reference's own recurrence
+// (both transitions and end-of-sequence behaviour, lines 253-326) for that
+// one pattern over the m+3k+1 characters that can matter.  Seeds are queued
+// per warp in shared memory and verified 32 at a time, in the same kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pm_planes.cuh"
+
+namespace pm {
+
+constexpr int SCAN_THREADS = 128;           // 4 warps, each owns 256 words of the tile
+constexpr int SCAN_STRIPS = 8;              // words per lane: w = warp*256 + s*32 + lane
+constexpr int POFF_STRIDE = 64;             // offsets per pattern row (PM_MAX_PATTERN_LEN)
+constexpr int SEEDQ_CAP = 512;              // per-warp seed queue entries
+
+struct ScanArgs {
+  const uint32_t *planes;   // [n_tiles][n_planes][TILE_WT]
+  const uint8_t *text;      // normalised stream shard (bytes)
+  uint64_t n;               // shard length
+  const uint32_t *poff;     // [n_slots+1][POFF_STRIDE] byte offsets into the smem planes
+  const uint8_t *plen;      // [n_slots]
+  unsigned long long *out;  // candidate keys: slot << 40 | pos
+  unsigned long long *count;
+  uint64_t cap;
+  int64_t lo, hi;           // emit candidates with lo <= pos < hi (local positions)
+  uint32_t tile0;           // first tile of the launch
+  uint32_t n_planes;        // planes per tile in HBM (n_sym + 1)
+  uint32_t n_sym;           // symbol planes copied to shared memory
+  uint32_t n_slots;
+  uint32_t slots_per_chunk; // patterns per blockIdx.y
+  uint32_t eos;
+  // edit mode only
+  const uint8_t *cls;       // [256] text byte -> class
+  const uint64_t *umask;    // [n_slots][n_cls] Shift-And masks per class
+  uint32_t n_cls;
+  const uint8_t *piece;     // [n_slots][8] piece boundaries (k+2 entries used)
+  unsigned long long *seed_count;
+};
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk copy (TMA) helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stage one tile's symbol planes in shared memory (plane n_sym of the smem
+// image is all ones: the "character" past the end of a short pattern).
+__device__ __forceinline__ void load_tile(const ScanArgs &a, uint32_t tile, uint32_t *s_planes,
+                                          uint64_t *bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, a.n_sym * (uint32_t)(TILE_WT * 4));
+    const uint32_t *src = a.planes + (uint64_t)tile * a.n_planes * TILE_WT;
+    for (uint32_t s = 0; s < a.n_sym; s++)
+      bulk_g2s(s_planes + s * TILE_WT, src + (uint64_t)s * TILE_WT, TILE_WT * 4, bar);
+  }
+  for (uint32_t i = threadIdx.x; i < TILE_WT; i += blockDim.x)
+    s_planes[a.n_sym * TILE_WT + i] = 0xffffffffu;
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+__device__ __forceinline__ bool window_has_eos(const ScanArgs &a, int64_t q, uint32_t m) {
+  for (uint32_t i = 0; i < m; i++)
+    if (a.text[q + i] == (uint8_t)a.eos) return true;
+  return false;
+}
+
+__device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t slot, int64_t pos) {
+  if (pos < a.lo || pos >= a.hi) return;
+  const unsigned long long at = atomicAdd(a.count, 1ULL);
+  if (at < a.cap) a.out[at] = ((unsigned long long)slot << 40) | (unsigned long long)pos;
+}
+
+// ---------------------------------------------------------------------------
+// Substitutions-only scan.  K+1 unary counter levels; FIRST_CHECK = group of 4
+// characters after which the warp starts voting on "everything dead".
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS)
+hamming_scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) uint32_t s_planes[];
+  __shared__ __align__(8) uint64_t s_bar;
+  constexpr int S = SCAN_STRIPS;
+  constexpr int FIRST_CHECK = (K == 0) ? 1 : (K <= 2 ? 2 : 3);  // 0-based group index
+  const uint32_t tile = a.tile0 + blockIdx.x;
+  load_tile(a, tile, s_planes, &s_bar);
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t w0 = warp * (32 * S) + lane;  // word of strip 0
+  const char *lane_base = reinterpret_cast<const char *>(s_planes) + 4u * w0;
+  const uint32_t slot0 = blockIdx.y * a.slots_per_chunk;
+  uint32_t slot1 = slot0 + a.slots_per_chunk;
+  if (slot1 > a.n_slots) slot1 = a.n_slots;
+
+  for (uint32_t slot = slot0; slot < slot1; ++slot) {
+    const uint32_t m = a.plen[slot];
+    const int ngroups = (int)((m + 3) >> 2);
+    const uint4 *offp = reinterpret_cast<const uint4 *>(a.poff + (size_t)slot * POFF_STRIDE);
+    uint32_t g[K + 1][S];
+#pragma unroll
+    for (int l = 0; l <= K; l++)
+#pragma unroll
+      for (int s = 0; s < S; s++) g[l][s] = 0u;
+    uint4 o = __ldg(offp);
+    bool dead = false;
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const uint4 on = __ldg(offp + grp + 1);  // rows are padded: always readable
+      const uint32_t offs[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + offs[c]);
+        uint32_t x[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) x[s] = p[s * 32];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+          const uint32_t nx = ~x[s];
+#pragma unroll
+          for (int l = K; l >= 1; l--) g[l][s] |= g[l - 1][s] & nx;
+          g[0][s] |= nx;
+        }
+      }
+      o = on;
+      if (grp >= FIRST_CHECK) {
+        uint32_t t = g[K][0];
+#pragma unroll
+        for (int s = 1; s < S; s++) t &= g[K][s];
+        if (__all_sync(0xffffffffu, t == 0xffffffffu)) {
+          dead = true;
+          break;
+        }
+      }
+    }
+    if (dead) continue;
+    // rare: some window survived all m characters
+#pragma unroll 1
+    for (int s = 0; s < S; s++) {
+      uint32_t surv = ~g[K][s];
+      while (surv) {
+        const int j = __ffs(surv) - 1;
+        surv &= surv - 1;
+        const int64_t q = (int64_t)tile * TILE_POS + (int64_t)j * TILE_W + (w0 + 32 * s);
+        if ((uint64_t)(q + m) <= a.n && !window_has_eos(a, q, m)) emit_candidate(a, slot, q + m);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Per-seed verification: the reference's k-error recurrence for ONE pattern,
+// restarted from the all-zero state (the state after an end-of-sequence
+// character) m+k characters before the first end position of interest.  Every
+// state bit at time t depends on at most the last m+k-1 characters (each
+// transition consumes a character or lowers the level), so from there on the
+// state equals the reference's.  Word = uint64_t: patterns up to 64 long.
+template <int K>
+__device__ __noinline__ void verify_seed(const ScanArgs &a, uint32_t slot, int64_t s_nominal) {
+  const uint32_t m = a.plen[slot];
+  const uint64_t *U = a.umask + (size_t)slot * a.n_cls;
+  const uint64_t last = 1ULL << (m - 1);
+  // end indices of interest: s+m-1-K .. s+m-1+K
+  int64_t t_lo = s_nominal + (int64_t)m - 1 - K;
+  int64_t t_hi = s_nominal + (int64_t)m - 1 + K;
+  if (t_hi >= (int64_t)a.n) t_hi = (int64_t)a.n - 1;
+  if (t_lo < 0) t_lo = 0;
+  int64_t t0 = t_lo - (int64_t)(m + K);
+  if (t0 < 0) t0 = 0;
+  uint64_t M[K + 1];
+#pragma unroll
+  for (int l = 0; l <= K; l++) M[l] = 0;
+  for (int64_t t = t0; t <= t_hi; ++t) {
+    const uint32_t ch = a.text[t];
+    const uint64_t u = U[a.cls[ch]];
+    // shift_and_inexact.cc:253-303, indels on; one word per pattern
+    uint64_t old_prev = M[0];
+    uint64_t nw = ((M[0] << 1) | 1ULL) & u;
+    M[0] = nw;
+    if (ch != a.eos) {
+#pragma unroll
+      for (int l = 1; l <= K; l++) {
+        const uint64_t old_l = M[l];
+        uint64_t v = ((old_l << 1) | 1ULL) & u;
+        v |= (old_prev << 1) | 1ULL | old_prev;  // substitution | insertion
+        v |= (M[l - 1] << 1) | 1ULL | M[l - 1];  // deletion | lower level (new)
+        M[l] = v;
+        old_prev = old_l;
+      }
+    } else {
+#pragma unroll
+      for (int l = 1; l <= K; l++) M[l] = ((M[l] << 1) | 1ULL) & u;
+    }
+    if (t >= t_lo && (M[K] & last)) emit_candidate(a, slot, t + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Edit-distance scan: exact occurrences of the k+1 pattern pieces (dense),
+// then verify_seed per occurrence (sparse, same kernel).
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS)
+edit_scan_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) uint32_t s_planes[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_queue[SCAN_THREADS / 32][SEEDQ_CAP];
+  __shared__ uint32_t s_qn[SCAN_THREADS / 32];
+  constexpr int S = SCAN_STRIPS;
+  const uint32_t tile = a.tile0 + blockIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_qn[warp] = 0;
+  load_tile(a, tile, s_planes, &s_bar);
+
+  const uint32_t w0 = warp * (32 * S) + lane;
+  const char *lane_base = reinterpret_cast<const char *>(s_planes) + 4u * w0;
+  const uint32_t slot0 = blockIdx.y * a.slots_per_chunk;
+  uint32_t slot1 = slot0 + a.slots_per_chunk;
+  if (slot1 > a.n_slots) slot1 = a.n_slots;
+  uint32_t *queue = s_queue[warp];
+  unsigned long long n_seeds = 0;
+
+  auto drain = [&](uint32_t count) {
+    // entries [0,count) of this warp's queue, 32 at a time
+    for (uint32_t base = 0; base < count; base += 32) {
+      if (base + lane < count) {
+        const uint32_t e = queue[base + lane];
+        const uint32_t slot = slot0 + (e >> 15);
+        const uint32_t qloc = e & 0x7fffu;  // j*TILE_W + w
+        verify_seed<K>(a, slot, (int64_t)tile * TILE_POS + qloc);
+      }
+    }
+    __syncwarp();
+  };
+
+  for (uint32_t slot = slot0; slot < slot1; ++slot) {
+    const uint32_t m = a.plen[slot];
+    const uint8_t *pc = a.piece + (size_t)slot * 8;
+    const uint32_t *offp = a.poff + (size_t)slot * POFF_STRIDE;
+    uint32_t E[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) E[s] = 0u;
+#pragma unroll 1
+    for (int j = 0; j <= K; j++) {
+      const uint32_t pa = pc[j], pb = pc[j + 1];
+      uint32_t A[S];
+#pragma unroll
+      for (int s = 0; s < S; s++) A[s] = 0xffffffffu;
+      for (uint32_t i = pa; i < pb; i++) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + __ldg(offp + i));
+#pragma unroll
+        for (int s = 0; s < S; s++) A[s] &= p[s * 32];
+      }
+#pragma unroll
+      for (int s = 0; s < S; s++) E[s] |= A[s];
+    }
+    (void)m;
+    uint32_t any = E[0];
+#pragma unroll
+    for (int s = 1; s < S; s++) any |= E[s];
+    if (__any_sync(0xffffffffu, any != 0u)) {
+      if (any) {
+#pragma unroll 1
+        for (int s = 0; s < S; s++) {
+          uint32_t e = E[s];
+          while (e) {
+            const int j = __ffs(e) - 1;
+            e &= e - 1;
+            const uint32_t qloc = (uint32_t)j * TILE_W + (w0 + 32 * s);
+            const uint32_t at = atomicAdd(&s_qn[warp], 1u);
+            if (at < (uint32_t)SEEDQ_CAP) queue[at] = ((slot - slot0) << 15) | qloc;
+            else verify_seed<K>(a, slot, (int64_t)tile * TILE_POS + qloc);  // queue full
+            n_seeds++;
+          }
+        }
+      }
+      __syncwarp();
+      const uint32_t qn = min(s_qn[warp], (uint32_t)SEEDQ_CAP);
+      __syncwarp();
+      if (qn >= (uint32_t)(SEEDQ_CAP - 256)) {
+        drain(qn);
+        if (lane == 0) s_qn[warp] = 0;
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
+  const uint32_t qn = min(s_qn[warp], (uint32_t)SEEDQ_CAP);
+  drain(qn);
+  // seed statistics: one atomic per warp
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) n_seeds += __shfl_xor_sync(0xffffffffu, n_seeds, d);
+  if (lane == 0 && a.seed_count) atomicAdd(a.seed_count, n_seeds);
+}
+
+}  // namespace pm

@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with the
+reference's golden vectors.  Integer / index work: the bar is bit-exact."""
+import random
+
+import numpy as np
+import pytest
+
+from conftest import as_tuples, records_of
+
+pytestmark = pytest.mark.gpu
+
+TILE_POS = 32768
+
+
+def _need_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("these tests need a CUDA device; the product has no CPU fallback")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu(built_lib):
+    _need_gpu()
+
+
+def test_golden_records_bit_exact(pkg, golden):
+    for case in golden["cases"]:
+        st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
+        got = pkg.primer_match(st, case["primers"], **case["params"])
+        assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
+
+
+def _params(seed):
+    rng = random.Random(seed)
+    k = rng.choice([0, 1, 2, 3])
+    indels = rng.random() < 0.5
+    wc = rng.random() < 0.4
+    tn = wc and rng.random() < 0.5
+    rc = rng.random() < 0.6
+    kw = dict(nseq=rng.choice([1, 3, 5]), seqlen=rng.choice([60, 400, 1500]),
+              nprimers=rng.choice([1, 2, 6, 12]), plen=rng.choice([(8, 12), (12, 22), (20, 20), (25, 32)]),
+              k=k, indels=indels, wc=wc, text_iupac=rng.choice([0, 0, 0.01, 0.05]),
+              lower=0.0 if (wc and k == 0) else rng.choice([0, 0, 0.02]), repeats=rng.random() < 0.7,
+              line=rng.choice([60, 70, 13]), crlf=rng.random() < 0.15)
+    return dict(k=k, indels=indels, wc=wc, tn=tn, rev_comp=rc), kw
+
+
+@pytest.mark.parametrize("seed", range(2000, 2080))
+def test_records_match_oracle_seeded(pkg, oracle, seed):
+    import casegen
+    params, kw = _params(seed)
+    fasta, primers = casegen.make_case(seed, **kw)
+    raw = fasta.encode()
+    want = oracle.primer_match(oracle.normalize_fasta(raw), primers, **params)
+    got = pkg.primer_match(pkg.normalize_fasta(raw), primers, **params)
+    assert as_tuples(got) == as_tuples(want)
+
+
+@pytest.mark.parametrize("k,indels,wc", [(0, False, False), (0, False, True), (1, False, False),
+                                         (2, False, False), (3, False, True), (1, True, False),
+                                         (2, True, False), (2, True, True), (3, True, False)])
+def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc):
+    """Raw candidate set of the dense scan on a text of several tiles, with
+    occurrences planted across the tile seams and the bit-row seams."""
+    import casegen
+    rng = random.Random(100 * k + 10 * indels + wc)
+    n = 2 * TILE_POS + 5000
+    primers = [casegen.rand_dna(rng, rng.randint(max(8, k + 6), 32)) for _ in range(10)]
+    primers[0] = "A" * 14
+    if wc:
+        primers[1] = "ACGRYACGTNACGTKMAC"
+        primers[2] = "WSACGTBDHVACGT"
+    seq = list(casegen.rand_dna(rng, n))
+    seams = [1024 * j + d for j in (1, 2, 31, 32, 33, 63, 64) for d in (-20, -3, 0, 5)] + \
+            [TILE_POS - 10, TILE_POS - 1, TILE_POS, 2 * TILE_POS - 7, n - 25, 3]
+    for at in seams:
+        p = rng.choice(primers)
+        q = "".join(c if c in "ACGT" else rng.choice("ACGT") for c in p)
+        q = casegen.mutate(rng, q, rng.randint(0, k), indels)
+        at = max(0, min(n - len(q), at))
+        seq[at:at + len(q)] = list(q)
+    seq[700:760] = list("A" * 60)
+    seq[TILE_POS - 30:TILE_POS + 30] = list("A" * 60)
+    for i in (5000, 5001, 40000):
+        seq[i] = "N"
+    seq = "".join(seq)
+    cut = 40123
+    fasta = ">a\n%s\n>b\n%s\n" % (seq[:cut], seq[cut:])
+    st = pkg.normalize_fasta(fasta.encode())
+    T = st.chars
+    if k == 0:
+        want = oracle.exact_scan(T, primers, wc, False)
+    else:
+        want = oracle.wm_scan(T, primers, k, indels, wc, False)
+    want = sorted({(int(b), int(a)) for a, b, _ in want})
+    sc = pkg.Scanner(k=k, indels=indels, wildcards=wc)
+    for i, p in enumerate(primers):
+        sc.add_pattern(p, i + 1)
+    sc.init()
+    sc.set_text(T)
+    got = sc.scan_candidates()
+    got = sorted((int(b), int(a)) for a, b in got)
+    sc.close()
+    assert len(want) > 20
+    assert got == want
+
+
+@pytest.mark.parametrize("k,indels", [(1, False), (2, True)])
+def test_shards_reproduce_whole_scan(pkg, k, indels):
+    """Partitioning the stream over several contexts (GPUs) with the documented
+    overlap gives exactly the hits of one whole-stream scan."""
+    import casegen
+    rng = random.Random(77 + k)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(8)] + ["A" * 16]
+    n = 3 * TILE_POS
+    seq = list(casegen.rand_dna(rng, n))
+    for _ in range(120):
+        q = casegen.mutate(rng, rng.choice(primers), rng.randint(0, k), indels)
+        at = rng.randrange(0, n - 40)
+        seq[at:at + len(q)] = list(q)
+    cuts = [30000, 61234, 80000]
+    for c in cuts:   # occurrences and a poly-A run straddling every cut
+        seq[c - 8:c + 12] = list(primers[0])
+    seq[cuts[1] + 100:cuts[1] + 160] = list("A" * 60)
+    st = pkg.normalize_fasta((">s\n" + "".join(seq) + "\n").encode())
+    T = st.chars
+
+    def run(begin, end, lo, hi):
+        sc = pkg.Scanner(k=k, indels=indels)
+        for i, p in enumerate(primers):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        ov = sc.shard_overlap()
+        a = max(0, lo - ov) if lo else 0
+        sc.set_text(T[a:hi], offset=a)
+        h = sc.find_patterns(begin, end)
+        sc.close()
+        return h
+
+    whole = run(0, pkg.INT64_MAX, 0, len(T))
+    parts = []
+    bounds = [0] + cuts + [len(T) + 1]
+    for i in range(len(bounds) - 1):
+        hi = min(len(T), bounds[i + 1] + 70000)
+        parts.append(run(bounds[i], bounds[i + 1], bounds[i], hi))
+    merged = np.concatenate(parts)
+    merged = merged[np.lexsort((merged["pattern_id"], merged["end"]))]
+    assert len(whole) > 50
+    assert merged.tobytes() == whole.tobytes()
+
+
+def test_full_size_properties(pkg):
+    """BASELINE-shaped run (1k 20-mers, both strands, k=2 mismatches) on 64 Mbp:
+    planted copies are all found with the planted distance, hit lists are
+    sorted, and the k=1 hits are a subset of the k=2 hits."""
+    import casegen
+    rng = random.Random(9)
+    nprim = 1000
+    primers = [casegen.rand_dna(rng, 20) for _ in range(nprim)]
+    n = 64 << 20
+    g = np.random.default_rng(3)
+    seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, n)]
+    planted = []
+    for j in range(400):
+        pi = rng.randrange(nprim)
+        q = casegen.mutate(rng, primers[pi], rng.randint(0, 2), False)
+        at = 1000 + j * 150000
+        seq[at:at + 20] = np.frombuffer(q.encode(), np.uint8)
+        planted.append((at, pi))
+    T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
+    pats = pkg.pattern_array(primers, True)
+    res = {}
+    for k in (1, 2):
+        sc = pkg.Scanner(k=k, indels=False)
+        for i, p in enumerate(pats):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(T)
+        h = sc.find_patterns()
+        sc.close()
+        assert np.all(np.diff(h["end"]) >= 0)
+        res[k] = {(int(r["end"]), int(r["pattern_id"])) for r in h}
+        if k == 2:
+            for at, pi in planted:
+                assert (at + 1 + 20, pi + 1) in res[k]
+            # hits report the true number of mismatches
+            for r in h[:200]:
+                s, e, pid = int(r["start"]), int(r["end"]), int(r["pattern_id"])
+                w = T[e - 20:e].tobytes().decode()
+                assert sum(a != b for a, b in zip(w, pats[pid - 1])) == int(r["editdist"])
+    assert res[1] <= res[2]
