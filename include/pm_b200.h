@@ -165,6 +165,8 @@ typedef struct pm_stats {
   uint64_t n_bogus;
   uint64_t kernel_launches; /* kernels of this library launched by the call    */
   uint64_t scan_items;      /* (tile, pattern-chunk) blocks of the scan kernel */
+  uint64_t scan_warp_steps; /* (warp, pattern character) steps the dense scan
+                               executed: each is 8 words x 32 positions        */
   float pack_ms;            /* device time of the last pack kernel             */
   float scan_ms;            /* device time of the dense scan kernel            */
   float total_ms;           /* device time of the whole call                   */
@@ -178,6 +180,10 @@ int pm_get_stats(pm_ctx *ctx, pm_stats *out);
 int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos,
                        uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
                        int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs);
+
+/* Diagnostic for the roofline: measured throughput of 3-input logic
+ * instructions (LOP3) on `device`, in 1e12 thread-level operations per second. */
+int pm_bench_int_peak(int device, double *lop3_tera_ops);
 
 /* util.cc:374-381 reverse_comp (IUPAC aware, util.cc:319-348): out must hold
  * strlen(pattern)+1 bytes.                                                    */

@@ -34,7 +34,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak"]
 
 
 class PmError(RuntimeError):
@@ -62,7 +62,7 @@ class Stats(C.Structure):
     _fields_ = [("text_len", C.c_uint64), ("n_patterns", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("n_candidates", C.c_uint64), ("n_chains", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
-                ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+                ("scan_warp_steps", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
@@ -104,6 +104,7 @@ def lib():
                                          C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.POINTER(C.c_uint64)]
         L.pm_reverse_comp.argtypes = [C.c_char_p, C.c_char_p]
+        L.pm_bench_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -160,6 +161,7 @@ class Scanner:
         opt = Options(device, index, k, int(indels), int(wildcards), int(text_n), eos)
         _check(lib().pm_create(C.byref(self._h), C.byref(opt)))
         self.k = k
+        self.indels = bool(indels)
         self._keep = None
 
     def close(self):
@@ -228,6 +230,27 @@ class Scanner:
         s = Stats()
         _check(lib().pm_get_stats(self._h, C.byref(s)))
         return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+
+def int_peak(device=0) -> float:
+    """Measured LOP3 throughput of the device, 1e12 thread-level ops/s."""
+    v = C.c_double(0)
+    _check(lib().pm_bench_int_peak(device, C.byref(v)))
+    return v.value
+
+
+def int_pipe_report(sc: "Scanner", scan_ms: float, device=0) -> dict:
+    """Integer-pipe roofline of the last dense scan of `sc`: useful logic
+    operations (the counter / AND-chain updates, nothing else) per second
+    against the measured LOP3 peak."""
+    st = sc.stats()
+    levels = (sc.k + 1) if not sc.indels or sc.k == 0 else 1
+    useful = st["scan_warp_steps"] * 8 * 32 * levels
+    peak = int_peak(device)
+    ach = useful / (scan_ms * 1e-3) / 1e12
+    return {"unit": "Tlop/s", "achieved": ach, "peak": peak, "frac": ach / peak if peak else None,
+            "useful_lops_per_launch": useful, "warp_steps": st["scan_warp_steps"],
+            "peak_source": "pm_bench_int_peak (LOP3 microbenchmark, same run)"}
 
 
 @dataclass(frozen=True, order=True)

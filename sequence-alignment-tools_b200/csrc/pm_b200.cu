@@ -332,6 +332,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   a.plen = c->d_plen.as<uint8_t>();
   a.count = c->d_counters + 0;
   a.seed_count = c->d_counters + 1;
+  a.work_count = c->d_counters + 5;
   a.lo = lo;
   a.hi = hi;
   a.tile0 = tile0;
@@ -374,6 +375,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     a.out = c->d_keys.as<unsigned long long>();
     a.cap = cap;
     PM_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
+    PM_CUDA(cudaMemsetAsync(c->d_counters + 5, 0, sizeof(unsigned long long), c->stream));
     PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // grid.x is limited to 2^31-1, grid.y to 65535
     if (chunks > 65535) return fail(PM_E_UNSUPPORTED, "too many pattern chunks");
@@ -382,7 +384,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->stats.kernel_launches++;
     c->stats.scan_items = (uint64_t)nt * chunks;
-    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 2 * sizeof(unsigned long long),
+    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 6 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -390,6 +392,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     c->stats.scan_ms = ms;
     count = c->h_counters[0];
     c->stats.n_seeds = c->h_counters[1];
+    c->stats.scan_warp_steps = c->h_counters[5];
     if (count <= cap) break;
     // candidate buffer too small: grow and rescan
     int rc = c->d_keys.ensure((size_t)count * 8 + 1024);
@@ -1030,6 +1033,36 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
   out[pos++] = eos;
   *out_len = pos;
   if (n_seqs) *n_seqs = nseq;
+  return PM_OK;
+}
+
+int pm_bench_int_peak(int device, double *lop3_tera_ops) {
+  if (!lop3_tera_ops) return fail(PM_E_ARG, "null argument");
+  PM_CUDA(cudaSetDevice(device));
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+  uint32_t *d = nullptr;
+  PM_CUDA(cudaMalloc(&d, 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int iters = 20000, blocks = n_sm * 8;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    cudaEventRecord(e0, 0);
+    pm::lop3_peak_kernel<<<blocks, 256>>>(d, iters);
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double ops = (double)blocks * 256.0 * iters * 64.0;
+    if (rep > 0 && ms > 0) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  PM_CUDA(cudaGetLastError());
+  *lop3_tera_ops = best;
   return PM_OK;
 }
 

@@ -65,6 +65,7 @@ struct ScanArgs {
   uint32_t n_cls;
   const uint8_t *piece;     // [n_slots][8] piece boundaries (k+2 entries used)
   unsigned long long *seed_count;
+  unsigned long long *work_count;  // executed (warp, pattern character) steps
 };
 
 // ---------------------------------------------------------------------------
@@ -157,6 +158,7 @@ hamming_scan_kernel(const ScanArgs a) {
   uint32_t slot1 = slot0 + a.slots_per_chunk;
   if (slot1 > a.n_slots) slot1 = a.n_slots;
 
+  uint32_t n_steps = 0;
   for (uint32_t slot = slot0; slot < slot1; ++slot) {
     const uint32_t m = a.plen[slot];
     const int ngroups = (int)((m + 3) >> 2);
@@ -186,6 +188,7 @@ hamming_scan_kernel(const ScanArgs a) {
         }
       }
       o = on;
+      n_steps += 4;
       if (grp >= FIRST_CHECK) {
         uint32_t t = g[K][0];
 #pragma unroll
@@ -209,6 +212,7 @@ hamming_scan_kernel(const ScanArgs a) {
       }
     }
   }
+  if (lane == 0 && a.work_count) atomicAdd(a.work_count, (unsigned long long)n_steps);
 }
 
 // ---------------------------------------------------------------------------
@@ -281,6 +285,7 @@ edit_scan_kernel(const ScanArgs a) {
   if (slot1 > a.n_slots) slot1 = a.n_slots;
   uint32_t *queue = s_queue[warp];
   unsigned long long n_seeds = 0;
+  uint32_t n_steps = 0;
 
   auto drain = [&](uint32_t count) {
     // entries [0,count) of this warp's queue, 32 at a time
@@ -308,6 +313,7 @@ edit_scan_kernel(const ScanArgs a) {
       uint32_t A[S];
 #pragma unroll
       for (int s = 0; s < S; s++) A[s] = 0xffffffffu;
+      n_steps += pb - pa;
       for (uint32_t i = pa; i < pb; i++) {
         const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + __ldg(offp + i));
 #pragma unroll
@@ -353,6 +359,28 @@ edit_scan_kernel(const ScanArgs a) {
 #pragma unroll
   for (int d = 16; d >= 1; d >>= 1) n_seeds += __shfl_xor_sync(0xffffffffu, n_seeds, d);
   if (lane == 0 && a.seed_count) atomicAdd(a.seed_count, n_seeds);
+  if (lane == 0 && a.work_count) atomicAdd(a.work_count, (unsigned long long)n_steps);
+}
+
+// ---------------------------------------------------------------------------
+// Integer-pipe yardstick for the roofline: dependent-but-plentiful LOP3 work,
+// no memory traffic.  8 x 3-input logic ops per thread per iteration.
+__global__ void __launch_bounds__(256)
+lop3_peak_kernel(uint32_t *out, int iters) {
+  uint32_t a[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) a[j] = (threadIdx.x + 1u) * 2654435761u + blockIdx.x * 40503u + j * 97u;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] = (a[j] | a[(j + 3) & 7]) & ~a[(j + 5) & 7];
+    }
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) x ^= a[j];
+  if (x == 0x12345u) out[0] = x;  // keeps the loop alive
 }
 
 }  // namespace pm
