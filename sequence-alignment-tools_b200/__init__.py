@@ -244,7 +244,8 @@ def int_pipe_report(sc: "Scanner", scan_ms: float, device=0) -> dict:
     operations (the counter / AND-chain updates, nothing else) per second
     against the measured LOP3 peak."""
     st = sc.stats()
-    levels = (sc.k + 1) if not sc.indels or sc.k == 0 else 1
+    # LOP3 per word per character: one per counter bit (pm_scan.cuh Counter<K>), one AND for seeds
+    levels = {0: 1, 1: 2, 2: 2, 3: 3}[sc.k] if (not sc.indels or sc.k == 0) else 1
     useful = st["scan_warp_steps"] * 8 * 32 * levels
     peak = int_peak(device)
     ach = useful / (scan_ms * 1e-3) / 1e12

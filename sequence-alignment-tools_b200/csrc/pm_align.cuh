@@ -66,7 +66,7 @@ __host__ __device__ inline int64_t align_textstart(int64_t e1, int m, int k) {
 // codes (if not null) receives the alignment codes in pattern order.
 __device__ inline void editdist_align(const AlignEnv &env, uint32_t slot, int64_t e1, int64_t e2,
                                       uint8_t *ws, uint8_t *codes, int max_codes, AlignResult &r) {
-  const int m = env.plen[slot];
+  const int m = env.plen[slot] & 0x7f;
   const uint8_t *pat = env.pat_chars + (size_t)slot * PAT_STRIDE;
   const int k = env.k;
   const int cvp = 5 * k + 1;  // pattern_alignment.cc:131
@@ -250,7 +250,7 @@ __global__ void chain_ws_kernel(const Chain *chains, uint64_t n, const uint8_t *
   const Chain c = chains[i];
   unsigned long long b = 0;
   if (c.first >= own_lo && c.first < own_hi) {
-    const int m = plen[c.slot];
+    const int m = plen[c.slot] & 0x7f;
     const int64_t buflen = c.last - align_textstart(c.first, m, k);
     b = (align_ws_bytes(m, buflen) + 15ull) & ~15ull;
   }

@@ -236,7 +236,7 @@ __global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *
   const unsigned long long key = keys[i];
   const uint32_t slot = (uint32_t)(key >> 40);
   const int64_t pos = (int64_t)(key & 0xffffffffffULL);
-  const int m = env.plen[slot];
+  const int m = env.plen[slot] & 0x7f;
   const uint8_t *pat = env.pat_chars + (size_t)slot * PAT_STRIDE;
   pm_hit out;
   memset(&out, 0, sizeof out);
@@ -778,7 +778,28 @@ int pm_init(pm_ctx *c) {
   }
   c->n_cls = (int)cls_mask.size();
 
-  std::vector<uint32_t> poff((ns + 1) * POFF_STRIDE, (uint32_t)c->n_sym * TILE_WT * 4u);
+  // Slot order: patterns sorted by their first four characters, so that the dense
+  // scan computes the counter state of a shared 4-character prefix once per run
+  // (PLEN_SHARE).  Slots are internal; hits carry the caller's pattern ids.
+  std::vector<size_t> order(ns);
+  for (size_t i = 0; i < ns; i++) order[i] = i;
+  auto prefix_key = [&](size_t i) {
+    const std::string &ps = c->pats[i].s;
+    uint32_t key = 0;
+    for (int j = 0; j < 4; j++)
+      key = key * 64u + (j < (int)ps.size() ? (uint32_t)sym_of[(unsigned char)ps[j]] + 1u : 0u);
+    return key;
+  };
+  std::stable_sort(order.begin(), order.end(),
+                   [&](size_t x, size_t y) { return prefix_key(x) < prefix_key(y); });
+  {
+    std::vector<Pattern> sorted;
+    sorted.reserve(ns);
+    for (size_t i = 0; i < ns; i++) sorted.push_back(c->pats[order[i]]);
+    c->pats.swap(sorted);
+  }
+
+  std::vector<uint32_t> poff((ns + 2) * POFF_STRIDE, (uint32_t)c->n_sym * TILE_WT * 4u);
   std::vector<uint8_t> plen(ns + 1, 0), patchars((ns + 1) * PAT_STRIDE, 0), piece((ns + 1) * 8, 0);
   std::vector<int16_t> lconst(ns + 1, 0), rconst(ns + 1, 0);
   std::vector<uint32_t> slotid(ns + 1, 0);
@@ -798,6 +819,8 @@ int pm_init(pm_ctx *c) {
       for (int cl = 0; cl < c->n_cls; cl++)
         if ((cls_mask[cl] >> s) & 1u) umask[i * c->n_cls + cl] |= 1ull << j;
     }
+    if (i > 0 && memcmp(&poff[i * POFF_STRIDE], &poff[(i - 1) * POFF_STRIDE], 4 * sizeof(uint32_t)) == 0)
+      plen[i] |= (uint8_t)PLEN_SHARE;
     // k+1 pieces, as even as possible (pigeonhole partition)
     for (int j = 0; j <= K + 1; j++) piece[i * 8 + j] = (uint8_t)((int64_t)m * j / (K + 1));
   }

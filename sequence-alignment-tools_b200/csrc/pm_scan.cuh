@@ -139,13 +139,65 @@ __device__ __forceinline__ void emit_candidate(const ScanArgs &a, uint32_t slot,
 }
 
 // ---------------------------------------------------------------------------
-// Substitutions-only scan.  K+1 unary counter levels; FIRST_CHECK = group of 4
-// characters after which the warp starts voting on "everything dead".
+// Saturating mismatch counters, one bit-slice per counter bit, 32 window starts
+// per word.  The encodings are chosen so that every next-state bit is a function
+// of three inputs, i.e. ONE LOP3 per counter bit per character:
+//   K=0  1 bit    0 -> 1(dead)
+//   K=1  2 bits   00 -> 01 -> 11(dead)                 (unary)
+//   K=2  2 bits   00 -> 01 -> 10 -> 11(dead)           (binary, saturating)
+//   K=3  3 bits   000 -> 001 -> 011 -> 111 -> 110(dead) (Johnson-like; found by
+//        exhaustive search over the 3-bit encodings of a 5-state counter)
+// nx = mismatch word (1 = the character does not match at that window start).
+template <int K> struct Counter;
+template <> struct Counter<0> {
+  static constexpr int NB = 1;
+  static __device__ __forceinline__ void step(uint32_t (&b)[1], uint32_t nx) { b[0] |= nx; }
+  static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[1]) { return b[0]; }
+};
+template <> struct Counter<1> {
+  static constexpr int NB = 2;
+  static __device__ __forceinline__ void step(uint32_t (&b)[2], uint32_t nx) {
+    b[1] |= b[0] & nx;
+    b[0] |= nx;
+  }
+  static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[2]) { return b[1]; }
+};
+template <> struct Counter<2> {
+  static constexpr int NB = 2;
+  static __device__ __forceinline__ void step(uint32_t (&b)[2], uint32_t nx) {
+    const uint32_t n1 = b[1] | (b[0] & nx);
+    const uint32_t n0 = (b[0] ^ nx) | (b[1] & b[0]);
+    b[1] = n1;
+    b[0] = n0;
+  }
+  static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[2]) { return b[1] & b[0]; }
+};
+template <> struct Counter<3> {
+  static constexpr int NB = 3;
+  static __device__ __forceinline__ void step(uint32_t (&b)[3], uint32_t nx) {
+    const uint32_t n0 = (~b[2] & (b[0] | nx)) | (b[0] & b[2] & ~nx);
+    const uint32_t n1 = b[1] | (b[0] & nx);
+    const uint32_t n2 = b[1] & (b[2] | nx);
+    b[0] = n0;
+    b[1] = n1;
+    b[2] = n2;
+  }
+  static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[3]) { return b[2] & ~b[0]; }
+};
+
+constexpr uint32_t PLEN_SHARE = 0x80u;  // plen flag: first 4 characters equal the previous slot's
+
+// Substitutions-only scan.  FIRST_CHECK = group of 4 characters after which the
+// warp starts voting on "everything dead".  Slots are sorted by their first four
+// characters on the host; the counter state after those four is computed once per
+// run of equal prefixes and reused (PLEN_SHARE).
 template <int K>
 __global__ void __launch_bounds__(SCAN_THREADS)
 hamming_scan_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) uint32_t s_planes[];
   __shared__ __align__(8) uint64_t s_bar;
+  using CT = Counter<K>;
+  constexpr int NB = CT::NB;
   constexpr int S = SCAN_STRIPS;
   constexpr int FIRST_CHECK = (K == 0) ? 1 : (K <= 2 ? 2 : 3);  // 0-based group index
   const uint32_t tile = a.tile0 + blockIdx.x;
@@ -158,41 +210,54 @@ hamming_scan_kernel(const ScanArgs a) {
   uint32_t slot1 = slot0 + a.slots_per_chunk;
   if (slot1 > a.n_slots) slot1 = a.n_slots;
 
+  uint32_t st[S][NB], base[S][NB];
+  auto four_chars = [&](const uint4 o) {
+    const uint32_t offs[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + offs[c]);
+      uint32_t x[S];
+#pragma unroll
+      for (int s = 0; s < S; s++) x[s] = p[s * 32];
+#pragma unroll
+      for (int s = 0; s < S; s++) CT::step(st[s], ~x[s]);
+    }
+  };
+
   uint32_t n_steps = 0;
   for (uint32_t slot = slot0; slot < slot1; ++slot) {
-    const uint32_t m = a.plen[slot];
+    const uint32_t pl = a.plen[slot];
+    const uint32_t m = pl & 0x7fu;
     const int ngroups = (int)((m + 3) >> 2);
     const uint4 *offp = reinterpret_cast<const uint4 *>(a.poff + (size_t)slot * POFF_STRIDE);
-    uint32_t g[K + 1][S];
+    uint4 o = __ldg(offp + 1);
+    if (!(pl & PLEN_SHARE) || slot == slot0) {
 #pragma unroll
-    for (int l = 0; l <= K; l++)
+      for (int s = 0; s < S; s++)
 #pragma unroll
-      for (int s = 0; s < S; s++) g[l][s] = 0u;
-    uint4 o = __ldg(offp);
+        for (int b = 0; b < NB; b++) st[s][b] = 0u;
+      four_chars(__ldg(offp));
+      n_steps += 4;
+#pragma unroll
+      for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int b = 0; b < NB; b++) base[s][b] = st[s][b];
+    } else {
+#pragma unroll
+      for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int b = 0; b < NB; b++) st[s][b] = base[s][b];
+    }
     bool dead = false;
-    for (int grp = 0; grp < ngroups; ++grp) {
+    for (int grp = 1; grp < ngroups; ++grp) {
       const uint4 on = __ldg(offp + grp + 1);  // rows are padded: always readable
-      const uint32_t offs[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-      for (int c = 0; c < 4; c++) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + offs[c]);
-        uint32_t x[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) x[s] = p[s * 32];
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-          const uint32_t nx = ~x[s];
-#pragma unroll
-          for (int l = K; l >= 1; l--) g[l][s] |= g[l - 1][s] & nx;
-          g[0][s] |= nx;
-        }
-      }
+      four_chars(o);
       o = on;
       n_steps += 4;
       if (grp >= FIRST_CHECK) {
-        uint32_t t = g[K][0];
+        uint32_t t = CT::dead(st[0]);
 #pragma unroll
-        for (int s = 1; s < S; s++) t &= g[K][s];
+        for (int s = 1; s < S; s++) t &= CT::dead(st[s]);
         if (__all_sync(0xffffffffu, t == 0xffffffffu)) {
           dead = true;
           break;
@@ -200,10 +265,10 @@ hamming_scan_kernel(const ScanArgs a) {
       }
     }
     if (dead) continue;
-    // rare: some window survived all m characters
-#pragma unroll 1
+    // rare: some window may have survived all m characters
+#pragma unroll
     for (int s = 0; s < S; s++) {
-      uint32_t surv = ~g[K][s];
+      uint32_t surv = ~CT::dead(st[s]);
       while (surv) {
         const int j = __ffs(surv) - 1;
         surv &= surv - 1;
@@ -224,7 +289,7 @@ hamming_scan_kernel(const ScanArgs a) {
 // state equals the reference's.  Word = uint64_t: patterns up to 64 long.
 template <int K>
 __device__ __noinline__ void verify_seed(const ScanArgs &a, uint32_t slot, int64_t s_nominal) {
-  const uint32_t m = a.plen[slot];
+  const uint32_t m = a.plen[slot] & 0x7fu;
   const uint64_t *U = a.umask + (size_t)slot * a.n_cls;
   const uint64_t last = 1ULL << (m - 1);
   // end indices of interest: s+m-1-K .. s+m-1+K
@@ -301,7 +366,7 @@ edit_scan_kernel(const ScanArgs a) {
   };
 
   for (uint32_t slot = slot0; slot < slot1; ++slot) {
-    const uint32_t m = a.plen[slot];
+    const uint32_t m = a.plen[slot] & 0x7fu;
     const uint8_t *pc = a.piece + (size_t)slot * 8;
     const uint32_t *offp = a.poff + (size_t)slot * POFF_STRIDE;
     uint32_t E[S];
@@ -367,19 +432,23 @@ edit_scan_kernel(const ScanArgs a) {
 // no memory traffic.  8 x 3-input logic ops per thread per iteration.
 __global__ void __launch_bounds__(256)
 lop3_peak_kernel(uint32_t *out, int iters) {
-  uint32_t a[8];
+  uint32_t a[16], b[16];
 #pragma unroll
-  for (int j = 0; j < 8; j++) a[j] = (threadIdx.x + 1u) * 2654435761u + blockIdx.x * 40503u + j * 97u;
+  for (int j = 0; j < 16; j++) a[j] = (threadIdx.x + 1u) * 2654435761u + blockIdx.x * 40503u + j * 0x9e3779b9u;
   for (int it = 0; it < iters; it++) {
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < 2; r++) {
+      // 16 independent 3-input logic ops per half round; every op mixes three
+      // different words, so nothing folds into a cheaper expression
 #pragma unroll
-      for (int j = 0; j < 8; j++) a[j] = (a[j] | a[(j + 3) & 7]) & ~a[(j + 5) & 7];
+      for (int j = 0; j < 16; j++) b[j] = (a[j] & a[(j + 5) & 15]) ^ a[(j + 11) & 15];
+#pragma unroll
+      for (int j = 0; j < 16; j++) a[j] = (b[j] | b[(j + 3) & 15]) ^ b[(j + 7) & 15];
     }
   }
   uint32_t x = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) x ^= a[j];
+  for (int j = 0; j < 16; j++) x ^= a[j];
   if (x == 0x12345u) out[0] = x;  // keeps the loop alive
 }
 
