@@ -120,10 +120,14 @@ int pm_init(pm_ctx *ctx);
  * stream[0] (0 for a whole database; the shard's first position when a
  * database is partitioned over several contexts / GPUs, in which case the
  * shard must carry PM_SHARD_OVERLAP(ctx) extra characters to the left of the
- * range it is asked to report).  _host copies through pinned staging
- * buffers; _device adopts a 4-byte-aligned device pointer that must stay
- * valid until the next pm_set_text_* / pm_destroy.  Both run the pack kernel
- * (per-symbol match bit-planes).                                              */
+ * range it is asked to report).  _host starts a chunked copy + pack pipeline
+ * on a private copy stream and returns; the scan of the next pm_find_patterns
+ * overlaps the rest of the transfer.  A page-locked `stream` is read directly
+ * and must stay unchanged until that next blocking call returns; pageable
+ * memory is staged through pinned buffers before the call returns.  _device
+ * adopts a 4-byte-aligned device pointer that must stay valid until the next
+ * pm_set_text_* / pm_destroy.  Both run the pack kernel (per-symbol match
+ * bit-planes).                                                                */
 int pm_set_text_host(pm_ctx *ctx, const uint8_t *stream, uint64_t n, int64_t stream_offset);
 int pm_set_text_device(pm_ctx *ctx, const uint8_t *d_stream, uint64_t n, int64_t stream_offset);
 

@@ -155,6 +155,13 @@ struct pm_ctx {
   uint32_t n_tiles = 0;
   void *stage[2] = {nullptr, nullptr};
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  // planes become ready chunk by chunk: tiles [previous tile_end, tile_end) after `ev`
+  // (ev == nullptr: packed on the main stream, no wait needed)
+  struct Chunk { uint32_t tile_end; cudaEvent_t ev; };
+  std::vector<Chunk> chunks;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  bool pack_timed = false;
   // work buffers
   DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands;
@@ -162,7 +169,7 @@ struct pm_ctx {
   unsigned long long *h_counters = nullptr;  // pinned [8]
   void *h_out = nullptr;                     // pinned result buffer
   size_t h_out_cap = 0;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   pm_stats stats;
 };
 
@@ -320,7 +327,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   if (nt < want_blocks) chunks = (uint32_t)((want_blocks + nt - 1) / nt);
   uint32_t spc = (uint32_t)((n_slots + chunks - 1) / chunks);
   if (spc < 8) spc = 8;
-  if (spc > 65536) spc = 65536;
+  if (spc > 512) spc = 512;  // keeps a block around a millisecond: short tails per launch
   chunks = (uint32_t)((n_slots + spc - 1) / spc);
 
   ScanArgs a;
@@ -379,10 +386,23 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // grid.x is limited to 2^31-1, grid.y to 65535
     if (chunks > 65535) return fail(PM_E_UNSUPPORTED, "too many pattern chunks");
-    kern<<<dim3(nt, chunks), SCAN_THREADS, smem, c->stream>>>(a);
-    PM_CUDA(cudaGetLastError());
+    {
+      uint32_t prev_end = 0;
+      for (const pm_ctx::Chunk &ch : c->chunks) {
+        const uint32_t t0 = std::max(prev_end, tile0), t1 = std::min(ch.tile_end, tile1);
+        prev_end = std::max(prev_end, ch.tile_end);
+        if (t1 <= t0) continue;
+        if (ch.ev) PM_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
+        a.tile0 = t0;
+        kern<<<dim3(t1 - t0, chunks), SCAN_THREADS, smem, c->stream>>>(a);
+        PM_CUDA(cudaGetLastError());
+        c->stats.kernel_launches++;
+      }
+      // the alignment kernels read the raw text: everything must have arrived
+      if (!c->chunks.empty() && c->chunks.back().ev)
+        PM_CUDA(cudaStreamWaitEvent(c->stream, c->chunks.back().ev, 0));
+    }
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
-    c->stats.kernel_launches++;
     c->stats.scan_items = (uint64_t)nt * chunks;
     PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 6 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
@@ -610,24 +630,52 @@ done:
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
     c->stats.total_ms = ms;
+    if (c->pack_timed && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess)
+      c->stats.pack_ms = ms;
+    else
+      cudaGetLastError();
   }
   if (c->stats.n_bogus)
     return fail(PM_E_BOGUS, "Bogus hit returned to primer_match main()");
   return PM_OK;
 }
 
-int pack_text(pm_ctx *c) {
-  c->n_tiles = (uint32_t)((c->n + TILE_POS - 1) / TILE_POS);
-  if (c->n_tiles == 0) return PM_OK;
-  const int n_planes = c->n_sym + 1;
-  int rc = c->d_planes.ensure((size_t)c->n_tiles * n_planes * TILE_WT * 4);
-  if (rc) return rc;
-  PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
-  pack_planes_kernel<<<c->n_tiles, PACK_THREADS, 0, c->stream>>>(
-      c->d_text, c->n, c->d_symmask.as<uint32_t>(), n_planes, c->opt.eos,
-      c->d_planes.as<uint32_t>());
+cudaEvent_t next_event(pm_ctx *c) {
+  if (c->ev_used == c->ev_pool.size()) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    c->ev_pool.push_back(e);
+  }
+  return c->ev_pool[c->ev_used++];
+}
+
+int pack_tiles(pm_ctx *c, uint32_t t0, uint32_t t1, cudaStream_t st) {
+  if (t1 <= t0) return PM_OK;
+  pack_planes_kernel<<<t1 - t0, PACK_THREADS, 0, st>>>(c->d_text, c->n, c->d_symmask.as<uint32_t>(),
+                                                       c->n_sym + 1, c->opt.eos,
+                                                       c->d_planes.as<uint32_t>(), t0);
   PM_CUDA(cudaGetLastError());
-  PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
+  return PM_OK;
+}
+
+int prepare_planes(pm_ctx *c) {
+  c->n_tiles = (uint32_t)((c->n + TILE_POS - 1) / TILE_POS);
+  c->chunks.clear();
+  c->ev_used = 0;
+  c->pack_timed = false;
+  if (c->n_tiles == 0) return PM_OK;
+  return c->d_planes.ensure((size_t)c->n_tiles * (c->n_sym + 1) * TILE_WT * 4);
+}
+
+// whole text already on the device: one pack launch on the main stream
+int pack_text(pm_ctx *c) {
+  int rc = prepare_planes(c);
+  if (rc || c->n_tiles == 0) return rc;
+  PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  if ((rc = pack_tiles(c, 0, c->n_tiles, c->stream))) return rc;
+  PM_CUDA(cudaEventRecord(c->ev[5], c->stream));
+  c->pack_timed = true;
+  c->chunks.push_back(pm_ctx::Chunk{c->n_tiles, nullptr});
   return PM_OK;
 }
 
@@ -682,7 +730,7 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
     delete c;
     return fail(PM_E_CUDA, "allocation of counters failed");
   }
-  for (int i = 0; i < 4; i++) cudaEventCreate(&c->ev[i]);
+  for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   *out = c;
@@ -707,8 +755,9 @@ void pm_destroy(pm_ctx *c) {
     if (c->stage[i]) cudaFreeHost(c->stage[i]);
     if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
   }
-  for (int i = 0; i < 4; i++)
+  for (int i = 0; i < 6; i++)
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+  for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
@@ -862,13 +911,7 @@ static int set_text_common(pm_ctx *c, uint64_t n, int64_t offset) {
   c->offset = offset;
   if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
   if (!c->inited) return PM_OK;  // packed by pm_init
-  int rc = pack_text(c);
-  if (rc) return rc;
-  PM_CUDA(cudaStreamSynchronize(c->stream));
-  float ms = 0;
-  if (c->n_tiles) cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-  c->stats.pack_ms = ms;
-  return PM_OK;
+  return pack_text(c);
 }
 
 int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offset) {
@@ -876,37 +919,64 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
   PM_CUDA(cudaSetDevice(c->opt.device));
   if (n && offset == 0 && stream[0] != c->opt.eos)
     return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
+  if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
   int rc = c->d_text_own.ensure(n + 64);
   if (rc) return rc;
   c->d_text = c->d_text_own.as<uint8_t>();
-  if (n) {
-    cudaPointerAttributes at;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&at, stream) == cudaSuccess)
-      pinned = (at.type == cudaMemoryTypeHost);
-    else
-      cudaGetLastError();
+  c->n = n;
+  c->offset = offset;
+  if (!n) return set_text_common(c, n, offset);
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, stream) == cudaSuccess)
+    pinned = (at.type == cudaMemoryTypeHost);
+  else
+    cudaGetLastError();
+  if (!c->inited) {  // not the reference's call order: plain copy now, pack in pm_init
+    PM_CUDA(cudaMemcpyAsync(c->d_text_own.p, stream, n, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+    return PM_OK;
+  }
+  // Pipeline: the copy stream moves the text in growing chunks and packs every tile
+  // whose characters (plus the 64-character extension) have arrived; the scan of
+  // pm_find_patterns waits chunk by chunk, so it overlaps the rest of the transfer.
+  if ((rc = prepare_planes(c))) return rc;
+  PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  PM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[4], 0));  // earlier work may still read the buffers
+  if (!pinned)
+    for (int i = 0; i < 2; i++)
+      if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
+  uint64_t done = 0, next = 64ull << 20;
+  uint32_t tiles_done = 0;
+  int which = 0;
+  while (done < n) {
+    uint64_t take = std::min<uint64_t>(next, n - done);
+    if (n - done - take < (32ull << 20)) take = n - done;  // no tiny last chunk
     if (pinned) {
-      PM_CUDA(cudaMemcpyAsync(c->d_text_own.p, stream, n, cudaMemcpyHostToDevice, c->stream));
+      PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done, stream + done, take,
+                              cudaMemcpyHostToDevice, c->copy_stream));
     } else {
-      // pageable source: double-buffered pinned staging
-      for (int i = 0; i < 2; i++)
-        if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
-      uint64_t done = 0;
-      int which = 0;
-      while (done < n) {
-        const size_t chunk = (size_t)std::min<uint64_t>(kStageBytes, n - done);
+      for (uint64_t o = 0; o < take; o += kStageBytes) {
+        const size_t part = (size_t)std::min<uint64_t>(kStageBytes, take - o);
         PM_CUDA(cudaEventSynchronize(c->stage_ev[which]));
-        memcpy(c->stage[which], stream + done, chunk);
-        PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done, c->stage[which], chunk,
-                                cudaMemcpyHostToDevice, c->stream));
-        PM_CUDA(cudaEventRecord(c->stage_ev[which], c->stream));
-        done += chunk;
+        memcpy(c->stage[which], stream + done + o, part);
+        PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done + o, c->stage[which], part,
+                                cudaMemcpyHostToDevice, c->copy_stream));
+        PM_CUDA(cudaEventRecord(c->stage_ev[which], c->copy_stream));
         which ^= 1;
       }
     }
+    done += take;
+    next *= 3;
+    const uint32_t ready = (done == n) ? c->n_tiles
+                                       : (uint32_t)((done > (uint64_t)TILE_EXT ? done - TILE_EXT : 0) / TILE_POS);
+    if ((rc = pack_tiles(c, tiles_done, ready, c->copy_stream))) return rc;
+    cudaEvent_t e = next_event(c);
+    PM_CUDA(cudaEventRecord(e, c->copy_stream));
+    c->chunks.push_back(pm_ctx::Chunk{ready, e});
+    tiles_done = std::max(tiles_done, ready);
   }
-  return set_text_common(c, n, offset);
+  return PM_OK;
 }
 
 int pm_set_text_device(pm_ctx *c, const uint8_t *d_stream, uint64_t n, int64_t offset) {

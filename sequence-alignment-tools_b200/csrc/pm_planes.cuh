@@ -42,13 +42,13 @@ constexpr int PACK_GROUP = 8;      // planes accumulated per pass over the tile
 __global__ void __launch_bounds__(PACK_THREADS)
 pack_planes_kernel(const uint8_t *__restrict__ text, uint64_t n,
                    const uint32_t *__restrict__ symmask, int n_planes, uint32_t eos_byte,
-                   uint32_t *__restrict__ planes) {
+                   uint32_t *__restrict__ planes, uint32_t tile_base) {
   __shared__ uint32_t s_mask[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_mask[i] = symmask[i];
   __syncthreads();
   const uint32_t q = threadIdx.x;
   if (q >= TILE_WT / 4) return;
-  const uint64_t tile = blockIdx.x;
+  const uint64_t tile = (uint64_t)tile_base + blockIdx.x;
   const uint64_t base = tile * (uint64_t)TILE_POS + 4u * q;
   const uint32_t eos4 = eos_byte * 0x01010101u;
   for (int p0 = 0; p0 < n_planes; p0 += PACK_GROUP) {

@@ -189,3 +189,38 @@ def test_full_size_properties(pkg):
                 w = T[e - 20:e].tobytes().decode()
                 assert sum(a != b for a, b in zip(w, pats[pid - 1])) == int(r["editdist"])
     assert res[1] <= res[2]
+
+
+def test_host_pipeline_equals_device_path(pkg):
+    """Pinned-host text goes through the chunked copy/pack/scan pipeline (several
+    chunks at this size); the result must equal the device-resident path."""
+    import torch
+    import casegen
+    rng = random.Random(5)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(40)]
+    n = 110 * (1 << 20) + 12345
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    d = lut[torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.uint8).long()]
+    d[0] = 10
+    d[-1] = 10
+    for j in range(300):   # planted copies, some right at the 64 MiB chunk seam
+        at = (64 << 20) - 150 + j if j < 280 else rng.randrange(1000, n - 1000)
+        p = torch.tensor(list(primers[j % 40].encode()), dtype=torch.uint8, device="cuda")
+        if j % 3 == 0:
+            d[at:at + 20] = p
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h.copy_(d)
+    torch.cuda.synchronize()
+    out = []
+    for src in (d, h, h.numpy().copy()):
+        sc = pkg.Scanner(k=2, indels=False)
+        for i, p in enumerate(pkg.pattern_array(primers, True)):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(src)
+        out.append(sc.find_patterns())
+        sc.close()
+    assert len(out[0]) >= 90
+    assert out[0].tobytes() == out[1].tobytes() == out[2].tobytes()
