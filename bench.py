@@ -371,8 +371,12 @@ def main():
         alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch
         hbm_achieved = alg_bytes / (mean_scan_ms * 1e-3) / 1e9
         cells = float(n + 2) * len(pats) * (K + 1)
+        # dram__bytes_read+write of one scan launch, from the ncu capture in profiles/README.md
+        # (268 Mbp: 567.6 MB with 4 pattern chunks), scaled to this launch's bases
+        traffic = None if args.indels else 2.115 * (n + 2)
         roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_achieved / hbm_peak, "traffic": None,
+                "frac": hbm_achieved / hbm_peak, "traffic": traffic,
+                "traffic_source": "ncu --set full capture profiles/README.md (r1b), bytes per base x bases",
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
                 "kernel": "hamming_scan_kernel<2>" if not args.indels else "edit_scan_kernel<2>",
                 "kernel_ms": mean_scan_ms,

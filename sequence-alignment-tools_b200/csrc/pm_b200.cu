@@ -347,6 +347,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   a.n_sym = (uint32_t)c->n_sym;
   a.n_slots = (uint32_t)n_slots;
   a.slots_per_chunk = spc;
+  a.n_chunks = chunks;
   a.eos = c->opt.eos;
   a.cls = c->d_cls.as<uint8_t>();
   a.umask = c->d_umask.as<uint64_t>();
@@ -385,7 +386,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     PM_CUDA(cudaMemsetAsync(c->d_counters + 5, 0, sizeof(unsigned long long), c->stream));
     PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // grid.x is limited to 2^31-1, grid.y to 65535
-    if (chunks > 65535) return fail(PM_E_UNSUPPORTED, "too many pattern chunks");
+    if ((uint64_t)nt * chunks > 0x7fffffffull) return fail(PM_E_UNSUPPORTED, "scan grid too large");
     {
       uint32_t prev_end = 0;
       for (const pm_ctx::Chunk &ch : c->chunks) {
@@ -394,7 +395,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         if (t1 <= t0) continue;
         if (ch.ev) PM_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
         a.tile0 = t0;
-        kern<<<dim3(t1 - t0, chunks), SCAN_THREADS, smem, c->stream>>>(a);
+        kern<<<(t1 - t0) * chunks, SCAN_THREADS, smem, c->stream>>>(a);
         PM_CUDA(cudaGetLastError());
         c->stats.kernel_launches++;
       }

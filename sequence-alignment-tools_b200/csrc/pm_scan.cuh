@@ -57,7 +57,8 @@ struct ScanArgs {
   uint32_t n_planes;        // planes per tile in HBM (n_sym + 1)
   uint32_t n_sym;           // symbol planes copied to shared memory
   uint32_t n_slots;
-  uint32_t slots_per_chunk; // patterns per blockIdx.y
+  uint32_t slots_per_chunk; // patterns per block; blockIdx.x = tile_local * n_chunks + chunk
+  uint32_t n_chunks;
   uint32_t eos;
   // edit mode only
   const uint8_t *cls;       // [256] text byte -> class
@@ -200,13 +201,14 @@ hamming_scan_kernel(const ScanArgs a) {
   constexpr int NB = CT::NB;
   constexpr int S = SCAN_STRIPS;
   constexpr int FIRST_CHECK = (K == 0) ? 1 : (K <= 2 ? 2 : 3);  // 0-based group index
-  const uint32_t tile = a.tile0 + blockIdx.x;
+  const uint32_t tile = a.tile0 + blockIdx.x / a.n_chunks;
+  const uint32_t chunk = blockIdx.x % a.n_chunks;  // chunks of one tile run back to back: planes stay in L2
   load_tile(a, tile, s_planes, &s_bar);
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t w0 = warp * (32 * S) + lane;  // word of strip 0
   const char *lane_base = reinterpret_cast<const char *>(s_planes) + 4u * w0;
-  const uint32_t slot0 = blockIdx.y * a.slots_per_chunk;
+  const uint32_t slot0 = chunk * a.slots_per_chunk;
   uint32_t slot1 = slot0 + a.slots_per_chunk;
   if (slot1 > a.n_slots) slot1 = a.n_slots;
 
@@ -338,14 +340,15 @@ edit_scan_kernel(const ScanArgs a) {
   __shared__ uint32_t s_queue[SCAN_THREADS / 32][SEEDQ_CAP];
   __shared__ uint32_t s_qn[SCAN_THREADS / 32];
   constexpr int S = SCAN_STRIPS;
-  const uint32_t tile = a.tile0 + blockIdx.x;
+  const uint32_t tile = a.tile0 + blockIdx.x / a.n_chunks;
+  const uint32_t chunk = blockIdx.x % a.n_chunks;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) s_qn[warp] = 0;
   load_tile(a, tile, s_planes, &s_bar);
 
   const uint32_t w0 = warp * (32 * S) + lane;
   const char *lane_base = reinterpret_cast<const char *>(s_planes) + 4u * w0;
-  const uint32_t slot0 = blockIdx.y * a.slots_per_chunk;
+  const uint32_t slot0 = chunk * a.slots_per_chunk;
   uint32_t slot1 = slot0 + a.slots_per_chunk;
   if (slot1 > a.n_slots) slot1 = a.n_slots;
   uint32_t *queue = s_queue[warp];

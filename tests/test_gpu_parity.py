@@ -205,11 +205,9 @@ def test_host_pipeline_equals_device_path(pkg):
     d = lut[torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.uint8).long()]
     d[0] = 10
     d[-1] = 10
-    for j in range(300):   # planted copies, some right at the 64 MiB chunk seam
-        at = (64 << 20) - 150 + j if j < 280 else rng.randrange(1000, n - 1000)
-        p = torch.tensor(list(primers[j % 40].encode()), dtype=torch.uint8, device="cuda")
-        if j % 3 == 0:
-            d[at:at + 20] = p
+    for j in range(140):   # planted copies, 100 of them around the 64 MiB chunk seam
+        at = (64 << 20) - 2000 + 41 * j if j < 100 else 5000 + 700001 * (j - 99)
+        d[at:at + 20] = torch.tensor(list(primers[j % 40].encode()), dtype=torch.uint8, device="cuda")
     h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     h.copy_(d)
     torch.cuda.synchronize()
@@ -222,5 +220,5 @@ def test_host_pipeline_equals_device_path(pkg):
         sc.set_text(src)
         out.append(sc.find_patterns())
         sc.close()
-    assert len(out[0]) >= 90
+    assert len(out[0]) >= 140
     assert out[0].tobytes() == out[1].tobytes() == out[2].tobytes()
