@@ -1,0 +1,77 @@
+"""Partitioning a database stream over ranks (one process per GPU) and gathering
+the per-rank hit lists.  No data-path collective: every rank scans its own
+shard; torch.distributed (NCCL on the GPUs, gloo in the CPU tests) only moves
+hit counts and the compacted hit records at the end.
+
+Ownership rule (include/pm_b200.h, pm_find_patterns): a hit belongs to the rank
+whose [begin, end) contains the FIRST raw candidate position of its chain.
+A shard therefore carries `overlap` = longest pattern + 3k + 2 characters of
+left context (candidate warm-up m+k, chain look-back 2k+1, alignment reach) and
+`right_guard` characters of right context so that a chain starting just before
+`end` can be followed to its last candidate.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Shard:
+    rank: int
+    begin: int     # owned candidate positions [begin, end)
+    end: int
+    load_lo: int   # stream[load_lo:load_hi] is what the rank loads (offset = load_lo)
+    load_hi: int
+
+
+def shard_plan(stream_len: int, world: int, overlap: int, right_guard: int = 1 << 16,
+               cut_points=None):
+    """Even split of candidate positions 0..stream_len (inclusive) over `world`
+    ranks.  `cut_points` (sorted stream positions, e.g. sequence separators) makes
+    the cuts snap to the nearest sequence boundary at or after the even cut."""
+    bounds = [0]
+    for r in range(1, world):
+        b = (stream_len + 1) * r // world
+        if cut_points is not None and len(cut_points):
+            i = int(np.searchsorted(cut_points, b, side="left"))
+            if i < len(cut_points):
+                b = int(cut_points[i])
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(stream_len + 1)
+    shards = []
+    for r in range(world):
+        begin, end = bounds[r], bounds[r + 1]
+        lo = max(0, begin - overlap) if r else 0
+        hi = min(stream_len, end + right_guard)
+        shards.append(Shard(r, begin, end, lo, hi))
+    return shards
+
+
+def gather_hits(local: np.ndarray, dist=None):
+    """All ranks contribute a structured hit array; every rank gets the
+    concatenation sorted by (end, pattern_id).  Two collectives: counts, then the
+    records as bytes (padded to the largest count)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    import torch
+    world = dist.get_world_size()
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([len(local)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    item = local.dtype.itemsize
+    mx = max(counts)
+    if mx == 0:
+        return local
+    buf = torch.zeros(mx * item, dtype=torch.uint8, device=dev)
+    if len(local):
+        buf[:len(local) * item] = torch.from_numpy(np.frombuffer(local.tobytes(), np.uint8).copy()).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    parts = [np.frombuffer(b.cpu().numpy().tobytes()[:c * item], dtype=local.dtype) for b, c in zip(bufs, counts)]
+    out = np.concatenate(parts)
+    return out[np.lexsort((out["pattern_id"], out["end"]))]
