@@ -76,6 +76,10 @@ typedef struct pm_options {
 typedef struct pm_hit {
   int64_t start;       /* pattern_alignment::start()                           */
   int64_t end;         /* %E  pattern_alignment::end()                         */
+  int64_t first;       /* pos of the first raw candidate of the hit's chain
+                          (= end for the exact indexes): the order in which
+                          the reference reports hits, and the ownership key
+                          of pm_find_patterns' [begin, end)                    */
   uint32_t pattern_id; /* id passed to pm_add_pattern                          */
   int32_t editdist;    /* %d  pattern_alignment::editdist()                    */
   int32_t value;       /* editdist_alignment::value() (DP score)               */
@@ -138,7 +142,8 @@ int pm_shard_overlap(pm_ctx *ctx);
 /* PatternMatch::find_patterns followed, per returned hit, by the final
  * alignment of primer_match.cc:1132-1153.  Reports the hits whose FIRST raw
  * candidate position (pm_candidate.pos of the head of its chain) lies in
- * [begin, end) of the global stream, sorted by (end, pattern_id).  *hits
+ * [begin, end) of the global stream, sorted by (first, pattern_id): the order
+ * the reference reports them in, up to ties.  *hits
  * points into pinned memory owned by the context, valid until the next call
  * on it.  Pass begin=0,end=INT64_MAX for the whole stream (what the reference
  * does).                                                                      */

@@ -1,0 +1,199 @@
+// pm_pattern_match.hpp -- C++ host mirror of the reference's PatternMatch
+// plugin surface (pattern_match.h:83-157, select.h:8-19) over the C ABI of
+// include/pm_b200.h.  Same method names, argument meaning and error behaviour
+// (fatal errors print the reference's message and exit(1)), so code written
+// against the reference classes reads the same here.
+//
+// Header-only; link with -lpm_b200.
+#ifndef PM_PATTERN_MATCH_HPP
+#define PM_PATTERN_MATCH_HPP
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pm_b200.h"
+
+namespace pmb200 {
+
+inline void fatal(const std::string &msg) {
+  std::cerr << msg << std::endl;
+  std::exit(1);
+}
+
+// The CharacterProducer of this library: the normalised stream of a FASTA
+// database (StreamedFastaFile, fasta_io.t:448-751) held in host memory, with
+// the header index FastaFile<H> keeps (fasta_io.t:140-215).
+class FastaStream {
+ public:
+  FastaStream() {}
+  bool load(const std::string &filename, bool upper_case, unsigned char eos) {
+    std::ifstream f(filename.c_str(), std::ios::binary);
+    if (!f) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    f.seekg(0);
+    raw_.resize((size_t)n);
+    if (n) f.read(&raw_[0], n);
+    return from_memory(upper_case, eos);
+  }
+  bool from_memory(bool upper_case, unsigned char eos) {
+    size_t nh = 2;
+    for (char ch : raw_) nh += (ch == '>');
+    chars_.resize(raw_.size() + 4);
+    key_.resize(nh);
+    hoff_.resize(nh);
+    hlen_.resize(nh);
+    uint64_t len = 0, ns = 0;
+    if (pm_normalize_fasta((const uint8_t *)raw_.data(), raw_.size(), upper_case, eos, chars_.data(), &len,
+                           key_.data(), hoff_.data(), hlen_.data(), nh, &ns) != PM_OK)
+      return false;
+    chars_.resize(len);
+    key_.resize(ns);
+    return true;
+  }
+  std::string &raw() { return raw_; }
+  const uint8_t *chars() const { return chars_.data(); }
+  uint64_t size() const { return chars_.size(); }
+  // set_header_item (fasta_io.t:152-168): the entry whose key is the last <= pos-1
+  long locate(int64_t pos) const {
+    long lo = 0, hi = (long)key_.size();
+    while (lo < hi) {
+      const long mid = (lo + hi) / 2;
+      if (key_[mid] <= pos - 1) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+  }
+  int64_t get_seq_pos(int64_t pos) const {  // fasta_io.t:194-202
+    const long i = locate(pos);
+    return i < 0 ? 0 : pos - key_[i];
+  }
+  unsigned long index(int64_t pos) const { const long i = locate(pos); return i < 0 ? 0 : (unsigned long)(i + 1); }
+  std::string header(int64_t pos) const {
+    const long i = locate(pos);
+    if (i < 0) return "";
+    return raw_.substr((size_t)hoff_[i], (size_t)(hlen_[i] > 0 ? hlen_[i] : 0));
+  }
+  std::string short_header(int64_t pos) const {  // first word, fasta_io.t:118-126
+    const std::string h = header(pos);
+    const size_t p = h.find_first_of(" \t");
+    return p == std::string::npos ? h : h.substr(0, p);
+  }
+  std::string text(int64_t a, int64_t b) const {
+    if (a < 0) a = 0;
+    if (b > (int64_t)chars_.size()) b = (int64_t)chars_.size();
+    return a < b ? std::string((const char *)chars_.data() + a, (size_t)(b - a)) : std::string();
+  }
+
+ private:
+  std::string raw_;
+  std::vector<uint8_t> chars_;
+  std::vector<int64_t> key_, hoff_, hlen_;
+};
+
+// pattern_hit_vector element (pattern_match.h:81): key = end position of the hit
+struct pattern_hit {
+  int64_t key;
+  unsigned long id;
+  unsigned char value;
+};
+typedef std::vector<pattern_hit> pattern_hit_vector;
+
+class PatternMatch {
+ public:
+  PatternMatch() : next_pattern_id_(0) {}
+  virtual ~PatternMatch() {}
+  virtual unsigned long add_pattern(std::string const &pat, unsigned long id = 0, int exact_start_bases = 0,
+                                    int exact_end_bases = 0) = 0;
+  virtual void init(FastaStream &cp) = 0;
+  virtual bool find_patterns(FastaStream &cp, pattern_hit_vector &pas, unsigned long minka = 1) = 0;
+  virtual void reset() = 0;
+
+ protected:
+  unsigned long next_pattern_id_;
+};
+
+// One index on one GPU.  find_patterns() scans the whole stream on its first
+// call and then hands the hits over `minka` at a time, like the reference's
+// indexes do (e.g. filter_bitvec.cc:229-231).
+class b200_index : public PatternMatch {
+ public:
+  b200_index(int index, unsigned k, char eos, bool wc, bool tn, bool indels, int device = 0)
+      : ctx_(0), hits_(0), nhits_(0), next_(0), scanned_(false) {
+    pm_options o;
+    std::memset(&o, 0, sizeof o);
+    o.device = device; o.index = index; o.k = (int)k; o.indels = indels; o.wildcards = wc; o.text_n = tn;
+    o.eos = (unsigned char)eos;
+    if (pm_create(&ctx_, &o) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+  }
+  ~b200_index() { pm_destroy(ctx_); }
+  unsigned long add_pattern(std::string const &pat, unsigned long id = 0, int esb = 0, int eeb = 0) {
+    if (id == 0) id = ++next_pattern_id_;
+    if (pm_add_pattern(ctx_, pat.c_str(), (uint32_t)id, esb, eeb) != PM_OK) {
+      // select.cc:88-91 prints this one when k >= pattern length
+      fatal(std::string("Fatal error: ") + pm_last_error());
+    }
+    return id;
+  }
+  void init(FastaStream &cp) {
+    if (pm_init(ctx_) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+    if (pm_set_text_host(ctx_, cp.chars(), cp.size(), 0) != PM_OK)
+      fatal(std::string("Fatal error: ") + pm_last_error());
+  }
+  bool find_patterns(FastaStream &, pattern_hit_vector &pas, unsigned long minka = 1) {
+    if (!scanned_) {
+      const int rc = pm_find_patterns(ctx_, 0, INT64_MAX, &hits_, &nhits_);
+      if (rc == PM_E_BOGUS) fatal("Bogus hit returned to primer_match main()");  // primer_match.cc:1249
+      if (rc != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+      scanned_ = true;
+    }
+    while (next_ < nhits_ && pas.size() < minka) {
+      const pm_hit &h = hits_[next_++];
+      pattern_hit ph = {h.end, h.pattern_id, (unsigned char)h.value};
+      pas.push_back(ph);
+      batch_.push_back(&h);
+    }
+    return next_ < nhits_;
+  }
+  void reset() { pm_reset(ctx_); scanned_ = false; next_ = 0; batch_.clear(); }
+  // the full records (alignment included) of the hits handed out by the last
+  // find_patterns() call, same order as `pas`
+  std::vector<const pm_hit *> &batch() { return batch_; }
+  pm_ctx *ctx() { return ctx_; }
+
+ private:
+  pm_ctx *ctx_;
+  const pm_hit *hits_;
+  uint64_t nhits_, next_;
+  bool scanned_;
+  std::vector<const pm_hit *> batch_;
+};
+
+// pick_pattern_index (select.cc:18-298) for the selections this library has.
+// pmselect 0 = automatic.  Selections whose *hit semantics* differ from what is
+// implemented (exact_halves 11-14, exact_bases 7-10, hash tables 6/15, suffix
+// tree) are refused rather than silently replaced.
+inline b200_index *pick_pattern_index(int pmselect, int nmismatch, bool wildcard, bool textn, bool indels,
+                                      char eos, int device = 0) {
+  int index;
+  switch (pmselect) {
+    case 0: index = PM_INDEX_AUTO; break;
+    case 1: case 2: case 3: index = PM_INDEX_KEYWORD_TREE; break;
+    case 4: index = PM_INDEX_SHIFT_AND; break;
+    case 5: index = PM_INDEX_FILTER_BITVEC; break;
+    default:
+      fatal("Fatal error: pattern index selection not available in the B200 build (use -N 0, 3, 4 or 5)");
+      return 0;
+  }
+  if (index == PM_INDEX_KEYWORD_TREE && wildcard) index = PM_INDEX_SHIFT_AND;
+  return new b200_index(index, (unsigned)nmismatch, eos, wildcard, textn, indels, device);
+}
+
+}  // namespace pmb200
+#endif

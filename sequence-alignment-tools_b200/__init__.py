@@ -49,7 +49,7 @@ class Options(C.Structure):
 
 
 class Hit(C.Structure):
-    _fields_ = [("start", C.c_int64), ("end", C.c_int64), ("pattern_id", C.c_uint32),
+    _fields_ = [("start", C.c_int64), ("end", C.c_int64), ("first", C.c_int64), ("pattern_id", C.c_uint32),
                 ("editdist", C.c_int32), ("value", C.c_int32), ("ncodes", C.c_uint32),
                 ("codes", C.c_uint8 * PM_MAX_CODES)]
 
@@ -65,7 +65,7 @@ class Stats(C.Structure):
                 ("scan_warp_steps", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
-HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
+HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
                       ("value", "<i4"), ("ncodes", "<u4"), ("codes", "u1", (PM_MAX_CODES,))])
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)
 

@@ -219,6 +219,7 @@ __global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64
   editdist_align(env, h.slot, h.end, h.end, ws + i * ws_stride, out.codes, PM_MAX_CODES, r);
   out.start = r.start + offset;
   out.end = r.end + offset;
+  out.first = h.first + offset;
   out.pattern_id = slot_id[h.slot];
   out.editdist = r.editdist;
   out.value = r.val;
@@ -228,8 +229,8 @@ __global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64
   // so traceback order already is left-to-right.
   if (r.editdist < 0 || r.editdist > env.k) atomicAdd(n_bogus, 1ULL);
   hits[i] = out;
-  // order: (end, pattern id); end < 2^40, id < 2^24
-  sortkey[i] = ((unsigned long long)(out.end & 0xffffffffffLL) << 24) |
+  // order: (first, pattern id); first < 2^40, id < 2^24
+  sortkey[i] = ((unsigned long long)(out.first & 0xffffffffffLL) << 24) |
                (unsigned long long)(out.pattern_id & 0xffffffu);
 }
 
@@ -260,6 +261,7 @@ __global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *
   }
   out.start = pos - m + offset;
   out.end = pos + offset;
+  out.first = pos + offset;
   out.pattern_id = slot_id[slot];
   out.editdist = sub;
   out.value = 0;

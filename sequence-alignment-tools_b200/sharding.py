@@ -51,7 +51,7 @@ def shard_plan(stream_len: int, world: int, overlap: int, right_guard: int = 1 <
 
 def gather_hits(local: np.ndarray, dist=None):
     """All ranks contribute a structured hit array; every rank gets the
-    concatenation sorted by (end, pattern_id).  Two collectives: counts, then the
+    concatenation sorted by (first, pattern_id).  Two collectives: counts, then the
     records as bytes (padded to the largest count)."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return local
@@ -74,4 +74,4 @@ def gather_hits(local: np.ndarray, dist=None):
     dist.all_gather(bufs, buf)
     parts = [np.frombuffer(b.cpu().numpy().tobytes()[:c * item], dtype=local.dtype) for b, c in zip(bufs, counts)]
     out = np.concatenate(parts)
-    return out[np.lexsort((out["pattern_id"], out["end"]))]
+    return out[np.lexsort((out["pattern_id"], out["first"]))]

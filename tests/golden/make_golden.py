@@ -48,6 +48,26 @@ def case_params(seed: int):
     return dict(k=k, indels=indels, wc=wc, tn=tn, rev_comp=rc), kw
 
 
+def cli_args(fasta_path, primers, params, extra=()):
+    """primer_match command line for a case (everything after the program name)."""
+    args = ["-i", fasta_path, "-p", " ".join(primers)]
+    if params["k"] > 0:
+        args += ["-k" if params["indels"] else "-K", str(params["k"]), "-N", "5"]
+    if params["rev_comp"]:
+        args.append("-r")
+    if params["wc"]:
+        args.append("-W" if params["tn"] else "-w")
+    return args + list(extra)
+
+
+def reference_stdout(fasta_path, primers, params, extra=()):
+    import subprocess
+    p = subprocess.run([O.REF_BIN] + cli_args(fasta_path, primers, params, extra), capture_output=True, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("reference failed")
+    return p.stdout.decode("latin-1")
+
+
 def main():
     if not O.ref_available():
         raise SystemExit("oracle/_ref/primer_match missing: run `make -C oracle` first")
@@ -67,10 +87,18 @@ def main():
             skipped += 1
             seed += 1
             continue
-        cases.append(dict(seed=seed, params=params, fasta=fasta, primers=primers,
-                          records=[[r.seq_index, r.seq_start, r.seq_end, r.strand, r.pattern_index,
-                                    r.editdist, r.stream_start, r.stream_end, r.alignment]
-                                   for r in recs]))
+        case = dict(seed=seed, params=params, fasta=fasta, primers=primers,
+                    records=[[r.seq_index, r.seq_start, r.seq_end, r.strand, r.pattern_index,
+                              r.editdist, r.stream_start, r.stream_end, r.alignment]
+                             for r in recs])
+        if len(cases) % 3 == 0:
+            # the tool's own text output: default alignment format, a custom one, counts
+            case["stdout_default"] = reference_stdout(path, primers, params)
+            case["stdout_custom"] = reference_stdout(path, primers, params,
+                                                     ["-A", "%H %f %5 %3 %l %q %p %t|%T|%Q|%A %| %^ %v %* %+ %%\\n"])
+            case["stdout_counts"] = reference_stdout(path, primers, params, ["-c"])
+            case["stdout_counts_agg"] = reference_stdout(path, primers, params, ["-C", "%i\\t%p\\t%c\\t%C\\n", "-a"])
+        cases.append(case)
         seed += 1
     # the reference's own primer lists (db/pat.txt, db/patwc.txt: BASELINE.json configs[0] and
     # configs[2]) against seeded DNA with mutated copies planted

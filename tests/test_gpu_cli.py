@@ -1,0 +1,84 @@
+"""The drop-in command line tool (bin/primer_match, C++ host code over the C
+ABI) against the text the UNMODIFIED reference printed for the same command
+lines (tests/golden/make_golden.py: default format, a custom -A format, -c and
+-C/-a counts).  Hit records are compared as multisets: the reference orders
+simultaneous hits of different primers by an unstable std::sort."""
+import importlib
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import PKG_NAME, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cli(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device; the tool has no CPU fallback")
+    build = importlib.import_module(PKG_NAME + ".build")
+    path = build.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def _args(fasta_path, primers, params, extra=()):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    return make_golden.cli_args(fasta_path, primers, params, extra)
+
+
+def _run(cli, args):
+    p = subprocess.run([cli] + args, capture_output=True, timeout=300)
+    assert p.returncode == 0, p.stderr.decode()[-500:]
+    return p.stdout.decode("latin-1")
+
+
+def _blocks(text, n):
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    assert len(lines) % n == 0
+    return sorted(tuple(lines[i:i + n]) for i in range(0, len(lines), n))
+
+
+def test_cli_output_matches_reference(cli, golden, tmp_path):
+    checked = 0
+    for case in golden["cases"]:
+        if "stdout_default" not in case:
+            continue
+        fa = tmp_path / ("c%s.fasta" % str(case["seed"]).replace(":", "_"))
+        fa.write_bytes(case["fasta"].encode("latin-1"))
+        prm, par = case["primers"], case["params"]
+        got = _run(cli, _args(str(fa), prm, par))
+        assert _blocks(got, 4) == _blocks(case["stdout_default"], 4), "default format, case %s" % case["seed"]
+        got = _run(cli, _args(str(fa), prm, par, ["-A", "%H %f %5 %3 %l %q %p %t|%T|%Q|%A %| %^ %v %* %+ %%\\n"]))
+        assert _blocks(got, 1) == _blocks(case["stdout_custom"], 1), "custom format, case %s" % case["seed"]
+        got = _run(cli, _args(str(fa), prm, par, ["-c"]))
+        assert got == case["stdout_counts"], "counts, case %s" % case["seed"]
+        got = _run(cli, _args(str(fa), prm, par, ["-C", "%i\\t%p\\t%c\\t%C\\n", "-a"]))
+        assert sorted(got.split("\n")) == sorted(case["stdout_counts_agg"].split("\n")), "aggregate counts, case %s" % case["seed"]
+        checked += 1
+    assert checked >= 15
+
+
+def test_cli_pattern_files_and_output_file(cli, golden, tmp_path):
+    case = [c for c in golden["cases"] if "stdout_default" in c and len(c["records"]) > 3][0]
+    fa = tmp_path / "db.fasta"
+    fa.write_bytes(case["fasta"].encode("latin-1"))
+    pf = tmp_path / "primers.txt"
+    pf.write_text("\n".join(case["primers"]) + "\n")
+    pfa = tmp_path / "primers.fasta"
+    pfa.write_text("".join(">p%d some primer\n%s\n" % (i, p) for i, p in enumerate(case["primers"])))
+    base = _args(str(fa), case["primers"], case["params"])
+    i = base.index("-p")
+    want = _blocks(case["stdout_default"], 4)
+    outf = tmp_path / "out.txt"
+    _run(cli, base[:i] + ["-P", str(pf)] + base[i + 2:] + ["-o", str(outf)])
+    assert _blocks(outf.read_text(), 4) == want
+    got = _run(cli, base[:i] + ["-F", str(pfa)] + base[i + 2:])
+    assert _blocks(got, 4) == want

@@ -144,7 +144,7 @@ def test_shards_reproduce_whole_scan(pkg, k, indels):
         hi = min(len(T), bounds[i + 1] + 70000)
         parts.append(run(bounds[i], bounds[i + 1], bounds[i], hi))
     merged = np.concatenate(parts)
-    merged = merged[np.lexsort((merged["pattern_id"], merged["end"]))]
+    merged = merged[np.lexsort((merged["pattern_id"], merged["first"]))]
     assert len(whole) > 50
     assert merged.tobytes() == whole.tobytes()
 
@@ -178,7 +178,7 @@ def test_full_size_properties(pkg):
         sc.set_text(T)
         h = sc.find_patterns()
         sc.close()
-        assert np.all(np.diff(h["end"]) >= 0)
+        assert np.all(np.diff(h["first"]) >= 0)
         res[k] = {(int(r["end"]), int(r["pattern_id"])) for r in h}
         if k == 2:
             for at, pi in planted:

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(pkg, built_lib):
 
 
 def test_struct_layouts_match_header(pkg):
-    assert C.sizeof(pkg.Hit) == 8 + 8 + 4 + 4 + 4 + 4 + pkg.PM_MAX_CODES
+    assert C.sizeof(pkg.Hit) == 8 + 8 + 8 + 4 + 4 + 4 + 4 + pkg.PM_MAX_CODES
     assert C.sizeof(pkg.Candidate) == 16
 
 

@@ -44,6 +44,7 @@ def _owned_hits(O, pkg, T, lo, pats, k, indels, begin, end):
                 al = O.editdist_align(T, pats[int(pid) - 1], int(e), int(e), k, indels)
                 rec = np.zeros(1, pkg.HIT_DTYPE)
                 rec["start"], rec["end"], rec["pattern_id"] = al.start + lo, al.end + lo, int(pid)
+                rec["first"] = first
                 rec["editdist"], rec["value"], rec["ncodes"] = al.editdist, al.val, len(al.codes)
                 rec["codes"][0, :len(al.codes)] = list(al.codes)
                 out.append(rec)
@@ -73,7 +74,7 @@ def _worker(rank, world, port, q):
     merged = sharding.gather_hits(local, dist)
     if rank == 0:
         whole = _owned_hits(O, pkg, T, 0, pats, k, indels, 0, len(T) + 1)
-        whole = whole[np.lexsort((whole["pattern_id"], whole["end"]))]
+        whole = whole[np.lexsort((whole["pattern_id"], whole["first"]))]
         q.put((len(whole), merged.tobytes() == whole.tobytes(), [len(local)]))
     dist.barrier()
     dist.destroy_process_group()
