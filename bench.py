@@ -38,10 +38,13 @@ PKG = "sequence-alignment-tools_b200"
 N_PRIMERS = 1000
 PRIMER_LEN = 20
 K = 2
+INDELS = 0
 
 
-def make_primers(seed=12345, n=N_PRIMERS, m=PRIMER_LEN):
+def make_primers(seed=12345, n=None, m=None):
     import numpy as np
+    n = N_PRIMERS if n is None else n
+    m = PRIMER_LEN if m is None else m
     g = np.random.default_rng(seed)
     a = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, (n, m))]
     return [bytes(r).decode() for r in a]
@@ -128,7 +131,7 @@ def run_reference_sample(primers, total_bases: int, procs: int, seed: int, workd
             f.write(b"\n")
         files.append(path)
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, "-K", str(K), "-r", "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
+    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fp in files]
     for p in ps:
         p.wait()
@@ -156,7 +159,7 @@ def run_oracle_sample(primers, total_bases: int, seed: int):
     T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
     st = O.Stream(T, np.array([1], np.int64), ["s"])
     t0 = time.perf_counter()
-    O.primer_match(st, primers, k=K, indels=False, rev_comp=True)
+    O.primer_match(st, primers, k=K, indels=bool(INDELS), rev_comp=True)
     return time.perf_counter() - t0
 
 
@@ -168,8 +171,9 @@ def cpu_cores():
 
 
 def config_dict(args, shard_bases):
-    return {"workload": "%d random %d-mer primers, k=%d mismatches (-K %d), both strands (-r), "
-                        "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN, K, K),
+    return {"workload": "%d random %d-mer primers, k=%d %s (%s %d), both strands (-r), "
+                        "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN, K, "edits" if INDELS else "mismatches",
+                                                           "-k" if INDELS else "-K", K),
             "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
             "index": "filter_bitvec (reference auto choice for this workload)",
             "l2": "inputs larger than L2 (%.1f GB stream + planes per pass)" % (shard_bases / 1e9),
@@ -225,10 +229,14 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bases", type=int, default=3_000_000_000, help="database shard per GPU")
     ap.add_argument("--indels", type=int, default=0, help="1: -k (edits) instead of -K")
+    ap.add_argument("--k", type=int, default=K, help="errors allowed (headline: 2)")
+    ap.add_argument("--plen", type=int, default=PRIMER_LEN, help="primer length (headline: 20)")
+    ap.add_argument("--nprimers", type=int, default=N_PRIMERS, help="primers before reverse complements (headline: 1000)")
     ap.add_argument("--cpu-bases-per-core", type=int, default=3_000_000)
     ap.add_argument("--ref-bases-per-core", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels)
     if args.impl == "reference":
         return main_reference(args)
 
@@ -378,7 +386,7 @@ def main():
                 "frac": hbm_achieved / hbm_peak, "traffic": traffic,
                 "traffic_source": "ncu --set full capture profiles/README.md (r1b), bytes per base x bases",
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "kernel": "hamming_scan_kernel<2>" if not args.indels else "edit_scan_kernel<2>",
+                "kernel": ("hamming_scan_kernel<%d>" % K) if not args.indels else ("edit_seed_kernel<%d> + edit_verify_kernel<%d>" % (K, K)),
                 "kernel_ms": mean_scan_ms,
                 "note": "the scan is integer-pipe bound, not HBM bound: see int_pipe",
                 "cell_updates_per_s": cells / (mean_scan_ms * 1e-3)}

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <cmath>
 #include <limits>
 #include <string>
 #include <vector>
@@ -164,7 +165,8 @@ struct pm_ctx {
   bool pack_timed = false;
   // work buffers
   DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
-      d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands;
+      d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
+  double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
   unsigned long long *d_counters = nullptr;  // [8]
   unsigned long long *h_counters = nullptr;  // pinned [8]
   void *h_out = nullptr;                     // pinned result buffer
@@ -354,15 +356,17 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   a.cls = c->d_cls.as<uint8_t>();
   a.umask = c->d_umask.as<uint64_t>();
   a.n_cls = (uint32_t)c->n_cls;
-  a.piece = c->d_piece.as<uint8_t>();
+  a.piece_end = c->d_piece.as<uint64_t>();
+  a.narrow = (c->max_len <= 32 && c->n_cls <= NARROW_CLS) ? 1u : 0u;
 
   const size_t smem = (size_t)(c->n_sym + 1) * TILE_WT * 4;
   void (*kern)(const ScanArgs) = nullptr;
+  void (*vkern)(const ScanArgs) = nullptr;
   if (edit) {
     switch (K) {
-      case 1: kern = edit_scan_kernel<1>; break;
-      case 2: kern = edit_scan_kernel<2>; break;
-      default: kern = edit_scan_kernel<3>; break;
+      case 1: kern = edit_seed_kernel<1>; vkern = edit_verify_kernel<1>; break;
+      case 2: kern = edit_seed_kernel<2>; vkern = edit_verify_kernel<2>; break;
+      default: kern = edit_seed_kernel<3>; vkern = edit_verify_kernel<3>; break;
     }
   } else {
     switch (K) {
@@ -381,11 +385,24 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     cap = c->d_keys.cap / 8;
   }
   uint64_t count = 0;
-  for (int attempt = 0; attempt < 3; attempt++) {
+  // edit mode: the seed list of one batch of tiles (dense kernel -> verify kernel)
+  uint32_t batch_tiles = nt;
+  if (edit) {
+    int rc = c->d_seeds.ensure((size_t)(64u << 20) * 8);
+    if (rc) return rc;
+    const double per_tile = std::max(1.0, c->seed_rate * (double)TILE_POS);
+    const double fit = (double)(c->d_seeds.cap / 8) / (2.0 * per_tile);
+    batch_tiles = (uint32_t)std::max(1.0, std::min((double)nt, fit));
+  }
+  for (int attempt = 0; attempt < 4; attempt++) {
     a.out = c->d_keys.as<unsigned long long>();
     a.cap = cap;
+    a.seeds = c->d_seeds.as<unsigned long long>();
+    a.seed_cap = c->d_seeds.cap / 8;
+    a.seed_n = c->d_counters + 6;
+    a.seed_overflow = c->d_counters + 7;
     PM_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
-    PM_CUDA(cudaMemsetAsync(c->d_counters + 5, 0, sizeof(unsigned long long), c->stream));
+    PM_CUDA(cudaMemsetAsync(c->d_counters + 5, 0, 3 * sizeof(unsigned long long), c->stream));
     PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // grid.x is limited to 2^31-1, grid.y to 65535
     if ((uint64_t)nt * chunks > 0x7fffffffull) return fail(PM_E_UNSUPPORTED, "scan grid too large");
@@ -396,10 +413,19 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         prev_end = std::max(prev_end, ch.tile_end);
         if (t1 <= t0) continue;
         if (ch.ev) PM_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
-        a.tile0 = t0;
-        kern<<<(t1 - t0) * chunks, SCAN_THREADS, smem, c->stream>>>(a);
-        PM_CUDA(cudaGetLastError());
-        c->stats.kernel_launches++;
+        for (uint32_t b0 = t0; b0 < t1; b0 += batch_tiles) {
+          const uint32_t b1 = std::min(t1, b0 + batch_tiles);
+          a.tile0 = b0;
+          if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
+          kern<<<(b1 - b0) * chunks, SCAN_THREADS, smem, c->stream>>>(a);
+          PM_CUDA(cudaGetLastError());
+          c->stats.kernel_launches++;
+          if (edit) {
+            vkern<<<n_sm * 8, VERIFY_THREADS, 0, c->stream>>>(a);
+            PM_CUDA(cudaGetLastError());
+            c->stats.kernel_launches++;
+          }
+        }
       }
       // the alignment kernels read the raw text: everything must have arrived
       if (!c->chunks.empty() && c->chunks.back().ev)
@@ -407,7 +433,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     }
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->stats.scan_items = (uint64_t)nt * chunks;
-    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 6 * sizeof(unsigned long long),
+    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 8 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -416,12 +442,19 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     count = c->h_counters[0];
     c->stats.n_seeds = c->h_counters[1];
     c->stats.scan_warp_steps = c->h_counters[5];
+    if (edit && c->h_counters[7]) {
+      // a batch produced more seeds than the list holds: smaller batches, then a larger list
+      if (batch_tiles > 1) batch_tiles = std::max(1u, batch_tiles / 8);
+      else if (int rc = c->d_seeds.ensure(c->d_seeds.cap * 4)) return rc;
+      if (attempt == 3) return fail(PM_E_NOMEM, "seed list overflow");
+      continue;
+    }
     if (count <= cap) break;
     // candidate buffer too small: grow and rescan
     int rc = c->d_keys.ensure((size_t)count * 8 + 1024);
     if (rc) return rc;
     cap = c->d_keys.cap / 8;
-    if (attempt == 2) return fail(PM_E_NOMEM, "candidate buffer overflow");
+    if (attempt == 3) return fail(PM_E_NOMEM, "candidate buffer overflow");
   }
   if (count == 0) return PM_OK;
 
@@ -749,7 +782,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_slotid,  &c->d_text_own, &c->d_planes, &c->d_keys,   &c->d_keys2,
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
-                    &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands};
+                    &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -852,7 +885,8 @@ int pm_init(pm_ctx *c) {
   }
 
   std::vector<uint32_t> poff((ns + 2) * POFF_STRIDE, (uint32_t)c->n_sym * TILE_WT * 4u);
-  std::vector<uint8_t> plen(ns + 1, 0), patchars((ns + 1) * PAT_STRIDE, 0), piece((ns + 1) * 8, 0);
+  std::vector<uint8_t> plen(ns + 1, 0), patchars((ns + 1) * PAT_STRIDE, 0);
+  std::vector<uint64_t> piece(ns + 1, 0);
   std::vector<int16_t> lconst(ns + 1, 0), rconst(ns + 1, 0);
   std::vector<uint32_t> slotid(ns + 1, 0);
   std::vector<uint64_t> umask((ns + 1) * (size_t)c->n_cls, 0);
@@ -874,7 +908,11 @@ int pm_init(pm_ctx *c) {
     if (i > 0 && memcmp(&poff[i * POFF_STRIDE], &poff[(i - 1) * POFF_STRIDE], 4 * sizeof(uint32_t)) == 0)
       plen[i] |= (uint8_t)PLEN_SHARE;
     // k+1 pieces, as even as possible (pigeonhole partition)
-    for (int j = 0; j <= K + 1; j++) piece[i * 8 + j] = (uint8_t)((int64_t)m * j / (K + 1));
+    for (int j = 1; j <= K + 1; j++) {
+      const int64_t e0 = (int64_t)m * (j - 1) / (K + 1), e1 = (int64_t)m * j / (K + 1);
+      piece[i] |= 1ull << (e1 - 1);
+      c->seed_rate += std::pow(0.25, (double)(e1 - e0));
+    }
   }
   // iupac_compatible as a 128x128 bit matrix
   std::vector<uint32_t> cbits(128 * 4, 0);
@@ -892,7 +930,7 @@ int pm_init(pm_ctx *c) {
                     {&c->d_compat, cbits.data(), cbits.size() * 4},
                     {&c->d_cls, cls.data(), cls.size()},
                     {&c->d_umask, umask.data(), umask.size() * 8},
-                    {&c->d_piece, piece.data(), piece.size()},
+                    {&c->d_piece, piece.data(), piece.size() * 8},
                     {&c->d_slotid, slotid.data(), slotid.size() * 4}};
   for (const Up &u : ups) {
     int rc = u.b->ensure(u.bytes);

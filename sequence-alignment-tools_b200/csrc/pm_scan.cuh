@@ -64,8 +64,13 @@ struct ScanArgs {
   const uint8_t *cls;       // [256] text byte -> class
   const uint64_t *umask;    // [n_slots][n_cls] Shift-And masks per class
   uint32_t n_cls;
-  const uint8_t *piece;     // [n_slots][8] piece boundaries (k+2 entries used)
-  unsigned long long *seed_count;
+  const uint64_t *piece_end; // [n_slots] bit i set: character i ends one of the k+1 pieces
+  uint32_t narrow;          // patterns <= 32 long and <= NARROW_CLS classes: 32-bit verifier
+  unsigned long long *seed_count;   // statistics: seeds verified
+  unsigned long long *seeds;        // seed list of the current batch: slot << 40 | window start
+  unsigned long long *seed_n;       // entries appended to it
+  unsigned long long *seed_overflow;
+  uint64_t seed_cap;
   unsigned long long *work_count;  // executed (warp, pattern character) steps
 };
 
@@ -288,12 +293,15 @@ hamming_scan_kernel(const ScanArgs a) {
 // character) m+k characters before the first end position of interest.  Every
 // state bit at time t depends on at most the last m+k-1 characters (each
 // transition consumes a character or lowers the level), so from there on the
-// state equals the reference's.  Word = uint64_t: patterns up to 64 long.
-template <int K>
-__device__ __noinline__ void verify_seed(const ScanArgs &a, uint32_t slot, int64_t s_nominal) {
+// state equals the reference's.  W = uint32_t when every pattern fits 32 bits
+// (masks then sit in shared memory, one row per lane), uint64_t otherwise.
+// Text is fetched four characters at a time so that the loads overlap.
+template <int K, typename W>
+__device__ __forceinline__ void verify_seed(const ScanArgs &a, uint32_t slot, int64_t s_nominal,
+                                         const uint8_t *cls, const W *U) {
   const uint32_t m = a.plen[slot] & 0x7fu;
-  const uint64_t *U = a.umask + (size_t)slot * a.n_cls;
-  const uint64_t last = 1ULL << (m - 1);
+  const W one = (W)1;
+  const W last = one << (m - 1);
   // end indices of interest: s+m-1-K .. s+m-1+K
   int64_t t_lo = s_nominal + (int64_t)m - 1 - K;
   int64_t t_hi = s_nominal + (int64_t)m - 1 + K;
@@ -301,40 +309,52 @@ __device__ __noinline__ void verify_seed(const ScanArgs &a, uint32_t slot, int64
   if (t_lo < 0) t_lo = 0;
   int64_t t0 = t_lo - (int64_t)(m + K);
   if (t0 < 0) t0 = 0;
-  uint64_t M[K + 1];
+  W M[K + 1];
 #pragma unroll
   for (int l = 0; l <= K; l++) M[l] = 0;
-  for (int64_t t = t0; t <= t_hi; ++t) {
-    const uint32_t ch = a.text[t];
-    const uint64_t u = U[a.cls[ch]];
-    // shift_and_inexact.cc:253-303, indels on; one word per pattern
-    uint64_t old_prev = M[0];
-    uint64_t nw = ((M[0] << 1) | 1ULL) & u;
-    M[0] = nw;
-    if (ch != a.eos) {
+  constexpr int B = 4;  // characters fetched together
+  for (int64_t tb = t0; tb <= t_hi; tb += B) {
+    uint32_t chs[B];
 #pragma unroll
-      for (int l = 1; l <= K; l++) {
-        const uint64_t old_l = M[l];
-        uint64_t v = ((old_l << 1) | 1ULL) & u;
-        v |= (old_prev << 1) | 1ULL | old_prev;  // substitution | insertion
-        v |= (M[l - 1] << 1) | 1ULL | M[l - 1];  // deletion | lower level (new)
-        M[l] = v;
-        old_prev = old_l;
+    for (int j = 0; j < B; j++) chs[j] = (tb + j <= t_hi) ? (uint32_t)a.text[tb + j] : a.eos;
+    W us[B];
+#pragma unroll
+    for (int j = 0; j < B; j++) us[j] = U[cls[chs[j]]];
+#pragma unroll
+    for (int j = 0; j < B; j++) {
+      const int64_t t = tb + j;
+      if (t > t_hi) break;
+      const W u = us[j];
+      // shift_and_inexact.cc:253-303, indels on; one word per pattern
+      W old_prev = M[0];
+      M[0] = ((M[0] << 1) | one) & u;
+      if (chs[j] != a.eos) {
+#pragma unroll
+        for (int l = 1; l <= K; l++) {
+          const W old_l = M[l];
+          W v = ((old_l << 1) | one) & u;
+          v |= (old_prev << 1) | one | old_prev;  // substitution | insertion
+          v |= (M[l - 1] << 1) | one | M[l - 1];  // deletion | lower level (new)
+          M[l] = v;
+          old_prev = old_l;
+        }
+      } else {
+#pragma unroll
+        for (int l = 1; l <= K; l++) M[l] = ((M[l] << 1) | one) & u;
       }
-    } else {
-#pragma unroll
-      for (int l = 1; l <= K; l++) M[l] = ((M[l] << 1) | 1ULL) & u;
+      if (t >= t_lo && (M[K] & last)) emit_candidate(a, slot, t + 1);
     }
-    if (t >= t_lo && (M[K] & last)) emit_candidate(a, slot, t + 1);
   }
 }
 
 // ---------------------------------------------------------------------------
-// Edit-distance scan: exact occurrences of the k+1 pattern pieces (dense),
-// then verify_seed per occurrence (sparse, same kernel).
+// Edit-distance scan, dense half: exact occurrences of the k+1 pattern pieces.
+// A seed = (slot, nominal window start).  Seeds are queued per warp in shared
+// memory and flushed to a global list with one atomic per flush; the sparse
+// half (edit_verify_kernel) runs verify_seed on that list.
 template <int K>
 __global__ void __launch_bounds__(SCAN_THREADS)
-edit_scan_kernel(const ScanArgs a) {
+edit_seed_kernel(const ScanArgs a) {
   extern __shared__ __align__(128) uint32_t s_planes[];
   __shared__ __align__(8) uint64_t s_bar;
   __shared__ uint32_t s_queue[SCAN_THREADS / 32][SEEDQ_CAP];
@@ -352,82 +372,106 @@ edit_scan_kernel(const ScanArgs a) {
   uint32_t slot1 = slot0 + a.slots_per_chunk;
   if (slot1 > a.n_slots) slot1 = a.n_slots;
   uint32_t *queue = s_queue[warp];
-  unsigned long long n_seeds = 0;
+  const unsigned long long tile_pos = (unsigned long long)tile * TILE_POS;
   uint32_t n_steps = 0;
 
-  auto drain = [&](uint32_t count) {
-    // entries [0,count) of this warp's queue, 32 at a time
-    for (uint32_t base = 0; base < count; base += 32) {
-      if (base + lane < count) {
-        const uint32_t e = queue[base + lane];
-        const uint32_t slot = slot0 + (e >> 15);
-        const uint32_t qloc = e & 0x7fffu;  // j*TILE_W + w
-        verify_seed<K>(a, slot, (int64_t)tile * TILE_POS + qloc);
-      }
-    }
+  auto put_global = [&](unsigned long long at, uint32_t e) {
+    if (at < a.seed_cap)
+      a.seeds[at] = ((unsigned long long)(slot0 + (e >> 15)) << 40) | (tile_pos + (e & 0x7fffu));
+    else
+      *a.seed_overflow = 1ULL;
+  };
+  auto flush = [&]() {
+    __syncwarp();
+    const uint32_t qn = min(s_qn[warp], (uint32_t)SEEDQ_CAP);
+    unsigned long long base = 0;
+    if (lane == 0 && qn) base = atomicAdd(a.seed_n, (unsigned long long)qn);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = lane; i < qn; i += 32) put_global(base + i, queue[i]);
+    __syncwarp();
+    if (lane == 0) s_qn[warp] = 0;
     __syncwarp();
   };
 
   for (uint32_t slot = slot0; slot < slot1; ++slot) {
     const uint32_t m = a.plen[slot] & 0x7fu;
-    const uint8_t *pc = a.piece + (size_t)slot * 8;
-    const uint32_t *offp = a.poff + (size_t)slot * POFF_STRIDE;
-    uint32_t E[S];
+    const int ngroups = (int)((m + 3) >> 2);
+    const uint64_t pend = a.piece_end[slot];  // bit i: character i is the last of a piece
+    const uint4 *offp = reinterpret_cast<const uint4 *>(a.poff + (size_t)slot * POFF_STRIDE);
+    uint32_t E[S], A[S];
 #pragma unroll
-    for (int s = 0; s < S; s++) E[s] = 0u;
-#pragma unroll 1
-    for (int j = 0; j <= K; j++) {
-      const uint32_t pa = pc[j], pb = pc[j + 1];
-      uint32_t A[S];
+    for (int s = 0; s < S; s++) { E[s] = 0u; A[s] = 0xffffffffu; }
+    uint4 o = __ldg(offp);
+    for (int grp = 0; grp < ngroups; ++grp) {
+      const uint4 on = __ldg(offp + grp + 1);
+      const uint32_t offs[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-      for (int s = 0; s < S; s++) A[s] = 0xffffffffu;
-      n_steps += pb - pa;
-      for (uint32_t i = pa; i < pb; i++) {
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + __ldg(offp + i));
+      for (int c = 0; c < 4; c++) {
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(lane_base + offs[c]);
 #pragma unroll
         for (int s = 0; s < S; s++) A[s] &= p[s * 32];
-      }
+        if ((pend >> (4 * grp + c)) & 1ull) {
 #pragma unroll
-      for (int s = 0; s < S; s++) E[s] |= A[s];
+          for (int s = 0; s < S; s++) { E[s] |= A[s]; A[s] = 0xffffffffu; }
+        }
+      }
+      o = on;
+      n_steps += 4;
     }
-    (void)m;
     uint32_t any = E[0];
 #pragma unroll
     for (int s = 1; s < S; s++) any |= E[s];
     if (__any_sync(0xffffffffu, any != 0u)) {
       if (any) {
-#pragma unroll 1
+#pragma unroll
         for (int s = 0; s < S; s++) {
           uint32_t e = E[s];
           while (e) {
             const int j = __ffs(e) - 1;
             e &= e - 1;
-            const uint32_t qloc = (uint32_t)j * TILE_W + (w0 + 32 * s);
+            const uint32_t ent = ((slot - slot0) << 15) | ((uint32_t)j * TILE_W + (w0 + 32 * s));
             const uint32_t at = atomicAdd(&s_qn[warp], 1u);
-            if (at < (uint32_t)SEEDQ_CAP) queue[at] = ((slot - slot0) << 15) | qloc;
-            else verify_seed<K>(a, slot, (int64_t)tile * TILE_POS + qloc);  // queue full
-            n_seeds++;
+            if (at < (uint32_t)SEEDQ_CAP) queue[at] = ent;
+            else put_global(atomicAdd(a.seed_n, 1ULL), ent);  // queue full: straight to the list
           }
         }
       }
       __syncwarp();
-      const uint32_t qn = min(s_qn[warp], (uint32_t)SEEDQ_CAP);
-      __syncwarp();
-      if (qn >= (uint32_t)(SEEDQ_CAP - 256)) {
-        drain(qn);
-        if (lane == 0) s_qn[warp] = 0;
-        __syncwarp();
-      }
+      if (s_qn[warp] >= (uint32_t)(SEEDQ_CAP / 2)) flush();
     }
   }
-  __syncwarp();
-  const uint32_t qn = min(s_qn[warp], (uint32_t)SEEDQ_CAP);
-  drain(qn);
-  // seed statistics: one atomic per warp
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) n_seeds += __shfl_xor_sync(0xffffffffu, n_seeds, d);
-  if (lane == 0 && a.seed_count) atomicAdd(a.seed_count, n_seeds);
+  flush();
   if (lane == 0 && a.work_count) atomicAdd(a.work_count, (unsigned long long)n_steps);
+}
+
+// Edit-distance scan, sparse half: one thread per seed.
+constexpr int NARROW_CLS = 8;  // classes per lane row of the shared mask table
+constexpr int VERIFY_THREADS = 128;
+
+template <int K>
+__global__ void __launch_bounds__(VERIFY_THREADS)
+edit_verify_kernel(const ScanArgs a) {
+  __shared__ uint8_t s_cls[256];
+  __shared__ uint32_t s_umask[VERIFY_THREADS][NARROW_CLS];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_cls[i] = a.cls[i];
+  __syncthreads();
+  unsigned long long count = *a.seed_n;
+  if (count > a.seed_cap) count = a.seed_cap;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long sd = a.seeds[i];
+    const uint32_t slot = (uint32_t)(sd >> 40);
+    const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL);
+    const uint64_t *src = a.umask + (size_t)slot * a.n_cls;
+    if (a.narrow) {
+      uint32_t *row = s_umask[threadIdx.x];
+      for (uint32_t cl = 0; cl < a.n_cls; cl++) row[cl] = (uint32_t)__ldg(src + cl);
+      verify_seed<K, uint32_t>(a, slot, s_nominal, s_cls, row);
+    } else {
+      verify_seed<K, uint64_t>(a, slot, s_nominal, s_cls, src);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.seed_count) atomicAdd(a.seed_count, count);
 }
 
 // ---------------------------------------------------------------------------
