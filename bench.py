@@ -39,6 +39,7 @@ N_PRIMERS = 1000
 PRIMER_LEN = 20
 K = 2
 INDELS = 0
+IUPAC = 0
 
 
 def make_primers(seed=12345, n=None, m=None):
@@ -47,6 +48,11 @@ def make_primers(seed=12345, n=None, m=None):
     m = PRIMER_LEN if m is None else m
     g = np.random.default_rng(seed)
     a = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, (n, m))]
+    if IUPAC:  # one to three ambiguity codes per primer, like the reference's db/patwc.txt
+        codes = np.frombuffer(b"RYKMSWBDHVN", np.uint8)
+        for r in a:
+            for _ in range(int(g.integers(1, 4))):
+                r[int(g.integers(0, m))] = codes[int(g.integers(0, len(codes)))]
     return [bytes(r).decode() for r in a]
 
 
@@ -131,7 +137,7 @@ def run_reference_sample(primers, total_bases: int, procs: int, seed: int, workd
             f.write(b"\n")
         files.append(path)
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
+    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", *(["-w"] if IUPAC else []), "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fp in files]
     for p in ps:
         p.wait()
@@ -229,6 +235,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bases", type=int, default=3_000_000_000, help="database shard per GPU")
     ap.add_argument("--indels", type=int, default=0, help="1: -k (edits) instead of -K")
+    ap.add_argument("--iupac", type=int, default=0, help="1: IUPAC wildcard primers (db/patwc.txt style), scanned with -w")
     ap.add_argument("--k", type=int, default=K, help="errors allowed (headline: 2)")
     ap.add_argument("--plen", type=int, default=PRIMER_LEN, help="primer length (headline: 20)")
     ap.add_argument("--nprimers", type=int, default=N_PRIMERS, help="primers before reverse complements (headline: 1000)")
@@ -236,7 +243,7 @@ def main():
     ap.add_argument("--ref-bases-per-core", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels)
+    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels, IUPAC=args.iupac)
     if args.impl == "reference":
         return main_reference(args)
 
@@ -276,6 +283,7 @@ def main():
     rs = np.random.default_rng(99 + rank)
     for j in range(64):
         p = bytearray(pats[int(rs.integers(0, len(pats)))].encode())
+        p = bytearray(c if c in b"ACGT" else b"ACGT"[int(rs.integers(0, 4))] for c in p)
         for _ in range(int(rs.integers(0, K + 1))):
             p[int(rs.integers(0, len(p)))] = b"ACGT"[int(rs.integers(0, 4))]
         at = int(rs.integers(1000, n - 1000))
@@ -284,7 +292,7 @@ def main():
     h_stream.copy_(d_stream)
     torch.cuda.synchronize()
 
-    sc = pkg.Scanner(k=K, indels=bool(args.indels), device=local_rank)
+    sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank)
     for i, p in enumerate(pats):
         sc.add_pattern(p, i + 1)
     sc.init()
@@ -375,7 +383,7 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        n_planes = 5
+        n_planes = sc.stats().get('n_planes', 5) if False else (5 if not args.iupac else 16)
         alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch
         hbm_achieved = alg_bytes / (mean_scan_ms * 1e-3) / 1e9
         cells = float(n + 2) * len(pats) * (K + 1)

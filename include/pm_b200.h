@@ -65,6 +65,15 @@ typedef struct pm_options {
   unsigned char eos; /* end-of-sequence character (-E, default '\n')           */
 } pm_options;
 
+/* Which device scan produces the candidates (the hit list is the same):
+ *   PLANES  bit-plane kernels (pm_scan.cuh): any alphabet, IUPAC, patterns <= 64
+ *   INDEX   q-gram index kernels (pm_index.cuh): <= 4 pattern symbols, no text
+ *           byte matching two of them, patterns <= 32
+ *   AUTO    INDEX when applicable, else PLANES                                 */
+#define PM_SCAN_AUTO 0
+#define PM_SCAN_PLANES 1
+#define PM_SCAN_INDEX 2
+
 #define PM_MAX_K 3
 #define PM_MAX_PATTERN_LEN 64
 #define PM_MAX_CODES 72 /* >= PM_MAX_PATTERN_LEN + PM_MAX_K + 1 */
@@ -103,6 +112,10 @@ const char *pm_version(void);
 int pm_create(pm_ctx **out, const pm_options *opt);
 /* delete kt                                                                   */
 void pm_destroy(pm_ctx *ctx);
+
+/* Select the device scan (before pm_init).  PM_SCAN_INDEX on patterns it cannot
+ * serve makes pm_init fail with PM_E_UNSUPPORTED.                              */
+int pm_set_scan_path(pm_ctx *ctx, int path);
 
 /* Device work of this context goes to `cuda_stream` (a cudaStream_t).         */
 int pm_set_stream(pm_ctx *ctx, void *cuda_stream);
@@ -176,6 +189,8 @@ typedef struct pm_stats {
   uint64_t scan_items;      /* (tile, pattern-chunk) blocks of the scan kernel */
   uint64_t scan_warp_steps; /* (warp, pattern character) steps the dense scan
                                executed: each is 8 words x 32 positions        */
+  uint32_t scan_path;       /* PM_SCAN_PLANES or PM_SCAN_INDEX                  */
+  uint32_t index_q;         /* q of the q-gram table (INDEX)                   */
   float pack_ms;            /* device time of the last pack kernel             */
   float scan_ms;            /* device time of the dense scan kernel            */
   float total_ms;           /* device time of the whole call                   */

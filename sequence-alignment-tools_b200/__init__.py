@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpm_b200.so")
 PM_OK = 0
 PM_E_ARG, PM_E_CUDA, PM_E_UNSUPPORTED, PM_E_NOMEM, PM_E_BOGUS = -1, -2, -3, -4, -5
 PM_INDEX_AUTO, PM_INDEX_KEYWORD_TREE, PM_INDEX_SHIFT_AND, PM_INDEX_FILTER_BITVEC = 0, 3, 4, 5
+PM_SCAN_AUTO, PM_SCAN_PLANES, PM_SCAN_INDEX = 0, 1, 2
 PM_MAX_CODES = 72
 INT64_MAX = (1 << 63) - 1
 EOS = 10
@@ -34,7 +35,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path"]
 
 
 class PmError(RuntimeError):
@@ -62,7 +63,7 @@ class Stats(C.Structure):
     _fields_ = [("text_len", C.c_uint64), ("n_patterns", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("n_candidates", C.c_uint64), ("n_chains", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
-                ("scan_warp_steps", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+                ("scan_warp_steps", C.c_uint64), ("scan_path", C.c_uint32), ("index_q", C.c_uint32), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
@@ -87,6 +88,7 @@ def lib():
         L.pm_destroy.argtypes = [C.c_void_p]
         L.pm_destroy.restype = None
         L.pm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.pm_set_scan_path.argtypes = [C.c_void_p, C.c_int]
         L.pm_add_pattern.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int]
         L.pm_init.argtypes = [C.c_void_p]
         L.pm_set_text_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
@@ -156,10 +158,12 @@ class Scanner:
     """One PatternMatch index on one GPU (pattern_match.h:83-157)."""
 
     def __init__(self, k=0, indels=True, wildcards=False, text_n=False, index=PM_INDEX_AUTO,
-                 device=0, eos=EOS):
+                 device=0, eos=EOS, scan_path=PM_SCAN_AUTO):
         self._h = C.c_void_p()
         opt = Options(device, index, k, int(indels), int(wildcards), int(text_n), eos)
         _check(lib().pm_create(C.byref(self._h), C.byref(opt)))
+        if scan_path != PM_SCAN_AUTO:
+            _check(lib().pm_set_scan_path(self._h, scan_path))
         self.k = k
         self.indels = bool(indels)
         self._keep = None
@@ -294,10 +298,11 @@ def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
 
 
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS, device=0, index=PM_INDEX_AUTO):
+                 eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO):
     """The reference's main loop on the GPU path: returns sorted HitRecords."""
     pats = pattern_array(primers, rev_comp)
-    sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos)
+    sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos,
+                 scan_path=scan_path)
     try:
         for i, p in enumerate(pats):
             sc.add_pattern(p, i + 1)

@@ -19,6 +19,7 @@
 #include "pm_align.cuh"
 #include "pm_planes.cuh"
 #include "pm_scan.cuh"
+#include "pm_index.cuh"
 
 namespace {
 
@@ -167,6 +168,11 @@ struct pm_ctx {
   DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
+  // q-gram index path (pm_index.cuh)
+  int scan_path = PM_SCAN_AUTO;  // requested
+  bool use_index = false;        // resolved in pm_init
+  int idx_q = 0;
+  DevBuf d_pk, d_bucket, d_entries, d_pat2, d_umask4, d_lin;
   unsigned long long *d_counters = nullptr;  // [8]
   unsigned long long *h_counters = nullptr;  // pinned [8]
   void *h_out = nullptr;                     // pinned result buffer
@@ -360,6 +366,32 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   a.narrow = (c->max_len <= 32 && c->n_cls <= NARROW_CLS) ? 1u : 0u;
 
   const size_t smem = (size_t)(c->n_sym + 1) * TILE_WT * 4;
+  IndexArgs ia;
+  memset(&ia, 0, sizeof ia);
+  void (*ikern)(const IndexArgs) = edit ? qgram_scan_kernel<true> : qgram_scan_kernel<false>;
+  void (*ivkern)(const IndexArgs) =
+      K <= 1 ? index_verify_kernel<1> : (K == 2 ? index_verify_kernel<2> : index_verify_kernel<3>);
+  size_t ismem = 0;
+  if (c->use_index) {
+    ia.pk = c->d_pk.as<uint2>();
+    ia.n = c->n;
+    ia.n16 = (uint64_t)c->n_tiles * (TILE_POS / 16);
+    ia.bucket = c->d_bucket.as<uint32_t>();
+    ia.entries = c->d_entries.as<uint32_t>();
+    ia.pat2 = c->d_pat2.as<uint64_t>();
+    ia.plen = c->d_plen.as<uint8_t>();
+    ia.piece_end = c->d_piece.as<uint64_t>();
+    ia.umask4 = c->d_umask4.as<uint32_t>();
+    ia.count = c->d_counters + 0;
+    ia.seed_count = c->d_counters + 1;
+    ia.work_count = c->d_counters + 5;
+    ia.lo = lo;
+    ia.hi = hi;
+    ia.q = (uint32_t)c->idx_q;
+    ia.k = (uint32_t)K;
+    if (c->idx_q <= IDX_SMEM_Q) ismem = ((size_t)1 << (2 * c->idx_q)) * 4 + 4;
+    PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
+  }
   void (*kern)(const ScanArgs) = nullptr;
   void (*vkern)(const ScanArgs) = nullptr;
   if (edit) {
@@ -394,7 +426,15 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     const double fit = (double)(c->d_seeds.cap / 8) / (2.0 * per_tile);
     batch_tiles = (uint32_t)std::max(1.0, std::min((double)nt, fit));
   }
+  // q-gram END positions the index path has to visit: window start in [p-31, p]
+  const int64_t ip_lo = q_lo, ip_hi = std::min<int64_t>((int64_t)c->n, q_hi + 32);
   for (int attempt = 0; attempt < 4; attempt++) {
+    ia.out = c->d_keys.as<unsigned long long>();
+    ia.cap = cap;
+    ia.seeds = c->d_seeds.as<unsigned long long>();
+    ia.seed_cap = c->d_seeds.cap / 8;
+    ia.seed_n = c->d_counters + 6;
+    ia.seed_overflow = c->d_counters + 7;
     a.out = c->d_keys.as<unsigned long long>();
     a.cap = cap;
     a.seeds = c->d_seeds.as<unsigned long long>();
@@ -413,6 +453,30 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         prev_end = std::max(prev_end, ch.tile_end);
         if (t1 <= t0) continue;
         if (ch.ev) PM_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
+        if (c->use_index) {
+          // a verification window reaches up to 63 characters past the q-gram: positions lag
+          // the packed tiles by 64 so that every window lies in words that are already packed
+          const int64_t lag = 64;
+          int64_t pb = std::max<int64_t>(ip_lo, (int64_t)t0 * TILE_POS - (t0 ? lag : 0));
+          const int64_t pe = std::min<int64_t>(ip_hi, ch.tile_end >= c->n_tiles ? (int64_t)c->n
+                                                                               : (int64_t)t1 * TILE_POS - lag);
+          const int64_t batch_pos = (int64_t)batch_tiles * TILE_POS;
+          for (; pb < pe; pb += batch_pos) {
+            ia.p_begin = pb;
+            ia.p_end = std::min<int64_t>(pe, pb + batch_pos);
+            const uint64_t span = (uint64_t)(ia.p_end - ia.p_begin);
+            if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
+            ikern<<<(unsigned)((span + IDX_BLOCK_POS - 1) / IDX_BLOCK_POS), IDX_THREADS, ismem, c->stream>>>(ia);
+            PM_CUDA(cudaGetLastError());
+            c->stats.kernel_launches++;
+            if (edit) {
+              ivkern<<<n_sm * 8, 128, 0, c->stream>>>(ia);
+              PM_CUDA(cudaGetLastError());
+              c->stats.kernel_launches++;
+            }
+          }
+          continue;
+        }
         for (uint32_t b0 = t0; b0 < t1; b0 += batch_tiles) {
           const uint32_t b1 = std::min(t1, b0 + batch_tiles);
           a.tile0 = b0;
@@ -433,6 +497,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     }
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->stats.scan_items = (uint64_t)nt * chunks;
+    c->stats.scan_path = c->use_index ? PM_SCAN_INDEX : PM_SCAN_PLANES;
+    c->stats.index_q = (uint32_t)c->idx_q;
     PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 8 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
@@ -476,7 +542,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
                                          c->d_keys2.as<unsigned long long>(), count, 0, end_bit,
                                          c->stream));
   c->stats.kernel_launches += 4;
-  if (edit) {
+  if (edit || c->use_index) {
     tb = c->d_tmp.cap;
     PM_CUDA(cub::DeviceSelect::Unique(c->d_tmp.p, tb, c->d_keys2.as<unsigned long long>(),
                                       c->d_keys.as<unsigned long long>(), c->d_counters + 2, count,
@@ -687,6 +753,13 @@ cudaEvent_t next_event(pm_ctx *c) {
 
 int pack_tiles(pm_ctx *c, uint32_t t0, uint32_t t1, cudaStream_t st) {
   if (t1 <= t0) return PM_OK;
+  if (c->use_index) {
+    const uint64_t w0 = (uint64_t)t0 * (TILE_POS / 16), w1 = (uint64_t)t1 * (TILE_POS / 16);
+    pack_linear_kernel<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, st>>>(
+        c->d_text, c->n, c->d_lin.as<uint8_t>(), c->opt.eos, c->d_pk.as<uint2>(), w0, w1);
+    PM_CUDA(cudaGetLastError());
+    return PM_OK;
+  }
   pack_planes_kernel<<<t1 - t0, PACK_THREADS, 0, st>>>(c->d_text, c->n, c->d_symmask.as<uint32_t>(),
                                                        c->n_sym + 1, c->opt.eos,
                                                        c->d_planes.as<uint32_t>(), t0);
@@ -700,6 +773,7 @@ int prepare_planes(pm_ctx *c) {
   c->ev_used = 0;
   c->pack_timed = false;
   if (c->n_tiles == 0) return PM_OK;
+  if (c->use_index) return c->d_pk.ensure((size_t)c->n_tiles * (TILE_POS / 16) * sizeof(uint2));
   return c->d_planes.ensure((size_t)c->n_tiles * (c->n_sym + 1) * TILE_WT * 4);
 }
 
@@ -782,7 +856,8 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_slotid,  &c->d_text_own, &c->d_planes, &c->d_keys,   &c->d_keys2,
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
-                    &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds};
+                    &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
+                    &c->d_bucket,  &c->d_entries, &c->d_pat2,  &c->d_umask4,   &c->d_lin};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -796,6 +871,15 @@ void pm_destroy(pm_ctx *c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
+}
+
+int pm_set_scan_path(pm_ctx *c, int path) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  if (c->inited) return fail(PM_E_ARG, "pm_set_scan_path after pm_init");
+  if (path != PM_SCAN_AUTO && path != PM_SCAN_PLANES && path != PM_SCAN_INDEX)
+    return fail(PM_E_ARG, "bad scan path");
+  c->scan_path = path;
+  return PM_OK;
 }
 
 int pm_set_stream(pm_ctx *c, void *cuda_stream) {
@@ -936,6 +1020,82 @@ int pm_init(pm_ctx *c) {
     int rc = u.b->ensure(u.bytes);
     if (rc) return rc;
     PM_CUDA(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+  }
+  // ---- q-gram index (pm_index.cuh): applicable? ------------------------------------------
+  {
+    bool ok = c->n_sym <= 4 && c->max_len <= 32 && ns > 0;
+    for (uint32_t msk : cls_mask)
+      if (__builtin_popcount(msk) > 1) ok = false;  // a text byte matching two symbols
+    int min_piece = 64;
+    size_t n_pieces = 0;
+    for (size_t i = 0; i < ns && ok; i++) {
+      const int m = (int)c->pats[i].s.size();
+      for (int j = 1; j <= K + 1; j++) {
+        const int e0 = m * (j - 1) / (K + 1), e1 = m * j / (K + 1);
+        min_piece = std::min(min_piece, e1 - e0);
+        n_pieces++;
+      }
+    }
+    if (min_piece < 3) ok = false;
+    int q = std::min(min_piece, IDX_QMAX);
+    if (ok) {
+      // smallest table that keeps the expected bucket occupancy low
+      int qq = std::min(q, 6);
+      while (qq < q && (double)n_pieces / std::pow(4.0, qq) > 0.3) qq++;
+      q = qq;
+      if ((double)n_pieces / std::pow(4.0, q) > 64.0) ok = false;  // buckets too crowded: planes are cheaper
+    }
+    if (c->scan_path == PM_SCAN_PLANES) ok = false;
+    if (c->scan_path == PM_SCAN_INDEX && !ok)
+      return fail(PM_E_UNSUPPORTED, "q-gram index scan not applicable to these patterns / options");
+    c->use_index = ok;
+    c->idx_q = ok ? q : 0;
+    if (ok) {
+      const size_t nb = (size_t)1 << (2 * q);
+      std::vector<uint32_t> bucket(nb + 1, 0), entries(n_pieces, 0), um4((ns + 1) * 4, 0);
+      std::vector<uint64_t> pat2(ns + 1, 0);
+      std::vector<uint32_t> keys(n_pieces), vals(n_pieces);
+      size_t e = 0;
+      for (size_t i = 0; i < ns; i++) {
+        const std::string &ps = c->pats[i].s;
+        const int m = (int)ps.size();
+        for (int j = 0; j < m; j++) {
+          const uint32_t sy = (uint32_t)sym_of[(unsigned char)ps[j]];
+          pat2[i] |= (uint64_t)sy << (2 * j);
+          um4[i * 4 + sy] |= 1u << j;
+        }
+        for (int j = 1; j <= K + 1; j++) {
+          const int e0 = m * (j - 1) / (K + 1);
+          uint32_t key = 0;  // first character of the q-gram in the highest digit (rolling code order)
+          for (int t = 0; t < q; t++) key = (key << 2) | (uint32_t)sym_of[(unsigned char)ps[e0 + t]];
+          keys[e] = key;
+          vals[e] = ((uint32_t)i << 6) | (uint32_t)e0;
+          bucket[key + 1]++;
+          e++;
+        }
+      }
+      for (size_t b = 0; b < nb; b++) bucket[b + 1] += bucket[b];
+      std::vector<uint32_t> fill(bucket.begin(), bucket.end() - 1);
+      for (size_t x = 0; x < n_pieces; x++) entries[fill[keys[x]]++] = vals[x];
+      // text byte -> code / flags
+      std::vector<uint8_t> lin(256, 0);
+      for (int b = 0; b < 256; b++) {
+        const uint32_t msk = symmask[b] & ((1u << c->n_sym) - 1u);
+        uint8_t v = msk ? (uint8_t)__builtin_ctz(msk) : (uint8_t)4;
+        if (b == c->opt.eos) v = 4 | 8;
+        lin[b] = v;
+      }
+      const Up iups[] = {{&c->d_bucket, bucket.data(), bucket.size() * 4},
+                         {&c->d_entries, entries.data(), std::max<size_t>(entries.size(), 1) * 4},
+                         {&c->d_pat2, pat2.data(), pat2.size() * 8},
+                         {&c->d_umask4, um4.data(), um4.size() * 4},
+                         {&c->d_lin, lin.data(), lin.size()}};
+      for (const Up &u : iups) {
+        int rc = u.b->ensure(u.bytes);
+        if (rc) return rc;
+        PM_CUDA(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
+      }
+    }
   }
   c->inited = true;
   // a text set before init (not the reference's order, but harmless) is packed now

@@ -23,10 +23,14 @@ def _gpu(built_lib):
     _need_gpu()
 
 
-def test_golden_records_bit_exact(pkg, golden):
+@pytest.mark.parametrize("path", ["auto", "planes"])
+def test_golden_records_bit_exact(pkg, golden, path):
+    """auto = q-gram index kernels where they apply (plain ACGT primers), bit-plane
+    kernels otherwise; planes = bit-plane kernels everywhere."""
+    sp = pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES
     for case in golden["cases"]:
         st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
-        got = pkg.primer_match(st, case["primers"], **case["params"])
+        got = pkg.primer_match(st, case["primers"], scan_path=sp, **case["params"])
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
 
 
@@ -52,14 +56,16 @@ def test_records_match_oracle_seeded(pkg, oracle, seed):
     fasta, primers = casegen.make_case(seed, **kw)
     raw = fasta.encode()
     want = oracle.primer_match(oracle.normalize_fasta(raw), primers, **params)
-    got = pkg.primer_match(pkg.normalize_fasta(raw), primers, **params)
-    assert as_tuples(got) == as_tuples(want)
+    for sp in (pkg.PM_SCAN_AUTO, pkg.PM_SCAN_PLANES):
+        got = pkg.primer_match(pkg.normalize_fasta(raw), primers, scan_path=sp, **params)
+        assert as_tuples(got) == as_tuples(want), "scan path %d" % sp
 
 
+@pytest.mark.parametrize("path", ["index", "planes"])
 @pytest.mark.parametrize("k,indels,wc", [(0, False, False), (0, False, True), (1, False, False),
                                          (2, False, False), (3, False, True), (1, True, False),
                                          (2, True, False), (2, True, True), (3, True, False)])
-def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc):
+def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
     """Raw candidate set of the dense scan on a text of several tiles, with
     occurrences planted across the tile seams and the bit-row seams."""
     import casegen
@@ -93,20 +99,29 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc):
     else:
         want = oracle.wm_scan(T, primers, k, indels, wc, False)
     want = sorted({(int(b), int(a)) for a, b, _ in want})
-    sc = pkg.Scanner(k=k, indels=indels, wildcards=wc)
+    if path == "index" and wc:
+        pytest.skip("IUPAC patterns are served by the bit-plane kernels")
+    sc = pkg.Scanner(k=k, indels=indels, wildcards=wc,
+                     scan_path=pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
     for i, p in enumerate(primers):
         sc.add_pattern(p, i + 1)
-    sc.init()
+    try:
+        sc.init()
+    except pkg.PmError as ex:
+        assert path == "index" and ex.code == pkg.PM_E_UNSUPPORTED   # pieces shorter than 3 characters
+        pytest.skip("pattern pieces too short for the q-gram index")
     sc.set_text(T)
     got = sc.scan_candidates()
+    assert sc.stats()["scan_path"] == (pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
     got = sorted((int(b), int(a)) for a, b in got)
     sc.close()
     assert len(want) > 20
     assert got == want
 
 
+@pytest.mark.parametrize("path", ["auto", "planes"])
 @pytest.mark.parametrize("k,indels", [(1, False), (2, True)])
-def test_shards_reproduce_whole_scan(pkg, k, indels):
+def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     """Partitioning the stream over several contexts (GPUs) with the documented
     overlap gives exactly the hits of one whole-stream scan."""
     import casegen
@@ -126,7 +141,7 @@ def test_shards_reproduce_whole_scan(pkg, k, indels):
     T = st.chars
 
     def run(begin, end, lo, hi):
-        sc = pkg.Scanner(k=k, indels=indels)
+        sc = pkg.Scanner(k=k, indels=indels, scan_path=pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES)
         for i, p in enumerate(primers):
             sc.add_pattern(p, i + 1)
         sc.init()
@@ -212,8 +227,9 @@ def test_host_pipeline_equals_device_path(pkg):
     h.copy_(d)
     torch.cuda.synchronize()
     out = []
-    for src in (d, h, h.numpy().copy()):
-        sc = pkg.Scanner(k=2, indels=False)
+    for src, sp in ((d, pkg.PM_SCAN_PLANES), (h, pkg.PM_SCAN_PLANES), (h.numpy().copy(), pkg.PM_SCAN_PLANES),
+                    (d, pkg.PM_SCAN_INDEX), (h, pkg.PM_SCAN_INDEX)):
+        sc = pkg.Scanner(k=2, indels=False, scan_path=sp)
         for i, p in enumerate(pkg.pattern_array(primers, True)):
             sc.add_pattern(p, i + 1)
         sc.init()
@@ -221,4 +237,4 @@ def test_host_pipeline_equals_device_path(pkg):
         out.append(sc.find_patterns())
         sc.close()
     assert len(out[0]) >= 140
-    assert out[0].tobytes() == out[1].tobytes() == out[2].tobytes()
+    assert all(o.tobytes() == out[0].tobytes() for o in out[1:])
