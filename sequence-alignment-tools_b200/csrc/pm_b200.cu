@@ -168,11 +168,13 @@ struct pm_ctx {
   DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
+  double idx_seed_rate = 0;  // same for the pair index (pair occurrences)
   // q-gram index path (pm_index.cuh)
   int scan_path = PM_SCAN_AUTO;  // requested
   bool use_index = false;        // resolved in pm_init
-  int idx_q = 0;
-  DevBuf d_pk, d_bucket, d_entries, d_pat2, d_umask4, d_lin;
+  int idx_q = 0;                 // piece length L of the pair index
+  DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap;
+  pm::IndexArgs idx_proto;       // level-1 / level-2 parameters filled by pm_init
   unsigned long long *d_counters = nullptr;  // [8]
   unsigned long long *h_counters = nullptr;  // pinned [8]
   void *h_out = nullptr;                     // pinned result buffer
@@ -368,28 +370,28 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   const size_t smem = (size_t)(c->n_sym + 1) * TILE_WT * 4;
   IndexArgs ia;
   memset(&ia, 0, sizeof ia);
-  void (*ikern)(const IndexArgs) = edit ? qgram_scan_kernel<true> : qgram_scan_kernel<false>;
+  void (*ikern)(const IndexArgs) = edit ? pair_scan_kernel<true> : pair_scan_kernel<false>;
   void (*ivkern)(const IndexArgs) =
       K <= 1 ? index_verify_kernel<1> : (K == 2 ? index_verify_kernel<2> : index_verify_kernel<3>);
   size_t ismem = 0;
   if (c->use_index) {
+    ia = c->idx_proto;
     ia.pk = c->d_pk.as<uint2>();
     ia.n = c->n;
     ia.n16 = (uint64_t)c->n_tiles * (TILE_POS / 16);
+    ia.bitmap = c->d_bitmap.as<uint32_t>();
     ia.bucket = c->d_bucket.as<uint32_t>();
-    ia.entries = c->d_entries.as<uint32_t>();
-    ia.pat2 = c->d_pat2.as<uint64_t>();
+    ia.entries = c->d_entries.as<uint2>();
+    ia.pacc = c->d_pacc.as<ulonglong4>();
     ia.plen = c->d_plen.as<uint8_t>();
-    ia.piece_end = c->d_piece.as<uint64_t>();
     ia.umask4 = c->d_umask4.as<uint32_t>();
     ia.count = c->d_counters + 0;
     ia.seed_count = c->d_counters + 1;
     ia.work_count = c->d_counters + 5;
     ia.lo = lo;
     ia.hi = hi;
-    ia.q = (uint32_t)c->idx_q;
     ia.k = (uint32_t)K;
-    if (c->idx_q <= IDX_SMEM_Q) ismem = ((size_t)1 << (2 * c->idx_q)) * 4 + 4;
+    ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * PAIR_QCAP * 8;
     PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
   }
   void (*kern)(const ScanArgs) = nullptr;
@@ -422,7 +424,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   if (edit) {
     int rc = c->d_seeds.ensure((size_t)(64u << 20) * 8);
     if (rc) return rc;
-    const double per_tile = std::max(1.0, c->seed_rate * (double)TILE_POS);
+    const double per_tile = std::max(1.0, (c->use_index ? c->idx_seed_rate : c->seed_rate) * (double)TILE_POS);
     const double fit = (double)(c->d_seeds.cap / 8) / (2.0 * per_tile);
     batch_tiles = (uint32_t)std::max(1.0, std::min((double)nt, fit));
   }
@@ -466,7 +468,10 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
             ia.p_end = std::min<int64_t>(pe, pb + batch_pos);
             const uint64_t span = (uint64_t)(ia.p_end - ia.p_begin);
             if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
-            ikern<<<(unsigned)((span + IDX_BLOCK_POS - 1) / IDX_BLOCK_POS), IDX_THREADS, ismem, c->stream>>>(ia);
+            const uint64_t warp_chunks = (span + 16 + 511) / 512;  // 512 positions per warp pass
+            const unsigned iblocks = (unsigned)std::max<uint64_t>(
+                1, std::min<uint64_t>((uint64_t)n_sm, (warp_chunks + PAIR_WARPS - 1) / PAIR_WARPS));
+            ikern<<<iblocks, PAIR_THREADS, ismem, c->stream>>>(ia);
             PM_CUDA(cudaGetLastError());
             c->stats.kernel_launches++;
             if (edit) {
@@ -755,7 +760,8 @@ int pack_tiles(pm_ctx *c, uint32_t t0, uint32_t t1, cudaStream_t st) {
   if (t1 <= t0) return PM_OK;
   if (c->use_index) {
     const uint64_t w0 = (uint64_t)t0 * (TILE_POS / 16), w1 = (uint64_t)t1 * (TILE_POS / 16);
-    pack_linear_kernel<<<(unsigned)((w1 - w0 + 255) / 256), 256, 0, st>>>(
+    const uint64_t per_block = 256ull * PACK_WORDS_PER_THREAD;
+    pack_linear_kernel<<<(unsigned)((w1 - w0 + per_block - 1) / per_block), 256, 0, st>>>(
         c->d_text, c->n, c->d_lin.as<uint8_t>(), c->opt.eos, c->d_pk.as<uint2>(), w0, w1);
     PM_CUDA(cudaGetLastError());
     return PM_OK;
@@ -857,7 +863,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
-                    &c->d_bucket,  &c->d_entries, &c->d_pat2,  &c->d_umask4,   &c->d_lin};
+                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1021,73 +1027,149 @@ int pm_init(pm_ctx *c) {
     if (rc) return rc;
     PM_CUDA(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
   }
-  // ---- q-gram index (pm_index.cuh): applicable? ------------------------------------------
+  // ---- pair-seed index (pm_index.cuh): applicable? ----------------------------------------
   {
-    bool ok = c->n_sym <= 4 && c->max_len <= 32 && ns > 0;
-    for (uint32_t msk : cls_mask)
-      if (__builtin_popcount(msk) > 1) ok = false;  // a text byte matching two symbols
-    int min_piece = 64;
-    size_t n_pieces = 0;
-    for (size_t i = 0; i < ns && ok; i++) {
-      const int m = (int)c->pats[i].s.size();
-      for (int j = 1; j <= K + 1; j++) {
-        const int e0 = m * (j - 1) / (K + 1), e1 = m * j / (K + 1);
-        min_piece = std::min(min_piece, e1 - e0);
-        n_pieces++;
+    const int P = K + 2;
+    const bool edit_mode = (K > 0 && c->opt.indels);
+    // text codes: without wildcards code = symbol; with wildcards the codes are the match
+    // classes of the text bytes 'A','C','G','T'
+    const uint32_t symbits = (c->n_sym >= 32) ? 0xffffffffu : ((1u << c->n_sym) - 1u);
+    uint32_t code_mask[4] = {0, 0, 0, 0};  // symbols matched by a text character of that code
+    int n_codes = 0;
+    bool ok = c->max_len <= 32 && ns > 0 && ns < (1u << 22);
+    if (!wc) {
+      if (c->n_sym > 4) ok = false;
+      n_codes = std::min(c->n_sym, 4);
+      for (int s2 = 0; s2 < n_codes; s2++) code_mask[s2] = 1u << s2;
+    } else {
+      n_codes = 4;
+      for (int cc = 0; cc < 4; cc++) code_mask[cc] = symmask[(unsigned char)"ACGT"[cc]] & symbits;
+    }
+    // every text byte must be one of the codes or match nothing
+    std::vector<uint8_t> lin(256, 0);
+    for (int b2 = 0; b2 < 256 && ok; b2++) {
+      const uint32_t msk = symmask[b2] & symbits;
+      uint8_t v = 4;  // matches nothing
+      if (msk) {
+        int code = -1;
+        for (int cc = 0; cc < n_codes; cc++)
+          if (code_mask[cc] == msk) { code = cc; break; }
+        if (code < 0) ok = false;  // an ambiguous text byte: bit-plane kernels
+        else v = (uint8_t)code;
+      }
+      if (b2 == c->opt.eos) v = 4 | 8;
+      lin[b2] = v;
+    }
+    int min_len = 64;
+    for (size_t i = 0; i < ns; i++) min_len = std::min<int>(min_len, (int)c->pats[i].s.size());
+    int L = std::min(PAIR_LMAX, min_len / P);
+    if (edit_mode) L = std::min(L, (32 - K) / P);
+    if (L < 4) ok = false;
+    if (c->scan_path == PM_SCAN_PLANES) ok = false;
+
+    std::vector<uint2> ents;
+    std::vector<uint32_t> dist;
+    if (ok) {
+      if (edit_mode) for (int d = L; d <= (P - 1) * L + K; d++) dist.push_back((uint32_t)d);
+      else for (int j = 1; j < P; j++) dist.push_back((uint32_t)(j * L));
+      if ((int)dist.size() > PAIR_MAX_ND) ok = false;
+    }
+    // accept sets of a pattern character over the text codes
+    auto accept4 = [&](unsigned char ch) {
+      uint32_t acc = 0;
+      const int sy = sym_of[ch];
+      for (int cc = 0; cc < n_codes; cc++)
+        if ((code_mask[cc] >> sy) & 1u) acc |= 1u << cc;
+      return acc;
+    };
+    if (ok) {
+      const size_t kMaxPerPair = 1024, kMaxEntries = (size_t)8 << 20;
+      std::vector<uint32_t> ka, kb;
+      auto expand = [&](const std::string &ps, int off, std::vector<uint32_t> &out) {
+        out.assign(1, 0u);
+        for (int t = 0; t < L; t++) {
+          const uint32_t acc = accept4((unsigned char)ps[off + t]);
+          std::vector<uint32_t> nxt;
+          for (uint32_t base : out)
+            for (int cc = 0; cc < 4; cc++)
+              if ((acc >> cc) & 1u) nxt.push_back(base | ((uint32_t)cc << (2 * t)));
+          out.swap(nxt);
+          if (out.size() > kMaxPerPair) return false;
+        }
+        return true;
+      };
+      for (size_t i = 0; i < ns && ok; i++) {
+        const std::string &ps = c->pats[i].s;
+        std::vector<std::vector<uint32_t>> piece_keys(P);
+        for (int pi = 0; pi < P && ok; pi++)
+          if (!expand(ps, pi * L, piece_keys[pi])) ok = false;
+        for (int pi = 0; pi < P && ok; pi++)
+          for (int pj = pi + 1; pj < P && ok; pj++) {
+            if (piece_keys[pi].size() * piece_keys[pj].size() > kMaxPerPair) { ok = false; break; }
+            for (int e = edit_mode ? -K : 0; e <= (edit_mode ? K : 0); e++) {
+              const int d = (pj - pi) * L + e;
+              if (d < L) continue;
+              const uint32_t di = edit_mode ? (uint32_t)(d - L) : (uint32_t)(pj - pi - 1);
+              const uint32_t meta = ((uint32_t)i << 10) | (di << 5) | (uint32_t)(pi * L);
+              for (uint32_t x : piece_keys[pi])
+                for (uint32_t y : piece_keys[pj]) ents.push_back(make_uint2(x | (y << (2 * L)), meta));
+            }
+            if (ents.size() > kMaxEntries) ok = false;
+          }
       }
     }
-    if (min_piece < 3) ok = false;
-    int q = std::min(min_piece, IDX_QMAX);
-    if (ok) {
-      // smallest table that keeps the expected bucket occupancy low
-      int qq = std::min(q, 6);
-      while (qq < q && (double)n_pieces / std::pow(4.0, qq) > 0.3) qq++;
-      q = qq;
-      if ((double)n_pieces / std::pow(4.0, q) > 64.0) ok = false;  // buckets too crowded: planes are cheaper
-    }
-    if (c->scan_path == PM_SCAN_PLANES) ok = false;
     if (c->scan_path == PM_SCAN_INDEX && !ok)
-      return fail(PM_E_UNSUPPORTED, "q-gram index scan not applicable to these patterns / options");
+      return fail(PM_E_UNSUPPORTED, "pair-seed index scan not applicable to these patterns / options");
     c->use_index = ok;
-    c->idx_q = ok ? q : 0;
+    c->idx_q = ok ? L : 0;
     if (ok) {
-      const size_t nb = (size_t)1 << (2 * q);
-      std::vector<uint32_t> bucket(nb + 1, 0), entries(n_pieces, 0), um4((ns + 1) * 4, 0);
-      std::vector<uint64_t> pat2(ns + 1, 0);
-      std::vector<uint32_t> keys(n_pieces), vals(n_pieces);
-      size_t e = 0;
+      IndexArgs &ia = c->idx_proto;
+      memset(&ia, 0, sizeof ia);
+      ia.log_words = PAIR_LOG_WORDS;
+      ia.L = (uint32_t)L;
+      ia.nd = (uint32_t)dist.size();
+      ia.mult = 0x9E3779B1u;
+      for (size_t d = 0; d < dist.size(); d++) {
+        ia.dist[d] = dist[d];
+        ia.salt[d] = (uint32_t)d * 0x7F4A7C15u;
+      }
+      int lb = 10;
+      while (((size_t)1 << lb) < 2 * ents.size() && lb < 26) lb++;
+      ia.log_buckets = (uint32_t)lb;
+      const size_t nb = (size_t)1 << lb;
+      std::vector<uint32_t> bitmap((size_t)1 << ia.log_words, 0), bucket(nb + 1, 0);
+      std::vector<uint32_t> hs(ents.size());
+      for (size_t x = 0; x < ents.size(); x++) {
+        const uint32_t di = (ents[x].y >> 5) & 31u;
+        const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
+        bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
+        hs[x] = pair_hash2(ents[x].x, di, ia.log_buckets);
+        bucket[hs[x] + 1]++;
+      }
+      for (size_t b2 = 0; b2 < nb; b2++) bucket[b2 + 1] += bucket[b2];
+      std::vector<uint32_t> fill(bucket.begin(), bucket.end() - 1);
+      std::vector<uint2> sorted(std::max<size_t>(ents.size(), 1), make_uint2(0, 0));
+      for (size_t x = 0; x < ents.size(); x++) sorted[fill[hs[x]]++] = ents[x];
+      // expected seeds per base on uniform ACGT text (edit mode batches its seed list by this)
+      c->idx_seed_rate = (double)ents.size() / std::pow(4.0, 2.0 * L);
+      // per-code accept masks (bit 2j) and Shift-And masks (bit j)
+      std::vector<unsigned long long> pacc((ns + 1) * 4, 0);
+      std::vector<uint32_t> um4((ns + 1) * 4, 0);
       for (size_t i = 0; i < ns; i++) {
         const std::string &ps = c->pats[i].s;
-        const int m = (int)ps.size();
-        for (int j = 0; j < m; j++) {
-          const uint32_t sy = (uint32_t)sym_of[(unsigned char)ps[j]];
-          pat2[i] |= (uint64_t)sy << (2 * j);
-          um4[i * 4 + sy] |= 1u << j;
+        for (int j = 0; j < (int)ps.size(); j++) {
+          const uint32_t acc = accept4((unsigned char)ps[j]);
+          for (int cc = 0; cc < 4; cc++)
+            if ((acc >> cc) & 1u) {
+              pacc[i * 4 + cc] |= 1ull << (2 * j);
+              um4[i * 4 + cc] |= 1u << j;
+            }
         }
-        for (int j = 1; j <= K + 1; j++) {
-          const int e0 = m * (j - 1) / (K + 1);
-          uint32_t key = 0;  // first character of the q-gram in the highest digit (rolling code order)
-          for (int t = 0; t < q; t++) key = (key << 2) | (uint32_t)sym_of[(unsigned char)ps[e0 + t]];
-          keys[e] = key;
-          vals[e] = ((uint32_t)i << 6) | (uint32_t)e0;
-          bucket[key + 1]++;
-          e++;
-        }
-      }
-      for (size_t b = 0; b < nb; b++) bucket[b + 1] += bucket[b];
-      std::vector<uint32_t> fill(bucket.begin(), bucket.end() - 1);
-      for (size_t x = 0; x < n_pieces; x++) entries[fill[keys[x]]++] = vals[x];
-      // text byte -> code / flags
-      std::vector<uint8_t> lin(256, 0);
-      for (int b = 0; b < 256; b++) {
-        const uint32_t msk = symmask[b] & ((1u << c->n_sym) - 1u);
-        uint8_t v = msk ? (uint8_t)__builtin_ctz(msk) : (uint8_t)4;
-        if (b == c->opt.eos) v = 4 | 8;
-        lin[b] = v;
       }
       const Up iups[] = {{&c->d_bucket, bucket.data(), bucket.size() * 4},
-                         {&c->d_entries, entries.data(), std::max<size_t>(entries.size(), 1) * 4},
-                         {&c->d_pat2, pat2.data(), pat2.size() * 8},
+                         {&c->d_entries, sorted.data(), sorted.size() * 8},
+                         {&c->d_bitmap, bitmap.data(), bitmap.size() * 4},
+                         {&c->d_pacc, pacc.data(), pacc.size() * 8},
                          {&c->d_umask4, um4.data(), um4.size() * 4},
                          {&c->d_lin, lin.data(), lin.size()}};
       for (const Up &u : iups) {

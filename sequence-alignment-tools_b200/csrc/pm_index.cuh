@@ -1,33 +1,42 @@
-// pm_index.cuh -- text-driven q-gram index scan (sm_100a).
+// pm_index.cuh -- text-driven pair-seed index scan (sm_100a).
 //
 // The bit-plane kernels of pm_scan.cuh touch every (pattern, position) pair.
-// For DNA-like alphabets that is far more work than the problem needs: with at
-// most k errors one of the k+1 pieces of a pattern occurs exactly, so a text
-// position only has to look at the patterns whose piece starts with the q-gram
-// found there.  This is the role the reference gives its keyword tree / hash
-// table front ends (exact_bases.cc, exact_halves.cc, hash_table.cc); here it
-// is one flat table:
+// For DNA-like alphabets that is far more work than the problem needs.  Cut
+// the first P*L characters of every pattern into P = k+2 pieces of L
+// characters.  k errors damage at most k pieces, so every occurrence with
+// <= k errors holds two INTACT pieces i < j, and their text distance is
+//   substitutions : exactly (j-i)*L
+//   edits         : (j-i)*L - k .. (j-i)*L + k   (never less than L)
+// A text position p therefore only has to ask, for each distance d of that
+// small set D, "is (text[p..p+L), text[p+d..p+d+L)) a pair of some pattern?".
+// This is the role the reference gives its keyword tree / hash table front
+// ends (exact_bases.cc, exact_halves.cc, hash_table.cc), sharpened from one
+// piece to two so that the filter passes ~1 % of the positions instead of ~70 %.
 //
-//   bucket[code]        = first entry of the q-gram `code` (4^q + 1 uint32)
-//   entry               = slot << 6 | offset of the piece in its pattern
-//   q                   = min(shortest piece, 12), chosen on the host
+//   level 1  one bit per pair key in a 128 KB bitmap in SHARED memory:
+//            idx = key * mult + salt[d];  word = idx >> (32-log_words),
+//            bit = 31 - (idx & 31).  One LDS per (position, distance).
+//   level 2  survivors go to a per-warp queue and are resolved 32 at a time
+//            against the exact table in L2: bucket[hash2(key,d)] -> entries
+//            (key, slot << 10 | d_index << 5 | piece offset).
+//   verify   substitutions: XOR-free popcount on the packed window against the
+//            pattern's per-code accept masks (IUPAC pattern symbols are a mask
+//            with several codes set); edits: the reference's own recurrence
+//            (index_verify_kernel).
 //
-// and the text is kept 2 bits per character (+ 2 flag bits: "matches no
-// pattern symbol" and "end of sequence"), 16 characters per 8-byte word, so a
-// verification is a few loads, an XOR and a population count.
+// The text is kept 2 bits per character (+ 2 flag bits: "matches no pattern
+// symbol" and "end of sequence"), 16 characters per 8-byte word.
 //
 // Exactness.  The candidate set is the one of pm_scan.cuh / the reference:
 //   substitutions: the verifier counts the mismatches of the whole window and
 //     rejects windows holding an end-of-sequence character -- the level-k hit
 //     condition of shift_and_inexact.cc:253-326 without indels;
-//   edits: the table only proposes seeds (exact occurrence of a whole piece);
-//     the reference's own recurrence decides (verify_seed_packed below).
-// Pigeonhole makes the seeds a superset in both cases.
+//   edits: the table only proposes seeds; the reference's recurrence decides.
+// The pair lemma above makes the proposals a superset in both cases.
 //
-// Applicable when every text byte matches at most one pattern symbol, there
-// are at most 4 symbols and no pattern is longer than 32 (host checks); other
-// inputs (IUPAC patterns, text wildcards, long patterns) use the bit-plane
-// kernels.
+// Applicable when the text bytes fall into <= 4 match classes (+ "matches
+// nothing"), no pattern is longer than 32 and L >= 4 (host checks); other
+// inputs use the bit-plane kernels.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -35,33 +44,44 @@
 
 namespace pm {
 
-constexpr int IDX_THREADS = 128;
-constexpr int IDX_SEG = 128;                        // q-gram end positions per thread
-constexpr int IDX_BLOCK_POS = IDX_THREADS * IDX_SEG;  // 16384 positions per block
-constexpr int IDX_QMAX = 12;
-constexpr int IDX_SMEM_Q = 7;                       // bucket array in shared memory up to this q
+constexpr int PAIR_THREADS = 1024;            // one CTA per SM: the bitmap fills its shared memory
+constexpr int PAIR_WARPS = PAIR_THREADS / 32;
+constexpr int PAIR_QCAP = 128;                // per-warp queue of level-1 survivors
+constexpr int PAIR_MAX_ND = 32;
+constexpr int PAIR_LOG_WORDS = 15;            // 2^15 words = 128 KB = 2^20 bits
+constexpr int PAIR_LMAX = 8;
+constexpr int64_t SEED_BIAS = 64;             // seeds store (nominal window start + SEED_BIAS)
 
 struct IndexArgs {
   const uint2 *pk;          // [n16] x = 2-bit codes of 16 characters, y = flags (bit0 bad, bit1 eos)
   uint64_t n;               // shard length (characters)
   uint64_t n16;             // words in pk
-  const uint32_t *bucket;   // [4^q + 1]
-  const uint32_t *entries;  // slot << 6 | piece offset
-  const uint64_t *pat2;     // [n_slots] 2-bit codes of the pattern
+  // level 1
+  const uint32_t *bitmap;   // [1 << log_words]
+  uint32_t log_words;
+  uint32_t L;               // piece length
+  uint32_t nd;              // distances
+  uint32_t mult;            // odd multiplier of the level-1 hash
+  uint32_t dist[PAIR_MAX_ND];
+  uint32_t salt[PAIR_MAX_ND];
+  // level 2
+  const uint32_t *bucket;   // [(1 << log_buckets) + 1]
+  uint32_t log_buckets;
+  const uint2 *entries;     // x = key, y = slot << 10 | d_index << 5 | piece offset
+  // patterns
+  const ulonglong4 *pacc;   // [n_slots] bit 2j of .x/.y/.z/.w: character j accepts text code 0/1/2/3
   const uint8_t *plen;      // [n_slots]
-  const uint64_t *piece_end;  // [n_slots] bit i: character i ends a piece
   const uint32_t *umask4;   // [n_slots][4] Shift-And masks per text code (edit verifier)
   unsigned long long *out;  // candidates: slot << 40 | pos
   unsigned long long *count;
   uint64_t cap;
   int64_t lo, hi;           // emit candidates with lo <= pos < hi
-  int64_t p_begin, p_end;   // q-gram END positions handled by this launch
-  uint32_t q;
+  int64_t p_begin, p_end;   // first-piece positions handled by this launch
   uint32_t k;
   // edit mode: seeds instead of candidates
   unsigned long long *seeds, *seed_n, *seed_overflow, *seed_count;
   uint64_t seed_cap;
-  unsigned long long *work_count;  // table entries examined
+  unsigned long long *work_count;  // level-1 survivors (queue entries)
 };
 
 // 16-character words of the packed text.  Characters past the end read as end
@@ -70,8 +90,12 @@ __device__ __forceinline__ uint2 pk_load(const IndexArgs &a, int64_t w) {
   if (w < 0 || (uint64_t)w >= a.n16) return make_uint2(0u, 0xffffffffu);
   return __ldg(a.pk + w);
 }
+__device__ __forceinline__ uint32_t pk_codes(const IndexArgs &a, int64_t w) {
+  if (w < 0 || (uint64_t)w >= a.n16) return 0u;
+  return __ldg(&a.pk[w].x);
+}
 
-// codes and flags of the `len` (<= 32) characters starting at s, right-aligned
+// codes and flags of the 32 characters starting at s
 __device__ __forceinline__ void pk_window(const IndexArgs &a, int64_t s, uint64_t &codes, uint64_t &flags) {
   const int64_t w = s >> 4;  // arithmetic shift: s may be negative near the start
   const uint32_t sh = 2u * (uint32_t)(s & 15);
@@ -88,127 +112,200 @@ __device__ __forceinline__ void index_emit(const IndexArgs &a, uint32_t slot, in
   if (at < a.cap) a.out[at] = ((unsigned long long)slot << 40) | (unsigned long long)pos;
 }
 
-// EDIT = false: substitutions-only verifier inline, candidates out.
-// EDIT = true : whole-piece check, seeds out (verified by index_verify_kernel);
-//               seeds are queued per warp in shared memory and flushed with one
-//               global atomic per flush.
-constexpr int IDX_QCAP = 256;  // per-warp seed queue entries
+__host__ __device__ __forceinline__ uint32_t pair_hash1(uint32_t key, uint32_t mult, uint32_t salt) {
+  return key * mult + salt;
+}
+__host__ __device__ __forceinline__ uint32_t pair_hash2(uint32_t key, uint32_t di, uint32_t log_buckets) {
+  return ((key + di * 0x9E3779B1u) * 0x85EBCA6Bu) >> (32u - log_buckets);
+}
 
-template <bool EDIT>
-__global__ void __launch_bounds__(IDX_THREADS)
-qgram_scan_kernel(const IndexArgs a) {
-  extern __shared__ uint32_t s_bucket[];  // 4^q + 1 entries when q <= IDX_SMEM_Q
-  __shared__ unsigned long long s_queue[EDIT ? IDX_THREADS / 32 : 1][EDIT ? IDX_QCAP : 1];
-  __shared__ uint32_t s_qn[IDX_THREADS / 32];
-  const uint32_t q = a.q;
-  const uint32_t n_buckets = 1u << (2 * q);
-  const bool in_smem = q <= (uint32_t)IDX_SMEM_Q;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) s_qn[warp] = 0;
-  if (in_smem)
-    for (uint32_t i = threadIdx.x; i <= n_buckets; i += blockDim.x) s_bucket[i] = a.bucket[i];
-  __syncthreads();
-  const uint32_t *bucket = in_smem ? s_bucket : a.bucket;
-  const uint32_t qmask = n_buckets - 1u;
+// substitutions: mismatches of the whole window of `slot` starting at s
+__device__ __forceinline__ void pair_verify_window(const IndexArgs &a, uint32_t slot, int64_t s) {
+  const uint32_t m = a.plen[slot] & 0x7fu;
+  if (s < 0 || (uint64_t)(s + m) > a.n) return;
+  uint64_t codes, flags;
+  pk_window(a, s, codes, flags);
+  const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
+  const ulonglong2 acc01 = __ldg(accp), acc23 = __ldg(accp + 1);
+  ulonglong4 acc;
+  acc.x = acc01.x; acc.y = acc01.y; acc.z = acc23.x; acc.w = acc23.y;
+  constexpr uint64_t M5 = 0x5555555555555555ULL;
+  const uint64_t lenmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1ULL);
+  const uint64_t lo = codes & M5, hi = (codes >> 1) & M5;
+  const uint64_t match = (~(hi | lo) & acc.x) | (lo & ~hi & acc.y) | (hi & ~lo & acc.z) | (hi & lo & acc.w);
+  const uint64_t mis = (~match | flags) & M5 & lenmask;
+  if (__popcll(mis) <= (int)a.k && (flags & ~M5 & lenmask) == 0) index_emit(a, slot, s + m);
+}
 
-  // this thread's q-gram end positions [p0, p1) (empty past the end of the launch)
-  const int64_t p0 = a.p_begin + ((int64_t)blockIdx.x * IDX_THREADS + threadIdx.x) * IDX_SEG;
-  int64_t p1 = p0 + IDX_SEG;
-  if (p1 > a.p_end) p1 = a.p_end;
-  // start one word early: warms the rolling code with >= 16 >= q-1 characters
-  const int64_t w_first = (p0 >> 4) - 1;
-  uint32_t code = 0, run = 0;
-  unsigned long long n_entries = 0;
-
-  auto flush = [&]() {
-    if (!EDIT) return;
-    __syncwarp();
-    const uint32_t qn = min(s_qn[warp], (uint32_t)IDX_QCAP);
-    unsigned long long base = 0;
-    if (lane == 0 && qn) base = atomicAdd(a.seed_n, (unsigned long long)qn);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t i = lane; i < qn; i += 32) {
-      if (base + i < a.seed_cap) a.seeds[base + i] = s_queue[EDIT ? warp : 0][i];
-      else *a.seed_overflow = 1ULL;
-    }
-    __syncwarp();
-    if (lane == 0) s_qn[warp] = 0;
-    __syncwarp();
-  };
-
-  // every thread of the warp walks the same number of words: the flush points are uniform
-  constexpr int NW = IDX_SEG / 16 + 2;
-  for (int wi = 0; wi < NW; ++wi) {
-    const int64_t w = w_first + wi;
-    const uint2 v = pk_load(a, w);
-    uint32_t cw = v.x, fw = v.y;
-    const int64_t base = w << 4;
-#pragma unroll 4
-    for (int i = 0; i < 16; i++, cw >>= 2, fw >>= 2) {
-      code = ((code << 2) | (cw & 3u)) & qmask;
-      run = (fw & 3u) ? 0u : run + 1u;
-      const int64_t p = base + i;  // the q-gram ends here
-      if (run < q || p < p0 || p >= p1) continue;
-      uint32_t e0 = bucket[code];
-      const uint32_t e1 = bucket[code + 1];
-      for (; e0 < e1; ++e0) {
-        const uint32_t ent = __ldg(a.entries + e0);
-        const uint32_t slot = ent >> 6, off = ent & 63u;
-        const uint32_t m = a.plen[slot] & 0x7fu;
-        const int64_t s = p - (int64_t)q + 1 - (int64_t)off;  // window start
-        n_entries++;
-        // substitutions: the window must lie inside the stream; edits: a nominal window may
-        // hang over the end (trailing deletions), the verifier clamps
-        if (s < 0 || (!EDIT && (uint64_t)(s + m) > a.n)) continue;
-        uint64_t codes, flags;
-        pk_window(a, s, codes, flags);
-        const uint64_t lenmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1ULL);
-        const uint64_t diff = codes ^ __ldg(a.pat2 + slot);
-        const uint64_t mis = ((diff | (diff >> 1)) | flags) & 0x5555555555555555ULL & lenmask;
-        if (!EDIT) {
-          if (__popcll(mis) <= (int)a.k && (flags & 0xAAAAAAAAAAAAAAAAULL & lenmask) == 0)
-            index_emit(a, slot, s + m);
-        } else {
-          // the whole piece must match: characters off .. piece end
-          const uint64_t pe = __ldg(a.piece_end + slot) >> off;
-          const uint32_t plen_piece = (uint32_t)__ffsll((long long)pe);  // 1-based: piece length
-          const uint64_t pm = ((plen_piece >= 32) ? ~0ULL : ((1ULL << (2 * plen_piece)) - 1ULL)) << (2 * off);
-          if ((mis & pm) == 0) {
-            const unsigned long long sd = ((unsigned long long)slot << 40) | (unsigned long long)s;
-            const uint32_t at = atomicAdd(&s_qn[warp], 1u);
-            if (at < (uint32_t)IDX_QCAP) {
-              s_queue[EDIT ? warp : 0][at] = sd;
-            } else {  // queue full: straight to the list
-              const unsigned long long g = atomicAdd(a.seed_n, 1ULL);
-              if (g < a.seed_cap) a.seeds[g] = sd; else *a.seed_overflow = 1ULL;
-            }
-          }
-        }
-      }
-    }
-    if (EDIT) {
-      __syncwarp();
-      if (s_qn[warp] >= (uint32_t)(IDX_QCAP / 2)) flush();
+// Resolve one level-1 survivor (position p, distance index di) against the exact
+// table.  COLLECTIVE: called by all 32 lanes (valid = lane holds an entry); seeds are
+// appended with one global atomic per round.  Otherwise: one lane on its own.
+template <bool EDIT, bool COLLECTIVE>
+__device__ __forceinline__ void pair_resolve(const IndexArgs &a, bool valid, unsigned long long e,
+                                             uint32_t lane) {
+  const int64_t p = (int64_t)(e >> 6);
+  const uint32_t di = (uint32_t)(e & 63u);
+  const uint32_t L2 = 2u * a.L;
+  const uint64_t maskL = (1ULL << L2) - 1ULL;
+  uint32_t e0 = 0, e1 = 0, key = 0;
+  if (valid) {
+    uint64_t codes, flags;
+    pk_window(a, p, codes, flags);
+    const uint32_t d2 = 2u * a.dist[di];
+    key = (uint32_t)(codes & maskL) | ((uint32_t)((codes >> d2) & maskL) << L2);
+    if (((flags & maskL) | ((flags >> d2) & maskL)) == 0) {  // a flagged character matches nothing
+      const uint32_t h = pair_hash2(key, di, a.log_buckets);
+      e0 = __ldg(a.bucket + h);
+      e1 = __ldg(a.bucket + h + 1);
     }
   }
-  flush();
+  for (;;) {
+    const bool more = e0 < e1;
+    if (COLLECTIVE) {
+      if (!__any_sync(0xffffffffu, more)) break;
+    } else if (!more) {
+      break;
+    }
+    bool found = false;
+    uint32_t meta = 0;
+    if (more) {
+      const uint2 ent = __ldg(a.entries + e0);
+      ++e0;
+      meta = ent.y;
+      found = (ent.x == key) && (((meta >> 5) & 31u) == di);
+    }
+    const uint32_t slot = meta >> 10;
+    const int64_t s = p - (int64_t)(meta & 31u);  // nominal window start
+    if (!EDIT) {
+      if (found) pair_verify_window(a, slot, s);
+    } else {
+      const unsigned long long sd = ((unsigned long long)slot << 40) | (unsigned long long)(s + SEED_BIAS);
+      if (COLLECTIVE) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, found);
+        if (bal) {
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(a.seed_n, (unsigned long long)__popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (found) {
+            const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
+            if (at < a.seed_cap) a.seeds[at] = sd; else *a.seed_overflow = 1ULL;
+          }
+        }
+      } else if (found) {
+        const unsigned long long at = atomicAdd(a.seed_n, 1ULL);
+        if (at < a.seed_cap) a.seeds[at] = sd; else *a.seed_overflow = 1ULL;
+      }
+    }
+  }
+}
+
+// One warp owns chunks of 32 packed words (512 positions): lane l holds word l and
+// gets the next two words by shuffle, so the 16 positions of its word see their
+// 32-character context without any further load.
+template <bool EDIT>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+pair_scan_kernel(const __grid_constant__ IndexArgs a) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  __shared__ uint32_t s_qn[PAIR_WARPS];
+  const uint32_t n_words = 1u << a.log_words;
+  uint32_t *s_bitmap = s_mem;
+  unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
+    reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
+  if (lane == 0) s_qn[warp] = 0;
+  __syncthreads();
+  unsigned long long *queue = s_queue + warp * PAIR_QCAP;
+
+  const uint32_t wsh = 32u - a.log_words;
+  const uint32_t L2 = 2u * a.L;
+  const uint32_t maskL = (1u << L2) - 1u;       // L <= 8
+  const uint32_t maskHi = maskL << L2;
+  const uint32_t mult = a.mult;
+  const int64_t w_begin = a.p_begin >> 4;
+  const int64_t w_end = (a.p_end + 15) >> 4;
+  const int64_t n_chunks = (w_end - w_begin + 31) >> 5;
+  unsigned long long n_queued = 0;
+
+  auto drain = [&](bool final) {
+    for (;;) {
+      __syncwarp();
+      const uint32_t qn = min(s_qn[warp], (uint32_t)PAIR_QCAP);
+      if (qn == 0 || (!final && qn < 32u)) break;
+      const uint32_t take = min(qn, 32u);
+      const bool valid = lane < take;
+      const unsigned long long e = valid ? queue[qn - take + lane] : 0ULL;
+      __syncwarp();
+      if (lane == 0) s_qn[warp] = qn - take;
+      pair_resolve<EDIT, true>(a, valid, e, lane);
+    }
+  };
+
+  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+    const int64_t wc0 = w_begin + (c << 5);
+    const int64_t w = wc0 + lane;
+    const uint32_t mine = pk_codes(a, w);
+    const uint32_t extra = (lane < 2) ? pk_codes(a, wc0 + 32 + lane) : 0u;
+    const uint32_t x0 = __shfl_sync(0xffffffffu, extra, 0), x1 = __shfl_sync(0xffffffffu, extra, 1);
+    const uint32_t c0 = mine;
+    uint32_t c1 = __shfl_down_sync(0xffffffffu, mine, 1);
+    uint32_t c2 = __shfl_down_sync(0xffffffffu, mine, 2);
+    if (lane == 31) { c1 = x0; c2 = x1; }
+    if (lane == 30) c2 = x0;
+    const int64_t base = w << 4;
+
+    uint32_t av[16];
 #pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) n_entries += __shfl_xor_sync(0xffffffffu, n_entries, d);
-  if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_entries);
+    for (int i = 0; i < 16; i++) av[i] = __funnelshift_r(c0, c1, 2 * i) & maskL;
+
+    for (uint32_t di = 0; di < a.nd; ++di) {
+      const uint32_t s = 2u * (a.dist[di] - a.L);  // < 64
+      const uint32_t salt = a.salt[di];
+      const bool hiw = s >= 32u;
+      const uint32_t y0 = hiw ? c1 : c0, y1 = hiw ? c2 : c1, y2 = hiw ? 0u : c2;
+      const uint32_t X0 = __funnelshift_r(y0, y1, s), X1 = __funnelshift_r(y1, y2, s);  // shift taken mod 32
+      uint32_t hm = 0;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const uint32_t T = __funnelshift_r(X0, X1, 2 * i);
+        const uint32_t key = (T & maskHi) | av[i];
+        const uint32_t idx = key * mult + salt;
+        const uint32_t wrd = s_bitmap[idx >> wsh];
+        hm = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);  // bit 31-(idx&31) -> bit 0 of hm
+      }
+      // position i of the word sits in bit 15-i of hm
+      while (hm) {
+        const int b = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const int64_t p = base + (15 - b);
+        if (p < a.p_begin || p >= a.p_end) continue;
+        const unsigned long long e = ((unsigned long long)p << 6) | di;
+        n_queued++;
+        const uint32_t at = atomicAdd(&s_qn[warp], 1u);
+        if (at < (uint32_t)PAIR_QCAP) queue[at] = e;
+        else pair_resolve<EDIT, false>(a, true, e, lane);  // queue full: resolve on the spot
+      }
+    }
+    drain(false);
+  }
+  drain(true);
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) n_queued += __shfl_xor_sync(0xffffffffu, n_queued, d);
+  if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_queued);
 }
 
 // Edit verifier on the packed text: the recurrence of verify_seed (pm_scan.cuh)
 // with the character masks of the four codes in registers.
 template <int K>
 __global__ void __launch_bounds__(128)
-index_verify_kernel(const IndexArgs a) {
+index_verify_kernel(const __grid_constant__ IndexArgs a) {
   unsigned long long count = *a.seed_n;
   if (count > a.seed_cap) count = a.seed_cap;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long sd = a.seeds[i];
     const uint32_t slot = (uint32_t)(sd >> 40);
-    const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL);
+    const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL) - SEED_BIAS;
     const uint32_t m = a.plen[slot] & 0x7fu;
     const uint4 um = __ldg(reinterpret_cast<const uint4 *>(a.umask4) + slot);
     const uint32_t U[4] = {um.x, um.y, um.z, um.w};
@@ -264,40 +361,53 @@ index_verify_kernel(const IndexArgs a) {
 }
 
 // stream bytes -> packed words.  lin[b]: bits 0-1 code, bit 2 bad, bit 3 eos.
+// A character that matches no pattern symbol gets a position-dependent code, so
+// that a long run of them (the N blocks of a genome assembly) does not look like
+// a homopolymer to level 1; the flags keep it from ever matching.
+constexpr int PACK_WORDS_PER_THREAD = 8;
 __global__ void __launch_bounds__(256)
 pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ lin,
                    uint32_t eos_byte, uint2 *__restrict__ pk, uint64_t w_begin, uint64_t w_end) {
   __shared__ uint8_t s_lin[256];
   s_lin[threadIdx.x] = lin[threadIdx.x];
   __syncthreads();
-  const uint64_t w = w_begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= w_end) return;
-  const uint64_t base = w * 16;
-  uint32_t b[4];
-  if (base + 16 <= n) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + base));
-    b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-  } else {
+  const uint64_t w_first = w_begin + (uint64_t)blockIdx.x * (256 * PACK_WORDS_PER_THREAD) + threadIdx.x;
+#pragma unroll 2
+  for (int r = 0; r < PACK_WORDS_PER_THREAD; r++) {
+    const uint64_t w = w_first + (uint64_t)r * 256;
+    if (w >= w_end) return;
+    const uint64_t base = w * 16;
+    uint32_t b[4];
+    if (base + 16 <= n) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + base));
+      b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      uint32_t x = 0;
+      for (int j = 0; j < 4; j++) {
+        uint32_t x = 0;
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        const uint64_t i = base + 4 * j + r;
-        x |= (uint32_t)((i < n) ? text[i] : (uint8_t)eos_byte) << (8 * r);
+        for (int q = 0; q < 4; q++) {
+          const uint64_t i = base + 4 * j + q;
+          x |= (uint32_t)((i < n) ? text[i] : (uint8_t)eos_byte) << (8 * q);
+        }
+        b[j] = x;
       }
-      b[j] = x;
     }
-  }
-  uint32_t codes = 0, flags = 0;
+    uint32_t codes = 0, flags = 0;
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const uint32_t e = s_lin[(b[i >> 2] >> (8 * (i & 3))) & 0xffu];
-    codes |= (e & 3u) << (2 * i);
-    flags |= ((e >> 2) & 3u) << (2 * i);
+    for (int i = 0; i < 16; i++) {
+      const uint32_t e = s_lin[(b[i >> 2] >> (8 * (i & 3))) & 0xffu];
+      codes |= (e & 3u) << (2 * i);
+      flags |= ((e >> 2) & 3u) << (2 * i);
+    }
+    if (flags) {
+      const uint32_t bad = flags & 0x55555555u;
+      const uint32_t noise = ((uint32_t)w * 0x9E3779B1u) ^ ((uint32_t)w >> 7) * 0x85EBCA6Bu;
+      codes = (codes & ~(bad * 3u)) | (noise & (bad * 3u));
+    }
+    // a position past the end of the stream is an end-of-sequence character
+    pk[w] = make_uint2(codes, flags);
   }
-  // a position past the end of the stream is an end-of-sequence character
-  pk[w] = make_uint2(codes, flags);
 }
 
 }  // namespace pm
