@@ -182,7 +182,7 @@ def config_dict(args, shard_bases):
                                                            "-k" if INDELS else "-K", K),
             "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
             "index": "filter_bitvec (reference auto choice for this workload)",
-            "l2": "inputs larger than L2 (%.1f GB stream + planes per pass)" % (shard_bases / 1e9),
+            "l2": "inputs larger than L2 (%.1f GB stream + %.2f GB packed text per pass)" % (shard_bases / 1e9, shard_bases / 2e9),
             "partition": "one shard per GPU, cut at sequence boundaries"}
 
 
@@ -383,21 +383,40 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        n_planes = sc.stats().get('n_planes', 5) if False else (5 if not args.iupac else 16)
-        alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch
-        hbm_achieved = alg_bytes / (mean_scan_ms * 1e-3) / 1e9
+        st_last = sc.stats()
+        on_index = st_last["scan_path"] == pkg.PM_SCAN_INDEX
         cells = float(n + 2) * len(pats) * (K + 1)
-        # dram__bytes_read+write of one scan launch, from the ncu capture in profiles/README.md
-        # (268 Mbp: 567.6 MB with 4 pattern chunks), scaled to this launch's bases
-        traffic = None if args.indels else 2.115 * (n + 2)
+        if on_index:
+            # pair_scan_kernel reads the packed text once: one uint2 (codes, flags) per 16 characters
+            alg_bytes = (n + 2) * 0.5
+            # dram__bytes_read+write of one launch over 1.0e9 bases: 500.96 + 5.93 MB
+            # (ncu --set full, profiles/README.md, prof_pair_r1), scaled to this launch's bases
+            traffic = None if args.indels else 0.5069 * (n + 2)
+            kname = "pair_scan_kernel<%s>" % ("true" if args.indels and K else "false")
+            if args.indels and K:
+                kname += " + index_verify_kernel<%d>" % K
+            tsrc = "ncu --set full capture prof_pair_r1 (profiles/README.md), bytes per base x bases"
+        else:
+            n_planes = 5 if not args.iupac else 16
+            alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch
+            # (268 Mbp: 567.6 MB with 4 pattern chunks), scaled to this launch's bases
+            traffic = None if args.indels else 2.115 * (n + 2)
+            kname = ("hamming_scan_kernel<%d>" % K) if not args.indels else ("edit_seed_kernel<%d> + edit_verify_kernel<%d>" % (K, K))
+            tsrc = "ncu --set full capture prof_hamming_r1b (profiles/README.md), bytes per base x bases"
+        hbm_achieved = alg_bytes / (mean_scan_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": hbm_achieved / hbm_peak, "traffic": traffic,
-                "traffic_source": "ncu --set full capture profiles/README.md (r1b), bytes per base x bases",
+                "traffic_source": tsrc,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "kernel": ("hamming_scan_kernel<%d>" % K) if not args.indels else ("edit_seed_kernel<%d> + edit_verify_kernel<%d>" % (K, K)),
+                "kernel": kname,
                 "kernel_ms": mean_scan_ms,
-                "note": "the scan is integer-pipe bound, not HBM bound: see int_pipe",
-                "cell_updates_per_s": cells / (mean_scan_ms * 1e-3)}
+                "algorithmic_bytes_per_base": alg_bytes / (n + 2),
+                "note": "the scan is integer-pipe bound, not HBM bound (north star: the slower of the two): see int_pipe",
+                "cell_updates_per_s": cells / (mean_scan_ms * 1e-3),
+                "scan_path": "index" if on_index else "planes"}
+        if on_index:
+            roof["index"] = {"piece_len": st_last["index_q"], "pieces": st_last["index_pieces"],
+                             "distances": st_last["index_nd"], "entries": st_last["index_entries"]}
         try:
             ip = pkg.int_pipe_report(sc, mean_scan_ms, local_rank)
             roof["int_pipe"] = ip

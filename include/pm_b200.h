@@ -67,8 +67,8 @@ typedef struct pm_options {
 
 /* Which device scan produces the candidates (the hit list is the same):
  *   PLANES  bit-plane kernels (pm_scan.cuh): any alphabet, IUPAC, patterns <= 64
- *   INDEX   q-gram index kernels (pm_index.cuh): <= 4 pattern symbols, no text
- *           byte matching two of them, patterns <= 32
+ *   INDEX   pair-seed index kernels (pm_index.cuh): text bytes in <= 4 match
+ *           classes, patterns <= 32, pieces of >= 4 characters
  *   AUTO    INDEX when applicable, else PLANES                                 */
 #define PM_SCAN_AUTO 0
 #define PM_SCAN_PLANES 1
@@ -187,10 +187,15 @@ typedef struct pm_stats {
   uint64_t n_bogus;
   uint64_t kernel_launches; /* kernels of this library launched by the call    */
   uint64_t scan_items;      /* (tile, pattern-chunk) blocks of the scan kernel */
-  uint64_t scan_warp_steps; /* (warp, pattern character) steps the dense scan
-                               executed: each is 8 words x 32 positions        */
+  uint64_t scan_warp_steps; /* PLANES: (warp, pattern character) steps the dense
+                               scan executed, each 8 words x 32 positions;
+                               INDEX: level-1 survivor records sent to level 2 */
   uint32_t scan_path;       /* PM_SCAN_PLANES or PM_SCAN_INDEX                  */
-  uint32_t index_q;         /* q of the q-gram table (INDEX)                   */
+  uint32_t index_q;         /* INDEX: piece length L of the pair index          */
+  uint32_t index_nd;        /* INDEX: text distances looked up per position     */
+  uint32_t index_pieces;    /* INDEX: pieces per pattern (k + 2)                */
+  uint64_t index_lookups;   /* INDEX: level-1 lookups (positions x distances)   */
+  uint64_t index_entries;   /* INDEX: (pair key, distance, pattern) entries     */
   float pack_ms;            /* device time of the last pack kernel             */
   float scan_ms;            /* device time of the dense scan kernel            */
   float total_ms;           /* device time of the whole call                   */

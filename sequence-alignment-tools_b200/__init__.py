@@ -63,7 +63,9 @@ class Stats(C.Structure):
     _fields_ = [("text_len", C.c_uint64), ("n_patterns", C.c_uint64), ("n_seeds", C.c_uint64),
                 ("n_candidates", C.c_uint64), ("n_chains", C.c_uint64), ("n_hits", C.c_uint64),
                 ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
-                ("scan_warp_steps", C.c_uint64), ("scan_path", C.c_uint32), ("index_q", C.c_uint32), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+                ("scan_warp_steps", C.c_uint64), ("scan_path", C.c_uint32), ("index_q", C.c_uint32),
+                ("index_nd", C.c_uint32), ("index_pieces", C.c_uint32), ("index_lookups", C.c_uint64),
+                ("index_entries", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
@@ -243,15 +245,29 @@ def int_peak(device=0) -> float:
     return v.value
 
 
+# ALU-pipe instructions per level-1 lookup of pair_scan_kernel (SASS of the inner
+# loop: SHF window, LOP3 key, SHF word index, LEA address, SHF.L.W rotate, SHF.L.W
+# collect); the hash multiply is an IMAD on the FMA pipe and the LDS is on the LSU.
+PAIR_ALU_OPS_PER_LOOKUP = 6
+
+
 def int_pipe_report(sc: "Scanner", scan_ms: float, device=0) -> dict:
-    """Integer-pipe roofline of the last dense scan of `sc`: useful logic
-    operations (the counter / AND-chain updates, nothing else) per second
-    against the measured LOP3 peak."""
+    """Integer-pipe roofline of the last scan of `sc`: algorithmic logic
+    operations per second against the measured LOP3 peak.
+      PLANES  counter / AND-chain updates only (one LOP3 per counter bit per word)
+      INDEX   level-1 lookups x PAIR_ALU_OPS_PER_LOOKUP"""
     st = sc.stats()
+    peak = int_peak(device)
+    if st["scan_path"] == PM_SCAN_INDEX:
+        useful = st["index_lookups"] * PAIR_ALU_OPS_PER_LOOKUP
+        ach = useful / (scan_ms * 1e-3) / 1e12
+        return {"unit": "Tlop/s", "achieved": ach, "peak": peak, "frac": ach / peak if peak else None,
+                "useful_lops_per_launch": useful, "lookups": st["index_lookups"],
+                "alu_ops_per_lookup": PAIR_ALU_OPS_PER_LOOKUP, "level2_records": st["scan_warp_steps"],
+                "peak_source": "pm_bench_int_peak (LOP3 microbenchmark, same run)"}
     # LOP3 per word per character: one per counter bit (pm_scan.cuh Counter<K>), one AND for seeds
     levels = {0: 1, 1: 2, 2: 2, 3: 3}[sc.k] if (not sc.indels or sc.k == 0) else 1
     useful = st["scan_warp_steps"] * 8 * 32 * levels
-    peak = int_peak(device)
     ach = useful / (scan_ms * 1e-3) / 1e12
     return {"unit": "Tlop/s", "achieved": ach, "peak": peak, "frac": ach / peak if peak else None,
             "useful_lops_per_launch": useful, "warp_steps": st["scan_warp_steps"],

@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -169,6 +170,7 @@ struct pm_ctx {
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
   double idx_seed_rate = 0;  // same for the pair index (pair occurrences)
+  uint64_t idx_entries = 0;
   // q-gram index path (pm_index.cuh)
   int scan_path = PM_SCAN_AUTO;  // requested
   bool use_index = false;        // resolved in pm_init
@@ -371,6 +373,9 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   IndexArgs ia;
   memset(&ia, 0, sizeof ia);
   void (*ikern)(const IndexArgs) = edit ? pair_scan_kernel<true> : pair_scan_kernel<false>;
+  if (c->use_index && !edit) {
+    if (PairKernel sk = pair_sub_kernel((int)c->idx_proto.L, (int)c->idx_proto.nd)) ikern = sk;
+  }
   void (*ivkern)(const IndexArgs) =
       K <= 1 ? index_verify_kernel<1> : (K == 2 ? index_verify_kernel<2> : index_verify_kernel<3>);
   size_t ismem = 0;
@@ -391,7 +396,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     ia.lo = lo;
     ia.hi = hi;
     ia.k = (uint32_t)K;
-    ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * PAIR_QCAP * 8;
+    ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * 2 * PAIR_QCAP * 8;
     PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
   }
   void (*kern)(const ScanArgs) = nullptr;
@@ -430,7 +435,9 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   }
   // q-gram END positions the index path has to visit: window start in [p-31, p]
   const int64_t ip_lo = q_lo, ip_hi = std::min<int64_t>((int64_t)c->n, q_hi + 32);
+  uint64_t idx_lookups = 0;
   for (int attempt = 0; attempt < 4; attempt++) {
+    idx_lookups = 0;
     ia.out = c->d_keys.as<unsigned long long>();
     ia.cap = cap;
     ia.seeds = c->d_seeds.as<unsigned long long>();
@@ -472,6 +479,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
             const unsigned iblocks = (unsigned)std::max<uint64_t>(
                 1, std::min<uint64_t>((uint64_t)n_sm, (warp_chunks + PAIR_WARPS - 1) / PAIR_WARPS));
             ikern<<<iblocks, PAIR_THREADS, ismem, c->stream>>>(ia);
+            idx_lookups += span * ia.nd;
             PM_CUDA(cudaGetLastError());
             c->stats.kernel_launches++;
             if (edit) {
@@ -504,6 +512,10 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     c->stats.scan_items = (uint64_t)nt * chunks;
     c->stats.scan_path = c->use_index ? PM_SCAN_INDEX : PM_SCAN_PLANES;
     c->stats.index_q = (uint32_t)c->idx_q;
+    c->stats.index_nd = c->use_index ? c->idx_proto.nd : 0;
+    c->stats.index_pieces = c->use_index ? (uint32_t)(K + 2) : 0;
+    c->stats.index_lookups = idx_lookups;
+    c->stats.index_entries = c->use_index ? c->idx_entries : 0;
     PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 8 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
@@ -1152,6 +1164,7 @@ int pm_init(pm_ctx *c) {
       for (size_t x = 0; x < ents.size(); x++) sorted[fill[hs[x]]++] = ents[x];
       // expected seeds per base on uniform ACGT text (edit mode batches its seed list by this)
       c->idx_seed_rate = (double)ents.size() / std::pow(4.0, 2.0 * L);
+      c->idx_entries = ents.size();
       // per-code accept masks (bit 2j) and Shift-And masks (bit j)
       std::vector<unsigned long long> pacc((ns + 1) * 4, 0);
       std::vector<uint32_t> um4((ns + 1) * 4, 0);

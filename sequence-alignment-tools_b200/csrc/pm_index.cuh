@@ -18,7 +18,8 @@
 //            bit = 31 - (idx & 31).  One LDS per (position, distance).
 //   level 2  survivors go to a per-warp queue and are resolved 32 at a time
 //            against the exact table in L2: bucket[hash2(key,d)] -> entries
-//            (key, slot << 10 | d_index << 5 | piece offset).
+//            (key, slot << 10 | d_index << 5 | piece offset); matches go to a
+//            second queue and are verified 32 at a time.
 //   verify   substitutions: XOR-free popcount on the packed window against the
 //            pattern's per-code accept masks (IUPAC pattern symbols are a mask
 //            with several codes set); edits: the reference's own recurrence
@@ -46,7 +47,6 @@ namespace pm {
 
 constexpr int PAIR_THREADS = 1024;            // one CTA per SM: the bitmap fills its shared memory
 constexpr int PAIR_WARPS = PAIR_THREADS / 32;
-constexpr int PAIR_QCAP = 128;                // per-warp queue of level-1 survivors
 constexpr int PAIR_MAX_ND = 32;
 constexpr int PAIR_LOG_WORDS = 15;            // 2^15 words = 128 KB = 2^20 bits
 constexpr int PAIR_LMAX = 8;
@@ -81,7 +81,7 @@ struct IndexArgs {
   // edit mode: seeds instead of candidates
   unsigned long long *seeds, *seed_n, *seed_overflow, *seed_count;
   uint64_t seed_cap;
-  unsigned long long *work_count;  // level-1 survivors (queue entries)
+  unsigned long long *work_count;  // level-1 survivor records (word, distance) sent to stage A
 };
 
 // 16-character words of the packed text.  Characters past the end read as end
@@ -137,63 +137,86 @@ __device__ __forceinline__ void pair_verify_window(const IndexArgs &a, uint32_t 
   if (__popcll(mis) <= (int)a.k && (flags & ~M5 & lenmask) == 0) index_emit(a, slot, s + m);
 }
 
-// Resolve one level-1 survivor (position p, distance index di) against the exact
-// table.  COLLECTIVE: called by all 32 lanes (valid = lane holds an entry); seeds are
-// appended with one global atomic per round.  Otherwise: one lane on its own.
-template <bool EDIT, bool COLLECTIVE>
-__device__ __forceinline__ void pair_resolve(const IndexArgs &a, bool valid, unsigned long long e,
-                                             uint32_t lane) {
-  const int64_t p = (int64_t)(e >> 6);
-  const uint32_t di = (uint32_t)(e & 63u);
+// Level 2 and verification run as two warp-wide stages fed from per-warp queues in
+// shared memory, so that the rare work is done with (nearly) all 32 lanes busy:
+//   stage A  one record per lane = (packed word, distance index, 16-bit mask of the
+//            positions of that word whose level-1 bit was set): recompute the pair
+//            key of each set position, walk its bucket of the exact table;
+//   stage B  substitutions only: one (window start, slot) per lane, mismatch count.
+// Both queues belong to one warp and are only touched by warp-collective code, so
+// their fill counts live in (warp-uniform) registers and there are no atomics.
+constexpr int PAIR_QCAP = 64;  // entries per warp and queue: < 32 before a push of <= 32
+
+struct PairQueues {
+  unsigned long long *qa, *qb;  // this warp's queues
+  uint32_t na, nb;              // fill counts, warp-uniform
+};
+
+template <bool EDIT>
+__device__ __forceinline__ void pair_stage_b(const IndexArgs &a, bool valid, unsigned long long rec) {
+  if (EDIT || !valid) return;
+  pair_verify_window(a, (uint32_t)(rec & 0x3fffffu), (int64_t)(rec >> 22) - SEED_BIAS);
+}
+
+template <bool EDIT>
+__device__ __forceinline__ void pair_stage_a(const IndexArgs &a, PairQueues &q, bool valid,
+                                             unsigned long long rec, uint32_t lane) {
+  const int64_t w = (int64_t)(rec >> 21);
+  const uint32_t di = (uint32_t)(rec >> 16) & 31u;
+  uint32_t hm = valid ? (uint32_t)(rec & 0xffffu) : 0u;
   const uint32_t L2 = 2u * a.L;
-  const uint64_t maskL = (1ULL << L2) - 1ULL;
+  const uint32_t maskL = (1u << L2) - 1u;
+  const uint32_t d2 = 2u * a.dist[valid ? di : 0u];
+  uint32_t c0 = 0, c1 = 0, c2 = 0;
+  if (valid) { c0 = pk_codes(a, w); c1 = pk_codes(a, w + 1); c2 = pk_codes(a, w + 2); }
   uint32_t e0 = 0, e1 = 0, key = 0;
-  if (valid) {
-    uint64_t codes, flags;
-    pk_window(a, p, codes, flags);
-    const uint32_t d2 = 2u * a.dist[di];
-    key = (uint32_t)(codes & maskL) | ((uint32_t)((codes >> d2) & maskL) << L2);
-    if (((flags & maskL) | ((flags >> d2) & maskL)) == 0) {  // a flagged character matches nothing
+  int64_t p = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (;;) {
+    if (!__any_sync(0xffffffffu, (hm != 0u) || (e0 < e1))) break;
+    if (e0 >= e1 && hm) {  // next set position of the word
+      const int b = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const uint32_t i2 = 2u * (uint32_t)(15 - b);
+      const uint32_t v0 = __funnelshift_r(c0, c1, i2), v1 = __funnelshift_r(c1, c2, i2), v2 = c2 >> i2;
+      const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
+      key = (v0 & maskL) | ((hi & maskL) << L2);
       const uint32_t h = pair_hash2(key, di, a.log_buckets);
       e0 = __ldg(a.bucket + h);
       e1 = __ldg(a.bucket + h + 1);
-    }
-  }
-  for (;;) {
-    const bool more = e0 < e1;
-    if (COLLECTIVE) {
-      if (!__any_sync(0xffffffffu, more)) break;
-    } else if (!more) {
-      break;
+      p = (w << 4) + (15 - b);
     }
     bool found = false;
     uint32_t meta = 0;
-    if (more) {
+    if (e0 < e1) {
       const uint2 ent = __ldg(a.entries + e0);
       ++e0;
       meta = ent.y;
       found = (ent.x == key) && (((meta >> 5) & 31u) == di);
     }
+    const uint32_t bal = __ballot_sync(0xffffffffu, found);
+    if (bal == 0u) continue;
     const uint32_t slot = meta >> 10;
-    const int64_t s = p - (int64_t)(meta & 31u);  // nominal window start
-    if (!EDIT) {
-      if (found) pair_verify_window(a, slot, s);
+    const int64_t s = p - (int64_t)(meta & 31u) + SEED_BIAS;  // nominal window start, biased
+    const uint32_t rank = __popc(bal & lt), cnt = __popc(bal);
+    if (EDIT) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.seed_n, (unsigned long long)cnt);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (found) {
+        const unsigned long long at = base + rank;
+        if (at < a.seed_cap) a.seeds[at] = ((unsigned long long)slot << 40) | (unsigned long long)s;
+        else *a.seed_overflow = 1ULL;
+      }
     } else {
-      const unsigned long long sd = ((unsigned long long)slot << 40) | (unsigned long long)(s + SEED_BIAS);
-      if (COLLECTIVE) {
-        const uint32_t bal = __ballot_sync(0xffffffffu, found);
-        if (bal) {
-          unsigned long long base = 0;
-          if (lane == 0) base = atomicAdd(a.seed_n, (unsigned long long)__popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (found) {
-            const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
-            if (at < a.seed_cap) a.seeds[at] = sd; else *a.seed_overflow = 1ULL;
-          }
-        }
-      } else if (found) {
-        const unsigned long long at = atomicAdd(a.seed_n, 1ULL);
-        if (at < a.seed_cap) a.seeds[at] = sd; else *a.seed_overflow = 1ULL;
+      if (found) q.qb[q.nb + rank] = ((unsigned long long)s << 22) | slot;
+      q.nb += cnt;
+      if (q.nb >= 32u) {
+        __syncwarp();
+        const unsigned long long r = q.qb[q.nb - 32u + lane];
+        __syncwarp();
+        q.nb -= 32u;
+        pair_stage_b<EDIT>(a, true, r);
       }
     }
   }
@@ -206,40 +229,28 @@ template <bool EDIT>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  __shared__ uint32_t s_qn[PAIR_WARPS];
   const uint32_t n_words = 1u << a.log_words;
   uint32_t *s_bitmap = s_mem;
   unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
     reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
-  if (lane == 0) s_qn[warp] = 0;
   __syncthreads();
-  unsigned long long *queue = s_queue + warp * PAIR_QCAP;
+  PairQueues q;
+  q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
+  q.qb = q.qa + PAIR_QCAP;
+  q.na = q.nb = 0;
 
   const uint32_t wsh = 32u - a.log_words;
   const uint32_t L2 = 2u * a.L;
   const uint32_t maskL = (1u << L2) - 1u;       // L <= 8
   const uint32_t maskHi = maskL << L2;
   const uint32_t mult = a.mult;
+  const uint32_t lt = (1u << lane) - 1u;
   const int64_t w_begin = a.p_begin >> 4;
   const int64_t w_end = (a.p_end + 15) >> 4;
   const int64_t n_chunks = (w_end - w_begin + 31) >> 5;
   unsigned long long n_queued = 0;
-
-  auto drain = [&](bool final) {
-    for (;;) {
-      __syncwarp();
-      const uint32_t qn = min(s_qn[warp], (uint32_t)PAIR_QCAP);
-      if (qn == 0 || (!final && qn < 32u)) break;
-      const uint32_t take = min(qn, 32u);
-      const bool valid = lane < take;
-      const unsigned long long e = valid ? queue[qn - take + lane] : 0ULL;
-      __syncwarp();
-      if (lane == 0) s_qn[warp] = qn - take;
-      pair_resolve<EDIT, true>(a, valid, e, lane);
-    }
-  };
 
   for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
     const int64_t wc0 = w_begin + (c << 5);
@@ -252,7 +263,11 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
     uint32_t c2 = __shfl_down_sync(0xffffffffu, mine, 2);
     if (lane == 31) { c1 = x0; c2 = x1; }
     if (lane == 30) c2 = x0;
+    // positions of this word inside [p_begin, p_end): position i <-> bit 15-i
     const int64_t base = w << 4;
+    uint32_t vm = 0xffffu;
+    if (base < a.p_begin) vm &= (a.p_begin - base >= 16) ? 0u : (0xffffu >> (uint32_t)(a.p_begin - base));
+    if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
 
     uint32_t av[16];
 #pragma unroll
@@ -273,25 +288,169 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
         const uint32_t wrd = s_bitmap[idx >> wsh];
         hm = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);  // bit 31-(idx&31) -> bit 0 of hm
       }
-      // position i of the word sits in bit 15-i of hm
-      while (hm) {
-        const int b = __ffs(hm) - 1;
-        hm &= hm - 1;
-        const int64_t p = base + (15 - b);
-        if (p < a.p_begin || p >= a.p_end) continue;
-        const unsigned long long e = ((unsigned long long)p << 6) | di;
-        n_queued++;
-        const uint32_t at = atomicAdd(&s_qn[warp], 1u);
-        if (at < (uint32_t)PAIR_QCAP) queue[at] = e;
-        else pair_resolve<EDIT, false>(a, true, e, lane);  // queue full: resolve on the spot
+      hm &= vm;
+      const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);
+      if (bal) {
+        if (hm) q.qa[q.na + __popc(bal & lt)] = ((unsigned long long)w << 21) | (di << 16) | hm;
+        q.na += __popc(bal);
+        n_queued += __popc(bal);
+        if (q.na >= 32u) {
+          __syncwarp();
+          const unsigned long long rec = q.qa[q.na - 32u + lane];
+          __syncwarp();
+          q.na -= 32u;
+          pair_stage_a<EDIT>(a, q, true, rec, lane);
+        }
       }
     }
-    drain(false);
   }
-  drain(true);
-#pragma unroll
-  for (int d = 16; d >= 1; d >>= 1) n_queued += __shfl_xor_sync(0xffffffffu, n_queued, d);
+  // leftovers
+  __syncwarp();
+  {
+    const bool valid = lane < q.na;
+    const unsigned long long rec = valid ? q.qa[lane] : 0ULL;
+    __syncwarp();
+    q.na = 0;
+    pair_stage_a<EDIT>(a, q, valid, rec, lane);
+  }
+  __syncwarp();
+  if (!EDIT) {
+    const bool valid = lane < q.nb;
+    const unsigned long long rec = valid ? q.qb[lane] : 0ULL;
+    pair_stage_b<EDIT>(a, valid, rec);
+  }
   if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_queued);
+}
+
+// Substitution scan with compile-time piece length and distance count: the
+// distances are L, 2L, .., ND*L, so the shifted windows G[t] = text >> 2t are
+// shared between the lookups of different positions (position i at distance
+// (j+1)L uses G[i + jL]): 16 + (ND-1)L funnel shifts per word instead of 16*ND.
+// (Moving the word-index shift and the address LEA to the FMA pipe as IMAD.HI / IMAD
+// was measured and is not worth it: the kernel sits at ~80 % of the shared-memory
+// wavefront rate and ~85 % of the ALU rate at the same time, see DESIGN.md.)
+template <int L, int ND>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  const uint32_t n_words = 1u << a.log_words;
+  uint32_t *s_bitmap = s_mem;
+  unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
+    reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
+  __syncthreads();
+  PairQueues q;
+  q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
+  q.qb = q.qa + PAIR_QCAP;
+  q.na = q.nb = 0;
+
+  const uint32_t wsh = 32u - a.log_words;
+  constexpr uint32_t maskL = (1u << (2 * L)) - 1u;
+  constexpr uint32_t mask2L = (L >= 8) ? 0xffffffffu : ((1u << (4 * L)) - 1u);
+  constexpr uint32_t maskHi = mask2L & ~maskL;
+  constexpr int NG = 16 + (ND - 1) * L;
+  const uint32_t mult = a.mult;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int64_t w_begin = a.p_begin >> 4;
+  const int64_t w_end = (a.p_end + 15) >> 4;
+  const int64_t n_chunks = (w_end - w_begin + 31) >> 5;
+  unsigned long long n_queued = 0;
+  uint32_t salt[ND];
+#pragma unroll
+  for (int j = 0; j < ND; j++) salt[j] = a.salt[j];
+
+  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+    const int64_t wc0 = w_begin + (c << 5);
+    const int64_t w = wc0 + lane;
+    const uint32_t mine = pk_codes(a, w);
+    const uint32_t extra = (lane < 2) ? pk_codes(a, wc0 + 32 + lane) : 0u;
+    const uint32_t x0 = __shfl_sync(0xffffffffu, extra, 0), x1 = __shfl_sync(0xffffffffu, extra, 1);
+    uint32_t cw[4];
+    cw[0] = mine;
+    cw[1] = __shfl_down_sync(0xffffffffu, mine, 1);
+    cw[2] = __shfl_down_sync(0xffffffffu, mine, 2);
+    cw[3] = 0u;
+    if (lane == 31) { cw[1] = x0; cw[2] = x1; }
+    if (lane == 30) cw[2] = x0;
+    const int64_t base = w << 4;
+    uint32_t vm = 0xffffu;
+    if (base < a.p_begin) vm &= (a.p_begin - base >= 16) ? 0u : (0xffffu >> (uint32_t)(a.p_begin - base));
+    if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
+
+    uint32_t G[NG];
+#pragma unroll
+    for (int t = 0; t < NG; t++) G[t] = __funnelshift_r(cw[t >> 4], cw[(t >> 4) + 1], 2 * (t & 15));
+    uint32_t hm[ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++) hm[j] = 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t av = G[i] & maskL;
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        const uint32_t key = (j == 0) ? (G[i] & mask2L) : ((G[i + j * L] & maskHi) | av);
+        const uint32_t idx = key * mult + salt[j];
+        const uint32_t wrd = s_bitmap[idx >> wsh];
+        hm[j] = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm[j], 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ND; j++) {
+      const uint32_t h = hm[j] & vm;
+      const uint32_t bal = __ballot_sync(0xffffffffu, h != 0u);
+      if (bal) {
+        if (h) q.qa[q.na + __popc(bal & lt)] = ((unsigned long long)w << 21) | ((uint32_t)j << 16) | h;
+        q.na += __popc(bal);
+        n_queued += __popc(bal);
+        if (q.na >= 32u) {
+          __syncwarp();
+          const unsigned long long rec = q.qa[q.na - 32u + lane];
+          __syncwarp();
+          q.na -= 32u;
+          pair_stage_a<false>(a, q, true, rec, lane);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  {
+    const bool valid = lane < q.na;
+    const unsigned long long rec = valid ? q.qa[lane] : 0ULL;
+    __syncwarp();
+    q.na = 0;
+    pair_stage_a<false>(a, q, valid, rec, lane);
+  }
+  __syncwarp();
+  {
+    const bool valid = lane < q.nb;
+    const unsigned long long rec = valid ? q.qb[lane] : 0ULL;
+    pair_stage_b<false>(a, valid, rec);
+  }
+  if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_queued);
+}
+
+typedef void (*PairKernel)(const IndexArgs);
+template <int L>
+inline PairKernel pair_sub_kernel_nd(int nd) {
+  switch (nd) {
+    case 1: return pair_scan_sub_kernel<L, 1>;
+    case 2: return pair_scan_sub_kernel<L, 2>;
+    case 3: return pair_scan_sub_kernel<L, 3>;
+    case 4: return pair_scan_sub_kernel<L, 4>;
+  }
+  return nullptr;
+}
+// specialised substitution kernel for (L, nd), or nullptr (the generic kernel serves)
+inline PairKernel pair_sub_kernel(int L, int nd) {
+  switch (L) {
+    case 4: return pair_sub_kernel_nd<4>(nd);
+    case 5: return pair_sub_kernel_nd<5>(nd);
+    case 6: return pair_sub_kernel_nd<6>(nd);
+    case 7: return pair_sub_kernel_nd<7>(nd);
+    case 8: return pair_sub_kernel_nd<8>(nd);
+  }
+  return nullptr;
 }
 
 // Edit verifier on the packed text: the recurrence of verify_seed (pm_scan.cuh)
