@@ -196,6 +196,9 @@ typedef struct pm_stats {
   uint32_t index_pieces;    /* INDEX: pieces per pattern (k + 2)                */
   uint64_t index_lookups;   /* INDEX: level-1 lookups (positions x distances)   */
   uint64_t index_entries;   /* INDEX: (pair key, distance, pattern) entries     */
+  uint64_t n_ambiguous;     /* INDEX: text characters re-examined on the raw text
+                               (they match pattern symbols without being one of
+                               the four text codes, e.g. a text 'R' under -w)   */
   float pack_ms;            /* device time of the last pack kernel             */
   float scan_ms;            /* device time of the dense scan kernel            */
   float total_ms;           /* device time of the whole call                   */

@@ -65,7 +65,7 @@ class Stats(C.Structure):
                 ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
                 ("scan_warp_steps", C.c_uint64), ("scan_path", C.c_uint32), ("index_q", C.c_uint32),
                 ("index_nd", C.c_uint32), ("index_pieces", C.c_uint32), ("index_lookups", C.c_uint64),
-                ("index_entries", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+                ("index_entries", C.c_uint64), ("n_ambiguous", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),

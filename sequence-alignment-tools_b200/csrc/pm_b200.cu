@@ -133,6 +133,8 @@ struct Pattern {
 constexpr size_t kStageBytes = 64u << 20;       // pinned staging buffer (x2)
 constexpr uint64_t kWsBudget = 2ull << 30;      // alignment workspace per batch
 constexpr int64_t kRightGuard = 1 << 16;
+constexpr uint64_t kAmbCap = 1u << 20;          // ambiguous text characters the index path re-examines
+constexpr int kFallbackToPlanes = -100;        // internal: too many of them, rescan with the bit-plane kernels
 
 }  // namespace
 
@@ -173,12 +175,15 @@ struct pm_ctx {
   uint64_t idx_entries = 0;
   // q-gram index path (pm_index.cuh)
   int scan_path = PM_SCAN_AUTO;  // requested
-  bool use_index = false;        // resolved in pm_init
+  bool use_index = false;        // the loaded text is packed for / scanned by the pair index
+  bool index_ok = false;         // resolved in pm_init: the patterns can use the pair index
+  bool idx_has_amb = false;      // some text byte would be ambiguous (wildcards): pack lists them
+  DevBuf d_amb;
   int idx_q = 0;                 // piece length L of the pair index
   DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap;
   pm::IndexArgs idx_proto;       // level-1 / level-2 parameters filled by pm_init
-  unsigned long long *d_counters = nullptr;  // [8]
-  unsigned long long *h_counters = nullptr;  // pinned [8]
+  unsigned long long *d_counters = nullptr;  // [16]; [8] = ambiguous text characters of the packed text
+  unsigned long long *h_counters = nullptr;  // pinned [16]
   void *h_out = nullptr;                     // pinned result buffer
   size_t h_out_cap = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -508,6 +513,34 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
       if (!c->chunks.empty() && c->chunks.back().ev)
         PM_CUDA(cudaStreamWaitEvent(c->stream, c->chunks.back().ev, 0));
     }
+    if (c->use_index && c->idx_has_amb) {
+      // ambiguous text characters: their number is known once every chunk is packed
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 8, c->d_counters + 8, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      const uint64_t n_amb = c->h_counters[8];
+      c->stats.n_ambiguous = n_amb;
+      if (n_amb > kAmbCap) return kFallbackToPlanes;
+      if (n_amb && !edit) {
+        amb_sub_kernel<<<(unsigned)std::min<uint64_t>(n_amb, (uint64_t)n_sm * 16), 256, 0, c->stream>>>(
+            a, c->d_amb.as<unsigned long long>(), n_amb, (uint32_t)K);
+        PM_CUDA(cudaGetLastError());
+        c->stats.kernel_launches++;
+      } else if (n_amb) {
+        // seeds per ambiguous character and slot: (m + 2K) / (2K + 1) + 1 alignment-end windows
+        const uint64_t per_amb = (uint64_t)n_slots * ((uint64_t)(c->max_len + 2 * K) / (2 * K + 1) + 1);
+        const uint64_t batch = std::max<uint64_t>(1, a.seed_cap / std::max<uint64_t>(1, per_amb));
+        for (uint64_t a0 = 0; a0 < n_amb; a0 += batch) {
+          const uint64_t a1 = std::min(n_amb, a0 + batch);
+          PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
+          amb_seed_kernel<<<(unsigned)std::min<uint64_t>(a1 - a0, (uint64_t)n_sm * 16), 256, 0, c->stream>>>(
+              a, c->d_amb.as<unsigned long long>(), a0, a1, K);
+          vkern<<<n_sm * 8, VERIFY_THREADS, 0, c->stream>>>(a);
+          PM_CUDA(cudaGetLastError());
+          c->stats.kernel_launches += 2;
+        }
+      }
+    }
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
     c->stats.scan_items = (uint64_t)nt * chunks;
     c->stats.scan_path = c->use_index ? PM_SCAN_INDEX : PM_SCAN_PLANES;
@@ -602,6 +635,23 @@ int sort_hits(pm_ctx *c, uint64_t n) {
   return PM_OK;
 }
 
+int pack_text(pm_ctx *c);
+
+// run_scan, falling back to the bit-plane kernels when the text holds more ambiguous
+// characters than the index path is willing to re-examine one by one
+int run_scan_any(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
+  int rc = run_scan(c, lo, hi, n_out);
+  if (rc != kFallbackToPlanes) return rc;
+  if (c->scan_path == PM_SCAN_INDEX)
+    return fail(PM_E_UNSUPPORTED, "too many ambiguous text characters for the pair-seed index scan");
+  c->use_index = false;  // until the next pm_set_text_*
+  const uint64_t n_amb = c->stats.n_ambiguous;
+  if ((rc = pack_text(c))) return rc;
+  rc = run_scan(c, lo, hi, n_out);
+  c->stats.n_ambiguous = n_amb;
+  return rc;
+}
+
 int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
   *nhits = 0;
   if (!c->inited) return fail(PM_E_ARG, "pm_find_patterns before pm_init");
@@ -630,7 +680,7 @@ int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
     }
   }
   uint64_t ncand = 0;
-  int rc = run_scan(c, lo, hi, &ncand);
+  int rc = run_scan_any(c, lo, hi, &ncand);
   if (rc) return rc;
   c->stats.n_candidates = ncand;
   if (ncand == 0) goto done;
@@ -774,7 +824,8 @@ int pack_tiles(pm_ctx *c, uint32_t t0, uint32_t t1, cudaStream_t st) {
     const uint64_t w0 = (uint64_t)t0 * (TILE_POS / 16), w1 = (uint64_t)t1 * (TILE_POS / 16);
     const uint64_t per_block = 256ull * PACK_WORDS_PER_THREAD;
     pack_linear_kernel<<<(unsigned)((w1 - w0 + per_block - 1) / per_block), 256, 0, st>>>(
-        c->d_text, c->n, c->d_lin.as<uint8_t>(), c->opt.eos, c->d_pk.as<uint2>(), w0, w1);
+        c->d_text, c->n, c->d_lin.as<uint8_t>(), c->opt.eos, c->d_pk.as<uint2>(), w0, w1,
+        c->d_amb.as<unsigned long long>(), c->d_counters + 8, c->d_amb.p ? kAmbCap : 0);
     PM_CUDA(cudaGetLastError());
     return PM_OK;
   }
@@ -791,7 +842,11 @@ int prepare_planes(pm_ctx *c) {
   c->ev_used = 0;
   c->pack_timed = false;
   if (c->n_tiles == 0) return PM_OK;
-  if (c->use_index) return c->d_pk.ensure((size_t)c->n_tiles * (TILE_POS / 16) * sizeof(uint2));
+  if (c->use_index) {
+    if (c->idx_has_amb)
+      if (int rc = c->d_amb.ensure(kAmbCap * sizeof(unsigned long long))) return rc;
+    return c->d_pk.ensure((size_t)c->n_tiles * (TILE_POS / 16) * sizeof(uint2));
+  }
   return c->d_planes.ensure((size_t)c->n_tiles * (c->n_sym + 1) * TILE_WT * 4);
 }
 
@@ -800,6 +855,7 @@ int pack_text(pm_ctx *c) {
   int rc = prepare_planes(c);
   if (rc || c->n_tiles == 0) return rc;
   PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
+  PM_CUDA(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->stream));
   if ((rc = pack_tiles(c, 0, c->n_tiles, c->stream))) return rc;
   PM_CUDA(cudaEventRecord(c->ev[5], c->stream));
   c->pack_timed = true;
@@ -853,8 +909,8 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   c->opt.text_n = opt->text_n ? 1 : 0;
   c->index = index;
   memset(&c->stats, 0, sizeof c->stats);
-  if (cudaMalloc((void **)&c->d_counters, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMallocHost((void **)&c->h_counters, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
     delete c;
     return fail(PM_E_CUDA, "allocation of counters failed");
   }
@@ -875,7 +931,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
-                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap};
+                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_amb};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1059,6 +1115,7 @@ int pm_init(pm_ctx *c) {
     }
     // every text byte must be one of the codes or match nothing
     std::vector<uint8_t> lin(256, 0);
+    bool has_amb = false;
     for (int b2 = 0; b2 < 256 && ok; b2++) {
       const uint32_t msk = symmask[b2] & symbits;
       uint8_t v = 4;  // matches nothing
@@ -1066,8 +1123,9 @@ int pm_init(pm_ctx *c) {
         int code = -1;
         for (int cc = 0; cc < n_codes; cc++)
           if (code_mask[cc] == msk) { code = cc; break; }
-        if (code < 0) ok = false;  // an ambiguous text byte: bit-plane kernels
-        else v = (uint8_t)code;
+        if (code >= 0) v = (uint8_t)code;
+        else if (wc) { v = 4 | 16; has_amb = true; }  // ambiguous: packed as "bad" and listed
+        else ok = false;
       }
       if (b2 == c->opt.eos) v = 4 | 8;
       lin[b2] = v;
@@ -1132,7 +1190,8 @@ int pm_init(pm_ctx *c) {
     }
     if (c->scan_path == PM_SCAN_INDEX && !ok)
       return fail(PM_E_UNSUPPORTED, "pair-seed index scan not applicable to these patterns / options");
-    c->use_index = ok;
+    c->use_index = c->index_ok = ok;
+    c->idx_has_amb = ok && has_amb;
     c->idx_q = ok ? L : 0;
     if (ok) {
       IndexArgs &ia = c->idx_proto;
@@ -1203,6 +1262,7 @@ int pm_init(pm_ctx *c) {
 }
 
 static int set_text_common(pm_ctx *c, uint64_t n, int64_t offset) {
+  c->use_index = c->index_ok;
   c->n = n;
   c->offset = offset;
   if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
@@ -1219,6 +1279,7 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
   int rc = c->d_text_own.ensure(n + 64);
   if (rc) return rc;
   c->d_text = c->d_text_own.as<uint8_t>();
+  c->use_index = c->index_ok;
   c->n = n;
   c->offset = offset;
   if (!n) return set_text_common(c, n, offset);
@@ -1239,6 +1300,7 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
   if ((rc = prepare_planes(c))) return rc;
   PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
   PM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[4], 0));  // earlier work may still read the buffers
+  PM_CUDA(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->copy_stream));
   if (!pinned)
     for (int i = 0; i < 2; i++)
       if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
@@ -1327,7 +1389,7 @@ int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate
   if (begin < c->offset || lo < 0) lo = 0;
   if (end == std::numeric_limits<int64_t>::max() || hi > (int64_t)c->n + 1) hi = (int64_t)c->n + 1;
   uint64_t n = 0;
-  int rc = run_scan(c, lo, hi, &n);
+  int rc = run_scan_any(c, lo, hi, &n);
   if (rc) return rc;
   c->stats.n_candidates = n;
   if (!n) return PM_OK;

@@ -519,14 +519,20 @@ index_verify_kernel(const __grid_constant__ IndexArgs a) {
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.seed_count) atomicAdd(a.seed_count, count);
 }
 
-// stream bytes -> packed words.  lin[b]: bits 0-1 code, bit 2 bad, bit 3 eos.
+// stream bytes -> packed words.  lin[b]: bits 0-1 code, bit 2 bad, bit 3 eos,
+// bit 4 ambiguous (a text byte that matches pattern symbols but is none of the four
+// codes, e.g. a text 'R' under -w): packed as "bad" (the index kernels then never
+// over-count a match through it) and its position is appended to `amb`, so that
+// the windows around it can be re-examined on the raw text (amb_* kernels).
 // A character that matches no pattern symbol gets a position-dependent code, so
 // that a long run of them (the N blocks of a genome assembly) does not look like
 // a homopolymer to level 1; the flags keep it from ever matching.
 constexpr int PACK_WORDS_PER_THREAD = 8;
 __global__ void __launch_bounds__(256)
 pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ lin,
-                   uint32_t eos_byte, uint2 *__restrict__ pk, uint64_t w_begin, uint64_t w_end) {
+                   uint32_t eos_byte, uint2 *__restrict__ pk, uint64_t w_begin, uint64_t w_end,
+                   unsigned long long *__restrict__ amb, unsigned long long *__restrict__ amb_n,
+                   uint64_t amb_cap) {
   __shared__ uint8_t s_lin[256];
   s_lin[threadIdx.x] = lin[threadIdx.x];
   __syncthreads();
@@ -552,20 +558,76 @@ pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *
         b[j] = x;
       }
     }
-    uint32_t codes = 0, flags = 0;
+    uint32_t codes = 0, flags = 0, ambm = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t e = s_lin[(b[i >> 2] >> (8 * (i & 3))) & 0xffu];
       codes |= (e & 3u) << (2 * i);
       flags |= ((e >> 2) & 3u) << (2 * i);
+      ambm |= (e >> 4) << i;
     }
     if (flags) {
+      while (ambm) {
+        const int i = __ffs(ambm) - 1;
+        ambm &= ambm - 1;
+        const unsigned long long at = atomicAdd(amb_n, 1ULL);
+        if (at < amb_cap) amb[at] = base + (uint64_t)i;
+      }
       const uint32_t bad = flags & 0x55555555u;
       const uint32_t noise = ((uint32_t)w * 0x9E3779B1u) ^ ((uint32_t)w >> 7) * 0x85EBCA6Bu;
       codes = (codes & ~(bad * 3u)) | (noise & (bad * 3u));
     }
     // a position past the end of the stream is an end-of-sequence character
     pk[w] = make_uint2(codes, flags);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Ambiguous text characters (pack_linear_kernel's list): every window / alignment
+// that contains one is decided on the raw text with the general class masks of
+// pm_scan.cuh, for all patterns.  Rare by assumption (a handful in a genome
+// assembly); the host falls back to the bit-plane kernels when the list overflows.
+//
+// substitutions: every window start x-m+1 .. x of every slot
+__global__ void __launch_bounds__(256)
+amb_sub_kernel(const ScanArgs a, const unsigned long long *__restrict__ amb, uint64_t n_amb, uint32_t k) {
+  for (uint64_t ai = blockIdx.x; ai < n_amb; ai += gridDim.x) {
+    const int64_t x = (int64_t)amb[ai];
+    for (uint32_t idx = threadIdx.x; idx < a.n_slots * 32u; idx += blockDim.x) {
+      const uint32_t slot = idx >> 5, o = idx & 31u;
+      const uint32_t m = a.plen[slot] & 0x7fu;
+      if (o >= m) continue;
+      const int64_t s = x - (int64_t)o;
+      if (s < 0 || (uint64_t)(s + m) > a.n) continue;
+      const uint64_t *U = a.umask + (size_t)slot * a.n_cls;
+      uint32_t mis = 0;
+      bool ok = true;
+      for (uint32_t j = 0; j < m; j++) {
+        const uint32_t ch = a.text[s + j];
+        if (ch == a.eos) { ok = false; break; }
+        if (!((__ldg(U + a.cls[ch]) >> j) & 1ull) && ++mis > k) { ok = false; break; }
+      }
+      if (ok) emit_candidate(a, slot, s + m);
+    }
+  }
+}
+
+// edits: seeds for verify_seed covering every alignment end x .. x+m+K-1 of every slot
+__global__ void __launch_bounds__(256)
+amb_seed_kernel(const ScanArgs a, const unsigned long long *__restrict__ amb, uint64_t amb_begin,
+                uint64_t amb_end, int K) {
+  for (uint64_t ai = amb_begin + blockIdx.x; ai < amb_end; ai += gridDim.x) {
+    const int64_t x = (int64_t)amb[ai];
+    for (uint32_t slot = threadIdx.x; slot < a.n_slots; slot += blockDim.x) {
+      const int64_t m = a.plen[slot] & 0x7fu;
+      for (int64_t tc = x + K; tc - K <= x + m + K - 1; tc += 2 * K + 1) {
+        int64_t s_nominal = tc - m + 1;
+        if (s_nominal < 0) s_nominal = 0;
+        const unsigned long long at = atomicAdd(a.seed_n, 1ULL);
+        if (at < a.seed_cap) a.seeds[at] = ((unsigned long long)slot << 40) | (unsigned long long)s_nominal;
+        else *a.seed_overflow = 1ULL;
+      }
+    }
   }
 }
 

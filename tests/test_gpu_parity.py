@@ -25,8 +25,9 @@ def _gpu(built_lib):
 
 @pytest.mark.parametrize("path", ["auto", "planes"])
 def test_golden_records_bit_exact(pkg, golden, path):
-    """auto = q-gram index kernels where they apply (plain ACGT primers), bit-plane
-    kernels otherwise; planes = bit-plane kernels everywhere."""
+    """auto = pair-seed index kernels where they apply (DNA / IUPAC primers whose
+    pieces are long enough), bit-plane kernels otherwise; planes = bit-plane
+    kernels everywhere."""
     sp = pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES
     for case in golden["cases"]:
         st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
@@ -89,6 +90,11 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
     seq[TILE_POS - 30:TILE_POS + 30] = list("A" * 60)
     for i in (5000, 5001, 40000):
         seq[i] = "N"
+    if wc:   # ambiguous text characters, some of them inside planted occurrences
+        for at in seams[::3]:
+            seq[max(0, min(n - 1, at + rng.randint(0, 12)))] = rng.choice("RYKMSWBDHVN")
+        for _ in range(150):
+            seq[rng.randrange(n)] = rng.choice("RYKMSWBDHVN")
     seq = "".join(seq)
     cut = 40123
     fasta = ">a\n%s\n>b\n%s\n" % (seq[:cut], seq[cut:])
@@ -99,8 +105,6 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
     else:
         want = oracle.wm_scan(T, primers, k, indels, wc, False)
     want = sorted({(int(b), int(a)) for a, b, _ in want})
-    if path == "index" and wc:
-        pytest.skip("IUPAC patterns are served by the bit-plane kernels")
     sc = pkg.Scanner(k=k, indels=indels, wildcards=wc,
                      scan_path=pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
     for i, p in enumerate(primers):
@@ -162,6 +166,38 @@ def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     merged = merged[np.lexsort((merged["pattern_id"], merged["first"]))]
     assert len(whole) > 50
     assert merged.tobytes() == whole.tobytes()
+
+
+def test_many_ambiguous_characters_fall_back_to_planes(pkg):
+    """With -w a text 'R' matches the pattern symbols A, G and R: the pair index lists
+    such characters and re-examines their windows; past 2^20 of them it hands the
+    text to the bit-plane kernels.  Both routes must give the same hits."""
+    import casegen
+    rng = random.Random(31)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(6)] + ["ACGTRYACGTACGTNACGTA"]
+    n = 3_000_000
+    g = np.random.default_rng(5)
+    seq = np.frombuffer(b"ACGTRRR", np.uint8)[g.integers(0, 7, n)]
+    for j in range(60):
+        q = casegen.mutate(rng, "".join(c if c in "ACGT" else "A" for c in primers[j % 7]), rng.randint(0, 1), False)
+        at = 1000 + j * 40000
+        seq[at:at + len(q)] = np.frombuffer(q.encode(), np.uint8)
+    T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
+    out = {}
+    for name, sp in (("auto", pkg.PM_SCAN_AUTO), ("planes", pkg.PM_SCAN_PLANES)):
+        sc = pkg.Scanner(k=1, indels=False, wildcards=True, scan_path=sp)
+        for i, p in enumerate(primers):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(T)
+        out[name] = sc.find_patterns()
+        st = sc.stats()
+        assert st["scan_path"] == pkg.PM_SCAN_PLANES
+        if name == "auto":
+            assert st["n_ambiguous"] > (1 << 20)
+        sc.close()
+    assert len(out["planes"]) >= 40
+    assert out["auto"].tobytes() == out["planes"].tobytes()
 
 
 def test_full_size_properties(pkg):
