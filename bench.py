@@ -290,6 +290,13 @@ def main():
         d_stream[at:at + len(p)] = torch.tensor(list(p), dtype=torch.uint8, device=dev)
     h_stream = torch.empty(n + 2, dtype=torch.uint8, pin_memory=True)
     h_stream.copy_(d_stream)
+    # the same database as compress_seq -z would store it (.tbz table + .sqz bit stream,
+    # 3 bits per character for A C G T eos): what primer_match opens when the files exist
+    sqz_table = b"ACGT\n"
+    d_sqz = pkg.sqz_encode_torch(d_stream, sqz_table)
+    h_sqz = torch.empty(d_sqz.numel(), dtype=torch.uint8, pin_memory=True)
+    h_sqz.copy_(d_sqz)
+    del d_sqz
     torch.cuda.synchronize()
 
     sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank)
@@ -310,8 +317,11 @@ def main():
         scan_ms.append(st["scan_ms"])
         return nh, st
 
-    def step_e2e():
-        sc.set_text(h_stream)                      # H2D from pinned memory + pack
+    def step_e2e(compressed):
+        if compressed:
+            sc.set_text_sqz(h_sqz, sqz_table, n + 2)   # H2D of the .sqz bytes + unpack + pack
+        else:
+            sc.set_text(h_stream)                  # H2D of the stream from pinned memory + pack
         hits = sc.find_patterns()                  # ... + D2H of the hit list
         st = sc.stats()
         launches["n"] += 1 + st["kernel_launches"]
@@ -351,30 +361,36 @@ def main():
     n_launch = launches["n"]
     mean_scan_ms = sum(scan_ms) / max(1, len(scan_ms))
 
-    # end-to-end leg
-    for _ in range(min(args.warmup, 2)):
-        step_e2e()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    d2h = 0
-    for _ in range(args.steps):
-        hits, st = step_e2e()
-        d2h = hits.nbytes + 64
-        gather_counts(len(hits))
-    e3.record(stream)
-    barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    # end-to-end legs: host buffers in, hit list out.  "e2e" reads the database in the
+    # reference's compressed form, "e2e_stream" as the plain character stream.
+    e2e_ms, d2h, hit_sets = {}, 0, {}
+    for compressed in (True, False):
+        for _ in range(min(args.warmup, 2)):
+            step_e2e(compressed)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record(stream)
+        for _ in range(args.steps):
+            hits, st = step_e2e(compressed)
+            d2h = hits.nbytes + 64
+            gather_counts(len(hits))
+        e3.record(stream)
+        barrier()
+        e2e_ms[compressed] = e2.elapsed_time(e3)
+        hit_sets[compressed] = hits.tobytes()
+    assert hit_sets[True] == hit_sets[False], "compressed and plain input disagree"
+    ms_e2e, ms_e2e_stream = e2e_ms[True], e2e_ms[False]
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, mean_scan_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_e2e, mean_scan_ms, ms_e2e_stream], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, mean_scan_ms = (float(x) for x in t.tolist())
+        ms, ms_e2e, mean_scan_ms, ms_e2e_stream = (float(x) for x in t.tolist())
 
     if rank == 0:
         bases_total = float(n + 2) * world * args.steps
         value = bases_total / (ms * 1e-3) / 1e9
         e2e = bases_total / (ms_e2e * 1e-3) / 1e9
+        e2e_stream = bases_total / (ms_e2e_stream * 1e-3) / 1e9
         # roofline of the dominant kernel (the dense scan), per launch
         peaks = {}
         try:
@@ -392,9 +408,10 @@ def main():
             # dram__bytes_read+write of one launch over 1.0e9 bases: 500.96 + 5.93 MB
             # (ncu --set full, profiles/README.md, prof_pair_r1), scaled to this launch's bases
             traffic = None if args.indels else 0.5069 * (n + 2)
-            kname = "pair_scan_kernel<%s>" % ("true" if args.indels and K else "false")
             if args.indels and K:
-                kname += " + index_verify_kernel<%d>" % K
+                kname = "pair_scan_kernel<true> + index_verify_kernel<%d>" % K
+            else:
+                kname = "pair_scan_sub_kernel<%d, %d>" % (st_last["index_q"], st_last["index_nd"])
             tsrc = "ncu --set full capture prof_pair_r1 (profiles/README.md), bytes per base x bases"
         else:
             n_planes = 5 if not args.iupac else 16
@@ -427,8 +444,14 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
                 "data": "synthetic", "config": config_dict(args, n),
                 "hits_per_step": total_hits, "clocks": clocks,
-                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": (n + 2) * world,
-                        "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
+                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h_sqz.numel()) * world,
+                        "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
+                        "input": "pinned host buffer holding the database as compress_seq -z stores it "
+                                 "(.sqz, 3 bits per character; pm_set_text_sqz_host)"},
+                "e2e_stream": {"value": e2e_stream, "unit": "Gbp/s", "h2d_bytes_per_step": (n + 2) * world,
+                               "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_stream / args.steps,
+                               "input": "pinned host buffer holding the normalised character stream, "
+                                        "1 byte per character (pm_set_text_host)"},
                 "gpu_launches": n_launch, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             cores = cpu_cores()

@@ -148,6 +148,21 @@ int pm_init(pm_ctx *ctx);
 int pm_set_text_host(pm_ctx *ctx, const uint8_t *stream, uint64_t n, int64_t stream_offset);
 int pm_set_text_device(pm_ctx *ctx, const uint8_t *d_stream, uint64_t n, int64_t stream_offset);
 
+/* IndexedFastaFile<Compressed<...>> (select.t:94-106; char_io.t:18-215): the text is
+ * the `.sqz` bit stream `compress_seq -z true` writes (compress_seq.cc:745-870),
+ * which primer_match opens when the file exists (-D 0) or is asked for (-D 4).
+ * bits = pm_sqz_bits(table_size) bits per character, most significant bit first,
+ * character i at bit i*bits; `table` is the content of the `.tbz` file.  n_chars =
+ * characters of the stream (the `.seq` length); 0 = all the bytes hold (the writer
+ * pads its last buffer with end-of-sequence characters, which find nothing).  A
+ * shard (stream_offset > 0) must start on a byte boundary of the bit stream.
+ * Same pipeline as pm_set_text_host with 8/bits times fewer bytes over PCIe; the
+ * stream bytes are rebuilt on the device (unpack_sqz_kernel).                   */
+int pm_set_text_sqz_host(pm_ctx *ctx, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
+                         uint32_t table_size, uint64_t n_chars, int64_t stream_offset);
+/* bits per character of a .sqz stream with this table size (char_io.t:58-61).  */
+int pm_sqz_bits(uint32_t table_size);
+
 /* Characters of left context a shard needs so that every hit it reports is
  * identical to a whole-database scan: longest pattern + 3k + 2.              */
 int pm_shard_overlap(pm_ctx *ctx);

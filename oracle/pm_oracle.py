@@ -13,6 +13,7 @@ returned hit (lines 1132-1153) and the coordinates handed to alignformat
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 from dataclasses import dataclass
@@ -276,6 +277,82 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
         recs.append(HitRecord(idx, sps, spe, "R" if rc else "F", pid - (n if rc else 0), ed,
                               end - (end - start + 1) + 1, end, astr))
     return sorted(recs)
+
+
+# ---------------------------------------------------------------------------
+# compress_seq's compressed database (.tbz table + .sqz bit stream) and the
+# Compressed<> reader.  Plain loops, small inputs only.
+def sqz_table(chars, eos: int = EOS, dna_opt: bool = True) -> bytes:
+    """compress_seq.cc:683-722: observed characters (eos always) in byte order,
+    A C G T swapped to the front with -D true."""
+    obs = [False] * 256
+    obs[eos] = True
+    for ch in bytes(bytearray(chars)):
+        obs[ch] = True
+    order = list(range(256))
+    if dna_opt:
+        for i, ch in enumerate(b"ACGT"):
+            order[i] = ch
+            order[ch] = i
+    return bytes(order[i] for i in range(256) if obs[order[i]])
+
+
+def sqz_bits(table_size: int) -> int:
+    """char_io.t:58-61 / compress_seq.cc:766-769."""
+    bits = 1
+    while (1 << bits) < table_size:
+        bits += 1
+    return bits
+
+
+def sqz_encode(chars, table: bytes, eos: int = EOS) -> bytes:
+    """compress_seq.cc:745-870: codes of `bits` bits, most significant bit first, buffers of
+    lcm(bits, 8) bytes; the last buffer is filled up with eos characters."""
+    inv = {ch: i for i, ch in enumerate(table)}
+    bits = sqz_bits(len(table))
+    lcm = bits * 8 // math.gcd(bits, 8)
+    bufsize = lcm // 8 * 8
+    out = bytearray()
+    buf = bytearray(bufsize)
+    bytepos = bitpos = 0
+    data = list(bytes(bytearray(chars)))
+    i = 0
+    partial = False
+    while i < len(data) or partial:
+        partial = True
+        ch = data[i] if i < len(data) else eos
+        i += 1
+        code = inv[ch]
+        for b in range(bits - 1, -1, -1):
+            if (code >> b) & 1:
+                buf[bytepos] |= 0x80 >> bitpos
+            bitpos += 1
+            if bitpos == 8:
+                bitpos = 0
+                bytepos += 1
+        if bytepos == bufsize:
+            out += buf
+            buf = bytearray(bufsize)
+            bytepos = 0
+            partial = False
+    return bytes(out)
+
+
+def sqz_decode(sqz: bytes, table: bytes, n_chars: int = 0) -> np.ndarray:
+    """Compressed<>::getnch / getch, char_io.t:105-151: character i = table[bits
+    i*bits .. (i+1)*bits of the byte stream, most significant first]."""
+    bits = sqz_bits(len(table))
+    total = len(sqz) * 8 // bits
+    if n_chars == 0:
+        n_chars = total
+    out = np.zeros(n_chars, np.uint8)
+    for i in range(n_chars):
+        code = 0
+        for b in range(bits):
+            pos = i * bits + b
+            code = (code << 1) | ((sqz[pos >> 3] >> (7 - (pos & 7))) & 1)
+        out[i] = table[code]
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -33,7 +33,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 
 # every symbol include/pm_b200.h declares
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
-           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_shard_overlap", "pm_find_patterns",
+           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
            "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path"]
 
@@ -95,6 +95,9 @@ def lib():
         L.pm_init.argtypes = [C.c_void_p]
         L.pm_set_text_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
         L.pm_set_text_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
+        L.pm_set_text_sqz_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32,
+                                           C.c_uint64, C.c_int64]
+        L.pm_sqz_bits.argtypes = [C.c_uint32]
         L.pm_shard_overlap.argtypes = [C.c_void_p]
         L.pm_find_patterns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.POINTER(Hit)),
                                        C.POINTER(C.c_uint64)]
@@ -204,6 +207,19 @@ class Scanner:
         a = np.ascontiguousarray(chars, np.uint8)
         _check(lib().pm_set_text_host(self._h, C.c_void_p(a.ctypes.data), a.size, offset))
 
+    def set_text_sqz(self, sqz, table: bytes, n_chars: int = 0, offset: int = 0):
+        """The text as the .sqz bit stream of compress_seq -z (host memory: numpy uint8
+        array or a CPU torch tensor, pinned or not) with its .tbz character table."""
+        if hasattr(sqz, "data_ptr"):
+            assert not sqz.is_cuda
+            self._keep = sqz
+            ptr, nb = sqz.data_ptr(), sqz.numel()
+        else:
+            a = np.ascontiguousarray(sqz, np.uint8)
+            self._keep = a
+            ptr, nb = a.ctypes.data, a.size
+        _check(lib().pm_set_text_sqz_host(self._h, C.c_void_p(ptr), nb, bytes(table), len(table), n_chars, offset))
+
     def shard_overlap(self) -> int:
         return lib().pm_shard_overlap(self._h)
 
@@ -274,6 +290,70 @@ def int_pipe_report(sc: "Scanner", scan_ms: float, device=0) -> dict:
             "peak_source": "pm_bench_int_peak (LOP3 microbenchmark, same run)"}
 
 
+def sqz_table(chars: np.ndarray, eos: int = 10, dna_opt: bool = True) -> bytes:
+    """The .tbz character table compress_seq writes for a stream (compress_seq.cc:683-722):
+    the observed characters (the eos character counts as observed) in byte order, with
+    A, C, G, T swapped to the front when -D (the default) is on."""
+    obs = np.zeros(256, bool)
+    obs[np.unique(np.asarray(chars, np.uint8))] = True
+    obs[eos] = True
+    order = list(range(256))
+    if dna_opt:
+        for i, ch in enumerate(b"ACGT"):
+            order[i], order[ch] = ch, i
+    return bytes(o for o in order if obs[o])
+
+
+def sqz_encode(chars: np.ndarray, table: bytes, eos: int = 10) -> np.ndarray:
+    """compress_seq -z (compress_seq.cc:745-870): the stream as `bits` bits per character,
+    most significant bit first, padded with eos characters to a whole buffer of
+    lcm(bits, 8) bytes.  Vectorised numpy; the oracle holds the independent restatement."""
+    chars = np.asarray(chars, np.uint8)
+    inv = np.full(256, -1, np.int16)
+    inv[np.frombuffer(table, np.uint8)] = np.arange(len(table), dtype=np.int16)
+    bits = 1
+    while (1 << bits) < len(table):
+        bits += 1
+    bufsize = (bits * 8 // int(np.gcd(bits, 8))) // 8 * 8      # bytes per writer buffer
+    per_buf = bufsize * 8 // bits
+    n = len(chars)
+    nbuf = max(1, -(-n // per_buf))
+    if inv[eos] < 0 or (n and int(inv[chars].min()) < 0):
+        raise ValueError("character outside the table")
+    codes = np.full(nbuf * per_buf, inv[eos], np.uint8)
+    codes[:n] = inv[chars]
+    b = ((codes[:, None] >> np.arange(bits - 1, -1, -1, dtype=np.uint8)) & 1).astype(np.uint8)
+    return np.packbits(b.reshape(-1))
+
+
+def sqz_encode_torch(chars, table: bytes, eos: int = 10):
+    """sqz_encode for a (possibly device-resident) torch uint8 tensor; returns a uint8
+    tensor on the same device.  Used to prepare large synthetic databases."""
+    import torch
+    dev = chars.device
+    bits = 1
+    while (1 << bits) < len(table):
+        bits += 1
+    inv = torch.full((256,), 255, dtype=torch.uint8, device=dev)
+    inv[torch.tensor(list(table), dtype=torch.long, device=dev)] = torch.arange(len(table), dtype=torch.uint8, device=dev)
+    bufsize = (bits * 8 // int(np.gcd(bits, 8))) // 8 * 8
+    per_buf = bufsize * 8 // bits
+    n = chars.numel()
+    nbuf = max(1, -(-n // per_buf))
+    out = torch.empty(nbuf * bufsize, dtype=torch.uint8, device=dev)
+    shifts = torch.arange(bits - 1, -1, -1, dtype=torch.uint8, device=dev)
+    weights = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=dev)
+    step = per_buf * (1 << 18)
+    for a in range(0, nbuf * per_buf, step):
+        b = min(nbuf * per_buf, a + step)
+        codes = torch.full((b - a,), int(inv[eos]), dtype=torch.uint8, device=dev)
+        if a < n:
+            codes[:min(b, n) - a] = inv[chars[a:min(b, n)].long()]
+        bm = (codes[:, None] >> shifts) & 1
+        out[a * bits // 8:b * bits // 8] = (bm.reshape(-1, 8) * weights).sum(dim=1, dtype=torch.uint8)
+    return out
+
+
 @dataclass(frozen=True, order=True)
 class HitRecord:
     """One output record of primer_match, the fields alignformat() receives
@@ -314,8 +394,10 @@ def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
 
 
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO):
-    """The reference's main loop on the GPU path: returns sorted HitRecords."""
+                 eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO, sqz=None):
+    """The reference's main loop on the GPU path: returns sorted HitRecords.
+    sqz = (sqz bytes, tbz table, n_chars): load the text from compress_seq's compressed
+    form instead of stream.chars (stream still supplies the sequence index)."""
     pats = pattern_array(primers, rev_comp)
     sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos,
                  scan_path=scan_path)
@@ -323,7 +405,10 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
         for i, p in enumerate(pats):
             sc.add_pattern(p, i + 1)
         sc.init()
-        sc.set_text(stream.chars)
+        if sqz is not None:
+            sc.set_text_sqz(*sqz)
+        else:
+            sc.set_text(stream.chars)
         hits = sc.find_patterns()
         return hits_to_records(stream, hits, len(primers))
     finally:

@@ -153,7 +153,7 @@ struct pm_ctx {
   DevBuf d_symmask, d_poff, d_plen, d_patchars, d_lconst, d_rconst, d_compat, d_cls, d_umask,
       d_piece, d_slotid;
   // text
-  DevBuf d_text_own, d_planes;
+  DevBuf d_text_own, d_planes, d_sqz, d_sqztab;
   const uint8_t *d_text = nullptr;
   uint64_t n = 0;
   int64_t offset = 0;
@@ -931,7 +931,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
-                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_amb};
+                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_amb, &c->d_sqz, &c->d_sqztab};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1270,12 +1270,33 @@ static int set_text_common(pm_ctx *c, uint64_t n, int64_t offset) {
   return pack_text(c);
 }
 
-int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offset) {
-  if (!c || (!stream && n)) return fail(PM_E_ARG, "null argument");
-  PM_CUDA(cudaSetDevice(c->opt.device));
-  if (n && offset == 0 && stream[0] != c->opt.eos)
-    return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
-  if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
+// Host text -> device, as a pipeline on the private copy stream: the source moves in
+// growing chunks; every chunk is (for a .sqz source) unpacked to stream bytes and then
+// packed tile by tile as far as its characters (plus the 64-character extension) reach;
+// the scan of pm_find_patterns waits chunk by chunk, so it overlaps the rest of the
+// transfer.  bits == 0: the source is the stream itself.
+static int unpack_groups(pm_ctx *c, uint32_t bits, uint64_t n_bytes, uint64_t g0, uint64_t g1,
+                         cudaStream_t st) {
+  if (g1 <= g0) return PM_OK;
+  const uint64_t per_block = 256ull * SQZ_GROUPS_PER_THREAD;
+  const unsigned blocks = (unsigned)((g1 - g0 + per_block - 1) / per_block);
+  const uint8_t *src = c->d_sqz.as<uint8_t>(), *tab = c->d_sqztab.as<uint8_t>();
+  uint8_t *dst = c->d_text_own.as<uint8_t>();
+#define PM_UNPACK(B)                                                                            \
+  case B:                                                                                       \
+    unpack_sqz_kernel<B><<<blocks, 256, 0, st>>>(src, n_bytes, tab, c->opt.eos, dst, g0, g1, c->n); \
+    break;
+  switch (bits) {
+    PM_UNPACK(1) PM_UNPACK(2) PM_UNPACK(3) PM_UNPACK(4) PM_UNPACK(5) PM_UNPACK(6) PM_UNPACK(7) PM_UNPACK(8)
+    default: return fail(PM_E_ARG, "bits per character out of range");
+  }
+#undef PM_UNPACK
+  PM_CUDA(cudaGetLastError());
+  return PM_OK;
+}
+
+static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t bits, uint64_t n,
+                     int64_t offset) {
   int rc = c->d_text_own.ensure(n + 64);
   if (rc) return rc;
   c->d_text = c->d_text_own.as<uint8_t>();
@@ -1283,20 +1304,23 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
   c->n = n;
   c->offset = offset;
   if (!n) return set_text_common(c, n, offset);
+  uint8_t *d_dst = c->d_text_own.as<uint8_t>();
+  if (bits) {
+    if ((rc = c->d_sqz.ensure(n_bytes + 64))) return rc;
+    d_dst = c->d_sqz.as<uint8_t>();
+  }
   cudaPointerAttributes at;
   bool pinned = false;
-  if (cudaPointerGetAttributes(&at, stream) == cudaSuccess)
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
     pinned = (at.type == cudaMemoryTypeHost);
   else
     cudaGetLastError();
   if (!c->inited) {  // not the reference's call order: plain copy now, pack in pm_init
-    PM_CUDA(cudaMemcpyAsync(c->d_text_own.p, stream, n, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaMemcpyAsync(d_dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (bits && (rc = unpack_groups(c, bits, n_bytes, 0, (n + 15) / 16, c->stream))) return rc;
     PM_CUDA(cudaStreamSynchronize(c->stream));
     return PM_OK;
   }
-  // Pipeline: the copy stream moves the text in growing chunks and packs every tile
-  // whose characters (plus the 64-character extension) have arrived; the scan of
-  // pm_find_patterns waits chunk by chunk, so it overlaps the rest of the transfer.
   if ((rc = prepare_planes(c))) return rc;
   PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
   PM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[4], 0));  // earlier work may still read the buffers
@@ -1304,30 +1328,37 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
   if (!pinned)
     for (int i = 0; i < 2; i++)
       if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
-  uint64_t done = 0, next = 64ull << 20;
+  uint64_t done = 0, next = 64ull << 20, groups_done = 0;
   uint32_t tiles_done = 0;
   int which = 0;
-  while (done < n) {
-    uint64_t take = std::min<uint64_t>(next, n - done);
-    if (n - done - take < (32ull << 20)) take = n - done;  // no tiny last chunk
+  while (done < n_bytes) {
+    uint64_t take = std::min<uint64_t>(next, n_bytes - done);
+    if (n_bytes - done - take < (32ull << 20)) take = n_bytes - done;  // no tiny last chunk
     if (pinned) {
-      PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done, stream + done, take,
-                              cudaMemcpyHostToDevice, c->copy_stream));
+      PM_CUDA(cudaMemcpyAsync(d_dst + done, src + done, take, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
       for (uint64_t o = 0; o < take; o += kStageBytes) {
         const size_t part = (size_t)std::min<uint64_t>(kStageBytes, take - o);
         PM_CUDA(cudaEventSynchronize(c->stage_ev[which]));
-        memcpy(c->stage[which], stream + done + o, part);
-        PM_CUDA(cudaMemcpyAsync(c->d_text_own.as<uint8_t>() + done + o, c->stage[which], part,
-                                cudaMemcpyHostToDevice, c->copy_stream));
+        memcpy(c->stage[which], src + done + o, part);
+        PM_CUDA(cudaMemcpyAsync(d_dst + done + o, c->stage[which], part, cudaMemcpyHostToDevice,
+                                c->copy_stream));
         PM_CUDA(cudaEventRecord(c->stage_ev[which], c->copy_stream));
         which ^= 1;
       }
     }
     done += take;
     next *= 3;
-    const uint32_t ready = (done == n) ? c->n_tiles
-                                       : (uint32_t)((done > (uint64_t)TILE_EXT ? done - TILE_EXT : 0) / TILE_POS);
+    const bool last = (done == n_bytes);
+    uint64_t chars = n;  // characters of the stream that are on the device now
+    if (!last) chars = bits ? std::min<uint64_t>(n, (done * 8 / bits) & ~15ull) : done;
+    if (bits) {
+      const uint64_t g1 = last ? (n + 15) / 16 : chars / 16;
+      if ((rc = unpack_groups(c, bits, n_bytes, groups_done, g1, c->copy_stream))) return rc;
+      groups_done = std::max(groups_done, g1);
+    }
+    const uint32_t ready = last ? c->n_tiles
+                                : (uint32_t)((chars > (uint64_t)TILE_EXT ? chars - TILE_EXT : 0) / TILE_POS);
     if ((rc = pack_tiles(c, tiles_done, ready, c->copy_stream))) return rc;
     cudaEvent_t e = next_event(c);
     PM_CUDA(cudaEventRecord(e, c->copy_stream));
@@ -1335,6 +1366,45 @@ int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offse
     tiles_done = std::max(tiles_done, ready);
   }
   return PM_OK;
+}
+
+int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offset) {
+  if (!c || (!stream && n)) return fail(PM_E_ARG, "null argument");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  if (n && offset == 0 && stream[0] != c->opt.eos)
+    return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
+  if (n >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
+  return stream_in(c, stream, n, 0, n, offset);
+}
+
+int pm_sqz_bits(uint32_t table_size) {  // char_io.t:58-61
+  if (table_size == 0 || table_size > 256) return fail(PM_E_ARG, "character table size must be 1..256");
+  int bits = 1;
+  while ((1u << bits) < table_size) bits++;
+  return bits;
+}
+
+int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
+                         uint32_t table_size, uint64_t n_chars, int64_t offset) {
+  if (!c || (!sqz && n_bytes) || !table) return fail(PM_E_ARG, "null argument");
+  const int bits = pm_sqz_bits(table_size);
+  if (bits < 0) return bits;
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  const uint64_t held = n_bytes * 8 / (uint64_t)bits;
+  if (n_chars == 0) n_chars = held;  // the writer's padding reads as end-of-sequence characters
+  if (n_chars > held) return fail(PM_E_ARG, "n_chars exceeds what the compressed bytes hold");
+  if (n_chars >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "shard longer than 2^40 characters");
+  if (n_chars && offset == 0 && table[(sqz[0] >> (8 - bits)) & ((1u << bits) - 1u)] != c->opt.eos)
+    return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
+  uint8_t tab[256];
+  memset(tab, 0, sizeof tab);
+  memcpy(tab, table, table_size);
+  int rc = c->d_sqztab.ensure(256);
+  if (rc) return rc;
+  // the table is read by kernels on the copy stream, which starts after ev[4] of c->stream
+  PM_CUDA(cudaMemcpyAsync(c->d_sqztab.p, tab, 256, cudaMemcpyHostToDevice, c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  return stream_in(c, sqz, n_bytes, (uint32_t)bits, n_chars, offset);
 }
 
 int pm_set_text_device(pm_ctx *c, const uint8_t *d_stream, uint64_t n, int64_t offset) {

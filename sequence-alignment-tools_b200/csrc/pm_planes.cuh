@@ -85,4 +85,54 @@ pack_planes_kernel(const uint8_t *__restrict__ text, uint64_t n,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Compressed<> (char_io.t:18-215): the .sqz bit stream compress_seq -z writes
+// (compress_seq.cc:745-870) -> stream bytes.  `bits` per character, most
+// significant bit first, character i at bit i*bits of the byte stream; table =
+// contents of the .tbz file.  One thread turns 2*bits bytes into 16 characters
+// (16 characters always start on a byte boundary) and stores them as one uint4.
+// Characters at or past n_chars are written as end-of-sequence (the writer pads
+// its last buffer with them anyway).
+constexpr int SQZ_GROUPS_PER_THREAD = 4;
+template <int BITS>
+__global__ void __launch_bounds__(256)
+unpack_sqz_kernel(const uint8_t *__restrict__ sqz, uint64_t n_bytes, const uint8_t *__restrict__ table,
+                  uint32_t eos_byte, uint8_t *__restrict__ text, uint64_t g_begin, uint64_t g_end,
+                  uint64_t n_chars) {
+  constexpr uint32_t bits = BITS;
+  __shared__ uint8_t s_tab[256];
+  s_tab[threadIdx.x] = table[threadIdx.x];
+  __syncthreads();
+  const uint32_t mask = (1u << bits) - 1u;
+  const uint64_t g_first = g_begin + (uint64_t)blockIdx.x * (256 * SQZ_GROUPS_PER_THREAD) + threadIdx.x;
+#pragma unroll 1
+  for (int r = 0; r < SQZ_GROUPS_PER_THREAD; r++) {
+    const uint64_t g = g_first + (uint64_t)r * 256;  // group of 16 characters
+    if (g >= g_end) return;
+    const uint64_t b0 = g * 2ull * bits;
+    // 2*bits (<= 16) payload bytes, big-endian, plus one byte of slack for the 16-bit window
+    uint32_t by[5] = {0, 0, 0, 0, 0};  // by[j] = bytes 4j .. 4j+3, most significant first
+#pragma unroll
+    for (int j = 0; j < 2 * BITS; j++) {
+      const uint64_t at = b0 + j;
+      const uint32_t v = (at < n_bytes) ? (uint32_t)__ldg(sqz + at) : 0u;
+      by[j >> 2] |= v << (24 - 8 * (j & 3));
+    }
+    uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+      const uint32_t bit = (uint32_t)i * bits;        // < 128, known at compile time
+      const uint32_t wj = bit >> 5, sh = bit & 31u;
+      // 32-bit window starting at `bit` (big-endian bit order)
+      const uint32_t hi = by[wj], lo = by[wj + 1 < 5 ? wj + 1 : 4];
+      const uint32_t win = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+      const uint32_t code = (win >> (32u - bits)) & mask;
+      uint32_t ch = s_tab[code];
+      if (g * 16 + i >= n_chars) ch = eos_byte;
+      out[i >> 2] |= ch << (8 * (i & 3));
+    }
+    *reinterpret_cast<uint4 *>(text + g * 16) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
 }  // namespace pm
