@@ -405,14 +405,14 @@ def main():
         if on_index:
             # pair_scan_kernel reads the packed text once: one uint2 (codes, flags) per 16 characters
             alg_bytes = (n + 2) * 0.5
-            # dram__bytes_read+write of one launch over 1.0e9 bases: 500.96 + 5.93 MB
-            # (ncu --set full, profiles/README.md, prof_pair_r1), scaled to this launch's bases
-            traffic = None if args.indels else 0.5069 * (n + 2)
+            # dram__bytes_read+write of one launch over 3.0e9 bases: 1504.0 + 6.3 MB
+            # (ncu --set full, profiles/README.md, prof_pairsub_r1), scaled to this launch's bases
+            traffic = None if args.indels else 0.5034 * (n + 2)
             if args.indels and K:
                 kname = "pair_scan_kernel<true> + index_verify_kernel<%d>" % K
             else:
                 kname = "pair_scan_sub_kernel<%d, %d>" % (st_last["index_q"], st_last["index_nd"])
-            tsrc = "ncu --set full capture prof_pair_r1 (profiles/README.md), bytes per base x bases"
+            tsrc = "ncu --set full capture prof_pairsub_r1 (profiles/README.md), bytes per base x bases"
         else:
             n_planes = 5 if not args.iupac else 16
             alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch

@@ -343,7 +343,7 @@ def sqz_encode_torch(chars, table: bytes, eos: int = 10):
     out = torch.empty(nbuf * bufsize, dtype=torch.uint8, device=dev)
     shifts = torch.arange(bits - 1, -1, -1, dtype=torch.uint8, device=dev)
     weights = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=dev)
-    step = per_buf * (1 << 18)
+    step = per_buf * (1 << 21)
     for a in range(0, nbuf * per_buf, step):
         b = min(nbuf * per_buf, a + step)
         codes = torch.full((b - a,), int(inv[eos]), dtype=torch.uint8, device=dev)

@@ -1328,12 +1328,15 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
   if (!pinned)
     for (int i = 0; i < 2; i++)
       if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
-  uint64_t done = 0, next = 64ull << 20, groups_done = 0;
+  // constant chunks: what is left to do when the last byte has arrived is one chunk's
+  // unpack + pack + scan, so small chunks keep the tail short (a chunk costs ~6 launches)
+  const uint64_t chunk_bytes = bits ? (24ull << 20) : (64ull << 20);
+  uint64_t done = 0, groups_done = 0;
   uint32_t tiles_done = 0;
   int which = 0;
   while (done < n_bytes) {
-    uint64_t take = std::min<uint64_t>(next, n_bytes - done);
-    if (n_bytes - done - take < (32ull << 20)) take = n_bytes - done;  // no tiny last chunk
+    uint64_t take = std::min<uint64_t>(chunk_bytes, n_bytes - done);
+    if (n_bytes - done - take < chunk_bytes / 4) take = n_bytes - done;  // no tiny last chunk
     if (pinned) {
       PM_CUDA(cudaMemcpyAsync(d_dst + done, src + done, take, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
@@ -1348,7 +1351,6 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
       }
     }
     done += take;
-    next *= 3;
     const bool last = (done == n_bytes);
     uint64_t chars = n;  // characters of the stream that are on the device now
     if (!last) chars = bits ? std::min<uint64_t>(n, (done * 8 / bits) & ~15ull) : done;

@@ -109,7 +109,7 @@ def test_sqz_unpack_every_width(pkg, built_lib, table_size):
 
 @pytest.mark.gpu
 def test_sqz_pipeline_several_chunks(pkg, built_lib):
-    """A compressed source larger than the first 64 MiB chunk: unpack and pack follow the
+    """A compressed source of several 24 MiB chunks: unpack and pack follow the
     transfer chunk by chunk; the result equals the device-resident plain path."""
     import torch
     import casegen
@@ -123,7 +123,7 @@ def test_sqz_pipeline_several_chunks(pkg, built_lib):
     d[0] = 10
     d[-1] = 10
     d[50_000_000] = 10
-    seam = (64 << 20) * 8 // 3          # the character where the first source chunk ends
+    seam = (24 << 20) * 8 // 3          # the character where the first source chunk ends
     for j in range(120):
         at = seam - 1500 + 29 * j if j < 100 else 9000 + 9_000_001 * (j - 99)
         d[at:at + 20] = torch.tensor(list(primers[j % 30].encode()), dtype=torch.uint8, device="cuda")
