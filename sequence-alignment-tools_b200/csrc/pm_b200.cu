@@ -180,7 +180,7 @@ struct pm_ctx {
   bool idx_has_amb = false;      // some text byte would be ambiguous (wildcards): pack lists them
   DevBuf d_amb;
   int idx_q = 0;                 // piece length L of the pair index
-  DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap;
+  DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap, d_bitmap2;
   pm::IndexArgs idx_proto;       // level-1 / level-2 parameters filled by pm_init
   unsigned long long *d_counters = nullptr;  // [16]; [8] = ambiguous text characters of the packed text
   unsigned long long *h_counters = nullptr;  // pinned [16]
@@ -390,6 +390,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     ia.n = c->n;
     ia.n16 = (uint64_t)c->n_tiles * (TILE_POS / 16);
     ia.bitmap = c->d_bitmap.as<uint32_t>();
+    ia.bitmap2 = ia.log_words2 ? c->d_bitmap2.as<uint32_t>() : nullptr;
     ia.bucket = c->d_bucket.as<uint32_t>();
     ia.entries = c->d_entries.as<uint2>();
     ia.pacc = c->d_pacc.as<ulonglong4>();
@@ -401,7 +402,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     ia.lo = lo;
     ia.hi = hi;
     ia.k = (uint32_t)K;
-    ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * 2 * PAIR_QCAP * 8;
+    ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * 2 * PAIR_QCAP * 8 +
+            (ia.log_words2 ? ((size_t)4 << ia.log_words2) : 0);
     PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
   }
   void (*kern)(const ScanArgs) = nullptr;
@@ -931,7 +933,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
-                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_amb, &c->d_sqz, &c->d_sqztab};
+                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1202,18 +1204,30 @@ int pm_init(pm_ctx *c) {
       ia.mult = 0x9E3779B1u;
       for (size_t d = 0; d < dist.size(); d++) {
         ia.dist[d] = dist[d];
-        ia.salt[d] = (uint32_t)d * 0x7F4A7C15u;
+        // substitutions: one salt per distance keeps the three key sets apart.  edits: every pair
+        // is entered at 2k+1 neighbouring distances; sharing the bits between the distances
+        // (salt 0) sets (2k+1) times fewer of them, and level 2 still tells the distances apart
+        ia.salt[d] = edit_mode ? 0u : (uint32_t)d * 0x7F4A7C15u;
       }
       int lb = 10;
       while (((size_t)1 << lb) < 2 * ents.size() && lb < 26) lb++;
       ia.log_buckets = (uint32_t)lb;
       const size_t nb = (size_t)1 << lb;
+      // level 1b for edits: 64 KB keyed by (key, distance)
+      ia.log_words2 = edit_mode ? 14u : 0u;
+      ia.mult2 = 0x85EBCA6Bu;
+      for (size_t d = 0; d < dist.size(); d++) ia.salt2[d] = (uint32_t)(d + 1) * 0xC2B2AE35u;
+      std::vector<uint32_t> bitmap2(edit_mode ? ((size_t)1 << ia.log_words2) : 4, 0);
       std::vector<uint32_t> bitmap((size_t)1 << ia.log_words, 0), bucket(nb + 1, 0);
       std::vector<uint32_t> hs(ents.size());
       for (size_t x = 0; x < ents.size(); x++) {
         const uint32_t di = (ents[x].y >> 5) & 31u;
         const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
         bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
+        if (edit_mode) {
+          const uint32_t idx2 = ents[x].x * ia.mult2 + ia.salt2[di];
+          bitmap2[idx2 >> (32 - ia.log_words2)] |= 1u << (idx2 & 31u);
+        }
         hs[x] = pair_hash2(ents[x].x, di, ia.log_buckets);
         bucket[hs[x] + 1]++;
       }
@@ -1241,6 +1255,7 @@ int pm_init(pm_ctx *c) {
       const Up iups[] = {{&c->d_bucket, bucket.data(), bucket.size() * 4},
                          {&c->d_entries, sorted.data(), sorted.size() * 8},
                          {&c->d_bitmap, bitmap.data(), bitmap.size() * 4},
+                         {&c->d_bitmap2, bitmap2.data(), bitmap2.size() * 4},
                          {&c->d_pacc, pacc.data(), pacc.size() * 8},
                          {&c->d_umask4, um4.data(), um4.size() * 4},
                          {&c->d_lin, lin.data(), lin.size()}};

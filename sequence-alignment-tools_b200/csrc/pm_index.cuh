@@ -64,6 +64,11 @@ struct IndexArgs {
   uint32_t mult;            // odd multiplier of the level-1 hash
   uint32_t dist[PAIR_MAX_ND];
   uint32_t salt[PAIR_MAX_ND];
+  // level 1b (edits): a second, smaller bitmap keyed by (pair key, distance); 0 words = absent
+  const uint32_t *bitmap2;
+  uint32_t log_words2;
+  uint32_t mult2;
+  uint32_t salt2[PAIR_MAX_ND];
   // level 2
   const uint32_t *bucket;   // [(1 << log_buckets) + 1]
   uint32_t log_buckets;
@@ -232,9 +237,13 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   const uint32_t n_words = 1u << a.log_words;
   uint32_t *s_bitmap = s_mem;
   unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
+  const uint32_t n_words2 = a.bitmap2 ? (1u << a.log_words2) : 0u;
+  uint32_t *s_bitmap2 = s_mem + n_words + PAIR_WARPS * 2 * PAIR_QCAP * 2;  // behind the queues
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
     reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
+  for (uint32_t i = threadIdx.x; i < n_words2 / 4; i += blockDim.x)
+    reinterpret_cast<uint4 *>(s_bitmap2)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap2) + i);
   __syncthreads();
   PairQueues q;
   q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
@@ -242,6 +251,7 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   q.na = q.nb = 0;
 
   const uint32_t wsh = 32u - a.log_words;
+  const uint32_t wsh2 = 32u - a.log_words2;
   const uint32_t L2 = 2u * a.L;
   const uint32_t maskL = (1u << L2) - 1u;       // L <= 8
   const uint32_t maskHi = maskL << L2;
@@ -289,6 +299,20 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
         hm = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);  // bit 31-(idx&31) -> bit 0 of hm
       }
       hm &= vm;
+      if (n_words2 && hm) {
+        // level 1b: the shared bits of level 1 say "some distance"; ask the (key, distance) bitmap
+        const uint32_t salt2 = a.salt2[di];
+        uint32_t keep = 0u, rest = hm;
+        while (rest) {
+          const int b = __ffs(rest) - 1;
+          rest &= rest - 1;
+          const uint32_t i2 = 2u * (uint32_t)(15 - b);
+          const uint32_t key = (__funnelshift_r(X0, X1, i2) & maskHi) | (__funnelshift_r(c0, c1, i2) & maskL);
+          const uint32_t idx2 = key * a.mult2 + salt2;
+          if ((s_bitmap2[idx2 >> wsh2] >> (idx2 & 31u)) & 1u) keep |= 1u << b;
+        }
+        hm = keep;
+      }
       const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);
       if (bal) {
         if (hm) q.qa[q.na + __popc(bal & lt)] = ((unsigned long long)w << 21) | (di << 16) | hm;
