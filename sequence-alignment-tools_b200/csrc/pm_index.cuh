@@ -227,58 +227,149 @@ __device__ __forceinline__ void pair_stage_a(const IndexArgs &a, PairQueues &q, 
   }
 }
 
-// One warp owns chunks of 32 packed words (512 positions): lane l holds word l and
+// ---------------------------------------------------------------------------
+// Pieces shared by the three scan kernels below.  One persistent 1024-thread CTA per
+// SM; a warp owns chunks of 32 packed words (512 positions): lane l holds word l and
 // gets the next two words by shuffle, so the 16 positions of its word see their
 // 32-character context without any further load.
+struct PairCta {
+  uint32_t *bitmap;    // shared-memory copy of level 1
+  uint32_t *bitmap2;   // ... of level 1b (edits), or unused
+  uint32_t n_words2;
+  PairQueues q;
+  uint32_t lane, lt;
+  int64_t w_begin, n_chunks;
+  unsigned long long n_queued;
+};
+
+__device__ __forceinline__ void pair_cta_init(const IndexArgs &a, uint32_t *s_mem, PairCta &t) {
+  const uint32_t n_words = 1u << a.log_words;
+  t.bitmap = s_mem;
+  unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
+  t.n_words2 = a.bitmap2 ? (1u << a.log_words2) : 0u;
+  t.bitmap2 = s_mem + n_words + PAIR_WARPS * 2 * PAIR_QCAP * 2;  // behind the queues
+  for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
+    reinterpret_cast<uint4 *>(t.bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
+  for (uint32_t i = threadIdx.x; i < t.n_words2 / 4; i += blockDim.x)
+    reinterpret_cast<uint4 *>(t.bitmap2)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap2) + i);
+  __syncthreads();
+  t.lane = threadIdx.x & 31;
+  t.lt = (1u << t.lane) - 1u;
+  const uint32_t warp = threadIdx.x >> 5;
+  t.q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
+  t.q.qb = t.q.qa + PAIR_QCAP;
+  t.q.na = t.q.nb = 0;
+  t.w_begin = a.p_begin >> 4;
+  t.n_chunks = (((a.p_end + 15) >> 4) - t.w_begin + 31) >> 5;
+  t.n_queued = 0;
+}
+
+// codes of this lane's word and the two after it; mask of the word's positions that lie
+// inside [p_begin, p_end) (position i <-> bit 15-i)
+__device__ __forceinline__ void pair_load_words(const IndexArgs &a, const PairCta &t, int64_t chunk,
+                                                int64_t &w, uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                                uint32_t &vm) {
+  const int64_t wc0 = t.w_begin + (chunk << 5);
+  w = wc0 + t.lane;
+  const uint32_t mine = pk_codes(a, w);
+  const uint32_t extra = (t.lane < 2) ? pk_codes(a, wc0 + 32 + t.lane) : 0u;
+  const uint32_t x0 = __shfl_sync(0xffffffffu, extra, 0), x1 = __shfl_sync(0xffffffffu, extra, 1);
+  c0 = mine;
+  c1 = __shfl_down_sync(0xffffffffu, mine, 1);
+  c2 = __shfl_down_sync(0xffffffffu, mine, 2);
+  if (t.lane == 31) { c1 = x0; c2 = x1; }
+  if (t.lane == 30) c2 = x0;
+  const int64_t base = w << 4;
+  vm = 0xffffu;
+  if (base < a.p_begin) vm &= (a.p_begin - base >= 16) ? 0u : (0xffffu >> (uint32_t)(a.p_begin - base));
+  if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
+}
+
+// level 1b (edits): the shared bits of level 1 say "some distance"; keep the positions whose
+// (key, distance) bit is set as well.  Divergent, only for lanes with a hit.
+__device__ __forceinline__ uint32_t pair_level1b(const IndexArgs &a, const PairCta &t, uint32_t hm, uint32_t di,
+                                                 uint32_t c0, uint32_t c1, uint32_t c2) {
+  const uint32_t L2 = 2u * a.L, maskL = (1u << L2) - 1u;
+  const uint32_t d2 = 2u * a.dist[di], salt2 = a.salt2[di], wsh2 = 32u - a.log_words2;
+  uint32_t keep = 0u;
+  while (hm) {
+    const int b = __ffs(hm) - 1;
+    hm &= hm - 1;
+    const uint32_t i2 = 2u * (uint32_t)(15 - b);
+    const uint32_t v0 = __funnelshift_r(c0, c1, i2), v1 = __funnelshift_r(c1, c2, i2), v2 = c2 >> i2;
+    const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
+    const uint32_t key = (v0 & maskL) | ((hi & maskL) << L2);
+    const uint32_t idx2 = key * a.mult2 + salt2;
+    if ((t.bitmap2[idx2 >> wsh2] >> (idx2 & 31u)) & 1u) keep |= 1u << b;
+  }
+  return keep;
+}
+
+// queue the (word, distance, position mask) records of the warp; run stage A when 32 wait
+template <bool EDIT>
+__device__ __forceinline__ void pair_push(const IndexArgs &a, PairCta &t, int64_t w, uint32_t di, uint32_t hm) {
+  const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);
+  if (bal == 0u) return;
+  if (hm) t.q.qa[t.q.na + __popc(bal & t.lt)] = ((unsigned long long)w << 21) | (di << 16) | hm;
+  t.q.na += __popc(bal);
+  t.n_queued += __popc(bal);
+  if (t.q.na >= 32u) {
+    __syncwarp();
+    const unsigned long long rec = t.q.qa[t.q.na - 32u + t.lane];
+    __syncwarp();
+    t.q.na -= 32u;
+    pair_stage_a<EDIT>(a, t.q, true, rec, t.lane);
+  }
+}
+
+template <bool EDIT>
+__device__ __forceinline__ void pair_cta_finish(const IndexArgs &a, PairCta &t) {
+  __syncwarp();
+  {
+    const bool valid = t.lane < t.q.na;
+    const unsigned long long rec = valid ? t.q.qa[t.lane] : 0ULL;
+    __syncwarp();
+    t.q.na = 0;
+    pair_stage_a<EDIT>(a, t.q, valid, rec, t.lane);
+  }
+  __syncwarp();
+  if (!EDIT) {
+    const bool valid = t.lane < t.q.nb;
+    const unsigned long long rec = valid ? t.q.qb[t.lane] : 0ULL;
+    pair_stage_b<EDIT>(a, valid, rec);
+  }
+  if (t.lane == 0 && a.work_count) atomicAdd(a.work_count, t.n_queued);
+}
+
+// one level-1 lookup: bit 31-(idx&31) of the bitmap word -> shifted into bit 0 of hm
+__device__ __forceinline__ uint32_t pair_probe(const uint32_t *bitmap, uint32_t key, uint32_t mult, uint32_t salt,
+                                               uint32_t wsh, uint32_t hm) {
+  const uint32_t idx = key * mult + salt;
+  const uint32_t wrd = bitmap[idx >> wsh];
+  return __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);
+}
+
+// Generic kernel: run-time piece length and distance set, one distance after the other.
+// Serves the edit scans (13-19 distances: they are bound by the shared-memory wavefront
+// rate of the lookups themselves -- a variant sharing the shifted windows between the
+// distances of a group, as the substitution kernel below does, measured 5 % slower).
 template <bool EDIT>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  const uint32_t n_words = 1u << a.log_words;
-  uint32_t *s_bitmap = s_mem;
-  unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
-  const uint32_t n_words2 = a.bitmap2 ? (1u << a.log_words2) : 0u;
-  uint32_t *s_bitmap2 = s_mem + n_words + PAIR_WARPS * 2 * PAIR_QCAP * 2;  // behind the queues
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
-    reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
-  for (uint32_t i = threadIdx.x; i < n_words2 / 4; i += blockDim.x)
-    reinterpret_cast<uint4 *>(s_bitmap2)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap2) + i);
-  __syncthreads();
-  PairQueues q;
-  q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
-  q.qb = q.qa + PAIR_QCAP;
-  q.na = q.nb = 0;
-
+  PairCta t;
+  pair_cta_init(a, s_mem, t);
   const uint32_t wsh = 32u - a.log_words;
-  const uint32_t wsh2 = 32u - a.log_words2;
   const uint32_t L2 = 2u * a.L;
   const uint32_t maskL = (1u << L2) - 1u;       // L <= 8
   const uint32_t maskHi = maskL << L2;
   const uint32_t mult = a.mult;
-  const uint32_t lt = (1u << lane) - 1u;
-  const int64_t w_begin = a.p_begin >> 4;
-  const int64_t w_end = (a.p_end + 15) >> 4;
-  const int64_t n_chunks = (w_end - w_begin + 31) >> 5;
-  unsigned long long n_queued = 0;
+  const uint32_t warp = threadIdx.x >> 5;
 
-  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
-    const int64_t wc0 = w_begin + (c << 5);
-    const int64_t w = wc0 + lane;
-    const uint32_t mine = pk_codes(a, w);
-    const uint32_t extra = (lane < 2) ? pk_codes(a, wc0 + 32 + lane) : 0u;
-    const uint32_t x0 = __shfl_sync(0xffffffffu, extra, 0), x1 = __shfl_sync(0xffffffffu, extra, 1);
-    const uint32_t c0 = mine;
-    uint32_t c1 = __shfl_down_sync(0xffffffffu, mine, 1);
-    uint32_t c2 = __shfl_down_sync(0xffffffffu, mine, 2);
-    if (lane == 31) { c1 = x0; c2 = x1; }
-    if (lane == 30) c2 = x0;
-    // positions of this word inside [p_begin, p_end): position i <-> bit 15-i
-    const int64_t base = w << 4;
-    uint32_t vm = 0xffffu;
-    if (base < a.p_begin) vm &= (a.p_begin - base >= 16) ? 0u : (0xffffu >> (uint32_t)(a.p_begin - base));
-    if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
-
+  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < t.n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+    int64_t w;
+    uint32_t c0, c1, c2, vm;
+    pair_load_words(a, t, c, w, c0, c1, c2, vm);
     uint32_t av[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) av[i] = __funnelshift_r(c0, c1, 2 * i) & maskL;
@@ -291,59 +382,14 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
       const uint32_t X0 = __funnelshift_r(y0, y1, s), X1 = __funnelshift_r(y1, y2, s);  // shift taken mod 32
       uint32_t hm = 0;
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const uint32_t T = __funnelshift_r(X0, X1, 2 * i);
-        const uint32_t key = (T & maskHi) | av[i];
-        const uint32_t idx = key * mult + salt;
-        const uint32_t wrd = s_bitmap[idx >> wsh];
-        hm = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);  // bit 31-(idx&31) -> bit 0 of hm
-      }
+      for (int i = 0; i < 16; i++)
+        hm = pair_probe(t.bitmap, (__funnelshift_r(X0, X1, 2 * i) & maskHi) | av[i], mult, salt, wsh, hm);
       hm &= vm;
-      if (n_words2 && hm) {
-        // level 1b: the shared bits of level 1 say "some distance"; ask the (key, distance) bitmap
-        const uint32_t salt2 = a.salt2[di];
-        uint32_t keep = 0u, rest = hm;
-        while (rest) {
-          const int b = __ffs(rest) - 1;
-          rest &= rest - 1;
-          const uint32_t i2 = 2u * (uint32_t)(15 - b);
-          const uint32_t key = (__funnelshift_r(X0, X1, i2) & maskHi) | (__funnelshift_r(c0, c1, i2) & maskL);
-          const uint32_t idx2 = key * a.mult2 + salt2;
-          if ((s_bitmap2[idx2 >> wsh2] >> (idx2 & 31u)) & 1u) keep |= 1u << b;
-        }
-        hm = keep;
-      }
-      const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);
-      if (bal) {
-        if (hm) q.qa[q.na + __popc(bal & lt)] = ((unsigned long long)w << 21) | (di << 16) | hm;
-        q.na += __popc(bal);
-        n_queued += __popc(bal);
-        if (q.na >= 32u) {
-          __syncwarp();
-          const unsigned long long rec = q.qa[q.na - 32u + lane];
-          __syncwarp();
-          q.na -= 32u;
-          pair_stage_a<EDIT>(a, q, true, rec, lane);
-        }
-      }
+      if (t.n_words2 && hm) hm = pair_level1b(a, t, hm, di, c0, c1, c2);
+      pair_push<EDIT>(a, t, w, di, hm);
     }
   }
-  // leftovers
-  __syncwarp();
-  {
-    const bool valid = lane < q.na;
-    const unsigned long long rec = valid ? q.qa[lane] : 0ULL;
-    __syncwarp();
-    q.na = 0;
-    pair_stage_a<EDIT>(a, q, valid, rec, lane);
-  }
-  __syncwarp();
-  if (!EDIT) {
-    const bool valid = lane < q.nb;
-    const unsigned long long rec = valid ? q.qb[lane] : 0ULL;
-    pair_stage_b<EDIT>(a, valid, rec);
-  }
-  if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_queued);
+  pair_cta_finish<EDIT>(a, t);
 }
 
 // Substitution scan with compile-time piece length and distance count: the
@@ -351,60 +397,33 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
 // shared between the lookups of different positions (position i at distance
 // (j+1)L uses G[i + jL]): 16 + (ND-1)L funnel shifts per word instead of 16*ND.
 // (Moving the word-index shift and the address LEA to the FMA pipe as IMAD.HI / IMAD
-// was measured and is not worth it: the kernel sits at ~80 % of the shared-memory
-// wavefront rate and ~85 % of the ALU rate at the same time, see DESIGN.md.)
+// was measured and is not worth it: the kernel sits at ~94 % of the shared-memory
+// wavefront rate and ~87 % of the ALU rate at the same time, see DESIGN.md.)
 template <int L, int ND>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  const uint32_t n_words = 1u << a.log_words;
-  uint32_t *s_bitmap = s_mem;
-  unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
-    reinterpret_cast<uint4 *>(s_bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
-  __syncthreads();
-  PairQueues q;
-  q.qa = s_queue + (size_t)warp * (2 * PAIR_QCAP);
-  q.qb = q.qa + PAIR_QCAP;
-  q.na = q.nb = 0;
-
+  PairCta t;
+  pair_cta_init(a, s_mem, t);
   const uint32_t wsh = 32u - a.log_words;
   constexpr uint32_t maskL = (1u << (2 * L)) - 1u;
   constexpr uint32_t mask2L = (L >= 8) ? 0xffffffffu : ((1u << (4 * L)) - 1u);
   constexpr uint32_t maskHi = mask2L & ~maskL;
   constexpr int NG = 16 + (ND - 1) * L;
   const uint32_t mult = a.mult;
-  const uint32_t lt = (1u << lane) - 1u;
-  const int64_t w_begin = a.p_begin >> 4;
-  const int64_t w_end = (a.p_end + 15) >> 4;
-  const int64_t n_chunks = (w_end - w_begin + 31) >> 5;
-  unsigned long long n_queued = 0;
+  const uint32_t warp = threadIdx.x >> 5;
   uint32_t salt[ND];
 #pragma unroll
   for (int j = 0; j < ND; j++) salt[j] = a.salt[j];
 
-  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
-    const int64_t wc0 = w_begin + (c << 5);
-    const int64_t w = wc0 + lane;
-    const uint32_t mine = pk_codes(a, w);
-    const uint32_t extra = (lane < 2) ? pk_codes(a, wc0 + 32 + lane) : 0u;
-    const uint32_t x0 = __shfl_sync(0xffffffffu, extra, 0), x1 = __shfl_sync(0xffffffffu, extra, 1);
-    uint32_t cw[4];
-    cw[0] = mine;
-    cw[1] = __shfl_down_sync(0xffffffffu, mine, 1);
-    cw[2] = __shfl_down_sync(0xffffffffu, mine, 2);
+  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < t.n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+    int64_t w;
+    uint32_t cw[4], vm;
+    pair_load_words(a, t, c, w, cw[0], cw[1], cw[2], vm);
     cw[3] = 0u;
-    if (lane == 31) { cw[1] = x0; cw[2] = x1; }
-    if (lane == 30) cw[2] = x0;
-    const int64_t base = w << 4;
-    uint32_t vm = 0xffffu;
-    if (base < a.p_begin) vm &= (a.p_begin - base >= 16) ? 0u : (0xffffu >> (uint32_t)(a.p_begin - base));
-    if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
-
     uint32_t G[NG];
 #pragma unroll
-    for (int t = 0; t < NG; t++) G[t] = __funnelshift_r(cw[t >> 4], cw[(t >> 4) + 1], 2 * (t & 15));
+    for (int tt = 0; tt < NG; tt++) G[tt] = __funnelshift_r(cw[tt >> 4], cw[(tt >> 4) + 1], 2 * (tt & 15));
     uint32_t hm[ND];
 #pragma unroll
     for (int j = 0; j < ND; j++) hm[j] = 0u;
@@ -414,44 +433,13 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
       for (int j = 0; j < ND; j++) {
         const uint32_t key = (j == 0) ? (G[i] & mask2L) : ((G[i + j * L] & maskHi) | av);
-        const uint32_t idx = key * mult + salt[j];
-        const uint32_t wrd = s_bitmap[idx >> wsh];
-        hm[j] = __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm[j], 1);
+        hm[j] = pair_probe(t.bitmap, key, mult, salt[j], wsh, hm[j]);
       }
     }
 #pragma unroll
-    for (int j = 0; j < ND; j++) {
-      const uint32_t h = hm[j] & vm;
-      const uint32_t bal = __ballot_sync(0xffffffffu, h != 0u);
-      if (bal) {
-        if (h) q.qa[q.na + __popc(bal & lt)] = ((unsigned long long)w << 21) | ((uint32_t)j << 16) | h;
-        q.na += __popc(bal);
-        n_queued += __popc(bal);
-        if (q.na >= 32u) {
-          __syncwarp();
-          const unsigned long long rec = q.qa[q.na - 32u + lane];
-          __syncwarp();
-          q.na -= 32u;
-          pair_stage_a<false>(a, q, true, rec, lane);
-        }
-      }
-    }
+    for (int j = 0; j < ND; j++) pair_push<false>(a, t, w, (uint32_t)j, hm[j] & vm);
   }
-  __syncwarp();
-  {
-    const bool valid = lane < q.na;
-    const unsigned long long rec = valid ? q.qa[lane] : 0ULL;
-    __syncwarp();
-    q.na = 0;
-    pair_stage_a<false>(a, q, valid, rec, lane);
-  }
-  __syncwarp();
-  {
-    const bool valid = lane < q.nb;
-    const unsigned long long rec = valid ? q.qb[lane] : 0ULL;
-    pair_stage_b<false>(a, valid, rec);
-  }
-  if (lane == 0 && a.work_count) atomicAdd(a.work_count, n_queued);
+  pair_cta_finish<false>(a, t);
 }
 
 typedef void (*PairKernel)(const IndexArgs);
@@ -476,14 +464,19 @@ inline PairKernel pair_sub_kernel(int L, int nd) {
   }
   return nullptr;
 }
-
-// Edit verifier on the packed text: the recurrence of verify_seed (pm_scan.cuh)
-// with the character masks of the four codes in registers.
+// Edit verifier on the packed text: the recurrence of verify_seed (pm_scan.cuh) for one
+// (slot, nominal window start) per thread.  The span t0 .. t_hi (at most m+3K+1 <= 42
+// characters) is pulled into registers first, shifted so that character t0 sits at bit 0;
+// the four per-code Shift-And masks live in shared memory (one row per thread), so a
+// character costs one LDS instead of a chain of selects.
+constexpr int VERIFY_IDX_THREADS = 128;
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(VERIFY_IDX_THREADS)
 index_verify_kernel(const __grid_constant__ IndexArgs a) {
+  __shared__ uint32_t s_u[5][VERIFY_IDX_THREADS];  // [code][thread]; row 4 = flagged character (0)
   unsigned long long count = *a.seed_n;
   if (count > a.seed_cap) count = a.seed_cap;
+  s_u[4][threadIdx.x] = 0u;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long sd = a.seeds[i];
@@ -491,7 +484,10 @@ index_verify_kernel(const __grid_constant__ IndexArgs a) {
     const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL) - SEED_BIAS;
     const uint32_t m = a.plen[slot] & 0x7fu;
     const uint4 um = __ldg(reinterpret_cast<const uint4 *>(a.umask4) + slot);
-    const uint32_t U[4] = {um.x, um.y, um.z, um.w};
+    s_u[0][threadIdx.x] = um.x;
+    s_u[1][threadIdx.x] = um.y;
+    s_u[2][threadIdx.x] = um.z;
+    s_u[3][threadIdx.x] = um.w;
     const uint32_t last = 1u << (m - 1);
     int64_t t_lo = s_nominal + (int64_t)m - 1 - K;
     int64_t t_hi = s_nominal + (int64_t)m - 1 + K;
@@ -499,26 +495,25 @@ index_verify_kernel(const __grid_constant__ IndexArgs a) {
     if (t_lo < 0) t_lo = 0;
     int64_t t0 = t_lo - (int64_t)(m + K);
     if (t0 < 0) t0 = 0;
+    if (t_hi < t0) continue;
+    const int span = (int)(t_hi - t0) + 1;     // <= m + 3K + 1 <= 42
+    const int first_report = (int)(t_lo - t0);
+    // characters t0 .. t0+47 as 3 x (codes, flags), character t0 at bit 0
+    const int64_t wb = t0 >> 4;
+    const uint32_t sh = 2u * (uint32_t)(t0 & 15);
+    const uint2 p0 = pk_load(a, wb), p1 = pk_load(a, wb + 1), p2 = pk_load(a, wb + 2), p3 = pk_load(a, wb + 3);
+    uint32_t cw[3] = {__funnelshift_r(p0.x, p1.x, sh), __funnelshift_r(p1.x, p2.x, sh), __funnelshift_r(p2.x, p3.x, sh)};
+    uint32_t fw[3] = {__funnelshift_r(p0.y, p1.y, sh), __funnelshift_r(p1.y, p2.y, sh), __funnelshift_r(p2.y, p3.y, sh)};
     uint32_t M[K + 1];
 #pragma unroll
     for (int l = 0; l <= K; l++) M[l] = 0;
-    // up to 32+3K+1+32 < 80 characters: five packed words cover any alignment
-    const int64_t wb = t0 >> 4;
-    uint2 pw[6];
 #pragma unroll
-    for (int j = 0; j < 6; j++) pw[j] = pk_load(a, wb + j);
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      uint32_t cw = pw[j].x, fw = pw[j].y;
-      const int64_t base = (wb + j) << 4;
-      if (base > t_hi) break;
-#pragma unroll 4
-      for (int i = 0; i < 16; i++, cw >>= 2, fw >>= 2) {
-        const int64_t t = base + i;
-        if (t < t0 || t > t_hi) continue;
-        const uint32_t fl = fw & 3u;
-        const uint32_t c = cw & 3u;
-        const uint32_t u = fl ? 0u : (c == 0 ? U[0] : c == 1 ? U[1] : c == 2 ? U[2] : U[3]);
+    for (int j = 0; j < 3; j++) {
+      uint32_t c = cw[j], f = fw[j];
+      const int lim = min(16, span - 16 * j);
+      for (int i = 0; i < lim; i++, c >>= 2, f >>= 2) {
+        const uint32_t fl = f & 3u;
+        const uint32_t u = s_u[fl ? 4u : (c & 3u)][threadIdx.x];
         // shift_and_inexact.cc:253-303, indels on; one word per pattern
         uint32_t old_prev = M[0];
         M[0] = ((M[0] << 1) | 1u) & u;
@@ -536,7 +531,7 @@ index_verify_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
           for (int l = 1; l <= K; l++) M[l] = ((M[l] << 1) | 1u) & u;
         }
-        if (t >= t_lo && (M[K] & last)) index_emit(a, slot, t + 1);
+        if ((M[K] & last) && 16 * j + i >= first_report) index_emit(a, slot, t0 + 16 * j + i + 1);
       }
     }
   }
