@@ -228,6 +228,19 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
                        uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
                        int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs);
 
+/* The same on the device (pm_fasta.cuh): `raw` = the bytes of a FASTA file in host
+ * memory.  They are copied to the device and normalised there (a three-state machine
+ * over the raw bytes, composed with a prefix scan), then packed as by
+ * pm_set_text_device; stream_offset is 0.  Call after pm_init.  The sequence table
+ * (what SortSeqFastaFile keeps for get_seq_pos, fasta_io.t:163-202) is returned by
+ * pm_get_sequences: pointers into memory owned by the context, valid until the next
+ * pm_set_text_* call.  pm_get_text copies characters of the loaded stream back to the
+ * host (the alignment buffers primer_match prints with %t come from there).          */
+int pm_set_text_fasta_host(pm_ctx *ctx, const uint8_t *raw, uint64_t n_raw, int upper_case);
+int pm_get_sequences(pm_ctx *ctx, const int64_t **seq_key, const int64_t **hdr_off,
+                     const int64_t **hdr_len, uint64_t *n_seqs, uint64_t *stream_len);
+int pm_get_text(pm_ctx *ctx, uint64_t begin, uint64_t len, uint8_t *out);
+
 /* Diagnostic for the roofline: measured throughput of 3-input logic
  * instructions (LOP3) on `device`, in 1e12 thread-level operations per second. */
 int pm_bench_int_peak(int device, double *lop3_tera_ops);

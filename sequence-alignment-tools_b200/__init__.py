@@ -33,7 +33,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 
 # every symbol include/pm_b200.h declares
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
-           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_shard_overlap", "pm_find_patterns",
+           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
            "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path"]
 
@@ -98,6 +98,10 @@ def lib():
         L.pm_set_text_sqz_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32,
                                            C.c_uint64, C.c_int64]
         L.pm_sqz_bits.argtypes = [C.c_uint32]
+        L.pm_set_text_fasta_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        i64pp = C.POINTER(C.POINTER(C.c_int64))
+        L.pm_get_sequences.argtypes = [C.c_void_p, i64pp, i64pp, i64pp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.pm_get_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.pm_shard_overlap.argtypes = [C.c_void_p]
         L.pm_find_patterns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.POINTER(Hit)),
                                        C.POINTER(C.c_uint64)]
@@ -219,6 +223,36 @@ class Scanner:
             self._keep = a
             ptr, nb = a.ctypes.data, a.size
         _check(lib().pm_set_text_sqz_host(self._h, C.c_void_p(ptr), nb, bytes(table), len(table), n_chars, offset))
+
+    def set_text_fasta(self, raw, uc: bool = False, fetch_chars: bool = False) -> "Stream":
+        """The text as the bytes of a FASTA file (bytes, numpy uint8 array or CPU torch tensor,
+        pinned or not): normalised on the device (pm_fasta.cuh).  Returns the Stream with the
+        sequence table; its .chars are fetched from the device only when asked for."""
+        if hasattr(raw, "data_ptr"):
+            assert not raw.is_cuda
+            self._keep = raw
+            ptr, nb = raw.data_ptr(), raw.numel()
+            view = memoryview(raw.numpy())
+        else:
+            a = np.frombuffer(raw, np.uint8) if isinstance(raw, (bytes, bytearray, memoryview)) else np.ascontiguousarray(raw, np.uint8)
+            self._keep = a
+            ptr, nb = (a.ctypes.data if a.size else 0), a.size
+            view = memoryview(a)
+        _check(lib().pm_set_text_fasta_host(self._h, C.c_void_p(ptr), nb, int(uc)))
+        kp, op, lp = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        ns, sl = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().pm_get_sequences(self._h, C.byref(kp), C.byref(op), C.byref(lp), C.byref(ns), C.byref(sl)))
+        n = ns.value
+        key = np.array([kp[i] for i in range(n)], np.int64)
+        headers = [bytes(view[op[i]:op[i] + max(lp[i], 0)]).decode("latin-1") for i in range(n)]
+        chars = self.get_text(0, sl.value) if fetch_chars else None
+        return Stream(chars, key, headers)
+
+    def get_text(self, begin: int, length: int) -> np.ndarray:
+        out = np.zeros(length, np.uint8)
+        if length:
+            _check(lib().pm_get_text(self._h, begin, length, C.c_void_p(out.ctypes.data)))
+        return out
 
     def shard_overlap(self) -> int:
         return lib().pm_shard_overlap(self._h)

@@ -21,6 +21,7 @@
 #include "pm_planes.cuh"
 #include "pm_scan.cuh"
 #include "pm_index.cuh"
+#include "pm_fasta.cuh"
 
 namespace {
 
@@ -154,6 +155,10 @@ struct pm_ctx {
       d_piece, d_slotid;
   // text
   DevBuf d_text_own, d_planes, d_sqz, d_sqztab;
+  // device-side FASTA normalisation (pm_fasta.cuh)
+  DevBuf d_fa_raw, d_fa_map, d_fa_scan, d_fa_cnt, d_fa_chdr, d_fa_start, d_fa_nout, d_fa_nhdr, d_fa_ooff, d_fa_hoff,
+      d_fa_key, d_fa_hs, d_fa_he;
+  std::vector<int64_t> seq_key, seq_hdr_off, seq_hdr_len;  // sequence table of the last FASTA text
   const uint8_t *d_text = nullptr;
   uint64_t n = 0;
   int64_t offset = 0;
@@ -933,7 +938,10 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
                     &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
-                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab};
+                    &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab,
+                    &c->d_fa_raw, &c->d_fa_map, &c->d_fa_scan, &c->d_fa_cnt, &c->d_fa_chdr, &c->d_fa_start,
+                    &c->d_fa_nout, &c->d_fa_nhdr, &c->d_fa_ooff, &c->d_fa_hoff, &c->d_fa_key, &c->d_fa_hs,
+                    &c->d_fa_he};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1511,10 +1519,11 @@ int pm_get_stats(pm_ctx *c, pm_stats *out) {
 // StreamedFastaFile::getch, fasta_io.t:478-629 (eos_start = true): the stream
 // is eos, seq1, eos, seq2, ..., seqN, eos.  Sequence lines are joined; blanks,
 // CR and LF inside sequence data are dropped; '>' starts a header anywhere.
-int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos,
-                       uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
-                       int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs) {
-  if ((!raw && n) || !out || !out_len) return fail(PM_E_ARG, "null argument");
+// stop_early: return as soon as the first stream character after the initial eos
+// exists (*rp_out = raw bytes consumed); the closing eos is then not written.
+static void normalize_walk(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos, uint8_t *out,
+                           uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off, int64_t *hdr_len,
+                           uint64_t max_seqs, uint64_t *n_seqs, bool stop_early, uint64_t *rp_out) {
   uint64_t rp = 0, pos = 0, nseq = 0;
   int64_t lastkey = 0;
   auto put = [&](uint8_t ch) {
@@ -1523,6 +1532,7 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
   };
   if (n > 0) out[pos++] = eos;  // the stream opens with an end-of-sequence character
   while (rp < n) {
+    if (stop_early && pos > 1) break;
     uint8_t ch = raw[rp++];
     const bool blank = (ch == '\n' || ch == '\r' || ch == ' ');
     if (!blank && ch != '>') {
@@ -1568,9 +1578,188 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
       out[pos - 1] = eos;
     }
   }
-  out[pos++] = eos;
+  if (!(stop_early && rp < n)) out[pos++] = eos;
   *out_len = pos;
   if (n_seqs) *n_seqs = nseq;
+  if (rp_out) *rp_out = rp;
+}
+
+int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned char eos,
+                       uint8_t *out, uint64_t *out_len, int64_t *seq_key, int64_t *hdr_off,
+                       int64_t *hdr_len, uint64_t max_seqs, uint64_t *n_seqs) {
+  if ((!raw && n) || !out || !out_len) return fail(PM_E_ARG, "null argument");
+  normalize_walk(raw, n, upper_case, eos, out, out_len, seq_key, hdr_off, hdr_len, max_seqs, n_seqs, false,
+                 nullptr);
+  return PM_OK;
+}
+
+// The same on the device (pm_fasta.cuh): raw FASTA bytes in host memory -> stream in HBM.
+int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int upper_case) {
+  if (!c || (!raw && n_raw)) return fail(PM_E_ARG, "null argument");
+  if (!c->inited) return fail(PM_E_ARG, "pm_set_text_fasta_host before pm_init");
+  if (n_raw >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "file longer than 2^40 bytes");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  const unsigned char eos = c->opt.eos;
+  // host prefix: everything up to the first stream character (first-header rule)
+  std::vector<uint8_t> pre(n_raw < 64 ? n_raw + 4 : 8);
+  int64_t pk[4], po[4], pl[4];
+  uint64_t pre_len = 0, pre_seqs = 0, r0 = 0;
+  {
+    // the walk writes at most 2 bytes before it stops (eos + first character) unless the
+    // whole file is consumed, which only happens for files without any stream character
+    std::vector<uint8_t> tmp(n_raw < 64 ? n_raw + 4 : 0);
+    uint8_t small[8];
+    uint8_t *dst = n_raw < 64 ? tmp.data() : small;
+    bool all = n_raw < 64;
+    normalize_walk(raw, n_raw, upper_case, eos, dst, &pre_len, pk, po, pl, 4, &pre_seqs, !all, &r0);
+    if (!all && r0 >= n_raw) {  // no stream character at all: redo as a complete walk
+      all = true;
+    }
+    if (all) {
+      std::vector<uint8_t> full(n_raw + 4);
+      std::vector<int64_t> k2(n_raw / 2 + 4), o2(n_raw / 2 + 4), l2(n_raw / 2 + 4);
+      uint64_t len = 0, ns = 0;
+      normalize_walk(raw, n_raw, upper_case, eos, full.data(), &len, k2.data(), o2.data(), l2.data(),
+                     k2.size(), &ns, false, nullptr);
+      c->seq_key.assign(k2.begin(), k2.begin() + ns);
+      c->seq_hdr_off.assign(o2.begin(), o2.begin() + ns);
+      c->seq_hdr_len.assign(l2.begin(), l2.begin() + ns);
+      return stream_in(c, full.data(), len, 0, len, 0);
+    }
+    pre.assign(dst, dst + pre_len);
+    if (pre_seqs > 4) return fail(PM_E_UNSUPPORTED, "unexpected FASTA prefix");
+  }
+  const uint64_t n_seg = (n_raw - r0 + FA_SEG - 1) / FA_SEG;
+  int rc;
+  if ((rc = c->d_fa_raw.ensure(n_raw + 64))) return rc;
+  if ((rc = c->d_text_own.ensure(n_raw + 2 + 64))) return rc;
+  if ((rc = c->d_fa_map.ensure(n_seg))) return rc;
+  if ((rc = c->d_fa_scan.ensure(n_seg))) return rc;
+  if ((rc = c->d_fa_cnt.ensure(n_seg * 8))) return rc;
+  if ((rc = c->d_fa_chdr.ensure(n_seg * 4))) return rc;
+  if ((rc = c->d_fa_start.ensure(n_seg))) return rc;
+  if ((rc = c->d_fa_nout.ensure((n_seg + 1) * 4))) return rc;
+  if ((rc = c->d_fa_nhdr.ensure((n_seg + 1) * 4))) return rc;
+  if ((rc = c->d_fa_ooff.ensure((n_seg + 1) * 8))) return rc;
+  if ((rc = c->d_fa_hoff.ensure((n_seg + 1) * 8))) return rc;
+  cudaStream_t st = c->stream;
+  // raw bytes to the device (pinned memory is read directly, pageable memory is staged)
+  {
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, raw) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    if (pinned) {
+      PM_CUDA(cudaMemcpyAsync(c->d_fa_raw.p, raw, n_raw, cudaMemcpyHostToDevice, st));
+    } else {
+      for (int i = 0; i < 2; i++)
+        if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
+      int which = 0;
+      for (uint64_t o = 0; o < n_raw; o += kStageBytes) {
+        const size_t part = (size_t)std::min<uint64_t>(kStageBytes, n_raw - o);
+        PM_CUDA(cudaEventSynchronize(c->stage_ev[which]));
+        memcpy(c->stage[which], raw + o, part);
+        PM_CUDA(cudaMemcpyAsync(c->d_fa_raw.as<uint8_t>() + o, c->stage[which], part, cudaMemcpyHostToDevice, st));
+        PM_CUDA(cudaEventRecord(c->stage_ev[which], st));
+        which ^= 1;
+      }
+    }
+  }
+  const uint8_t *d_raw = c->d_fa_raw.as<uint8_t>();
+  fasta_summary_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(
+      d_raw, r0, n_raw, n_seg, c->d_fa_map.as<uint8_t>(), c->d_fa_cnt.as<unsigned long long>(),
+      c->d_fa_chdr.as<uint32_t>());
+  PM_CUDA(cudaGetLastError());
+  size_t tb = 0, tb2 = 0;
+  cub::DeviceScan::InclusiveScan(nullptr, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(), FaCompose(),
+                                 (int64_t)n_seg, st);
+  cub::DeviceScan::ExclusiveScan(nullptr, tb2, c->d_fa_nout.as<uint32_t>(), c->d_fa_ooff.as<unsigned long long>(),
+                                 cub::Sum(), 0ull, (int64_t)(n_seg + 1), st);
+  tb = std::max(tb, tb2);
+  if ((rc = c->d_tmp.ensure(tb))) return rc;
+  tb = c->d_tmp.cap;
+  PM_CUDA(cub::DeviceScan::InclusiveScan(c->d_tmp.p, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(),
+                                         FaCompose(), (int64_t)n_seg, st));
+  PM_CUDA(cudaMemsetAsync(c->d_fa_nout.as<uint32_t>() + n_seg, 0, 4, st));
+  PM_CUDA(cudaMemsetAsync(c->d_fa_nhdr.as<uint32_t>() + n_seg, 0, 4, st));
+  fasta_select_kernel<<<nblocks(n_seg, 256), 256, 0, st>>>(
+      c->d_fa_scan.as<uint8_t>(), c->d_fa_cnt.as<unsigned long long>(), c->d_fa_chdr.as<uint32_t>(), n_seg,
+      c->d_fa_start.as<uint8_t>(), c->d_fa_nout.as<uint32_t>(), c->d_fa_nhdr.as<uint32_t>());
+  PM_CUDA(cudaGetLastError());
+  tb = c->d_tmp.cap;
+  PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_tmp.p, tb, c->d_fa_nout.as<uint32_t>(),
+                                         c->d_fa_ooff.as<unsigned long long>(), cub::Sum(), 0ull,
+                                         (int64_t)(n_seg + 1), st));
+  tb = c->d_tmp.cap;
+  PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_tmp.p, tb, c->d_fa_nhdr.as<uint32_t>(),
+                                         c->d_fa_hoff.as<unsigned long long>(), cub::Sum(), 0ull,
+                                         (int64_t)(n_seg + 1), st));
+  unsigned long long totals[2] = {0, 0};
+  PM_CUDA(cudaMemcpyAsync(&totals[0], c->d_fa_ooff.as<unsigned long long>() + n_seg, 8, cudaMemcpyDeviceToHost, st));
+  PM_CUDA(cudaMemcpyAsync(&totals[1], c->d_fa_hoff.as<unsigned long long>() + n_seg, 8, cudaMemcpyDeviceToHost, st));
+  PM_CUDA(cudaStreamSynchronize(st));
+  const uint64_t n = pre_len + totals[0] + 1;       // + the closing eos
+  const uint64_t n_hdr = pre_seqs + totals[1];
+  if (n > n_raw + 2) return fail(PM_E_CUDA, "FASTA normalisation produced an impossible length");
+  const size_t tab = std::max<uint64_t>(n_hdr, 1) * 8;
+  if ((rc = c->d_fa_key.ensure(tab))) return rc;
+  if ((rc = c->d_fa_hs.ensure(tab))) return rc;
+  if ((rc = c->d_fa_he.ensure(tab))) return rc;
+  if (n_hdr) {
+    fill_i64_kernel<<<nblocks(n_hdr, 256), 256, 0, st>>>(c->d_fa_he.as<long long>(), n_hdr, (long long)n_raw);
+    PM_CUDA(cudaGetLastError());
+  }
+  uint8_t *d_stream = c->d_text_own.as<uint8_t>();
+  fasta_write_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(
+      d_raw, r0, n_raw, n_seg, c->d_fa_start.as<uint8_t>(), c->d_fa_ooff.as<unsigned long long>(),
+      c->d_fa_hoff.as<unsigned long long>(), upper_case, eos, d_stream, pre_len, pre_seqs,
+      c->d_fa_key.as<long long>(), c->d_fa_hs.as<long long>(), c->d_fa_he.as<long long>());
+  PM_CUDA(cudaGetLastError());
+  PM_CUDA(cudaMemcpyAsync(d_stream, pre.data(), pre_len, cudaMemcpyHostToDevice, st));
+  PM_CUDA(cudaMemsetAsync(d_stream + (n - 1), eos, 1, st));
+  // sequence table back to the host
+  c->seq_key.assign(n_hdr, 0);
+  c->seq_hdr_off.assign(n_hdr, 0);
+  c->seq_hdr_len.assign(n_hdr, 0);
+  if (n_hdr > pre_seqs) {
+    const size_t cnt = (size_t)(n_hdr - pre_seqs);
+    PM_CUDA(cudaMemcpyAsync(c->seq_key.data() + pre_seqs, c->d_fa_key.as<long long>() + pre_seqs, cnt * 8,
+                            cudaMemcpyDeviceToHost, st));
+    PM_CUDA(cudaMemcpyAsync(c->seq_hdr_off.data() + pre_seqs, c->d_fa_hs.as<long long>() + pre_seqs, cnt * 8,
+                            cudaMemcpyDeviceToHost, st));
+    PM_CUDA(cudaMemcpyAsync(c->seq_hdr_len.data() + pre_seqs, c->d_fa_he.as<long long>() + pre_seqs, cnt * 8,
+                            cudaMemcpyDeviceToHost, st));
+  }
+  PM_CUDA(cudaStreamSynchronize(st));
+  for (uint64_t i = 0; i < pre_seqs; i++) {
+    c->seq_key[i] = pk[i];
+    c->seq_hdr_off[i] = po[i];
+    c->seq_hdr_len[i] = pl[i];
+  }
+  for (uint64_t i = pre_seqs; i < n_hdr; i++)
+    c->seq_hdr_len[i] = c->seq_hdr_len[i] - c->seq_hdr_off[i] - 1;  // hend - hstart - 1 (fasta_io.t:548)
+  c->d_text = d_stream;
+  return set_text_common(c, n, 0);
+}
+
+int pm_get_sequences(pm_ctx *c, const int64_t **seq_key, const int64_t **hdr_off, const int64_t **hdr_len,
+                     uint64_t *n_seqs, uint64_t *stream_len) {
+  if (!c || !n_seqs) return fail(PM_E_ARG, "null argument");
+  if (seq_key) *seq_key = c->seq_key.data();
+  if (hdr_off) *hdr_off = c->seq_hdr_off.data();
+  if (hdr_len) *hdr_len = c->seq_hdr_len.data();
+  *n_seqs = c->seq_key.size();
+  if (stream_len) *stream_len = c->n;
+  return PM_OK;
+}
+
+int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
+  if (!c || (!out && len)) return fail(PM_E_ARG, "null argument");
+  if (begin + len > c->n || !c->d_text) return fail(PM_E_ARG, "range outside the loaded text");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  if (!c->chunks.empty() && c->chunks.back().ev) PM_CUDA(cudaStreamWaitEvent(c->stream, c->chunks.back().ev, 0));
+  PM_CUDA(cudaMemcpyAsync(out, c->d_text + begin, len, cudaMemcpyDeviceToHost, c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
   return PM_OK;
 }
 
