@@ -297,6 +297,24 @@ def main():
     h_sqz = torch.empty(d_sqz.numel(), dtype=torch.uint8, pin_memory=True)
     h_sqz.copy_(d_sqz)
     del d_sqz
+    # ... and as the FASTA file it came from: one record per sequence, 80 bases per line
+    parts = []
+    bounds = [0] + list(range(seq_len, n + 1, seq_len)) + [n + 1]
+    nl = torch.tensor([10], dtype=torch.uint8, device=dev)
+    for si in range(len(bounds) - 1):
+        a, b = bounds[si] + 1, bounds[si + 1]          # bases of this sequence: d_stream[a:b]
+        if b <= a:
+            continue
+        body = d_stream[a:b]
+        full = (b - a) // 80 * 80
+        lines = torch.cat([body[:full].view(-1, 80), nl.expand(full // 80, 1)], dim=1).reshape(-1)
+        parts += [torch.tensor(list(b">synthetic%d random DNA\n" % si), dtype=torch.uint8, device=dev), lines]
+        if b - a > full:
+            parts += [body[full:], nl]
+    d_fasta = torch.cat(parts)
+    h_fasta = torch.empty(d_fasta.numel(), dtype=torch.uint8, pin_memory=True)
+    h_fasta.copy_(d_fasta)
+    del d_fasta, parts
     torch.cuda.synchronize()
 
     sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank)
@@ -317,9 +335,11 @@ def main():
         scan_ms.append(st["scan_ms"])
         return nh, st
 
-    def step_e2e(compressed):
-        if compressed:
+    def step_e2e(source):
+        if source == "sqz":
             sc.set_text_sqz(h_sqz, sqz_table, n + 2)   # H2D of the .sqz bytes + unpack + pack
+        elif source == "fasta":
+            sc.set_text_fasta(h_fasta)             # H2D of the file + normalisation on the device + pack
         else:
             sc.set_text(h_stream)                  # H2D of the stream from pinned memory + pack
         hits = sc.find_patterns()                  # ... + D2H of the hit list
@@ -364,33 +384,34 @@ def main():
     # end-to-end legs: host buffers in, hit list out.  "e2e" reads the database in the
     # reference's compressed form, "e2e_stream" as the plain character stream.
     e2e_ms, d2h, hit_sets = {}, 0, {}
-    for compressed in (True, False):
+    for source in ("sqz", "stream", "fasta"):
         for _ in range(min(args.warmup, 2)):
-            step_e2e(compressed)
+            step_e2e(source)
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record(stream)
         for _ in range(args.steps):
-            hits, st = step_e2e(compressed)
+            hits, st = step_e2e(source)
             d2h = hits.nbytes + 64
             gather_counts(len(hits))
         e3.record(stream)
         barrier()
-        e2e_ms[compressed] = e2.elapsed_time(e3)
-        hit_sets[compressed] = hits.tobytes()
-    assert hit_sets[True] == hit_sets[False], "compressed and plain input disagree"
-    ms_e2e, ms_e2e_stream = e2e_ms[True], e2e_ms[False]
+        e2e_ms[source] = e2.elapsed_time(e3)
+        hit_sets[source] = hits.tobytes()
+    assert hit_sets["sqz"] == hit_sets["stream"] == hit_sets["fasta"], "the three input forms disagree"
+    ms_e2e, ms_e2e_stream, ms_e2e_fasta = e2e_ms["sqz"], e2e_ms["stream"], e2e_ms["fasta"]
 
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, mean_scan_ms, ms_e2e_stream], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_e2e, mean_scan_ms, ms_e2e_stream, ms_e2e_fasta], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, mean_scan_ms, ms_e2e_stream = (float(x) for x in t.tolist())
+        ms, ms_e2e, mean_scan_ms, ms_e2e_stream, ms_e2e_fasta = (float(x) for x in t.tolist())
 
     if rank == 0:
         bases_total = float(n + 2) * world * args.steps
         value = bases_total / (ms * 1e-3) / 1e9
         e2e = bases_total / (ms_e2e * 1e-3) / 1e9
         e2e_stream = bases_total / (ms_e2e_stream * 1e-3) / 1e9
+        e2e_fasta = bases_total / (ms_e2e_fasta * 1e-3) / 1e9
         # roofline of the dominant kernel (the dense scan), per launch
         peaks = {}
         try:
@@ -452,6 +473,10 @@ def main():
                                "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_stream / args.steps,
                                "input": "pinned host buffer holding the normalised character stream, "
                                         "1 byte per character (pm_set_text_host)"},
+                "e2e_fasta": {"value": e2e_fasta, "unit": "Gbp/s", "h2d_bytes_per_step": int(h_fasta.numel()) * world,
+                              "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_fasta / args.steps,
+                              "input": "pinned host buffer holding the FASTA file (80 bases per line), normalised "
+                                       "on the device (pm_set_text_fasta_host); copy and scan do not overlap yet"},
                 "gpu_launches": n_launch, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             cores = cpu_cores()

@@ -27,12 +27,15 @@ inline void fatal(const std::string &msg) {
   std::exit(1);
 }
 
-// The CharacterProducer of this library: the normalised stream of a FASTA
-// database (StreamedFastaFile, fasta_io.t:448-751) held in host memory, with
-// the header index FastaFile<H> keeps (fasta_io.t:140-215).
+// The CharacterProducer of this library: a FASTA database as StreamedFastaFile
+// presents it (fasta_io.t:448-751), with the header index FastaFile<H> keeps
+// (fasta_io.t:140-215).  The raw file is read into host memory; the normalised
+// stream is built on the device when an index adopts the stream (b200_index::init
+// -> pm_set_text_fasta_host) and only the sequence table comes back.  Without a
+// device (normalise_on_host) the stream is built by pm_normalize_fasta.
 class FastaStream {
  public:
-  FastaStream() {}
+  FastaStream() : ctx_(0), stream_len_(0), upper_case_(false), eos_('\n') {}
   bool load(const std::string &filename, bool upper_case, unsigned char eos) {
     std::ifstream f(filename.c_str(), std::ios::binary);
     if (!f) return false;
@@ -41,9 +44,11 @@ class FastaStream {
     f.seekg(0);
     raw_.resize((size_t)n);
     if (n) f.read(&raw_[0], n);
-    return from_memory(upper_case, eos);
+    upper_case_ = upper_case;
+    eos_ = eos;
+    return true;
   }
-  bool from_memory(bool upper_case, unsigned char eos) {
+  bool normalise_on_host() {
     size_t nh = 2;
     for (char ch : raw_) nh += (ch == '>');
     chars_.resize(raw_.size() + 4);
@@ -51,16 +56,29 @@ class FastaStream {
     hoff_.resize(nh);
     hlen_.resize(nh);
     uint64_t len = 0, ns = 0;
-    if (pm_normalize_fasta((const uint8_t *)raw_.data(), raw_.size(), upper_case, eos, chars_.data(), &len,
+    if (pm_normalize_fasta((const uint8_t *)raw_.data(), raw_.size(), upper_case_, eos_, chars_.data(), &len,
                            key_.data(), hoff_.data(), hlen_.data(), nh, &ns) != PM_OK)
       return false;
     chars_.resize(len);
     key_.resize(ns);
+    stream_len_ = len;
+    return true;
+  }
+  // hand the raw bytes to the device and keep its sequence table
+  bool normalise_on_device(pm_ctx *ctx) {
+    if (pm_set_text_fasta_host(ctx, (const uint8_t *)raw_.data(), raw_.size(), upper_case_) != PM_OK) return false;
+    const int64_t *k = 0, *o = 0, *l = 0;
+    uint64_t ns = 0, len = 0;
+    if (pm_get_sequences(ctx, &k, &o, &l, &ns, &len) != PM_OK) return false;
+    key_.assign(k, k + ns);
+    hoff_.assign(o, o + ns);
+    hlen_.assign(l, l + ns);
+    stream_len_ = len;
+    ctx_ = ctx;
     return true;
   }
   std::string &raw() { return raw_; }
-  const uint8_t *chars() const { return chars_.data(); }
-  uint64_t size() const { return chars_.size(); }
+  uint64_t size() const { return stream_len_; }
   // set_header_item (fasta_io.t:152-168): the entry whose key is the last <= pos-1
   long locate(int64_t pos) const {
     long lo = 0, hi = (long)key_.size();
@@ -85,16 +103,26 @@ class FastaStream {
     const size_t p = h.find_first_of(" \t");
     return p == std::string::npos ? h : h.substr(0, p);
   }
+  // characters [a, b) of the stream (the text primer_match prints next to an alignment)
   std::string text(int64_t a, int64_t b) const {
     if (a < 0) a = 0;
-    if (b > (int64_t)chars_.size()) b = (int64_t)chars_.size();
-    return a < b ? std::string((const char *)chars_.data() + a, (size_t)(b - a)) : std::string();
+    if (b > (int64_t)stream_len_) b = (int64_t)stream_len_;
+    if (a >= b) return std::string();
+    if (!ctx_) return std::string((const char *)chars_.data() + a, (size_t)(b - a));
+    std::string out((size_t)(b - a), '\0');
+    if (pm_get_text(ctx_, (uint64_t)a, (uint64_t)(b - a), (uint8_t *)&out[0]) != PM_OK)
+      fatal(std::string("Fatal error: ") + pm_last_error());
+    return out;
   }
 
  private:
   std::string raw_;
   std::vector<uint8_t> chars_;
   std::vector<int64_t> key_, hoff_, hlen_;
+  pm_ctx *ctx_;
+  uint64_t stream_len_;
+  bool upper_case_;
+  unsigned char eos_;
 };
 
 // pattern_hit_vector element (pattern_match.h:81): key = end position of the hit
@@ -143,8 +171,7 @@ class b200_index : public PatternMatch {
   }
   void init(FastaStream &cp) {
     if (pm_init(ctx_) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
-    if (pm_set_text_host(ctx_, cp.chars(), cp.size(), 0) != PM_OK)
-      fatal(std::string("Fatal error: ") + pm_last_error());
+    if (!cp.normalise_on_device(ctx_)) fatal(std::string("Fatal error: ") + pm_last_error());
   }
   bool find_patterns(FastaStream &, pattern_hit_vector &pas, unsigned long minka = 1) {
     if (!scanned_) {

@@ -183,6 +183,7 @@ struct pm_ctx {
   bool use_index = false;        // the loaded text is packed for / scanned by the pair index
   bool index_ok = false;         // resolved in pm_init: the patterns can use the pair index
   bool idx_has_amb = false;      // some text byte would be ambiguous (wildcards): pack lists them
+  bool idx_dna_fast = false;     // text codes are (byte >> 1) & 3 for A, C, G, T: table-free pack
   DevBuf d_amb;
   int idx_q = 0;                 // piece length L of the pair index
   DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap, d_bitmap2;
@@ -464,6 +465,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     a.seed_overflow = c->d_counters + 7;
     PM_CUDA(cudaMemsetAsync(c->d_counters, 0, 2 * sizeof(unsigned long long), c->stream));
     PM_CUDA(cudaMemsetAsync(c->d_counters + 5, 0, 3 * sizeof(unsigned long long), c->stream));
+    cudaStream_t ls = c->stream;
     PM_CUDA(cudaEventRecord(c->ev[0], c->stream));
     // grid.x is limited to 2^31-1, grid.y to 65535
     if ((uint64_t)nt * chunks > 0x7fffffffull) return fail(PM_E_UNSUPPORTED, "scan grid too large");
@@ -473,7 +475,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         const uint32_t t0 = std::max(prev_end, tile0), t1 = std::min(ch.tile_end, tile1);
         prev_end = std::max(prev_end, ch.tile_end);
         if (t1 <= t0) continue;
-        if (ch.ev) PM_CUDA(cudaStreamWaitEvent(c->stream, ch.ev, 0));
+        if (ch.ev) PM_CUDA(cudaStreamWaitEvent(ls, ch.ev, 0));
         if (c->use_index) {
           // a verification window reaches up to 63 characters past the q-gram: positions lag
           // the packed tiles by 64 so that every window lies in words that are already packed
@@ -486,16 +488,16 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
             ia.p_begin = pb;
             ia.p_end = std::min<int64_t>(pe, pb + batch_pos);
             const uint64_t span = (uint64_t)(ia.p_end - ia.p_begin);
-            if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
+            if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), ls));
             const uint64_t warp_chunks = (span + 16 + 511) / 512;  // 512 positions per warp pass
             const unsigned iblocks = (unsigned)std::max<uint64_t>(
                 1, std::min<uint64_t>((uint64_t)n_sm, (warp_chunks + PAIR_WARPS - 1) / PAIR_WARPS));
-            ikern<<<iblocks, PAIR_THREADS, ismem, c->stream>>>(ia);
+            ikern<<<iblocks, PAIR_THREADS, ismem, ls>>>(ia);
             idx_lookups += span * ia.nd;
             PM_CUDA(cudaGetLastError());
             c->stats.kernel_launches++;
             if (edit) {
-              ivkern<<<n_sm * 8, 128, 0, c->stream>>>(ia);
+              ivkern<<<n_sm * 8, 128, 0, ls>>>(ia);
               PM_CUDA(cudaGetLastError());
               c->stats.kernel_launches++;
             }
@@ -505,12 +507,12 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         for (uint32_t b0 = t0; b0 < t1; b0 += batch_tiles) {
           const uint32_t b1 = std::min(t1, b0 + batch_tiles);
           a.tile0 = b0;
-          if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
-          kern<<<(b1 - b0) * chunks, SCAN_THREADS, smem, c->stream>>>(a);
+          if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), ls));
+          kern<<<(b1 - b0) * chunks, SCAN_THREADS, smem, ls>>>(a);
           PM_CUDA(cudaGetLastError());
           c->stats.kernel_launches++;
           if (edit) {
-            vkern<<<n_sm * 8, VERIFY_THREADS, 0, c->stream>>>(a);
+            vkern<<<n_sm * 8, VERIFY_THREADS, 0, ls>>>(a);
             PM_CUDA(cudaGetLastError());
             c->stats.kernel_launches++;
           }
@@ -518,7 +520,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
       }
       // the alignment kernels read the raw text: everything must have arrived
       if (!c->chunks.empty() && c->chunks.back().ev)
-        PM_CUDA(cudaStreamWaitEvent(c->stream, c->chunks.back().ev, 0));
+        PM_CUDA(cudaStreamWaitEvent(ls, c->chunks.back().ev, 0));
     }
     if (c->use_index && c->idx_has_amb) {
       // ambiguous text characters: their number is known once every chunk is packed
@@ -832,7 +834,8 @@ int pack_tiles(pm_ctx *c, uint32_t t0, uint32_t t1, cudaStream_t st) {
     const uint64_t per_block = 256ull * PACK_WORDS_PER_THREAD;
     pack_linear_kernel<<<(unsigned)((w1 - w0 + per_block - 1) / per_block), 256, 0, st>>>(
         c->d_text, c->n, c->d_lin.as<uint8_t>(), c->opt.eos, c->d_pk.as<uint2>(), w0, w1,
-        c->d_amb.as<unsigned long long>(), c->d_counters + 8, c->d_amb.p ? kAmbCap : 0);
+        c->d_amb.as<unsigned long long>(), c->d_counters + 8, c->d_amb.p ? kAmbCap : 0,
+        c->idx_dna_fast ? 1 : 0);
     PM_CUDA(cudaGetLastError());
     return PM_OK;
   }
@@ -857,7 +860,9 @@ int prepare_planes(pm_ctx *c) {
   return c->d_planes.ensure((size_t)c->n_tiles * (c->n_sym + 1) * TILE_WT * 4);
 }
 
-// whole text already on the device: one pack launch on the main stream
+// whole text already on the device: one pack launch on the main stream.  (Packing chunk
+// by chunk on a second stream under the scan of the previous chunk was tried -- 28-warp scan
+// CTAs leave registers for one pack block per SM -- and gained nothing: DESIGN.md.)
 int pack_text(pm_ctx *c) {
   int rc = prepare_planes(c);
   if (rc || c->n_tiles == 0) return rc;
@@ -924,6 +929,7 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+
   *out = c;
   return PM_OK;
 }
@@ -1115,13 +1121,24 @@ int pm_init(pm_ctx *c) {
     uint32_t code_mask[4] = {0, 0, 0, 0};  // symbols matched by a text character of that code
     int n_codes = 0;
     bool ok = c->max_len <= 32 && ns > 0 && ns < (1u << 22);
+    // DNA: code = (byte >> 1) & 3 for the bytes A, C, T, G (0, 1, 2, 3), which the pack kernel
+    // computes without its table (pack_linear_kernel's fast path)
+    bool dna_codes = wc;
     if (!wc) {
       if (c->n_sym > 4) ok = false;
-      n_codes = std::min(c->n_sym, 4);
-      for (int s2 = 0; s2 < n_codes; s2++) code_mask[s2] = 1u << s2;
+      dna_codes = true;
+      for (unsigned char ch : sym_char)
+        if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') dna_codes = false;
+      if (dna_codes) {
+        n_codes = 4;
+        for (int s2 = 0; s2 < c->n_sym; s2++) code_mask[(sym_char[s2] >> 1) & 3] = 1u << s2;
+      } else {
+        n_codes = std::min(c->n_sym, 4);
+        for (int s2 = 0; s2 < n_codes; s2++) code_mask[s2] = 1u << s2;
+      }
     } else {
       n_codes = 4;
-      for (int cc = 0; cc < 4; cc++) code_mask[cc] = symmask[(unsigned char)"ACGT"[cc]] & symbits;
+      for (int cc = 0; cc < 4; cc++) code_mask[cc] = symmask[(unsigned char)"ACTG"[cc]] & symbits;
     }
     // every text byte must be one of the codes or match nothing
     std::vector<uint8_t> lin(256, 0);
@@ -1137,9 +1154,14 @@ int pm_init(pm_ctx *c) {
         else if (wc) { v = 4 | 16; has_amb = true; }  // ambiguous: packed as "bad" and listed
         else ok = false;
       }
+      // the four bytes of the fast path carry their arithmetic code even when no pattern
+      // symbol matches them (no accept mask has that code set then: same as "matches nothing")
+      if (dna_codes && (b2 == 'A' || b2 == 'C' || b2 == 'G' || b2 == 'T')) v = (uint8_t)((b2 >> 1) & 3);
       if (b2 == c->opt.eos) v = 4 | 8;
       lin[b2] = v;
     }
+    c->idx_dna_fast = ok && dna_codes && c->opt.eos != 'A' && c->opt.eos != 'C' && c->opt.eos != 'G' &&
+                      c->opt.eos != 'T';
     int min_len = 64;
     for (size_t i = 0; i < ns; i++) min_len = std::min<int>(min_len, (int)c->pats[i].s.size());
     int L = std::min(PAIR_LMAX, min_len / P);
@@ -1532,7 +1554,9 @@ static void normalize_walk(const uint8_t *raw, uint64_t n, int upper_case, unsig
   };
   if (n > 0) out[pos++] = eos;  // the stream opens with an end-of-sequence character
   while (rp < n) {
-    if (stop_early && pos > 1) break;
+    // (and the raw position is 16-byte aligned, so that the device can load uint4; a header
+    // consumes many bytes at once, hence the cap)
+    if (stop_early && pos > 1 && ((rp & 15) == 0 || rp > 4096)) break;
     uint8_t ch = raw[rp++];
     const bool blank = (ch == '\n' || ch == '\r' || ch == ' ');
     if (!blank && ch != '>') {
@@ -1601,19 +1625,25 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
   PM_CUDA(cudaSetDevice(c->opt.device));
   const unsigned char eos = c->opt.eos;
   // host prefix: everything up to the first stream character (first-header rule)
-  std::vector<uint8_t> pre(n_raw < 64 ? n_raw + 4 : 8);
-  int64_t pk[4], po[4], pl[4];
+  std::vector<uint8_t> pre;
+  std::vector<int64_t> pk, po, pl;
   uint64_t pre_len = 0, pre_seqs = 0, r0 = 0;
   {
-    // the walk writes at most 2 bytes before it stops (eos + first character) unless the
-    // whole file is consumed, which only happens for files without any stream character
-    std::vector<uint8_t> tmp(n_raw < 64 ? n_raw + 4 : 0);
-    uint8_t small[8];
-    uint8_t *dst = n_raw < 64 ? tmp.data() : small;
-    bool all = n_raw < 64;
-    normalize_walk(raw, n_raw, upper_case, eos, dst, &pre_len, pk, po, pl, 4, &pre_seqs, !all, &r0);
-    if (!all && r0 >= n_raw) {  // no stream character at all: redo as a complete walk
-      all = true;
+    // the early-stopping walk reads at most ~4 KB past the first stream character
+    const bool tiny = n_raw < 16384;
+    const size_t room = tiny ? n_raw + 4 : 16384 + 4;
+    std::vector<uint8_t> tmp(room);
+    pk.assign(room / 2 + 4, 0);
+    po.assign(room / 2 + 4, 0);
+    pl.assign(room / 2 + 4, 0);
+    bool all = tiny;
+    if (!all) {
+      // find how far the walk would go without writing past the buffer: the stream never grows
+      // faster than the raw position, and the walk stops within 4096 + one header of raw bytes;
+      // a header longer than the buffer sends the whole file down the host path
+      normalize_walk(raw, std::min<uint64_t>(n_raw, 16384), upper_case, eos, tmp.data(), &pre_len, pk.data(),
+                     po.data(), pl.data(), pk.size(), &pre_seqs, true, &r0);
+      if (r0 >= std::min<uint64_t>(n_raw, 16384)) all = true;  // no stream character in the first 16 KB
     }
     if (all) {
       std::vector<uint8_t> full(n_raw + 4);
@@ -1626,8 +1656,7 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
       c->seq_hdr_len.assign(l2.begin(), l2.begin() + ns);
       return stream_in(c, full.data(), len, 0, len, 0);
     }
-    pre.assign(dst, dst + pre_len);
-    if (pre_seqs > 4) return fail(PM_E_UNSUPPORTED, "unexpected FASTA prefix");
+    pre.assign(tmp.begin(), tmp.begin() + pre_len);
   }
   const uint64_t n_seg = (n_raw - r0 + FA_SEG - 1) / FA_SEG;
   int rc;
@@ -1710,7 +1739,8 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
     PM_CUDA(cudaGetLastError());
   }
   uint8_t *d_stream = c->d_text_own.as<uint8_t>();
-  fasta_write_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(
+  PM_CUDA(cudaFuncSetAttribute(fasta_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_WRITE_SMEM));
+  fasta_write_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, FA_WRITE_SMEM, st>>>(
       d_raw, r0, n_raw, n_seg, c->d_fa_start.as<uint8_t>(), c->d_fa_ooff.as<unsigned long long>(),
       c->d_fa_hoff.as<unsigned long long>(), upper_case, eos, d_stream, pre_len, pre_seqs,
       c->d_fa_key.as<long long>(), c->d_fa_hs.as<long long>(), c->d_fa_he.as<long long>());

@@ -52,13 +52,34 @@ struct FaCompose {
   }
 };
 
-__device__ __forceinline__ uint4 fa_load16(const uint8_t *raw, uint64_t at, uint64_t n) {
-  if (at + 16 <= n && ((reinterpret_cast<uintptr_t>(raw + at) & 15) == 0))
-    return __ldg(reinterpret_cast<const uint4 *>(raw + at));
-  uint32_t w[4] = {0, 0, 0, 0};
-  for (int j = 0; j < 16; j++)
-    if (at + j < n) w[j >> 2] |= (uint32_t)raw[at + j] << (8 * (j & 3));
-  return make_uint4(w[0], w[1], w[2], w[3]);
+// A block owns FA_THREADS * FA_SEG = 32 KB of raw bytes.  They are brought into shared
+// memory with coalesced 16-byte loads; thread t then walks its own 256-byte segment, which
+// sits at byte t * (FA_SEG + 4) so that the 32 lanes of a warp read 32 different banks.
+constexpr int FA_ROW = FA_SEG + 4;   // padded segment row
+constexpr int FA_STAGE_BYTES = FA_THREADS * FA_ROW;
+
+__device__ __forceinline__ void fa_stage_block(const uint8_t *__restrict__ raw, uint64_t begin, uint64_t n_raw,
+                                               uint32_t *s_in) {
+  // begin = first raw byte of the block; bytes at or past n_raw read as 0 and are never used
+  const uint32_t mis = (uint32_t)((uintptr_t)(raw + begin) & 15u);
+  if (mis == 0 && begin + (uint64_t)FA_THREADS * FA_SEG <= n_raw) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(raw + begin);
+    for (uint32_t i = threadIdx.x; i < FA_THREADS * FA_SEG / 16; i += FA_THREADS) {
+      const uint4 v = __ldg(src + i);
+      const uint32_t seg = i / (FA_SEG / 16), q = i % (FA_SEG / 16);
+      uint32_t *dst = s_in + seg * (FA_ROW / 4) + q * 4;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  } else {  // unaligned start (the host prefix ends anywhere) or the last block: word by word
+    for (uint32_t i = threadIdx.x; i < FA_THREADS * FA_SEG / 4; i += FA_THREADS) {
+      const uint64_t at = begin + 4ull * i;
+      uint32_t v = 0;
+      for (int j = 0; j < 4; j++)
+        if (at + j < n_raw) v |= (uint32_t)raw[at + j] << (8 * j);
+      s_in[(i / (FA_SEG / 4)) * (FA_ROW / 4) + (i % (FA_SEG / 4))] = v;
+    }
+  }
+  __syncthreads();
 }
 
 // pass 1: per segment, the state map and the counts for each of the three start states
@@ -66,19 +87,22 @@ __global__ void __launch_bounds__(FA_THREADS)
 fasta_summary_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw, uint64_t n_seg,
                      uint8_t *__restrict__ fmap, unsigned long long *__restrict__ cnt_out,
                      uint32_t *__restrict__ cnt_hdr) {
-  const uint64_t g = (uint64_t)blockIdx.x * FA_THREADS + threadIdx.x;
+  __shared__ uint32_t s_in[FA_STAGE_BYTES / 4];
+  const uint64_t g0 = (uint64_t)blockIdx.x * FA_THREADS;
+  fa_stage_block(raw, r0 + g0 * FA_SEG, n_raw, s_in);
+  const uint64_t g = g0 + threadIdx.x;
   if (g >= n_seg) return;
   const uint64_t begin = r0 + g * FA_SEG;
+  const int len = (int)((n_raw - begin < (uint64_t)FA_SEG) ? (n_raw - begin) : (uint64_t)FA_SEG);
+  const uint32_t *row = s_in + threadIdx.x * (FA_ROW / 4);
   uint32_t st[3] = {FA_SEQ, FA_HDR, FA_SKIP}, out[3] = {0, 0, 0}, hdr[3] = {0, 0, 0};
-  for (int q = 0; q < FA_SEG / 16; q++) {
-    const uint64_t at = begin + 16 * q;
-    if (at >= n_raw) break;
-    const uint4 v = fa_load16(raw, at, n_raw);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int q = 0; q < FA_SEG / 4; q++) {
+    if (4 * q >= len) break;
+    const uint32_t w = row[q];
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      if (at + j >= n_raw) break;
-      const uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+    for (int j = 0; j < 4; j++) {
+      if (4 * q + j >= len) break;
+      const uint32_t b = (w >> (8 * j)) & 0xffu;
       const bool gt = (b == '>'), blank = fa_blank(b);
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -109,7 +133,10 @@ fasta_select_kernel(const uint8_t *__restrict__ fscan, const unsigned long long 
 }
 
 // pass 2: write the stream and the sequence table.  out_base = stream index of the first
-// byte the device writes; hdr_base = sequences registered by the host prefix.
+// byte the device writes; hdr_base = sequences registered by the host prefix.  The block's
+// output is collected in shared memory at the same 16-byte phase as its place in the
+// stream, so that everything but its first and last few bytes leaves as aligned uint4.
+constexpr int FA_WRITE_SMEM = FA_STAGE_BYTES + FA_THREADS * FA_SEG + 32;
 __global__ void __launch_bounds__(FA_THREADS)
 fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw, uint64_t n_seg,
                    const uint8_t *__restrict__ start, const unsigned long long *__restrict__ out_off,
@@ -117,7 +144,9 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
                    uint8_t *__restrict__ stream, uint64_t out_base, uint64_t hdr_base,
                    long long *__restrict__ seq_key, long long *__restrict__ hdr_start,
                    long long *__restrict__ hdr_end) {
-  __shared__ uint8_t s_out[FA_THREADS * FA_SEG];
+  extern __shared__ __align__(16) uint32_t s_dyn[];
+  uint32_t *s_in = s_dyn;
+  uint8_t *s_out = reinterpret_cast<uint8_t *>(s_dyn + FA_STAGE_BYTES / 4);
   __shared__ unsigned long long s_base, s_end;
   const uint64_t g0 = (uint64_t)blockIdx.x * FA_THREADS;
   const uint64_t g = g0 + threadIdx.x;
@@ -126,26 +155,28 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
     const uint64_t g_last = (g0 + FA_THREADS < n_seg) ? g0 + FA_THREADS : n_seg;
     s_end = out_off[g_last];  // out_off has n_seg + 1 entries
   }
-  __syncthreads();
+  fa_stage_block(raw, r0 + g0 * FA_SEG, n_raw, s_in);   // ends with __syncthreads()
+  uint8_t *dst = stream + out_base + s_base;             // where the block's output goes
+  const uint32_t phase = (uint32_t)((uintptr_t)dst & 15u);
   if (g < n_seg) {
     const uint64_t begin = r0 + g * FA_SEG;
+    const int len = (int)((n_raw - begin < (uint64_t)FA_SEG) ? (n_raw - begin) : (uint64_t)FA_SEG);
+    const uint32_t *row = s_in + threadIdx.x * (FA_ROW / 4);
     uint32_t st = start[g];
-    uint32_t o = (uint32_t)(out_off[g] - s_base);   // position inside the block's output
-    uint64_t h = hdr_base + hdr_off[g];             // index of the next header to start
-    for (int q = 0; q < FA_SEG / 16; q++) {
-      const uint64_t at = begin + 16 * q;
-      if (at >= n_raw) break;
-      const uint4 v = fa_load16(raw, at, n_raw);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o = phase + (uint32_t)(out_off[g] - s_base);   // position inside s_out
+    uint64_t h = hdr_base + hdr_off[g];                     // index of the next header to start
+    for (int q = 0; q < FA_SEG / 4; q++) {
+      if (4 * q >= len) break;
+      const uint32_t w = row[q];
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        if (at + j >= n_raw) break;
-        uint32_t b = (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+      for (int j = 0; j < 4; j++) {
+        if (4 * q + j >= len) break;
+        uint32_t b = (w >> (8 * j)) & 0xffu;
         if (st == FA_SEQ) {
           if (b == '>') {
             s_out[o] = (uint8_t)eos;
-            seq_key[h] = (long long)(out_base + s_base + o + 1);  // first base of the sequence
-            hdr_start[h] = (long long)(at + j + 1);
+            seq_key[h] = (long long)(out_base + s_base + (o - phase) + 1);  // first base of the sequence
+            hdr_start[h] = (long long)(begin + 4 * q + j + 1);
             h++;
             o++;
           } else if (!fa_blank(b)) {
@@ -153,16 +184,27 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
             s_out[o++] = (uint8_t)b;
           }
         } else if (st == FA_HDR && (b == '\n' || b == '\r')) {
-          hdr_end[h - 1] = (long long)(at + j + 1);   // the header in progress is the last one started
+          hdr_end[h - 1] = (long long)(begin + 4 * q + j + 1);   // the header in progress is the last one started
         }
         st = fa_next(st, b);
       }
     }
   }
   __syncthreads();
+  // s_out[phase .. phase+total) -> dst[0 .. total); s_out index i and address dst - phase + i
+  // have the same 16-byte phase
   const uint32_t total = (uint32_t)(s_end - s_base);
-  uint8_t *dst = stream + out_base + s_base;
-  for (uint32_t i = threadIdx.x; i < total; i += FA_THREADS) dst[i] = s_out[i];
+  const uint32_t lo = phase, hi = phase + total;
+  const uint32_t a16 = (lo + 15u) & ~15u, b16 = hi & ~15u;   // aligned interior [a16, b16)
+  uint8_t *base = dst - phase;
+  if (a16 < b16) {
+    for (uint32_t i = lo + threadIdx.x; i < a16; i += FA_THREADS) base[i] = s_out[i];
+    for (uint32_t i = a16 / 16 + threadIdx.x; i < b16 / 16; i += FA_THREADS)
+      reinterpret_cast<uint4 *>(base)[i] = reinterpret_cast<const uint4 *>(s_out)[i];
+    for (uint32_t i = b16 + threadIdx.x; i < hi; i += FA_THREADS) base[i] = s_out[i];
+  } else {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += FA_THREADS) base[i] = s_out[i];
+  }
 }
 
 __global__ void fill_i64_kernel(long long *p, uint64_t n, long long v) {

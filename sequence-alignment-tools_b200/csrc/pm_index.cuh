@@ -366,7 +366,7 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   const uint32_t mult = a.mult;
   const uint32_t warp = threadIdx.x >> 5;
 
-  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < t.n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     int64_t w;
     uint32_t c0, c1, c2, vm;
     pair_load_words(a, t, c, w, c0, c1, c2, vm);
@@ -416,7 +416,7 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
   for (int j = 0; j < ND; j++) salt[j] = a.salt[j];
 
-  for (int64_t c = (int64_t)blockIdx.x * PAIR_WARPS + warp; c < t.n_chunks; c += (int64_t)gridDim.x * PAIR_WARPS) {
+  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     int64_t w;
     uint32_t cw[4], vm;
     pair_load_words(a, t, c, w, cw[0], cw[1], cw[2], vm);
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(256)
 pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *__restrict__ lin,
                    uint32_t eos_byte, uint2 *__restrict__ pk, uint64_t w_begin, uint64_t w_end,
                    unsigned long long *__restrict__ amb, unsigned long long *__restrict__ amb_n,
-                   uint64_t amb_cap) {
+                   uint64_t amb_cap, int dna_fast) {
   __shared__ uint8_t s_lin[256];
   s_lin[threadIdx.x] = lin[threadIdx.x];
   __syncthreads();
@@ -575,6 +575,24 @@ pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *
           x |= (uint32_t)((i < n) ? text[i] : (uint8_t)eos_byte) << (8 * q);
         }
         b[j] = x;
+      }
+    }
+    if (dna_fast) {
+      // A C G T only (the usual case): code = (byte >> 1) & 3, four characters per word.  The
+      // bits outside the code must be 0x41 (A, C, G) or 0x50 (T); x * 0x01041040 gathers the
+      // four 2-bit codes of a word (one per byte) into its top byte: byte j moves up by
+      // 24 - 6j bits, and the other partial products stay below bit 24 or leave the word.
+      uint32_t bad = 0, cw = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t x4 = b[j];
+        const uint32_t is_t = (x4 >> 2) & ~(x4 >> 1) & 0x01010101u;
+        bad |= (x4 & 0xF9F9F9F9u) ^ (0x41414141u + is_t * 15u);
+        cw |= ((((x4 >> 1) & 0x03030303u) * 0x01041040u) >> 24) << (8 * j);
+      }
+      if (bad == 0) {
+        pk[w] = make_uint2(cw, 0u);
+        continue;
       }
     }
     uint32_t codes = 0, flags = 0, ambm = 0;
