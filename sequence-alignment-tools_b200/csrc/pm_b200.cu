@@ -143,7 +143,8 @@ struct pm_ctx {
   pm_options opt;
   int index = 0;  // resolved PM_INDEX_*
   cudaStream_t stream = 0;
-  cudaStream_t copy_stream = 0;
+  cudaStream_t copy_stream = 0;   // host -> device copies only, back to back
+  cudaStream_t prep_stream = 0;   // unpack / pack kernels of the chunks that have arrived
   std::vector<Pattern> pats;
   bool inited = false;
   int max_len = 0;
@@ -929,6 +930,7 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&c->prep_stream, cudaStreamNonBlocking);
 
   *out = c;
   return PM_OK;
@@ -960,6 +962,7 @@ void pm_destroy(pm_ctx *c) {
     if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
   delete c;
 }
 
@@ -1369,7 +1372,8 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
   if ((rc = prepare_planes(c))) return rc;
   PM_CUDA(cudaEventRecord(c->ev[4], c->stream));
   PM_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev[4], 0));  // earlier work may still read the buffers
-  PM_CUDA(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->copy_stream));
+  PM_CUDA(cudaStreamWaitEvent(c->prep_stream, c->ev[4], 0));
+  PM_CUDA(cudaMemsetAsync(c->d_counters + 8, 0, sizeof(unsigned long long), c->prep_stream));
   if (!pinned)
     for (int i = 0; i < 2; i++)
       if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
@@ -1399,16 +1403,20 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
     const bool last = (done == n_bytes);
     uint64_t chars = n;  // characters of the stream that are on the device now
     if (!last) chars = bits ? std::min<uint64_t>(n, (done * 8 / bits) & ~15ull) : done;
+    // the kernels of this chunk run on the prep stream, so that the next copy starts at once
+    cudaEvent_t arrived = next_event(c);
+    PM_CUDA(cudaEventRecord(arrived, c->copy_stream));
+    PM_CUDA(cudaStreamWaitEvent(c->prep_stream, arrived, 0));
     if (bits) {
       const uint64_t g1 = last ? (n + 15) / 16 : chars / 16;
-      if ((rc = unpack_groups(c, bits, n_bytes, groups_done, g1, c->copy_stream))) return rc;
+      if ((rc = unpack_groups(c, bits, n_bytes, groups_done, g1, c->prep_stream))) return rc;
       groups_done = std::max(groups_done, g1);
     }
     const uint32_t ready = last ? c->n_tiles
                                 : (uint32_t)((chars > (uint64_t)TILE_EXT ? chars - TILE_EXT : 0) / TILE_POS);
-    if ((rc = pack_tiles(c, tiles_done, ready, c->copy_stream))) return rc;
+    if ((rc = pack_tiles(c, tiles_done, ready, c->prep_stream))) return rc;
     cudaEvent_t e = next_event(c);
-    PM_CUDA(cudaEventRecord(e, c->copy_stream));
+    PM_CUDA(cudaEventRecord(e, c->prep_stream));
     c->chunks.push_back(pm_ctx::Chunk{ready, e});
     tiles_done = std::max(tiles_done, ready);
   }
