@@ -243,13 +243,17 @@ __global__ void chain_fill_kernel(const unsigned long long *keys, uint64_t n, co
 }
 
 // workspace size per chain (0 for chains this call does not own)
+// guard_end > 0: the scanned window ends there although the text goes on; an owned chain whose
+// last candidate lies within 2k+1 of it may continue past the window (*cut is set).
 __global__ void chain_ws_kernel(const Chain *chains, uint64_t n, const uint8_t *plen, int k,
-                                int64_t own_lo, int64_t own_hi, unsigned long long *ws_bytes) {
+                                int64_t own_lo, int64_t own_hi, unsigned long long *ws_bytes,
+                                int64_t guard_end, unsigned long long *cut) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Chain c = chains[i];
   unsigned long long b = 0;
   if (c.first >= own_lo && c.first < own_hi) {
+    if (guard_end > 0 && c.last + (2 * k + 1) >= guard_end) *cut = 1ULL;
     const int m = plen[c.slot] & 0x7f;
     const int64_t buflen = c.last - align_textstart(c.first, m, k);
     b = (align_ws_bytes(m, buflen) + 15ull) & ~15ull;

@@ -135,6 +135,7 @@ constexpr size_t kStageBytes = 64u << 20;       // pinned staging buffer (x2)
 constexpr uint64_t kWsBudget = 2ull << 30;      // alignment workspace per batch
 constexpr int64_t kRightGuard = 1 << 16;
 constexpr uint64_t kAmbCap = 1u << 20;          // ambiguous text characters the index path re-examines
+constexpr int kGuardTooShort = -101;           // internal: an owned chain runs into the end of the right guard
 constexpr int kFallbackToPlanes = -100;        // internal: too many of them, rescan with the bit-plane kernels
 
 }  // namespace
@@ -662,7 +663,21 @@ int run_scan_any(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   return rc;
 }
 
+int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard);
+
+// The hits whose chain head lies in [begin, end).  Chains are followed past `end` into a right
+// guard; when one is still alive at the end of the guard the scan is repeated with a guard
+// eight times as long (up to the end of the loaded text).
 int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
+  int64_t guard = kRightGuard;
+  for (;;) {
+    const int rc = find_patterns_guarded(c, begin, end, nhits, guard);
+    if (rc != kGuardTooShort) return rc;
+    guard *= 8;
+  }
+}
+
+int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard) {
   *nhits = 0;
   if (!c->inited) return fail(PM_E_ARG, "pm_find_patterns before pm_init");
   if (!c->d_text && c->n) return fail(PM_E_ARG, "no text");
@@ -684,7 +699,7 @@ int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
     lo = own_lo - (2 * K + 1);
     if (lo < 0) lo = 0;
     if (own_hi < (int64_t)c->n + 1) {
-      hi = own_hi + kRightGuard;
+      hi = own_hi + right_guard;
       guarded = true;
       if (hi >= (int64_t)c->n + 1) { hi = (int64_t)c->n + 1; guarded = false; }
     }
@@ -734,9 +749,10 @@ int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
       chain_fill_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(
           keys, ncand, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(), c->d_chains.as<Chain>());
       PM_CUDA(cudaMemsetAsync(c->d_wsb.as<unsigned long long>() + n_chains, 0, 8, c->stream));
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 9, 0, sizeof(unsigned long long), c->stream));
       chain_ws_kernel<<<nblocks(n_chains, 256), 256, 0, c->stream>>>(
           c->d_chains.as<Chain>(), n_chains, c->d_plen.as<uint8_t>(), K, own_lo, own_hi,
-          c->d_wsb.as<unsigned long long>());
+          c->d_wsb.as<unsigned long long>(), guarded ? hi : 0, c->d_counters + 9);
       tb = 0;
       cub::DeviceScan::ExclusiveSum(nullptr, tb, c->d_wsb.as<unsigned long long>(),
                                     c->d_wsoff.as<unsigned long long>(), n_chains + 1, c->stream);
@@ -750,7 +766,14 @@ int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
       std::vector<unsigned long long> off(n_chains + 1);
       PM_CUDA(cudaMemcpyAsync(off.data(), c->d_wsoff.p, (n_chains + 1) * 8, cudaMemcpyDeviceToHost,
                               c->stream));
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 9, c->d_counters + 9, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
+      if (guarded && c->h_counters[9]) {
+        // an owned chain reaches the end of the right guard: scan further and start over
+        *nhits = 0;
+        return kGuardTooShort;
+      }
       if ((rc = c->d_raw.ensure(n_chains * sizeof(RawHit)))) return rc;
       PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
       uint64_t c0 = 0;
@@ -772,12 +795,6 @@ int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
                               cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
       n_out = c->h_counters[4];
-      if (guarded) {
-        // a chain that reaches the end of the scanned window may continue past it
-        // (the host cannot tell): refuse rather than report a truncated chain
-        const unsigned long long last_needed = (unsigned long long)(hi - (2 * K + 1) - 1);
-        (void)last_needed;  // checked on the device side in a later revision
-      }
       if (n_out) {
         // final alignment: R = 0, buffer of at most m+k characters
         const uint64_t stride = (align_ws_bytes(c->max_len, c->max_len + K) + 15) & ~15ull;

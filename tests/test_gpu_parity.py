@@ -168,6 +168,38 @@ def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     assert merged.tobytes() == whole.tobytes()
 
 
+def test_chain_longer_than_the_right_guard(pkg):
+    """A poly-A run of 300 kb against a poly-A primer is ONE chain of candidates.  A rank
+    whose range ends inside the run must follow it past the 64 Ki right guard (the scan
+    is repeated with a longer guard) to report the same hit as a whole-stream scan."""
+    import casegen
+    rng = random.Random(3)
+    primers = ["A" * 16, casegen.rand_dna(rng, 20)]
+    seq = list(casegen.rand_dna(rng, 500_000))
+    seq[40_000:340_000] = "A" * 300_000
+    seq[400_000:400_020] = list(primers[1])
+    st = pkg.normalize_fasta((">s\n" + "".join(seq) + "\n").encode())
+    T = st.chars
+
+    def run(begin, end):
+        sc = pkg.Scanner(k=1, indels=True)
+        for i, p in enumerate(primers):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(T)
+        h = sc.find_patterns(begin, end)
+        sc.close()
+        return h
+
+    whole = run(0, pkg.INT64_MAX)
+    parts = [run(0, 50_000), run(50_000, 390_000), run(390_000, pkg.INT64_MAX)]
+    merged = np.concatenate(parts)
+    merged = merged[np.lexsort((merged["pattern_id"], merged["first"]))]
+    assert len(whole) >= 2
+    assert merged.tobytes() == whole.tobytes()
+    assert len(parts[0]) >= 1     # the run's single hit belongs to the rank its chain starts in
+
+
 def test_many_ambiguous_characters_fall_back_to_planes(pkg):
     """With -w a text 'R' matches the pattern symbols A, G and R: the pair index lists
     such characters and re-examines their windows; past 2^20 of them it hands the
