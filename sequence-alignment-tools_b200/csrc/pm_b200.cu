@@ -411,7 +411,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     ia.hi = hi;
     ia.k = (uint32_t)K;
     ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * 2 * PAIR_QCAP * 8 +
-            (ia.log_words2 ? ((size_t)4 << ia.log_words2) : 0);
+            ((ia.log_words2 && !ia.b2_global) ? ((size_t)4 << ia.log_words2) : 0);
     PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
   }
   void (*kern)(const ScanArgs) = nullptr;
@@ -1263,18 +1263,23 @@ int pm_init(pm_ctx *c) {
       while (((size_t)1 << lb) < 2 * ents.size() && lb < 26) lb++;
       ia.log_buckets = (uint32_t)lb;
       const size_t nb = (size_t)1 << lb;
-      // level 1b for edits: 64 KB keyed by (key, distance)
-      ia.log_words2 = edit_mode ? 14u : 0u;
+      // level 1b: 64 KB of shared memory keyed by (key, distance) for edits; 16 MB of global
+      // memory (L2-resident) once level 1 saturates (its 2^20 bits pass ~entries / 2^20 of the
+      // positions)
+      const bool big_set = ents.size() > 32768;
+      ia.b2_global = big_set ? 1u : 0u;
+      ia.log_words2 = big_set ? 22u : (edit_mode ? 14u : 0u);
       ia.mult2 = 0x85EBCA6Bu;
       for (size_t d = 0; d < dist.size(); d++) ia.salt2[d] = (uint32_t)(d + 1) * 0xC2B2AE35u;
-      std::vector<uint32_t> bitmap2(edit_mode ? ((size_t)1 << ia.log_words2) : 4, 0);
+      const bool have2 = ia.log_words2 != 0;
+      std::vector<uint32_t> bitmap2(have2 ? ((size_t)1 << ia.log_words2) : 4, 0);
       std::vector<uint32_t> bitmap((size_t)1 << ia.log_words, 0), bucket(nb + 1, 0);
       std::vector<uint32_t> hs(ents.size());
       for (size_t x = 0; x < ents.size(); x++) {
         const uint32_t di = (ents[x].y >> 5) & 31u;
         const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
         bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
-        if (edit_mode) {
+        if (have2) {
           const uint32_t idx2 = ents[x].x * ia.mult2 + ia.salt2[di];
           bitmap2[idx2 >> (32 - ia.log_words2)] |= 1u << (idx2 & 31u);
         }

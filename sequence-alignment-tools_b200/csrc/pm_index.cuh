@@ -64,9 +64,13 @@ struct IndexArgs {
   uint32_t mult;            // odd multiplier of the level-1 hash
   uint32_t dist[PAIR_MAX_ND];
   uint32_t salt[PAIR_MAX_ND];
-  // level 1b (edits): a second, smaller bitmap keyed by (pair key, distance); 0 words = absent
+  // level 1b: a second bitmap keyed by (pair key, distance), consulted only for the positions
+  // that passed level 1; log_words2 == 0: absent.  Edits: 64 KB in the shared memory level 1
+  // leaves free.  Large pattern sets (level 1 saturates beyond ~30 k entries): 16 MB in
+  // global memory, L2-resident (b2_global).
   const uint32_t *bitmap2;
   uint32_t log_words2;
+  uint32_t b2_global;
   uint32_t mult2;
   uint32_t salt2[PAIR_MAX_ND];
   // level 2
@@ -233,8 +237,8 @@ __device__ __forceinline__ void pair_stage_a(const IndexArgs &a, PairQueues &q, 
 // gets the next two words by shuffle, so the 16 positions of its word see their
 // 32-character context without any further load.
 struct PairCta {
-  uint32_t *bitmap;    // shared-memory copy of level 1
-  uint32_t *bitmap2;   // ... of level 1b (edits), or unused
+  uint32_t *bitmap;          // shared-memory copy of level 1
+  const uint32_t *bitmap2;   // level 1b: shared-memory copy, or the global table (b2_global)
   uint32_t n_words2;
   PairQueues q;
   uint32_t lane, lt;
@@ -247,11 +251,13 @@ __device__ __forceinline__ void pair_cta_init(const IndexArgs &a, uint32_t *s_me
   t.bitmap = s_mem;
   unsigned long long *s_queue = reinterpret_cast<unsigned long long *>(s_mem + n_words);
   t.n_words2 = a.bitmap2 ? (1u << a.log_words2) : 0u;
-  t.bitmap2 = s_mem + n_words + PAIR_WARPS * 2 * PAIR_QCAP * 2;  // behind the queues
+  uint32_t *s_bitmap2 = s_mem + n_words + PAIR_WARPS * 2 * PAIR_QCAP * 2;  // behind the queues
+  t.bitmap2 = a.b2_global ? a.bitmap2 : s_bitmap2;
   for (uint32_t i = threadIdx.x; i < n_words / 4; i += blockDim.x)
     reinterpret_cast<uint4 *>(t.bitmap)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap) + i);
-  for (uint32_t i = threadIdx.x; i < t.n_words2 / 4; i += blockDim.x)
-    reinterpret_cast<uint4 *>(t.bitmap2)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap2) + i);
+  if (!a.b2_global)
+    for (uint32_t i = threadIdx.x; i < t.n_words2 / 4; i += blockDim.x)
+      reinterpret_cast<uint4 *>(s_bitmap2)[i] = __ldg(reinterpret_cast<const uint4 *>(a.bitmap2) + i);
   __syncthreads();
   t.lane = threadIdx.x & 31;
   t.lt = (1u << t.lane) - 1u;
@@ -300,7 +306,8 @@ __device__ __forceinline__ uint32_t pair_level1b(const IndexArgs &a, const PairC
     const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
     const uint32_t key = (v0 & maskL) | ((hi & maskL) << L2);
     const uint32_t idx2 = key * a.mult2 + salt2;
-    if ((t.bitmap2[idx2 >> wsh2] >> (idx2 & 31u)) & 1u) keep |= 1u << b;
+    const uint32_t wrd = a.b2_global ? __ldg(a.bitmap2 + (idx2 >> wsh2)) : t.bitmap2[idx2 >> wsh2];
+    if ((wrd >> (idx2 & 31u)) & 1u) keep |= 1u << b;
   }
   return keep;
 }
@@ -392,6 +399,34 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   pair_cta_finish<EDIT>(a, t);
 }
 
+// level 1b for large pattern sets (substitutions): level 1 passes a sizeable fraction of the
+// positions there; ask the L2-resident (key, distance) table before anything is queued.  The
+// 16 loads of a lane are independent, so their latencies overlap.  Kept out of line: its 32
+// temporaries must not cost the lookup loop its registers.
+template <int L>
+__device__ __noinline__ uint32_t pair_level1b_global(const IndexArgs &a, uint32_t h, int j, uint32_t c0,
+                                                     uint32_t c1, uint32_t c2) {
+  if (__all_sync(0xffffffffu, h == 0u)) return 0u;
+  constexpr uint32_t L2 = 2 * L;
+  constexpr uint32_t maskL = (1u << L2) - 1u;
+  const uint32_t wsh2 = 32u - a.log_words2;
+  const uint32_t salt2 = a.salt2[j];
+  const uint32_t d2 = 2u * (uint32_t)(j + 1) * L;   // bit distance of the second piece
+  uint32_t wrd[16], idx2[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint32_t v0 = __funnelshift_r(c0, c1, 2 * i), v1 = __funnelshift_r(c1, c2, 2 * i), v2 = c2 >> (2 * i);
+    const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
+    const uint32_t key = (v0 & maskL) | ((hi & maskL) << L2);
+    idx2[i] = key * a.mult2 + salt2;
+    wrd[i] = ((h >> (15 - i)) & 1u) ? __ldg(a.bitmap2 + (idx2[i] >> wsh2)) : 0u;
+  }
+  uint32_t keep = 0u;
+#pragma unroll
+  for (int i = 0; i < 16; i++) keep |= ((wrd[i] >> (idx2[i] & 31u)) & 1u) << (15 - i);
+  return keep;
+}
+
 // Substitution scan with compile-time piece length and distance count: the
 // distances are L, 2L, .., ND*L, so the shifted windows G[t] = text >> 2t are
 // shared between the lookups of different positions (position i at distance
@@ -435,6 +470,10 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
         const uint32_t key = (j == 0) ? (G[i] & mask2L) : ((G[i + j * L] & maskHi) | av);
         hm[j] = pair_probe(t.bitmap, key, mult, salt[j], wsh, hm[j]);
       }
+    }
+    if (a.b2_global) {
+#pragma unroll
+      for (int j = 0; j < ND; j++) hm[j] = pair_level1b_global<L>(a, hm[j] & vm, j, cw[0], cw[1], cw[2]);
     }
 #pragma unroll
     for (int j = 0; j < ND; j++) pair_push<false>(a, t, w, (uint32_t)j, hm[j] & vm);

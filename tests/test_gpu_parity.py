@@ -168,6 +168,37 @@ def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     assert merged.tobytes() == whole.tobytes()
 
 
+@pytest.mark.parametrize("k,indels", [(0, False), (1, False), (1, True)])
+def test_large_pattern_set_uses_the_l2_filter(pkg, k, indels):
+    """18 000 primers x 2 strands: the 2^20-bit level-1 bitmap saturates and the L2-resident
+    level-1b table takes over.  Same hits as the bit-plane kernels."""
+    import casegen
+    rng = random.Random(40 + k)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(18000)]
+    n = 1_500_000
+    g = np.random.default_rng(8)
+    seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, n)].copy()
+    for j in range(300):
+        q = casegen.mutate(rng, primers[rng.randrange(len(primers))], rng.randint(0, k), indels)
+        at = 500 + j * 4900
+        seq[at:at + len(q)] = np.frombuffer(q.encode(), np.uint8)
+    T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
+    pats = pkg.pattern_array(primers, True)
+    out = {}
+    for name, sp in (("index", pkg.PM_SCAN_INDEX), ("planes", pkg.PM_SCAN_PLANES)):
+        sc = pkg.Scanner(k=k, indels=indels, scan_path=sp)
+        for i, p in enumerate(pats):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(T)
+        out[name] = sc.find_patterns()
+        if name == "index":
+            assert sc.stats()["index_entries"] > 32768
+        sc.close()
+    assert len(out["planes"]) >= 300
+    assert out["index"].tobytes() == out["planes"].tobytes()
+
+
 def test_chain_longer_than_the_right_guard(pkg):
     """A poly-A run of 300 kb against a poly-A primer is ONE chain of candidates.  A rank
     whose range ends inside the run must follow it past the 64 Ki right guard (the scan
