@@ -351,9 +351,8 @@ def main():
         if world == 1:
             return nh
         t = torch.tensor([nh], dtype=torch.int64, device=dev)
-        out = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(out, t)
-        return int(sum(int(o.item()) for o in out))
+        dist.all_reduce(t)                      # NCCL: the hit counts of all shards, summed
+        return int(t.item())
 
     def barrier():
         if world > 1:

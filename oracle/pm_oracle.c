@@ -506,3 +506,170 @@ int pmo_exact_wc_align(const uint8_t *T, long L, const char *pat, int64_t end,
   }
   return sub;
 }
+
+/* ------------------------------------------------------------------------- */
+/* primer_alignment::global_align, primer_alignment.cc:9-462, as exact_halves */
+/* uses it: yesno_ = true (no traceback), dna_mut_ = false.  text[0..textlen) */
+/* is aligned against pat from its left end (dirn > 0) or from its right end  */
+/* (dirn < 0) inside a band of +-maxdist (0 without indels).  lmatch / rmatch */
+/* are the reference's `unsigned int` parameters: exact_halves passes         */
+/* lmatch_ - pattern1.length() computed in unsigned arithmetic, and the       */
+/* result lands in the int variables lbexact / rbexact (lines 43-52).         */
+/* Line 97 of the reference reads `patch` before it is assigned; the          */
+/* comparison is taken as false here (the pins decide: goldens made with the  */
+/* reference's automatic index choice for k = 1).                             */
+/* Returns the function's bool; *matchlen = bestpos, *value = bestval.        */
+#define PA_M 1 /* equal / wildcard equal / substitution: the diagonal move */
+#define PA_I 2
+#define PA_D 4
+#define PA_V 8
+int pmo_primer_global_align(const uint8_t *text, unsigned textlen, const char *pat, int dirn,
+                            unsigned lmatch, unsigned rmatch, int maxdist, uint8_t eos, int wc,
+                            int tn, int indels, int *matchlen, int *value) {
+  compat_init();
+  const unsigned patlen = (unsigned)strlen(pat);
+  const unsigned textlenp1 = textlen + 1, patlenp1 = patlen + 1;
+  unsigned *dp = (unsigned *)malloc(sizeof(unsigned) * (size_t)textlenp1 * patlenp1);
+  unsigned *best = (unsigned *)malloc(sizeof(unsigned) * (size_t)textlenp1 * patlenp1);
+  for (size_t i = 0; i < (size_t)textlenp1 * patlenp1; i++) { dp[i] = 0x3fffffff; best[i] = 0; }
+#define PIDX(p, t) ((size_t)(p) * textlenp1 + (size_t)(t))
+  int lbexact = 0, rbexact = (int)patlenp1;
+  const int cv = 5 * maxdist + 1;
+  if (dirn < 0) {
+    if (lmatch > 0) rbexact = (int)(patlenp1 - lmatch);
+    if (rmatch > 0) lbexact = (int)rmatch;
+  } else {
+    if (lmatch > 0) lbexact = (int)lmatch;
+    if (rmatch > 0) rbexact = (int)(patlenp1 - rmatch);
+  }
+  const int kk = indels ? maxdist : 0;
+  int p, t, lb, ub, ret = 0;
+  dp[0] = 0;
+  ub = kk;
+  if (patlen < (unsigned)ub) ub = (int)patlen;
+  for (p = 1; p <= ub; p++) {
+    if (!indels || p < lbexact || p >= rbexact) { dp[PIDX(p, 0)] = (unsigned)cv; best[PIDX(p, 0)] = PA_V; }
+    else { dp[PIDX(p, 0)] = dp[PIDX(p - 1, 0)] + 1; best[PIDX(p, 0)] = PA_D; }
+  }
+  ub = kk;
+  if (textlen < (unsigned)ub) ub = (int)textlen;
+  for (t = 1; t <= ub; t++) {
+    const uint8_t textch = dirn > 0 ? text[t - 1] : text[textlen - t];
+    if (!indels || 0 < lbexact || 0 >= rbexact || textch == eos) { dp[PIDX(0, t)] = (unsigned)cv; best[PIDX(0, t)] = PA_V; }
+    else { dp[PIDX(0, t)] = dp[PIDX(0, t - 1)] + 1; best[PIDX(0, t)] = PA_I; }
+  }
+  for (p = 1; p <= (int)patlen; p++) {
+    lb = p - kk;
+    if (lb < 1) lb = 1;
+    ub = p + kk;
+    if (textlen < (unsigned)ub) ub = (int)textlen;
+    int bestscorerow = cv;
+    for (t = lb; t <= ub; t++) {
+      uint8_t textch, patch;
+      if (dirn > 0) { textch = text[t - 1]; patch = (uint8_t)pat[p - 1]; }
+      else { textch = text[textlen - t]; patch = (uint8_t)pat[patlen - p]; }
+      int v, v1;
+      unsigned ac, ac1;
+      if (textch == patch) { v = (int)dp[PIDX(p - 1, t - 1)]; ac = PA_M; }
+      else if (wc && textch < 128 && patch < 128 && g_compat[textch][patch] && (tn || textch != 'N')) {
+        v = (int)dp[PIDX(p - 1, t - 1)]; ac = PA_M;
+      } else if (textch == eos || patch == eos || p <= lbexact || p >= rbexact) { v = cv; ac = PA_V; }
+      else { v = (int)dp[PIDX(p - 1, t - 1)] + 1; ac = PA_M; }
+      if (textch == eos || patch == eos || !indels || t <= lb || p < lbexact || p >= rbexact) { v1 = cv; ac1 = PA_V; }
+      else { v1 = (int)dp[PIDX(p, t - 1)] + 1; ac1 = PA_I; }
+      if (v1 < v) { v = v1; ac = ac1; } else if (v1 == v) ac |= ac1;
+      if (!indels || t >= ub || p <= lbexact || p >= rbexact) { v1 = cv; ac1 = PA_V; }
+      else { v1 = (int)dp[PIDX(p - 1, t)] + 1; ac1 = PA_D; }
+      if (v1 < v) { v = v1; ac = ac1; } else if (v1 == v) ac |= ac1;
+      dp[PIDX(p, t)] = (unsigned)v;
+      best[PIDX(p, t)] = ac;
+      if (bestscorerow > v) bestscorerow = v;
+    }
+    if (bestscorerow > maxdist) goto done;
+  }
+  {
+    int bestpos = (int)(patlen - (unsigned)kk);
+    if (textlen < (unsigned)bestpos) bestpos = (int)textlen;
+    if (bestpos < 0) bestpos = 0;
+    int bestval = (int)dp[PIDX(patlen, bestpos)];
+    ub = (int)patlen + kk;
+    if (textlen < (unsigned)ub) ub = (int)textlen;
+    for (int k2 = bestpos + 1; k2 <= ub; k2++) {
+      const int val = (int)dp[PIDX(patlen, k2)];
+      if (val < bestval || (val <= bestval && (best[PIDX(patlen, k2)] & PA_M))) { bestval = val; bestpos = k2; }
+    }
+    p = (int)patlen;
+    t = bestpos;
+    if (t < p - kk || t > p + kk) goto done;
+    *matchlen = bestpos;
+    *value = bestval;
+    ret = 1;
+  }
+done:
+  free(dp);
+  free(best);
+  return ret;
+#undef PIDX
+}
+
+/* ------------------------------------------------------------------------- */
+/* exact_halves::find_patterns, exact_halves.cc:118-199 (+ init, 201-224):    */
+/* exact occurrences of the two halves of every pattern (inner index ids:     */
+/* left half 2i-1, right half 2i), taken in the order (position, inner id     */
+/* descending); a left-half occurrence ending at pos is extended to the right */
+/* (primer_alignment_lmatch, primer_alignment.cc:581-658: text [pos, pos +    */
+/* |right| + k), end = pos + matchlen), a right-half occurrence ending at pos */
+/* to the left (primer_alignment_rmatch, 660-741: text [max(0, pos - m - k),  */
+/* pos - |right|), end = pos); a hit is reported when its end lies beyond the */
+/* pattern's last reported end (+ 2k with indels).  half_hits: occurrences of */
+/* the 2*npat half patterns (pid = inner id), any order.  Output (end, pid,   */
+/* val) with pid = outer pattern id.                                          */
+static int half_hit_cmp(const void *a, const void *b) {
+  const pmo_hit *x = (const pmo_hit *)a, *y = (const pmo_hit *)b;
+  if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+  return x->pid > y->pid ? -1 : (x->pid < y->pid ? 1 : 0);
+}
+long pmo_exact_halves(const uint8_t *T, long L, int npat, const char *const *pats,
+                      pmo_hit *half_hits, long nhalf, int k, uint8_t eos, int wc, int tn, int indels,
+                      const int *lconst, const int *rconst, pmo_hit *out, long cap) {
+  qsort(half_hits, (size_t)nhalf, sizeof(pmo_hit), half_hit_cmp);
+  int64_t *lasthit = (int64_t *)calloc((size_t)npat + 1, sizeof(int64_t));
+  long n = 0;
+  uint8_t buf[512];
+  for (long i = 0; i < nhalf; i++) {
+    const int hid = half_hits[i].pid;          /* inner id */
+    const int pid = (hid + 1) / 2;             /* outer pattern */
+    const int64_t pos = half_hits[i].pos;
+    const char *pat = pats[pid - 1];
+    const int m = (int)strlen(pat), l1 = m / 2, l2 = m - l1;
+    const unsigned esb = (unsigned)(lconst ? lconst[pid - 1] : 0), eeb = (unsigned)(rconst ? rconst[pid - 1] : 0);
+    int matchlen = 0, value = 0, ok;
+    int64_t end;
+    if (hid % 2 == 1) {
+      const int buflen = l2 + k;
+      for (int j = 0; j < buflen; j++) buf[j] = stream_at(T, L, pos + j);
+      ok = pmo_primer_global_align(buf, (unsigned)buflen, pat + l1, 1, esb - (unsigned)l1, eeb, k, eos, wc, tn,
+                                   indels, &matchlen, &value);
+      end = pos + matchlen;
+    } else {
+      int64_t textstart = 0;
+      const int patlen = l1 + l2 + k;
+      if (pos > (int64_t)patlen) textstart = pos - patlen;
+      const int buflen = (int)(pos - l2 - textstart);
+      char left[80];
+      memcpy(left, pat, (size_t)l1);
+      left[l1] = 0;
+      for (int j = 0; j < buflen; j++) buf[j] = stream_at(T, L, textstart + j);
+      ok = pmo_primer_global_align(buf, (unsigned)(buflen < 0 ? 0 : buflen), left, -1, esb, eeb - (unsigned)l2, k, eos, wc,
+                                   tn, indels, &matchlen, &value);
+      end = pos;
+    }
+    if (ok && end > lasthit[pid] + (indels ? 2 * k : 0)) {
+      if (n < cap) { out[n].pos = end; out[n].pid = pid; out[n].val = value; }
+      n++;
+      lasthit[pid] = end;
+    }
+  }
+  free(lasthit);
+  return n;
+}

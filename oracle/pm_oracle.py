@@ -63,6 +63,10 @@ def lib():
                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int), C.POINTER(C.c_int), u8p,
                                          C.POINTER(C.c_int)]
+        L.pmo_exact_halves.restype = C.c_long
+        L.pmo_exact_halves.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_Hit), C.c_long,
+                                       C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), C.POINTER(_Hit), C.c_long]
         L.pmo_filter_chains.restype = C.c_long
         L.pmo_filter_chains.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p),
                                         C.POINTER(_Hit), C.c_long, C.c_int, C.c_uint8, C.c_int,
@@ -237,10 +241,38 @@ def pattern_array(primers, rev_comp: bool):
     return pats
 
 
+def exact_halves(chars, pats, k: int, indels: bool, wc=False, tn=False, eos=EOS):
+    """exact_halves::find_patterns: (end, pattern id, value) of every reported hit."""
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    halves = []
+    for p in pats:
+        halves += [p[:len(p) // 2], p[len(p) // 2:]]      # inner ids 2i-1, 2i (exact_halves.cc:201-224)
+    hh = exact_scan(chars, halves, wc, tn)
+    n = len(hh)
+    hb = (_Hit * max(n, 1))()
+    for i, (pos, pid, _) in enumerate(hh):
+        hb[i].pos, hb[i].pid, hb[i].val = int(pos), int(pid), 0
+    out = (_Hit * max(n, 1))()
+    m = L.pmo_exact_halves(_u8(chars), len(chars), len(pats), _pats(pats), hb, n, k, eos, int(wc), int(tn),
+                           int(indels), None, None, out, max(n, 1))
+    return np.array([[out[i].pos, out[i].pid, out[i].val] for i in range(m)], np.int64).reshape(-1, 3)
+
+
+def auto_index(primers, k: int) -> str:
+    """pick_pattern_index (select.cc:100-141) for a streamed FASTA database without exact-base
+    constraints and a build with -DNOPRIMEGEN: exact_halves for k == 1 and primers of at least
+    8 characters, filter_bitvec for every other k > 0."""
+    if k == 1 and min(len(p) for p in primers) >= 8:
+        return "exact_halves"
+    return "filter_bitvec" if k > 0 else "exact"
+
+
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS):
-    """Whole path, as the reference runs it with `-N 5` for k>0 (filter_bitvec)
-    and its automatic choice for k==0 (keyword_tree, or shift_and under -w/-W).
+                 eos=EOS, index="filter_bitvec"):
+    """Whole path, as the reference runs it with `-N 5` for k>0 (index="filter_bitvec"), with its
+    exact_halves index (index="exact_halves": the automatic choice for k == 1), and its
+    automatic choice for k==0 (keyword_tree, or shift_and under -w/-W).
     Returns a sorted list of HitRecord."""
     n = len(primers)
     pats = pattern_array(primers, rev_comp)
@@ -248,6 +280,8 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
     recs = []
     if k == 0:
         hits = exact_scan(T, pats, wc, tn)
+    elif index == "exact_halves":
+        hits = exact_halves(T, pats, k, indels, wc, tn, eos)
     else:
         cands = wm_scan(T, pats, k, indels, wc, tn, eos)
         hits = filter_chains(T, pats, cands, k, indels, wc, tn, None, None, eos)

@@ -44,6 +44,12 @@ def golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def halves_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "exact_halves_golden.json")) as f:
+        return json.load(f)
+
+
 def records_of(case):
     return [tuple(r) for r in case["records"]]
 

@@ -51,3 +51,16 @@ def test_oracle_hamming_candidates_are_mismatch_counts(oracle):
                 if int((w != pa).sum()) <= k:
                     want.add((t + 1, pi + 1))
         assert got == want
+
+
+def test_oracle_exact_halves_matches_reference_golden(oracle, halves_golden):
+    """k = 1 with the reference's automatic index choice (exact_halves over its exact index,
+    primer_alignment.cc DP), and exact_halves forced with k = 2."""
+    assert len(halves_golden["cases"]) >= 40
+    assert sum(len(c["records"]) for c in halves_golden["cases"]) > 300
+    for case in halves_golden["cases"]:
+        st = oracle.normalize_fasta(case["fasta"].encode("latin-1"))
+        if case["select"] == 0:
+            assert oracle.auto_index(case["primers"], case["params"]["k"]) == "exact_halves"
+        got = oracle.primer_match(st, case["primers"], index="exact_halves", **case["params"])
+        assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
