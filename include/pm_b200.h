@@ -43,13 +43,22 @@ extern "C" {
  *   keyword_tree / shift_and : every exact occurrence (k must be 0)
  *   filter_bitvec            : shift_and_inexact candidates, chained and
  *                              re-aligned (filter_bitvec.cc:126-236)
- * PM_INDEX_AUTO follows pick_pattern_index for the selections available here:
- * keyword_tree when k==0 without wildcards, shift_and when k==0 with
- * wildcards, filter_bitvec when k>0.                                          */
+ *   exact_halves             : exact_halves over the exact index (k > 0; complete
+ *                              only for k == 1, as in the reference)
+ * PM_INDEX_AUTO follows pick_pattern_index (select.cc:100-141, a streamed FASTA
+ * database, build with -DNOPRIMEGEN) for the selections available here:
+ * keyword_tree when k==0 without wildcards, shift_and when k==0 with wildcards;
+ * for k == 1 exact_halves when every pattern has at least 8 characters and the
+ * exact-base constraints (-5/-3) are shorter than half the patterns on average
+ * (resolved in pm_init, when the patterns are known); filter_bitvec otherwise.  */
 #define PM_INDEX_AUTO 0
 #define PM_INDEX_KEYWORD_TREE 3  /* select.cc:221-229, keyword_tree.t:427      */
 #define PM_INDEX_SHIFT_AND 4     /* select.cc:230-233, shift_and.cc:204        */
 #define PM_INDEX_FILTER_BITVEC 5 /* select.cc:234-237, filter_bitvec.cc:126    */
+#define PM_INDEX_EXACT_HALVES 13 /* select.cc:246-261 (-N 11..14), exact_halves.cc:118:
+                                    exact occurrences of the pattern halves, each
+                                    extended by primer_alignment (primer_alignment.cc);
+                                    what pick_pattern_index takes for k == 1           */
 
 typedef struct pm_ctx pm_ctx;
 

@@ -23,6 +23,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpm_b200.so")
 PM_OK = 0
 PM_E_ARG, PM_E_CUDA, PM_E_UNSUPPORTED, PM_E_NOMEM, PM_E_BOGUS = -1, -2, -3, -4, -5
 PM_INDEX_AUTO, PM_INDEX_KEYWORD_TREE, PM_INDEX_SHIFT_AND, PM_INDEX_FILTER_BITVEC = 0, 3, 4, 5
+PM_INDEX_EXACT_HALVES = 13
 PM_SCAN_AUTO, PM_SCAN_PLANES, PM_SCAN_INDEX = 0, 1, 2
 PM_MAX_CODES = 72
 INT64_MAX = (1 << 63) - 1
@@ -430,6 +431,7 @@ def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
                  eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO, sqz=None):
     """The reference's main loop on the GPU path: returns sorted HitRecords.
+    index: a -N selection; PM_INDEX_AUTO follows pick_pattern_index (exact_halves for k == 1).
     sqz = (sqz bytes, tbz table, n_chars): load the text from compress_seq's compressed
     form instead of stream.chars (stream still supplies the sequence index)."""
     pats = pattern_array(primers, rev_comp)

@@ -22,6 +22,7 @@
 #include "pm_scan.cuh"
 #include "pm_index.cuh"
 #include "pm_fasta.cuh"
+#include "pm_halves.cuh"
 
 namespace {
 
@@ -148,6 +149,9 @@ struct pm_ctx {
   cudaStream_t prep_stream = 0;   // unpack / pack kernels of the chunks that have arrived
   std::vector<Pattern> pats;
   bool inited = false;
+  bool index_auto = false;   // pm_create got PM_INDEX_AUTO with k > 0: resolved in pm_init
+  pm_ctx *inner = nullptr;   // exact_halves: the exact index over the 2N pattern halves
+  DevBuf d_half_rec, d_half_key, d_half_key2, d_half_ord, d_half_ord2;
   int max_len = 0;
   // symbols
   int n_sym = 0;
@@ -705,7 +709,27 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
     }
   }
   uint64_t ncand = 0;
-  int rc = run_scan_any(c, lo, hi, &ncand);
+  int rc;
+  if (c->inner) {
+    // exact_halves: every exact occurrence of a pattern half up to the end of the range (the
+    // `lasthit` rule looks back, so the scan starts where the loaded text starts)
+    guarded = false;
+    rc = run_scan_any(c->inner, 0, own_hi, &ncand);
+    const pm_stats &is = c->inner->stats;
+    c->stats.scan_ms = is.scan_ms;
+    c->stats.scan_path = is.scan_path;
+    c->stats.scan_items = is.scan_items;
+    c->stats.scan_warp_steps = is.scan_warp_steps;
+    c->stats.index_q = is.index_q;
+    c->stats.index_nd = is.index_nd;
+    c->stats.index_pieces = is.index_pieces;
+    c->stats.index_lookups = is.index_lookups;
+    c->stats.index_entries = is.index_entries;
+    c->stats.n_ambiguous = is.n_ambiguous;
+    c->stats.kernel_launches += is.kernel_launches;
+  } else {
+    rc = run_scan_any(c, lo, hi, &ncand);
+  }
   if (rc) return rc;
   c->stats.n_candidates = ncand;
   if (ncand == 0) goto done;
@@ -713,7 +737,41 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
     const AlignEnv env = make_env(c);
     const unsigned long long *keys = c->d_keys.as<unsigned long long>();
     uint64_t n_out = 0;
-    if (K == 0) {
+    if (c->inner) {
+      // extend every half occurrence over the other half, order them as exact_halves.cc:113-116
+      // does, apply its lasthit rule per pattern
+      if ((rc = c->d_half_rec.ensure(ncand * sizeof(HalfRec)))) return rc;
+      if ((rc = c->d_half_key.ensure(ncand * 8))) return rc;
+      if ((rc = c->d_half_key2.ensure(ncand * 8))) return rc;
+      if ((rc = c->d_half_ord.ensure(ncand * 4))) return rc;
+      if ((rc = c->d_half_ord2.ensure(ncand * 4))) return rc;
+      if ((rc = c->d_raw.ensure(ncand * sizeof(RawHit)))) return rc;
+      halves_extend_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
+          env, c->inner->d_keys.as<unsigned long long>(), ncand, c->inner->d_slotid.as<uint32_t>(),
+          c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>());
+      iota_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(c->d_half_ord.as<uint32_t>(), ncand);
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_half_key.as<unsigned long long>(),
+                                      c->d_half_key2.as<unsigned long long>(), c->d_half_ord.as<uint32_t>(),
+                                      c->d_half_ord2.as<uint32_t>(), ncand, 0, 64, c->stream);
+      if ((rc = c->d_tmp.ensure(tb))) return rc;
+      tb = c->d_tmp.cap;
+      PM_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tb, c->d_half_key.as<unsigned long long>(),
+                                              c->d_half_key2.as<unsigned long long>(),
+                                              c->d_half_ord.as<uint32_t>(), c->d_half_ord2.as<uint32_t>(), ncand,
+                                              0, 64, c->stream));
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
+      const uint32_t n_slots = (uint32_t)c->pats.size();
+      halves_report_kernel<<<nblocks(n_slots, 128), 128, 0, c->stream>>>(
+          c->d_half_key2.as<unsigned long long>(), c->d_half_ord2.as<uint32_t>(), c->d_half_rec.as<HalfRec>(),
+          ncand, n_slots, K, c->opt.indels, own_lo, own_hi, c->d_raw.as<RawHit>(), c->d_counters + 4, ncand);
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches += 6;
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      n_out = c->h_counters[4];
+    } else if (K == 0) {
       if ((rc = c->d_hits.ensure(ncand * sizeof(pm_hit)))) return rc;
       if ((rc = c->d_sortk.ensure(ncand * 8))) return rc;
       PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
@@ -795,19 +853,19 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
                               cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
       n_out = c->h_counters[4];
-      if (n_out) {
-        // final alignment: R = 0, buffer of at most m+k characters
-        const uint64_t stride = (align_ws_bytes(c->max_len, c->max_len + K) + 15) & ~15ull;
-        if ((rc = c->d_ws.ensure(n_out * stride))) return rc;
-        if ((rc = c->d_hits.ensure(n_out * sizeof(pm_hit)))) return rc;
-        if ((rc = c->d_sortk.ensure(n_out * 8))) return rc;
-        final_align_kernel<<<nblocks(n_out, 64), 64, 0, c->stream>>>(
-            env, c->d_raw.as<RawHit>(), n_out, stride, c->d_ws.as<uint8_t>(),
-            c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
-            c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
-        PM_CUDA(cudaGetLastError());
-        c->stats.kernel_launches++;
-      }
+    }
+    if (K > 0 && n_out) {
+      // final alignment: R = 0, buffer of at most m+k characters
+      const uint64_t stride = (align_ws_bytes(c->max_len, c->max_len + K) + 15) & ~15ull;
+      if ((rc = c->d_ws.ensure(n_out * stride))) return rc;
+      if ((rc = c->d_hits.ensure(n_out * sizeof(pm_hit)))) return rc;
+      if ((rc = c->d_sortk.ensure(n_out * 8))) return rc;
+      final_align_kernel<<<nblocks(n_out, 64), 64, 0, c->stream>>>(
+          env, c->d_raw.as<RawHit>(), n_out, stride, c->d_ws.as<uint8_t>(),
+          c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
+          c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches++;
     }
     if (n_out) {
       if ((rc = sort_hits(c, n_out))) return rc;
@@ -906,8 +964,9 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   *out = nullptr;
   if (opt->k < 0 || opt->k > PM_MAX_K) return fail(PM_E_UNSUPPORTED, "k out of range (0..3)");
   int index = opt->index;
+  bool index_auto = false;
   if (index == PM_INDEX_AUTO) {
-    if (opt->k > 0) index = PM_INDEX_FILTER_BITVEC;
+    if (opt->k > 0) { index = PM_INDEX_FILTER_BITVEC; index_auto = true; }  // or exact_halves: pm_init decides
     else index = opt->wildcards ? PM_INDEX_SHIFT_AND : PM_INDEX_KEYWORD_TREE;
   }
   switch (index) {
@@ -922,6 +981,10 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
       break;
     case PM_INDEX_FILTER_BITVEC:
       if (opt->k == 0) return fail(PM_E_ARG, "filter_bitvec needs k > 0");
+      break;
+    case 11: case 12: case PM_INDEX_EXACT_HALVES: case 14:  // over any of the exact indexes: same hit list
+      if (opt->k == 0) return fail(PM_E_ARG, "exact_halves needs k > 0");
+      index = PM_INDEX_EXACT_HALVES;
       break;
     default:
       return fail(PM_E_UNSUPPORTED, "index selection not implemented");
@@ -938,6 +1001,7 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   c->opt.wildcards = opt->wildcards ? 1 : 0;
   c->opt.text_n = opt->text_n ? 1 : 0;
   c->index = index;
+  c->index_auto = index_auto;
   memset(&c->stats, 0, sizeof c->stats);
   if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost((void **)&c->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
@@ -955,6 +1019,8 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
 
 void pm_destroy(pm_ctx *c) {
   if (!c) return;
+  if (c->inner) pm_destroy(c->inner);
+  c->inner = nullptr;
   cudaSetDevice(c->opt.device);
   cudaDeviceSynchronize();
   DevBuf *bufs[] = {&c->d_symmask, &c->d_poff,   &c->d_plen,   &c->d_patchars, &c->d_lconst,
@@ -966,7 +1032,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab,
                     &c->d_fa_raw, &c->d_fa_map, &c->d_fa_scan, &c->d_fa_cnt, &c->d_fa_chdr, &c->d_fa_start,
                     &c->d_fa_nout, &c->d_fa_nhdr, &c->d_fa_ooff, &c->d_fa_hoff, &c->d_fa_key, &c->d_fa_hs,
-                    &c->d_fa_he};
+                    &c->d_fa_he, &c->d_half_rec, &c->d_half_key, &c->d_half_key2, &c->d_half_ord, &c->d_half_ord2};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -995,6 +1061,7 @@ int pm_set_scan_path(pm_ctx *c, int path) {
 int pm_set_stream(pm_ctx *c, void *cuda_stream) {
   if (!c) return fail(PM_E_ARG, "null context");
   c->stream = (cudaStream_t)cuda_stream;
+  if (c->inner) c->inner->stream = c->stream;
   return PM_OK;
 }
 
@@ -1131,8 +1198,40 @@ int pm_init(pm_ctx *c) {
     if (rc) return rc;
     PM_CUDA(cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice));
   }
+  // ---- pick_pattern_index for k == 1 (select.cc:120-126): exact_halves ---------------------
+  if (c->index_auto && K == 1 && ns > 0) {
+    long min_length = 1 << 30, cumbooldiff = 0, cumdiff = 0;
+    for (const Pattern &p : c->pats) {
+      const long len = (long)p.s.size(), ex = std::max(p.esb, p.eeb);
+      min_length = std::min(min_length, len);
+      cumdiff += ex - len / 2;
+      cumbooldiff += (ex - len / 2 >= 0) ? 1 : 0;
+    }
+    // a streamed FASTA database has CharacterProducer::size() == 256 (char_io.h:96)
+    if (min_length >= 8 && (cumbooldiff <= 0 || cumdiff <= 0)) c->index = PM_INDEX_EXACT_HALVES;
+  }
+  if (c->index == PM_INDEX_EXACT_HALVES) {
+    // the exact index over the halves: inner pattern ids 2i+1 (left), 2i+2 (right) for slot i
+    // (exact_halves.cc:201-224)
+    pm_options io = c->opt;
+    io.k = 0;
+    io.indels = 0;
+    io.index = c->opt.wildcards ? PM_INDEX_SHIFT_AND : PM_INDEX_KEYWORD_TREE;
+    int rc = pm_create(&c->inner, &io);
+    if (rc) return rc;
+    c->inner->scan_path = (c->scan_path == PM_SCAN_PLANES) ? PM_SCAN_PLANES : PM_SCAN_AUTO;
+    c->inner->stream = c->stream;
+    for (size_t i = 0; i < ns; i++) {
+      const std::string &ps = c->pats[i].s;
+      const size_t l1 = ps.size() / 2;
+      if (l1 == 0) return fail(PM_E_ARG, "exact_halves needs patterns of at least 2 characters");
+      if ((rc = pm_add_pattern(c->inner, ps.substr(0, l1).c_str(), (uint32_t)(2 * i + 1), 0, 0))) return rc;
+      if ((rc = pm_add_pattern(c->inner, ps.substr(l1).c_str(), (uint32_t)(2 * i + 2), 0, 0))) return rc;
+    }
+    if ((rc = pm_init(c->inner))) return rc;
+  }
   // ---- pair-seed index (pm_index.cuh): applicable? ----------------------------------------
-  {
+  if (!c->inner) {
     const int P = K + 2;
     const bool edit_mode = (K > 0 && c->opt.indels);
     // text codes: without wildcards code = symbol; with wildcards the codes are the match
@@ -1324,10 +1423,22 @@ int pm_init(pm_ctx *c) {
   c->inited = true;
   // a text set before init (not the reference's order, but harmless) is packed now
   if (c->d_text && c->n) {
-    int rc = pack_text(c);
+    int rc = c->inner ? pm_set_text_device(c->inner, c->d_text, c->n, c->offset) : pack_text(c);
     if (rc) return rc;
     PM_CUDA(cudaStreamSynchronize(c->stream));
   }
+  return PM_OK;
+}
+
+// exact_halves: the text lives in (and is packed for) the inner context; this one adopts it
+static int adopt_inner_text(pm_ctx *c, int rc) {
+  if (rc) return rc;
+  c->d_text = c->inner->d_text;
+  c->n = c->inner->n;
+  c->offset = c->inner->offset;
+  c->seq_key = c->inner->seq_key;
+  c->seq_hdr_off = c->inner->seq_hdr_off;
+  c->seq_hdr_len = c->inner->seq_hdr_len;
   return PM_OK;
 }
 
@@ -1447,6 +1558,7 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
 
 int pm_set_text_host(pm_ctx *c, const uint8_t *stream, uint64_t n, int64_t offset) {
   if (!c || (!stream && n)) return fail(PM_E_ARG, "null argument");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_host(c->inner, stream, n, offset));
   PM_CUDA(cudaSetDevice(c->opt.device));
   if (n && offset == 0 && stream[0] != c->opt.eos)
     return fail(PM_E_ARG, "a stream at offset 0 must begin with the end-of-sequence character");
@@ -1464,6 +1576,7 @@ int pm_sqz_bits(uint32_t table_size) {  // char_io.t:58-61
 int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
                          uint32_t table_size, uint64_t n_chars, int64_t offset) {
   if (!c || (!sqz && n_bytes) || !table) return fail(PM_E_ARG, "null argument");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_sqz_host(c->inner, sqz, n_bytes, table, table_size, n_chars, offset));
   const int bits = pm_sqz_bits(table_size);
   if (bits < 0) return bits;
   PM_CUDA(cudaSetDevice(c->opt.device));
@@ -1486,6 +1599,7 @@ int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const 
 
 int pm_set_text_device(pm_ctx *c, const uint8_t *d_stream, uint64_t n, int64_t offset) {
   if (!c || (!d_stream && n)) return fail(PM_E_ARG, "null argument");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_device(c->inner, d_stream, n, offset));
   if ((reinterpret_cast<uintptr_t>(d_stream) & 3) != 0)
     return fail(PM_E_ARG, "device stream must be 4-byte aligned");
   PM_CUDA(cudaSetDevice(c->opt.device));
@@ -1528,6 +1642,8 @@ int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate
   *cands = nullptr;
   *ncands = 0;
   if (!c->inited) return fail(PM_E_ARG, "pm_scan_candidates before pm_init");
+  if (c->inner)
+    return fail(PM_E_UNSUPPORTED, "raw candidates are defined for the bit-vector and exact indexes, not exact_halves");
   PM_CUDA(cudaSetDevice(c->opt.device));
   memset(&c->stats, 0, offsetof(pm_stats, pack_ms));
   c->stats.text_len = c->n;
@@ -1556,6 +1672,7 @@ int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate
 
 int pm_reset(pm_ctx *c) {
   if (!c) return fail(PM_E_ARG, "null context");
+  if (c->inner) pm_reset(c->inner);
   c->d_text = nullptr;
   c->n = 0;
   c->n_tiles = 0;
@@ -1651,6 +1768,7 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
 int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int upper_case) {
   if (!c || (!raw && n_raw)) return fail(PM_E_ARG, "null argument");
   if (!c->inited) return fail(PM_E_ARG, "pm_set_text_fasta_host before pm_init");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_fasta_host(c->inner, raw, n_raw, upper_case));
   if (n_raw >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "file longer than 2^40 bytes");
   PM_CUDA(cudaSetDevice(c->opt.device));
   const unsigned char eos = c->opt.eos;

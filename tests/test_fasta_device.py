@@ -75,7 +75,8 @@ def test_golden_records_from_raw_fasta(pkg, built_lib, golden):
         raw = case["fasta"].encode("latin-1")
         p = case["params"]
         pats = pkg.pattern_array(case["primers"], p["rev_comp"])
-        sc = pkg.Scanner(k=p["k"], indels=p["indels"], wildcards=p["wc"], text_n=p["tn"])
+        sc = pkg.Scanner(k=p["k"], indels=p["indels"], wildcards=p["wc"], text_n=p["tn"],
+                         index=pkg.PM_INDEX_FILTER_BITVEC if p["k"] > 0 else pkg.PM_INDEX_AUTO)   # goldens: -N 5
         for i, q in enumerate(pats):
             sc.add_pattern(q, i + 1)
         sc.init()

@@ -12,6 +12,11 @@ pytestmark = pytest.mark.gpu
 TILE_POS = 32768
 
 
+def _n5(pkg, params):
+    """The goldens of make_golden.py and the oracle's default are `-N 5` (filter_bitvec) for k > 0."""
+    return pkg.PM_INDEX_FILTER_BITVEC if params["k"] > 0 else pkg.PM_INDEX_AUTO
+
+
 def _need_gpu():
     import torch
     if not torch.cuda.is_available():
@@ -31,8 +36,34 @@ def test_golden_records_bit_exact(pkg, golden, path):
     sp = pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES
     for case in golden["cases"]:
         st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
-        got = pkg.primer_match(st, case["primers"], scan_path=sp, **case["params"])
+        got = pkg.primer_match(st, case["primers"], scan_path=sp, index=_n5(pkg, case["params"]), **case["params"])
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
+
+
+@pytest.mark.parametrize("path", ["auto", "planes"])
+def test_exact_halves_golden_records_bit_exact(pkg, halves_golden, path):
+    """k = 1 with the automatic index choice (exact_halves, select.cc:120-126) and exact_halves
+    forced with k = 2: the records the reference printed."""
+    sp = pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES
+    for case in halves_golden["cases"]:
+        st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
+        index = pkg.PM_INDEX_AUTO if case["select"] == 0 else pkg.PM_INDEX_EXACT_HALVES
+        got = pkg.primer_match(st, case["primers"], scan_path=sp, index=index, **case["params"])
+        assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
+
+
+@pytest.mark.parametrize("seed", range(3000, 3040))
+def test_exact_halves_matches_oracle_seeded(pkg, oracle, seed):
+    import casegen
+    params, kw = _params(seed)
+    params["k"] = kw["k"] = 1
+    fasta, primers = casegen.make_case(seed, **kw)
+    if min(len(p) for p in primers) < 8:
+        pytest.skip("pick_pattern_index takes filter_bitvec for primers shorter than 8")
+    raw = fasta.encode()
+    want = oracle.primer_match(oracle.normalize_fasta(raw), primers, index="exact_halves", **params)
+    got = pkg.primer_match(pkg.normalize_fasta(raw), primers, **params)      # PM_INDEX_AUTO
+    assert as_tuples(got) == as_tuples(want)
 
 
 def _params(seed):
@@ -58,7 +89,7 @@ def test_records_match_oracle_seeded(pkg, oracle, seed):
     raw = fasta.encode()
     want = oracle.primer_match(oracle.normalize_fasta(raw), primers, **params)
     for sp in (pkg.PM_SCAN_AUTO, pkg.PM_SCAN_PLANES):
-        got = pkg.primer_match(pkg.normalize_fasta(raw), primers, scan_path=sp, **params)
+        got = pkg.primer_match(pkg.normalize_fasta(raw), primers, scan_path=sp, index=_n5(pkg, params), **params)
         assert as_tuples(got) == as_tuples(want), "scan path %d" % sp
 
 
@@ -105,7 +136,7 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
     else:
         want = oracle.wm_scan(T, primers, k, indels, wc, False)
     want = sorted({(int(b), int(a)) for a, b, _ in want})
-    sc = pkg.Scanner(k=k, indels=indels, wildcards=wc,
+    sc = pkg.Scanner(k=k, indels=indels, wildcards=wc, index=_n5(pkg, dict(k=k)),
                      scan_path=pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
     for i, p in enumerate(primers):
         sc.add_pattern(p, i + 1)
@@ -145,7 +176,8 @@ def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     T = st.chars
 
     def run(begin, end, lo, hi):
-        sc = pkg.Scanner(k=k, indels=indels, scan_path=pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES)
+        sc = pkg.Scanner(k=k, indels=indels, index=pkg.PM_INDEX_FILTER_BITVEC,
+                         scan_path=pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES)
         for i, p in enumerate(primers):
             sc.add_pattern(p, i + 1)
         sc.init()
@@ -168,8 +200,9 @@ def test_shards_reproduce_whole_scan(pkg, k, indels, path):
     assert merged.tobytes() == whole.tobytes()
 
 
-@pytest.mark.parametrize("k,indels", [(0, False), (1, False), (1, True)])
-def test_large_pattern_set_uses_the_l2_filter(pkg, k, indels):
+@pytest.mark.parametrize("k,indels,halves", [(0, False, False), (1, False, False), (1, True, False),
+                                             (1, False, True), (1, True, True)])
+def test_large_pattern_set_uses_the_l2_filter(pkg, k, indels, halves):
     """18 000 primers x 2 strands: the 2^20-bit level-1 bitmap saturates and the L2-resident
     level-1b table takes over.  Same hits as the bit-plane kernels."""
     import casegen
@@ -186,7 +219,8 @@ def test_large_pattern_set_uses_the_l2_filter(pkg, k, indels):
     pats = pkg.pattern_array(primers, True)
     out = {}
     for name, sp in (("index", pkg.PM_SCAN_INDEX), ("planes", pkg.PM_SCAN_PLANES)):
-        sc = pkg.Scanner(k=k, indels=indels, scan_path=sp)
+        sc = pkg.Scanner(k=k, indels=indels, scan_path=sp,
+                         index=pkg.PM_INDEX_EXACT_HALVES if halves else _n5(pkg, dict(k=k)))
         for i, p in enumerate(pats):
             sc.add_pattern(p, i + 1)
         sc.init()
@@ -213,7 +247,7 @@ def test_chain_longer_than_the_right_guard(pkg):
     T = st.chars
 
     def run(begin, end):
-        sc = pkg.Scanner(k=1, indels=True)
+        sc = pkg.Scanner(k=1, indels=True, index=pkg.PM_INDEX_FILTER_BITVEC)
         for i, p in enumerate(primers):
             sc.add_pattern(p, i + 1)
         sc.init()
@@ -248,7 +282,7 @@ def test_many_ambiguous_characters_fall_back_to_planes(pkg):
     T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
     out = {}
     for name, sp in (("auto", pkg.PM_SCAN_AUTO), ("planes", pkg.PM_SCAN_PLANES)):
-        sc = pkg.Scanner(k=1, indels=False, wildcards=True, scan_path=sp)
+        sc = pkg.Scanner(k=1, indels=False, wildcards=True, scan_path=sp, index=pkg.PM_INDEX_FILTER_BITVEC)
         for i, p in enumerate(primers):
             sc.add_pattern(p, i + 1)
         sc.init()
