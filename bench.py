@@ -40,6 +40,7 @@ PRIMER_LEN = 20
 K = 2
 INDELS = 0
 IUPAC = 0
+SELECT = 0
 
 
 def make_primers(seed=12345, n=None, m=None):
@@ -137,7 +138,7 @@ def run_reference_sample(primers, total_bases: int, procs: int, seed: int, workd
             f.write(b"\n")
         files.append(path)
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", *(["-w"] if IUPAC else []), "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
+    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", *(["-w"] if IUPAC else []), *(["-N", str(SELECT)] if SELECT else []), "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fp in files]
     for p in ps:
         p.wait()
@@ -181,7 +182,7 @@ def config_dict(args, shard_bases):
                         "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN, K, "edits" if INDELS else "mismatches",
                                                            "-k" if INDELS else "-K", K),
             "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
-            "index": "filter_bitvec (reference auto choice for this workload)",
+            "index": ("-N %d" % SELECT) if SELECT else ("automatic (pick_pattern_index): " + ("exact index" if K == 0 else "exact_halves" if (K == 1 and PRIMER_LEN >= 8) else "filter_bitvec")),
             "l2": "inputs larger than L2 (%.1f GB stream + %.2f GB packed text per pass)" % (shard_bases / 1e9, shard_bases / 2e9),
             "partition": "one shard per GPU, cut at sequence boundaries"}
 
@@ -239,11 +240,14 @@ def main():
     ap.add_argument("--k", type=int, default=K, help="errors allowed (headline: 2)")
     ap.add_argument("--plen", type=int, default=PRIMER_LEN, help="primer length (headline: 20)")
     ap.add_argument("--nprimers", type=int, default=N_PRIMERS, help="primers before reverse complements (headline: 1000)")
+    ap.add_argument("--N", type=int, default=0, dest="select",
+                    help="primer_match -N: pattern index (0 automatic, 5 filter_bitvec, 13 exact_halves)")
     ap.add_argument("--cpu-bases-per-core", type=int, default=3_000_000)
     ap.add_argument("--ref-bases-per-core", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels, IUPAC=args.iupac)
+    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels, IUPAC=args.iupac,
+                     SELECT=args.select)
     if args.impl == "reference":
         return main_reference(args)
 
@@ -317,7 +321,7 @@ def main():
     del d_fasta, parts
     torch.cuda.synchronize()
 
-    sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank)
+    sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank, index=args.select)
     for i, p in enumerate(pats):
         sc.add_pattern(p, i + 1)
     sc.init()

@@ -746,9 +746,16 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
       if ((rc = c->d_half_ord.ensure(ncand * 4))) return rc;
       if ((rc = c->d_half_ord2.ensure(ncand * 4))) return rc;
       if ((rc = c->d_raw.ensure(ncand * sizeof(RawHit)))) return rc;
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 10, 0, sizeof(unsigned long long), c->stream));
       halves_extend_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
           env, c->inner->d_keys.as<unsigned long long>(), ncand, c->inner->d_slotid.as<uint32_t>(),
-          c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>());
+          c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>(), c->d_counters + 10);
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 10, c->d_counters + 10, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      ncand = c->h_counters[10];   // from here on: the occurrences that extended
+      c->stats.n_chains = ncand;
+      if (ncand == 0) goto done;
       iota_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(c->d_half_ord.as<uint32_t>(), ncand);
       size_t tb = 0;
       cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_half_key.as<unsigned long long>(),

@@ -12,7 +12,8 @@
 //   1. the exact occurrences of the 2N halves come from an inner context (the
 //      same pair-seed index scan as every k = 0 search);
 //   2. halves_extend_kernel: one thread per occurrence runs the banded DP with
-//      two rolling rows in local memory and writes (end, value, ok);
+//      two rolling rows in local memory; the few that extend are appended to a
+//      compact list of (end, value);
 //   3. the records are sorted by (pattern, position, right half first) -- the
 //      order exact_halves.cc:113-116 gives them -- and halves_report_kernel walks
 //      each pattern's run with the reference's `lasthit` rule, one thread per
@@ -138,7 +139,7 @@ __device__ __forceinline__ bool primer_global_align(const AlignEnv &env, const u
 __global__ void __launch_bounds__(128)
 halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ keys, uint64_t n,
                      const uint32_t *__restrict__ inner_id, HalfRec *__restrict__ rec,
-                     unsigned long long *__restrict__ sortkey) {
+                     unsigned long long *__restrict__ sortkey, unsigned long long *__restrict__ n_ok) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = keys[i];
@@ -169,9 +170,11 @@ halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ 
     r.end = pos;
   }
   r.value = value;
-  rec[i] = r;
+  if (!r.ok) return;   // most occurrences of a half do not extend: only the others are kept
+  const unsigned long long at = atomicAdd(n_ok, 1ULL);
+  rec[at] = r;
   // exact_halves.cc:113-116: by position, then inner id DESCENDING (the right half first)
-  sortkey[i] = ((unsigned long long)slot << 42) | ((unsigned long long)pos << 1) | (left ? 1ull : 0ull);
+  sortkey[at] = ((unsigned long long)slot << 42) | ((unsigned long long)pos << 1) | (left ? 1ull : 0ull);
 }
 
 // one thread per pattern: its run of sorted records, the `lasthit` rule of
