@@ -458,6 +458,18 @@ def main():
         if on_index:
             roof["index"] = {"piece_len": st_last["index_q"], "pieces": st_last["index_pieces"],
                              "distances": st_last["index_nd"], "entries": st_last["index_entries"]}
+        if on_index and not args.indels and K > 0 and st_last["index_pieces"] == K + 2:
+            # the pipe that actually binds pair_scan_sub_kernel: shared-memory wavefronts.  One level-1
+            # lookup is one lane of an LDS; 32 lanes hitting 32 random banks take 3.76 wavefronts
+            # (l1tex__data_pipe_lsu_wavefronts_mem_shared / smsp__sass_inst_executed_op_shared_ld of the
+            # ncu capture prof_pairsub_r1); an SM retires one wavefront per clock.
+            wf = st_last["index_lookups"] * 3.76 / 32.0
+            sm_clock = (clocks.get("sm_mhz") or 1965) * 1e6
+            lsu_peak = 148 * sm_clock
+            roof["smem_wavefronts"] = {"unit": "Gwavefront/s", "achieved": wf / (mean_scan_ms * 1e-3) / 1e9,
+                                       "peak": lsu_peak / 1e9, "frac": wf / (mean_scan_ms * 1e-3) / lsu_peak,
+                                       "wavefronts_per_warp_lds": 3.76,
+                                       "note": "ncu (profiles/README.md): l1tex data pipe 93.9 % busy incl. queue traffic"}
         try:
             ip = pkg.int_pipe_report(sc, mean_scan_ms, local_rank)
             roof["int_pipe"] = ip
