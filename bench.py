@@ -491,7 +491,7 @@ def main():
                 "e2e_fasta": {"value": e2e_fasta, "unit": "Gbp/s", "h2d_bytes_per_step": int(h_fasta.numel()) * world,
                               "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_fasta / args.steps,
                               "input": "pinned host buffer holding the FASTA file (80 bases per line), normalised "
-                                       "on the device (pm_set_text_fasta_host); copy and scan do not overlap yet"},
+                                       "on the device chunk by chunk while the copy runs (pm_set_text_fasta_host); pack and scan follow"},
                 "gpu_launches": n_launch, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:
             cores = cpu_cores()

@@ -163,7 +163,7 @@ struct pm_ctx {
   DevBuf d_text_own, d_planes, d_sqz, d_sqztab;
   // device-side FASTA normalisation (pm_fasta.cuh)
   DevBuf d_fa_raw, d_fa_map, d_fa_scan, d_fa_cnt, d_fa_chdr, d_fa_start, d_fa_nout, d_fa_nhdr, d_fa_ooff, d_fa_hoff,
-      d_fa_key, d_fa_hs, d_fa_he;
+      d_fa_key, d_fa_hs, d_fa_he, d_fa_tmp;
   std::vector<int64_t> seq_key, seq_hdr_off, seq_hdr_len;  // sequence table of the last FASTA text
   const uint8_t *d_text = nullptr;
   uint64_t n = 0;
@@ -1039,7 +1039,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab,
                     &c->d_fa_raw, &c->d_fa_map, &c->d_fa_scan, &c->d_fa_cnt, &c->d_fa_chdr, &c->d_fa_start,
                     &c->d_fa_nout, &c->d_fa_nhdr, &c->d_fa_ooff, &c->d_fa_hoff, &c->d_fa_key, &c->d_fa_hs,
-                    &c->d_fa_he, &c->d_half_rec, &c->d_half_key, &c->d_half_key2, &c->d_half_ord, &c->d_half_ord2};
+                    &c->d_fa_he, &c->d_fa_tmp, &c->d_half_rec, &c->d_half_key, &c->d_half_key2, &c->d_half_ord, &c->d_half_ord2};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1813,93 +1813,111 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
     }
     pre.assign(tmp.begin(), tmp.begin() + pre_len);
   }
-  const uint64_t n_seg = (n_raw - r0 + FA_SEG - 1) / FA_SEG;
+  // The file is taken in chunks: the copy stream moves chunk j+1 while the prep stream
+  // normalises chunk j (summary -> scan of the state maps -> counts -> two exclusive sums ->
+  // write); the state / stream length / header count after a chunk are carried on the device
+  // (d_counters[11..13]), so the host does not wait between chunks.
+  const uint64_t kChunk = (uint64_t)FA_THREADS * FA_SEG * 2048;   // 64 MiB of raw bytes, whole blocks
+  const uint64_t n_seg_max = std::min<uint64_t>(kChunk, n_raw - r0 + FA_SEG) / FA_SEG + 1;
+  const uint64_t hdr_cap = std::min<uint64_t>(n_raw / 32 + 1024, 1ull << 27);
   int rc;
   if ((rc = c->d_fa_raw.ensure(n_raw + 64))) return rc;
   if ((rc = c->d_text_own.ensure(n_raw + 2 + 64))) return rc;
-  if ((rc = c->d_fa_map.ensure(n_seg))) return rc;
-  if ((rc = c->d_fa_scan.ensure(n_seg))) return rc;
-  if ((rc = c->d_fa_cnt.ensure(n_seg * 8))) return rc;
-  if ((rc = c->d_fa_chdr.ensure(n_seg * 4))) return rc;
-  if ((rc = c->d_fa_start.ensure(n_seg))) return rc;
-  if ((rc = c->d_fa_nout.ensure((n_seg + 1) * 4))) return rc;
-  if ((rc = c->d_fa_nhdr.ensure((n_seg + 1) * 4))) return rc;
-  if ((rc = c->d_fa_ooff.ensure((n_seg + 1) * 8))) return rc;
-  if ((rc = c->d_fa_hoff.ensure((n_seg + 1) * 8))) return rc;
-  cudaStream_t st = c->stream;
-  // raw bytes to the device (pinned memory is read directly, pageable memory is staged)
+  if ((rc = c->d_fa_map.ensure(n_seg_max))) return rc;
+  if ((rc = c->d_fa_scan.ensure(n_seg_max))) return rc;
+  if ((rc = c->d_fa_cnt.ensure(n_seg_max * 8))) return rc;
+  if ((rc = c->d_fa_chdr.ensure(n_seg_max * 4))) return rc;
+  if ((rc = c->d_fa_start.ensure(n_seg_max))) return rc;
+  if ((rc = c->d_fa_nout.ensure((n_seg_max + 1) * 4))) return rc;
+  if ((rc = c->d_fa_nhdr.ensure((n_seg_max + 1) * 4))) return rc;
+  if ((rc = c->d_fa_ooff.ensure((n_seg_max + 1) * 8))) return rc;
+  if ((rc = c->d_fa_hoff.ensure((n_seg_max + 1) * 8))) return rc;
+  if ((rc = c->d_fa_key.ensure(hdr_cap * 8))) return rc;
+  if ((rc = c->d_fa_hs.ensure(hdr_cap * 8))) return rc;
+  if ((rc = c->d_fa_he.ensure(hdr_cap * 8))) return rc;
   {
-    cudaPointerAttributes at;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&at, raw) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
-    else cudaGetLastError();
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceScan::InclusiveScan(nullptr, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(), FaCompose(),
+                                   (int64_t)n_seg_max, c->prep_stream);
+    cub::DeviceScan::ExclusiveScan(nullptr, tb2, c->d_fa_nout.as<uint32_t>(), c->d_fa_ooff.as<unsigned long long>(),
+                                   cub::Sum(), 0ull, (int64_t)(n_seg_max + 1), c->prep_stream);
+    if ((rc = c->d_fa_tmp.ensure(std::max(tb, tb2)))) return rc;
+  }
+  PM_CUDA(cudaFuncSetAttribute(fasta_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_WRITE_SMEM));
+  cudaStream_t cs = c->copy_stream, st = c->prep_stream;
+  unsigned long long *carry = c->d_counters + 11;   // [state, stream bytes, headers], + [14] overflow
+  PM_CUDA(cudaEventRecord(c->ev[4], c->stream));    // earlier work of the context may still read the buffers
+  PM_CUDA(cudaStreamWaitEvent(cs, c->ev[4], 0));
+  PM_CUDA(cudaStreamWaitEvent(st, c->ev[4], 0));
+  PM_CUDA(cudaMemsetAsync(carry, 0, 4 * sizeof(unsigned long long), st));
+  fill_i64_kernel<<<nblocks(hdr_cap, 256), 256, 0, st>>>(c->d_fa_he.as<long long>(), hdr_cap, (long long)n_raw);
+  PM_CUDA(cudaGetLastError());
+  cudaPointerAttributes pat_;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&pat_, raw) == cudaSuccess) pinned = (pat_.type == cudaMemoryTypeHost);
+  else cudaGetLastError();
+  if (!pinned)
+    for (int i = 0; i < 2; i++)
+      if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
+  int which = 0;
+  uint8_t *d_raw_w = c->d_fa_raw.as<uint8_t>();
+  const uint8_t *d_raw = d_raw_w;
+  uint8_t *d_stream = c->d_text_own.as<uint8_t>();
+  c->ev_used = 0;
+  for (uint64_t a0 = r0; a0 < n_raw; a0 += kChunk) {
+    const uint64_t a1 = std::min(n_raw, a0 + kChunk);
     if (pinned) {
-      PM_CUDA(cudaMemcpyAsync(c->d_fa_raw.p, raw, n_raw, cudaMemcpyHostToDevice, st));
+      PM_CUDA(cudaMemcpyAsync(d_raw_w + a0, raw + a0, a1 - a0, cudaMemcpyHostToDevice, cs));
     } else {
-      for (int i = 0; i < 2; i++)
-        if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
-      int which = 0;
-      for (uint64_t o = 0; o < n_raw; o += kStageBytes) {
-        const size_t part = (size_t)std::min<uint64_t>(kStageBytes, n_raw - o);
+      for (uint64_t o = a0; o < a1; o += kStageBytes) {
+        const size_t part = (size_t)std::min<uint64_t>(kStageBytes, a1 - o);
         PM_CUDA(cudaEventSynchronize(c->stage_ev[which]));
         memcpy(c->stage[which], raw + o, part);
-        PM_CUDA(cudaMemcpyAsync(c->d_fa_raw.as<uint8_t>() + o, c->stage[which], part, cudaMemcpyHostToDevice, st));
-        PM_CUDA(cudaEventRecord(c->stage_ev[which], st));
+        PM_CUDA(cudaMemcpyAsync(d_raw_w + o, c->stage[which], part, cudaMemcpyHostToDevice, cs));
+        PM_CUDA(cudaEventRecord(c->stage_ev[which], cs));
         which ^= 1;
       }
     }
-  }
-  const uint8_t *d_raw = c->d_fa_raw.as<uint8_t>();
-  fasta_summary_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, 0, st>>>(
-      d_raw, r0, n_raw, n_seg, c->d_fa_map.as<uint8_t>(), c->d_fa_cnt.as<unsigned long long>(),
-      c->d_fa_chdr.as<uint32_t>());
-  PM_CUDA(cudaGetLastError());
-  size_t tb = 0, tb2 = 0;
-  cub::DeviceScan::InclusiveScan(nullptr, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(), FaCompose(),
-                                 (int64_t)n_seg, st);
-  cub::DeviceScan::ExclusiveScan(nullptr, tb2, c->d_fa_nout.as<uint32_t>(), c->d_fa_ooff.as<unsigned long long>(),
-                                 cub::Sum(), 0ull, (int64_t)(n_seg + 1), st);
-  tb = std::max(tb, tb2);
-  if ((rc = c->d_tmp.ensure(tb))) return rc;
-  tb = c->d_tmp.cap;
-  PM_CUDA(cub::DeviceScan::InclusiveScan(c->d_tmp.p, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(),
-                                         FaCompose(), (int64_t)n_seg, st));
-  PM_CUDA(cudaMemsetAsync(c->d_fa_nout.as<uint32_t>() + n_seg, 0, 4, st));
-  PM_CUDA(cudaMemsetAsync(c->d_fa_nhdr.as<uint32_t>() + n_seg, 0, 4, st));
-  fasta_select_kernel<<<nblocks(n_seg, 256), 256, 0, st>>>(
-      c->d_fa_scan.as<uint8_t>(), c->d_fa_cnt.as<unsigned long long>(), c->d_fa_chdr.as<uint32_t>(), n_seg,
-      c->d_fa_start.as<uint8_t>(), c->d_fa_nout.as<uint32_t>(), c->d_fa_nhdr.as<uint32_t>());
-  PM_CUDA(cudaGetLastError());
-  tb = c->d_tmp.cap;
-  PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_tmp.p, tb, c->d_fa_nout.as<uint32_t>(),
-                                         c->d_fa_ooff.as<unsigned long long>(), cub::Sum(), 0ull,
-                                         (int64_t)(n_seg + 1), st));
-  tb = c->d_tmp.cap;
-  PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_tmp.p, tb, c->d_fa_nhdr.as<uint32_t>(),
-                                         c->d_fa_hoff.as<unsigned long long>(), cub::Sum(), 0ull,
-                                         (int64_t)(n_seg + 1), st));
-  unsigned long long totals[2] = {0, 0};
-  PM_CUDA(cudaMemcpyAsync(&totals[0], c->d_fa_ooff.as<unsigned long long>() + n_seg, 8, cudaMemcpyDeviceToHost, st));
-  PM_CUDA(cudaMemcpyAsync(&totals[1], c->d_fa_hoff.as<unsigned long long>() + n_seg, 8, cudaMemcpyDeviceToHost, st));
-  PM_CUDA(cudaStreamSynchronize(st));
-  const uint64_t n = pre_len + totals[0] + 1;       // + the closing eos
-  const uint64_t n_hdr = pre_seqs + totals[1];
-  if (n > n_raw + 2) return fail(PM_E_CUDA, "FASTA normalisation produced an impossible length");
-  const size_t tab = std::max<uint64_t>(n_hdr, 1) * 8;
-  if ((rc = c->d_fa_key.ensure(tab))) return rc;
-  if ((rc = c->d_fa_hs.ensure(tab))) return rc;
-  if ((rc = c->d_fa_he.ensure(tab))) return rc;
-  if (n_hdr) {
-    fill_i64_kernel<<<nblocks(n_hdr, 256), 256, 0, st>>>(c->d_fa_he.as<long long>(), n_hdr, (long long)n_raw);
+    cudaEvent_t arrived = next_event(c);
+    PM_CUDA(cudaEventRecord(arrived, cs));
+    PM_CUDA(cudaStreamWaitEvent(st, arrived, 0));
+    const uint64_t n_seg = (a1 - a0 + FA_SEG - 1) / FA_SEG;
+    const unsigned fb = (unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS);
+    // the kernels index raw bytes from the chunk start; n_raw bounds the last chunk
+    fasta_summary_kernel<<<fb, FA_THREADS, 0, st>>>(d_raw, a0, a1, n_seg, c->d_fa_map.as<uint8_t>(),
+                                                    c->d_fa_cnt.as<unsigned long long>(), c->d_fa_chdr.as<uint32_t>());
+    size_t tb = c->d_fa_tmp.cap;
+    PM_CUDA(cub::DeviceScan::InclusiveScan(c->d_fa_tmp.p, tb, c->d_fa_map.as<uint8_t>(), c->d_fa_scan.as<uint8_t>(),
+                                           FaCompose(), (int64_t)n_seg, st));
+    PM_CUDA(cudaMemsetAsync(c->d_fa_nout.as<uint32_t>() + n_seg, 0, 4, st));
+    PM_CUDA(cudaMemsetAsync(c->d_fa_nhdr.as<uint32_t>() + n_seg, 0, 4, st));
+    fasta_select_kernel<<<nblocks(n_seg, 256), 256, 0, st>>>(
+        c->d_fa_scan.as<uint8_t>(), c->d_fa_cnt.as<unsigned long long>(), c->d_fa_chdr.as<uint32_t>(), n_seg,
+        c->d_fa_start.as<uint8_t>(), c->d_fa_nout.as<uint32_t>(), c->d_fa_nhdr.as<uint32_t>(), carry);
+    tb = c->d_fa_tmp.cap;
+    PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_fa_tmp.p, tb, c->d_fa_nout.as<uint32_t>(),
+                                           c->d_fa_ooff.as<unsigned long long>(), cub::Sum(), 0ull,
+                                           (int64_t)(n_seg + 1), st));
+    tb = c->d_fa_tmp.cap;
+    PM_CUDA(cub::DeviceScan::ExclusiveScan(c->d_fa_tmp.p, tb, c->d_fa_nhdr.as<uint32_t>(),
+                                           c->d_fa_hoff.as<unsigned long long>(), cub::Sum(), 0ull,
+                                           (int64_t)(n_seg + 1), st));
+    fasta_write_kernel<<<fb, FA_THREADS, FA_WRITE_SMEM, st>>>(
+        d_raw, a0, a1, n_seg, c->d_fa_start.as<uint8_t>(), c->d_fa_ooff.as<unsigned long long>(),
+        c->d_fa_hoff.as<unsigned long long>(), upper_case, eos, d_stream, pre_len, pre_seqs,
+        c->d_fa_key.as<long long>(), c->d_fa_hs.as<long long>(), c->d_fa_he.as<long long>(), carry, hdr_cap,
+        carry + 3);
+    fasta_carry_kernel<<<1, 32, 0, st>>>(c->d_fa_scan.as<uint8_t>(), n_seg, c->d_fa_ooff.as<unsigned long long>(),
+                                         c->d_fa_hoff.as<unsigned long long>(), carry);
     PM_CUDA(cudaGetLastError());
   }
-  uint8_t *d_stream = c->d_text_own.as<uint8_t>();
-  PM_CUDA(cudaFuncSetAttribute(fasta_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_WRITE_SMEM));
-  fasta_write_kernel<<<(unsigned)((n_seg + FA_THREADS - 1) / FA_THREADS), FA_THREADS, FA_WRITE_SMEM, st>>>(
-      d_raw, r0, n_raw, n_seg, c->d_fa_start.as<uint8_t>(), c->d_fa_ooff.as<unsigned long long>(),
-      c->d_fa_hoff.as<unsigned long long>(), upper_case, eos, d_stream, pre_len, pre_seqs,
-      c->d_fa_key.as<long long>(), c->d_fa_hs.as<long long>(), c->d_fa_he.as<long long>());
-  PM_CUDA(cudaGetLastError());
+  unsigned long long totals[4] = {0, 0, 0, 0};
+  PM_CUDA(cudaMemcpyAsync(totals, carry, sizeof totals, cudaMemcpyDeviceToHost, st));
+  PM_CUDA(cudaStreamSynchronize(st));
+  if (totals[3]) return fail(PM_E_UNSUPPORTED, "more FASTA records than the sequence table holds (2^27)");
+  const uint64_t n = pre_len + totals[1] + 1;       // + the closing eos
+  const uint64_t n_hdr = pre_seqs + totals[2];
+  if (n > n_raw + 2) return fail(PM_E_CUDA, "FASTA normalisation produced an impossible length");
   PM_CUDA(cudaMemcpyAsync(d_stream, pre.data(), pre_len, cudaMemcpyHostToDevice, st));
   PM_CUDA(cudaMemsetAsync(d_stream + (n - 1), eos, 1, st));
   // sequence table back to the host
@@ -1924,7 +1942,7 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
   for (uint64_t i = pre_seqs; i < n_hdr; i++)
     c->seq_hdr_len[i] = c->seq_hdr_len[i] - c->seq_hdr_off[i] - 1;  // hend - hstart - 1 (fasta_io.t:548)
   c->d_text = d_stream;
-  return set_text_common(c, n, 0);
+  return set_text_common(c, n, 0);   // prep stream is drained: pack on the main stream
 }
 
 int pm_get_sequences(pm_ctx *c, const int64_t **seq_key, const int64_t **hdr_off, const int64_t **hdr_len,

@@ -11,7 +11,9 @@
 //     SKIP  any  -> SEQ  (the byte after a CR that ended a header is swallowed,
 //                         fasta_io.t:532-533, whatever it is)
 //
-// and state machines compose: every thread summarises 256 raw bytes as the map
+// and state machines compose: the file is taken in chunks as they arrive over PCIe (the
+// state, the stream length and the header count after a chunk are carried in device
+// memory); within a chunk every thread summarises 256 raw bytes as the map
 // "state before -> state after" plus, per start state, how many stream bytes and
 // headers it produces (fasta_summary_kernel); an inclusive scan of the maps under
 // composition (CUB, 1 byte per segment) gives every segment its start state; two
@@ -120,13 +122,18 @@ fasta_summary_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_ra
 }
 
 // between the scans: the counts that belong to the segment's actual start state
+// The file is processed in chunks as it arrives; what one chunk hands to the next lives in
+// device memory, so no chunk waits for the host: carry[0] = state after the last byte,
+// carry[1] = stream bytes written, carry[2] = headers started.
 __global__ void __launch_bounds__(256)
 fasta_select_kernel(const uint8_t *__restrict__ fscan, const unsigned long long *__restrict__ cnt_out,
                     const uint32_t *__restrict__ cnt_hdr, uint64_t n_seg, uint8_t *__restrict__ start,
-                    uint32_t *__restrict__ n_out, uint32_t *__restrict__ n_hdr) {
+                    uint32_t *__restrict__ n_out, uint32_t *__restrict__ n_hdr,
+                    const unsigned long long *__restrict__ carry) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_seg) return;
-  const uint32_t s = g ? (fscan[g - 1] & 3u) : FA_SEQ;
+  const uint32_t s0 = (uint32_t)carry[0];                    // state the chunk starts in
+  const uint32_t s = g ? ((fscan[g - 1] >> (2 * s0)) & 3u) : s0;
   start[g] = (uint8_t)s;
   n_out[g] = (uint32_t)(cnt_out[g] >> (16 * s)) & 0xffffu;
   n_hdr[g] = (cnt_hdr[g] >> (8 * s)) & 0xffu;
@@ -141,9 +148,12 @@ __global__ void __launch_bounds__(FA_THREADS)
 fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw, uint64_t n_seg,
                    const uint8_t *__restrict__ start, const unsigned long long *__restrict__ out_off,
                    const unsigned long long *__restrict__ hdr_off, int upper_case, uint32_t eos,
-                   uint8_t *__restrict__ stream, uint64_t out_base, uint64_t hdr_base,
+                   uint8_t *__restrict__ stream, uint64_t out_base0, uint64_t hdr_base0,
                    long long *__restrict__ seq_key, long long *__restrict__ hdr_start,
-                   long long *__restrict__ hdr_end) {
+                   long long *__restrict__ hdr_end, const unsigned long long *__restrict__ carry,
+                   uint64_t hdr_cap, unsigned long long *__restrict__ hdr_overflow) {
+  const uint64_t out_base = out_base0 + carry[1];   // + what earlier chunks wrote
+  const uint64_t hdr_base = hdr_base0 + carry[2];
   extern __shared__ __align__(16) uint32_t s_dyn[];
   uint32_t *s_in = s_dyn;
   uint8_t *s_out = reinterpret_cast<uint8_t *>(s_dyn + FA_STAGE_BYTES / 4);
@@ -175,8 +185,12 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
         if (st == FA_SEQ) {
           if (b == '>') {
             s_out[o] = (uint8_t)eos;
-            seq_key[h] = (long long)(out_base + s_base + (o - phase) + 1);  // first base of the sequence
-            hdr_start[h] = (long long)(begin + 4 * q + j + 1);
+            if (h < hdr_cap) {
+              seq_key[h] = (long long)(out_base + s_base + (o - phase) + 1);  // first base of the sequence
+              hdr_start[h] = (long long)(begin + 4 * q + j + 1);
+            } else {
+              *hdr_overflow = 1ULL;
+            }
             h++;
             o++;
           } else if (!fa_blank(b)) {
@@ -184,7 +198,7 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
             s_out[o++] = (uint8_t)b;
           }
         } else if (st == FA_HDR && (b == '\n' || b == '\r')) {
-          hdr_end[h - 1] = (long long)(begin + 4 * q + j + 1);   // the header in progress is the last one started
+          if (h - 1 < hdr_cap) hdr_end[h - 1] = (long long)(begin + 4 * q + j + 1);   // the header in progress
         }
         st = fa_next(st, b);
       }
@@ -205,6 +219,17 @@ fasta_write_kernel(const uint8_t *__restrict__ raw, uint64_t r0, uint64_t n_raw,
   } else {
     for (uint32_t i = lo + threadIdx.x; i < hi; i += FA_THREADS) base[i] = s_out[i];
   }
+}
+
+// after a chunk: fold its totals into the carry
+__global__ void fasta_carry_kernel(const uint8_t *__restrict__ fscan, uint64_t n_seg,
+                                   const unsigned long long *__restrict__ out_off,
+                                   const unsigned long long *__restrict__ hdr_off, unsigned long long *carry) {
+  if (threadIdx.x || blockIdx.x) return;
+  const uint32_t s0 = (uint32_t)carry[0];
+  carry[0] = (fscan[n_seg - 1] >> (2 * s0)) & 3u;
+  carry[1] += out_off[n_seg];
+  carry[2] += hdr_off[n_seg];
 }
 
 __global__ void fill_i64_kernel(long long *p, uint64_t n, long long v) {
