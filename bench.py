@@ -178,8 +178,10 @@ def cpu_cores():
 
 
 def config_dict(args, shard_bases):
-    return {"workload": "%d random %d-mer primers, k=%d %s (%s %d), both strands (-r), "
-                        "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN, K, "edits" if INDELS else "mismatches",
+    return {"workload": "%d random %d-mer primers%s, k=%d %s (%s %d), both strands (-r), "
+                        "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN,
+                                                           " with 1-3 IUPAC codes each (-w)" if IUPAC else "", K,
+                                                           "edits" if INDELS else "mismatches",
                                                            "-k" if INDELS else "-K", K),
             "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
             "index": ("-N %d" % SELECT) if SELECT else ("automatic (pick_pattern_index): " + ("exact index" if K == 0 else "exact_halves" if (K == 1 and PRIMER_LEN >= 8) else "filter_bitvec")),

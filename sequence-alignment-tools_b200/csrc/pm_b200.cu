@@ -1372,7 +1372,10 @@ int pm_init(pm_ctx *c) {
       // level 1b: 64 KB of shared memory keyed by (key, distance) for edits; 16 MB of global
       // memory (L2-resident) once level 1 saturates (its 2^20 bits pass ~entries / 2^20 of the
       // positions)
-      const bool big_set = ents.size() > 32768;
+      // measured crossover (1 Gbp, 2000-20000 primers): below ~100 k entries the queue stages cope with
+      // level 1's false positives faster than 16 extra L2 loads per word do
+      static const size_t big_set_entries = getenv("PM_BIG_SET_ENTRIES") ? (size_t)atoll(getenv("PM_BIG_SET_ENTRIES")) : 100000;
+      const bool big_set = ents.size() > big_set_entries;
       ia.b2_global = big_set ? 1u : 0u;
       ia.log_words2 = big_set ? 22u : (edit_mode ? 14u : 0u);
       ia.mult2 = 0x85EBCA6Bu;

@@ -66,7 +66,7 @@ struct IndexArgs {
   uint32_t salt[PAIR_MAX_ND];
   // level 1b: a second bitmap keyed by (pair key, distance), consulted only for the positions
   // that passed level 1; log_words2 == 0: absent.  Edits: 64 KB in the shared memory level 1
-  // leaves free.  Large pattern sets (level 1 saturates beyond ~30 k entries): 16 MB in
+  // leaves free.  Large pattern sets (level 1 saturates: beyond ~100 k entries): 16 MB in
   // global memory, L2-resident (b2_global).
   const uint32_t *bitmap2;
   uint32_t log_words2;
