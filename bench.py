@@ -186,7 +186,8 @@ def config_dict(args, shard_bases):
             "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
             "index": ("-N %d" % SELECT) if SELECT else ("automatic (pick_pattern_index): " + ("exact index" if K == 0 else "exact_halves" if (K == 1 and PRIMER_LEN >= 8) else "filter_bitvec")),
             "l2": "inputs larger than L2 (%.1f GB stream + %.2f GB packed text per pass)" % (shard_bases / 1e9, shard_bases / 2e9),
-            "partition": "one shard per GPU, cut at sequence boundaries"}
+            "partition": "one shard per GPU, cut at sequence boundaries",
+            "host_mem": args.host_mem}
 
 
 def main_reference(args):
@@ -244,6 +245,8 @@ def main():
     ap.add_argument("--nprimers", type=int, default=N_PRIMERS, help="primers before reverse complements (headline: 1000)")
     ap.add_argument("--N", type=int, default=0, dest="select",
                     help="primer_match -N: pattern index (0 automatic, 5 filter_bitvec, 13 exact_halves)")
+    ap.add_argument("--host-mem", default="wc", choices=["pinned", "wc"],
+                    help="host buffers of the end-to-end legs: torch pinned memory, or write-combined pages (pm_host_alloc)")
     ap.add_argument("--cpu-bases-per-core", type=int, default=3_000_000)
     ap.add_argument("--ref-bases-per-core", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,14 +297,22 @@ def main():
             p[int(rs.integers(0, len(p)))] = b"ACGT"[int(rs.integers(0, 4))]
         at = int(rs.integers(1000, n - 1000))
         d_stream[at:at + len(p)] = torch.tensor(list(p), dtype=torch.uint8, device=dev)
-    h_stream = torch.empty(n + 2, dtype=torch.uint8, pin_memory=True)
-    h_stream.copy_(d_stream)
+    def host_copy(d_t):
+        """The tensor's bytes in page-locked host memory (what a pinned file reader would hold)."""
+        if args.host_mem == "wc":
+            hb = pkg.HostBuffer(d_t.numel(), write_combined=True)
+            torch.from_numpy(hb.array).copy_(d_t)
+            return hb
+        h = torch.empty(d_t.numel(), dtype=torch.uint8, pin_memory=True)
+        h.copy_(d_t)
+        return h
+
+    h_stream = host_copy(d_stream)
     # the same database as compress_seq -z would store it (.tbz table + .sqz bit stream,
     # 3 bits per character for A C G T eos): what primer_match opens when the files exist
     sqz_table = b"ACGT\n"
     d_sqz = pkg.sqz_encode_torch(d_stream, sqz_table)
-    h_sqz = torch.empty(d_sqz.numel(), dtype=torch.uint8, pin_memory=True)
-    h_sqz.copy_(d_sqz)
+    h_sqz = host_copy(d_sqz)
     del d_sqz
     # ... and as the FASTA file it came from: one record per sequence, 80 bases per line
     parts = []
@@ -318,8 +329,7 @@ def main():
         if b - a > full:
             parts += [body[full:], nl]
     d_fasta = torch.cat(parts)
-    h_fasta = torch.empty(d_fasta.numel(), dtype=torch.uint8, pin_memory=True)
-    h_fasta.copy_(d_fasta)
+    h_fasta = host_copy(d_fasta)
     del d_fasta, parts
     torch.cuda.synchronize()
 

@@ -250,6 +250,13 @@ int pm_get_sequences(pm_ctx *ctx, const int64_t **seq_key, const int64_t **hdr_o
                      const int64_t **hdr_len, uint64_t *n_seqs, uint64_t *stream_len);
 int pm_get_text(pm_ctx *ctx, uint64_t begin, uint64_t len, uint8_t *out);
 
+/* Page-locked host buffers for the database (the pinned reader side of the input
+ * path): pm_set_text_host / _sqz_host / _fasta_host read such memory directly by DMA.
+ * write_combined != 0 asks for write-combined pages: right for a buffer the CPU only
+ * fills (file read) and never reads back.                                            */
+int pm_host_alloc(uint64_t bytes, int write_combined, void **out);
+int pm_host_free(void *p);
+
 /* Diagnostic for the roofline: measured throughput of 3-input logic
  * instructions (LOP3) on `device`, in 1e12 thread-level operations per second. */
 int pm_bench_int_peak(int device, double *lop3_tera_ops);

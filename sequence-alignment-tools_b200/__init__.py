@@ -34,7 +34,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 
 # every symbol include/pm_b200.h declares
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
-           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_shard_overlap", "pm_find_patterns",
+           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
            "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path"]
 
@@ -103,6 +103,8 @@ def lib():
         i64pp = C.POINTER(C.POINTER(C.c_int64))
         L.pm_get_sequences.argtypes = [C.c_void_p, i64pp, i64pp, i64pp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.pm_get_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.pm_host_alloc.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+        L.pm_host_free.argtypes = [C.c_void_p]
         L.pm_shard_overlap.argtypes = [C.c_void_p]
         L.pm_find_patterns.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.POINTER(Hit)),
                                        C.POINTER(C.c_uint64)]
@@ -323,6 +325,38 @@ def int_pipe_report(sc: "Scanner", scan_ms: float, device=0) -> dict:
     return {"unit": "Tlop/s", "achieved": ach, "peak": peak, "frac": ach / peak if peak else None,
             "useful_lops_per_launch": useful, "warp_steps": st["scan_warp_steps"],
             "peak_source": "pm_bench_int_peak (LOP3 microbenchmark, same run)"}
+
+
+class HostBuffer:
+    """Page-locked host memory from pm_host_alloc, as a numpy uint8 view (.array)."""
+
+    def __init__(self, nbytes: int, write_combined: bool = False):
+        p = C.c_void_p()
+        _check(lib().pm_host_alloc(nbytes, int(write_combined), C.byref(p)))
+        self.ptr, self.nbytes = p.value, nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(nbytes, 1)).from_address(self.ptr))[:nbytes]
+
+    def data_ptr(self):
+        return self.ptr
+
+    def numel(self):
+        return self.nbytes
+
+    is_cuda = False
+
+    def numpy(self):
+        return self.array
+
+    def free(self):
+        if self.ptr:
+            lib().pm_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def sqz_table(chars: np.ndarray, eos: int = 10, dna_opt: bool = True) -> bytes:

@@ -1969,6 +1969,21 @@ int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
   return PM_OK;
 }
 
+// Page-locked host memory for database buffers (what pm_set_text_*_host read directly).
+// write_combined: the CPU only ever fills such a buffer front to back (read(2) / mmap copy),
+// and the DMA engine then reads it without snooping the CPU caches.
+int pm_host_alloc(uint64_t bytes, int write_combined, void **out) {
+  if (!out) return fail(PM_E_ARG, "null argument");
+  *out = nullptr;
+  PM_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  return PM_OK;
+}
+
+int pm_host_free(void *p) {
+  if (p) PM_CUDA(cudaFreeHost(p));
+  return PM_OK;
+}
+
 int pm_bench_int_peak(int device, double *lop3_tera_ops) {
   if (!lop3_tera_ops) return fail(PM_E_ARG, "null argument");
   PM_CUDA(cudaSetDevice(device));
