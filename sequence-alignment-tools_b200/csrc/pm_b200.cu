@@ -1,6 +1,7 @@
 // pm_b200.cu -- context, host logic and the extern "C" boundary (include/pm_b200.h)
-// of the B200-native PrimerMatch database scan.  Kernels: pm_planes.cuh (pack),
-// pm_scan.cuh (dense scan), pm_align.cuh (chains + alignment).
+// of the B200-native PrimerMatch database scan.  Kernels: pm_index.cuh (pack + pair-seed
+// index scan), pm_fasta.cuh (FASTA normalisation), pm_planes.cuh / pm_scan.cuh (bit-plane
+// scan, .sqz unpack), pm_halves.cuh (exact_halves), pm_align.cuh (chains + alignment).
 //
 // There is no CPU path in here: every entry point that touches text or
 // patterns runs on the CUDA device of the context or fails.
@@ -184,7 +185,7 @@ struct pm_ctx {
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
   double idx_seed_rate = 0;  // same for the pair index (pair occurrences)
   uint64_t idx_entries = 0;
-  // q-gram index path (pm_index.cuh)
+  // pair-seed index path (pm_index.cuh)
   int scan_path = PM_SCAN_AUTO;  // requested
   bool use_index = false;        // the loaded text is packed for / scanned by the pair index
   bool index_ok = false;         // resolved in pm_init: the patterns can use the pair index
@@ -452,7 +453,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     const double fit = (double)(c->d_seeds.cap / 8) / (2.0 * per_tile);
     batch_tiles = (uint32_t)std::max(1.0, std::min((double)nt, fit));
   }
-  // q-gram END positions the index path has to visit: window start in [p-31, p]
+  // first-piece positions the index path has to visit: a window starts at most 31 characters earlier
   const int64_t ip_lo = q_lo, ip_hi = std::min<int64_t>((int64_t)c->n, q_hi + 32);
   uint64_t idx_lookups = 0;
   for (int attempt = 0; attempt < 4; attempt++) {
@@ -483,7 +484,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
         if (t1 <= t0) continue;
         if (ch.ev) PM_CUDA(cudaStreamWaitEvent(ls, ch.ev, 0));
         if (c->use_index) {
-          // a verification window reaches up to 63 characters past the q-gram: positions lag
+          // a verification window reaches up to 63 characters past the first piece: positions lag
           // the packed tiles by 64 so that every window lies in words that are already packed
           const int64_t lag = 64;
           int64_t pb = std::max<int64_t>(ip_lo, (int64_t)t0 * TILE_POS - (t0 ? lag : 0));
