@@ -673,3 +673,51 @@ long pmo_exact_halves(const uint8_t *T, long L, int npat, const char *const *pat
   free(lasthit);
   return n;
 }
+
+/* ------------------------------------------------------------------------- */
+/* exact_bases::find_patterns, exact_bases.cc:68-124 (+ init, 126-159): what  */
+/* pick_pattern_index takes when the exact-base constraints (-s/-e/-5/-3) are */
+/* at least 6 long (select.cc:131-133).  The exact part of pattern i is its   */
+/* first esb characters (esb >= eeb) or its last eeb characters; every exact  */
+/* occurrence of it (part_hits, pid = pattern id) is extended over the rest   */
+/* by primer_alignment_lmatch / _rmatch; every success is a hit (no dedupe).  */
+long pmo_exact_bases(const uint8_t *T, long L, int npat, const char *const *pats,
+                     const pmo_hit *part_hits, long nparts, int k, uint8_t eos, int wc, int tn, int indels,
+                     const int *lconst, const int *rconst, pmo_hit *out, long cap) {
+  (void)npat;
+  long n = 0;
+  uint8_t buf[512];
+  char part[80];
+  for (long i = 0; i < nparts; i++) {
+    const int pid = part_hits[i].pid;
+    const int64_t pos = part_hits[i].pos;
+    const char *pat = pats[pid - 1];
+    const int m = (int)strlen(pat), esb = lconst[pid - 1], eeb = rconst[pid - 1];
+    int matchlen = 0, value = 0, ok;
+    int64_t end;
+    if (esb >= eeb) {
+      const int l1 = esb, l2 = m - esb, buflen = l2 + k;
+      for (int j = 0; j < buflen; j++) buf[j] = stream_at(T, L, pos + j);
+      ok = pmo_primer_global_align(buf, (unsigned)buflen, pat + l1, 1, (unsigned)esb - (unsigned)l1, (unsigned)eeb, k,
+                                   eos, wc, tn, indels, &matchlen, &value);
+      end = pos + matchlen;
+    } else {
+      const int l2 = eeb, l1 = m - eeb;
+      int64_t textstart = 0;
+      const int patlen = l1 + l2 + k;
+      if (pos > (int64_t)patlen) textstart = pos - patlen;
+      const int buflen = (int)(pos - l2 - textstart);
+      memcpy(part, pat, (size_t)l1);
+      part[l1] = 0;
+      for (int j = 0; j < buflen; j++) buf[j] = stream_at(T, L, textstart + j);
+      ok = pmo_primer_global_align(buf, (unsigned)(buflen < 0 ? 0 : buflen), part, -1, (unsigned)esb,
+                                   (unsigned)eeb - (unsigned)l2, k, eos, wc, tn, indels, &matchlen, &value);
+      end = pos;
+    }
+    if (ok) {
+      if (n < cap) { out[n].pos = end; out[n].pid = pid; out[n].val = value; }
+      n++;
+    }
+  }
+  return n;
+}

@@ -67,6 +67,10 @@ def lib():
         L.pmo_exact_halves.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_Hit), C.c_long,
                                        C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), C.POINTER(_Hit), C.c_long]
+        L.pmo_exact_bases.restype = C.c_long
+        L.pmo_exact_bases.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p), C.POINTER(_Hit), C.c_long,
+                                      C.c_int, C.c_uint8, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int), C.POINTER(_Hit), C.c_long]
         L.pmo_filter_chains.restype = C.c_long
         L.pmo_filter_chains.argtypes = [u8p, C.c_long, C.c_int, C.POINTER(C.c_char_p),
                                         C.POINTER(_Hit), C.c_long, C.c_int, C.c_uint8, C.c_int,
@@ -241,7 +245,7 @@ def pattern_array(primers, rev_comp: bool):
     return pats
 
 
-def exact_halves(chars, pats, k: int, indels: bool, wc=False, tn=False, eos=EOS):
+def exact_halves(chars, pats, k: int, indels: bool, wc=False, tn=False, eos=EOS, lconst=None, rconst=None):
     """exact_halves::find_patterns: (end, pattern id, value) of every reported hit."""
     L = lib()
     chars = np.ascontiguousarray(chars, np.uint8)
@@ -254,37 +258,115 @@ def exact_halves(chars, pats, k: int, indels: bool, wc=False, tn=False, eos=EOS)
     for i, (pos, pid, _) in enumerate(hh):
         hb[i].pos, hb[i].pid, hb[i].val = int(pos), int(pid), 0
     out = (_Hit * max(n, 1))()
+    lc = (C.c_int * len(pats))(*lconst) if lconst is not None else None
+    rc = (C.c_int * len(pats))(*rconst) if rconst is not None else None
     m = L.pmo_exact_halves(_u8(chars), len(chars), len(pats), _pats(pats), hb, n, k, eos, int(wc), int(tn),
-                           int(indels), None, None, out, max(n, 1))
+                           int(indels), lc, rc, out, max(n, 1))
     return np.array([[out[i].pos, out[i].pid, out[i].val] for i in range(m)], np.int64).reshape(-1, 3)
 
 
-def auto_index(primers, k: int) -> str:
-    """pick_pattern_index (select.cc:100-141) for a streamed FASTA database without exact-base
-    constraints and a build with -DNOPRIMEGEN: exact_halves for k == 1 and primers of at least
-    8 characters, filter_bitvec for every other k > 0."""
-    if k == 1 and min(len(p) for p in primers) >= 8:
+def pattern_constraints(primers, rev_comp: bool, stlen=0, edlen=0, fplen=0, tplen=0):
+    """exact_start_bases / exact_end_bases of every pattern of pattern_array(): the -s / -e / -5 / -3
+    options of primer_match (a negative value is the `~n` form: all but n characters),
+    primer_match.cc:990-1060.  For a reverse complement 5' and 3' swap ends."""
+    first, second = [], []
+    for p in primers:
+        ln = len(p)
+        f = stlen if stlen > 0 else 0
+        f = max(f, fplen)
+        if edlen < 0:
+            f = max(f, ln + edlen)
+        if tplen < 0:
+            f = max(f, ln + tplen)
+        s_ = edlen if edlen > 0 else 0
+        s_ = max(s_, tplen)
+        if stlen < 0:
+            s_ = max(s_, ln + stlen)
+        if fplen < 0:
+            s_ = max(s_, ln + fplen)
+        first.append(f)
+        second.append(s_)
+    if rev_comp:
+        for p in primers:
+            ln = len(p)
+            f = stlen if stlen > 0 else 0
+            f = max(f, tplen)
+            if edlen < 0:
+                f = max(f, ln + edlen)
+            if fplen < 0:
+                f = max(f, ln + fplen)
+            s_ = edlen if edlen > 0 else 0
+            s_ = max(s_, fplen)
+            if stlen < 0:
+                s_ = max(s_, ln + stlen)
+            if tplen < 0:
+                s_ = max(s_, ln + tplen)
+            first.append(f)
+            second.append(s_)
+    return first, second
+
+
+def exact_bases(chars, pats, k: int, indels: bool, lconst, rconst, wc=False, tn=False, eos=EOS):
+    """exact_bases::find_patterns: (end, pattern id, value) of every hit."""
+    L = lib()
+    chars = np.ascontiguousarray(chars, np.uint8)
+    parts = [p[:a] if a >= b else p[len(p) - b:] for p, a, b in zip(pats, lconst, rconst)]
+    hh = exact_scan(chars, parts, wc, tn)
+    n = len(hh)
+    hb = (_Hit * max(n, 1))()
+    for i, (pos, pid, _) in enumerate(hh):
+        hb[i].pos, hb[i].pid, hb[i].val = int(pos), int(pid), 0
+    out = (_Hit * max(n, 1))()
+    lc = (C.c_int * len(pats))(*lconst)
+    rc = (C.c_int * len(pats))(*rconst)
+    m = L.pmo_exact_bases(_u8(chars), len(chars), len(pats), _pats(pats), hb, n, k, eos, int(wc), int(tn),
+                          int(indels), lc, rc, out, max(n, 1))
+    return np.array([[out[i].pos, out[i].pid, out[i].val] for i in range(m)], np.int64).reshape(-1, 3)
+
+
+def auto_index(primers, k: int, lconst=None, rconst=None) -> str:
+    """pick_pattern_index (select.cc:32-141) for a streamed FASTA database (CharacterProducer::size()
+    == 256), no -x seed length and a build with -DNOPRIMEGEN.  primers = the pattern array
+    (reverse complements included when -r)."""
+    if k == 0:
+        return "exact"
+    n = len(primers)
+    lconst = lconst or [0] * n
+    rconst = rconst or [0] * n
+    ex = [max(a, b) for a, b in zip(lconst, rconst)]
+    min_length = min(len(p) for p in primers)
+    cumdiff = sum(e - len(p) // 2 for e, p in zip(ex, primers))
+    cumbooldiff = sum(1 for e, p in zip(ex, primers) if e - len(p) // 2 >= 0)
+    if k == 1 and min_length >= 8 and (cumbooldiff <= 0 or cumdiff <= 0):
         return "exact_halves"
-    return "filter_bitvec" if k > 0 else "exact"
+    if min(ex) >= 6:
+        return "exact_bases"
+    return "filter_bitvec"
 
 
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS, index="filter_bitvec"):
+                 eos=EOS, index="filter_bitvec", stlen=0, edlen=0, fplen=0, tplen=0):
     """Whole path, as the reference runs it with `-N 5` for k>0 (index="filter_bitvec"), with its
-    exact_halves index (index="exact_halves": the automatic choice for k == 1), and its
-    automatic choice for k==0 (keyword_tree, or shift_and under -w/-W).
+    exact_halves / exact_bases indexes (index="exact_halves" / "exact_bases"; index="auto" follows
+    pick_pattern_index), and its automatic choice for k==0 (keyword_tree, or shift_and under
+    -w/-W).  stlen / edlen / fplen / tplen = the -s / -e / -5 / -3 options.
     Returns a sorted list of HitRecord."""
     n = len(primers)
     pats = pattern_array(primers, rev_comp)
+    lconst, rconst = pattern_constraints(primers, rev_comp, stlen, edlen, fplen, tplen)
     T = stream.chars
     recs = []
+    if index == "auto":
+        index = auto_index(pats, k, lconst, rconst)
     if k == 0:
         hits = exact_scan(T, pats, wc, tn)
     elif index == "exact_halves":
-        hits = exact_halves(T, pats, k, indels, wc, tn, eos)
+        hits = exact_halves(T, pats, k, indels, wc, tn, eos, lconst, rconst)
+    elif index == "exact_bases":
+        hits = exact_bases(T, pats, k, indels, lconst, rconst, wc, tn, eos)
     else:
         cands = wm_scan(T, pats, k, indels, wc, tn, eos)
-        hits = filter_chains(T, pats, cands, k, indels, wc, tn, None, None, eos)
+        hits = filter_chains(T, pats, cands, k, indels, wc, tn, lconst, rconst, eos)
     for pos, pid, _ in hits:
         pos, pid = int(pos), int(pid)
         pat = pats[pid - 1]
@@ -299,7 +381,7 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
                 raise AssertionError("Bogus hit (primer_match.cc:1249)")
             astr = "".join(CODE_CHARS[c] for c in codes)
         else:
-            al = editdist_align(T, pat, pos, pos, k, indels, wc, tn, 0, 0, eos)
+            al = editdist_align(T, pat, pos, pos, k, indels, wc, tn, lconst[pid - 1], rconst[pid - 1], eos)
             if al.editdist < 0 or al.editdist > k:
                 raise AssertionError("Bogus hit (primer_match.cc:1249)")
             start, end, ed, astr = al.start, al.end, al.editdist, al.string

@@ -50,6 +50,12 @@ def halves_golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def constraints_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "constraints_golden.json")) as f:
+        return json.load(f)
+
+
 def records_of(case):
     return [tuple(r) for r in case["records"]]
 

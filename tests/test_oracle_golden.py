@@ -64,3 +64,15 @@ def test_oracle_exact_halves_matches_reference_golden(oracle, halves_golden):
             assert oracle.auto_index(case["primers"], case["params"]["k"]) == "exact_halves"
         got = oracle.primer_match(st, case["primers"], index="exact_halves", **case["params"])
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
+
+
+def test_oracle_with_exact_base_constraints_matches_reference_golden(oracle, constraints_golden):
+    """-s / -e / -5 / -3: the constraints inside every alignment, and the index they make
+    pick_pattern_index choose (exact_bases from 6 characters on)."""
+    cases = constraints_golden["cases"]
+    assert len(cases) >= 40 and {c["index"] for c in cases} >= {"exact_bases", "exact_halves", "filter_bitvec"}
+    for case in cases:
+        st = oracle.normalize_fasta(case["fasta"].encode("latin-1"))
+        got = oracle.primer_match(st, case["primers"], index="auto" if case["select"] == 0 else "filter_bitvec",
+                                  **case["params"], **case["constraints"])
+        assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
