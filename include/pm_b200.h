@@ -50,11 +50,17 @@ extern "C" {
  * keyword_tree when k==0 without wildcards, shift_and when k==0 with wildcards;
  * for k == 1 exact_halves when every pattern has at least 8 characters and the
  * exact-base constraints (-5/-3) are shorter than half the patterns on average
- * (resolved in pm_init, when the patterns are known); filter_bitvec otherwise.  */
+ * (resolved in pm_init, when the patterns are known); otherwise, for k > 0,
+ * exact_bases when every pattern has at least 6 constrained characters, else
+ * filter_bitvec.                                                                   */
 #define PM_INDEX_AUTO 0
 #define PM_INDEX_KEYWORD_TREE 3  /* select.cc:221-229, keyword_tree.t:427      */
 #define PM_INDEX_SHIFT_AND 4     /* select.cc:230-233, shift_and.cc:204        */
 #define PM_INDEX_FILTER_BITVEC 5 /* select.cc:234-237, filter_bitvec.cc:126    */
+#define PM_INDEX_EXACT_BASES 9   /* select.cc:238-245 (-N 7..10), exact_bases.cc:68: exact
+                                    occurrences of the constrained prefix / suffix (-s/-e/-5/-3),
+                                    extended by primer_alignment; what pick_pattern_index takes
+                                    when every pattern has >= 6 constrained characters   */
 #define PM_INDEX_EXACT_HALVES 13 /* select.cc:246-261 (-N 11..14), exact_halves.cc:118:
                                     exact occurrences of the pattern halves, each
                                     extended by primer_alignment (primer_alignment.cc);

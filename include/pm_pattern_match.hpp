@@ -204,7 +204,7 @@ class b200_index : public PatternMatch {
 
 // pick_pattern_index (select.cc:18-298) for the selections this library has.
 // pmselect 0 = automatic.  Selections whose *hit semantics* differ from what is
-// implemented (exact_bases 7-10, hash tables 6/15, suffix
+// implemented (hash tables 6/15, suffix
 // tree) are refused rather than silently replaced.
 inline b200_index *pick_pattern_index(int pmselect, int nmismatch, bool wildcard, bool textn, bool indels,
                                       char eos, int device = 0) {
@@ -214,9 +214,10 @@ inline b200_index *pick_pattern_index(int pmselect, int nmismatch, bool wildcard
     case 1: case 2: case 3: index = PM_INDEX_KEYWORD_TREE; break;
     case 4: index = PM_INDEX_SHIFT_AND; break;
     case 5: index = PM_INDEX_FILTER_BITVEC; break;
+    case 7: case 8: case 9: case 10: index = PM_INDEX_EXACT_BASES; break;
     case 11: case 12: case 13: case 14: index = PM_INDEX_EXACT_HALVES; break;
     default:
-      fatal("Fatal error: pattern index selection not available in the B200 build (use -N 0, 3, 4, 5 or 11-14)");
+      fatal("Fatal error: pattern index selection not available in the B200 build (use -N 0, 3, 4, 5 or 7-14)");
       return 0;
   }
   if (index == PM_INDEX_KEYWORD_TREE && wildcard) index = PM_INDEX_SHIFT_AND;

@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpm_b200.so")
 PM_OK = 0
 PM_E_ARG, PM_E_CUDA, PM_E_UNSUPPORTED, PM_E_NOMEM, PM_E_BOGUS = -1, -2, -3, -4, -5
 PM_INDEX_AUTO, PM_INDEX_KEYWORD_TREE, PM_INDEX_SHIFT_AND, PM_INDEX_FILTER_BITVEC = 0, 3, 4, 5
-PM_INDEX_EXACT_HALVES = 13
+PM_INDEX_EXACT_BASES, PM_INDEX_EXACT_HALVES = 9, 13
 PM_SCAN_AUTO, PM_SCAN_PLANES, PM_SCAN_INDEX = 0, 1, 2
 PM_MAX_CODES = 72
 INT64_MAX = (1 << 63) - 1
@@ -446,6 +446,28 @@ def pattern_array(primers, rev_comp: bool):
     return pats
 
 
+def pattern_constraints(primers, rev_comp: bool, stlen=0, edlen=0, fplen=0, tplen=0):
+    """primer_match.cc:990-1060: exact_start_bases / exact_end_bases of every pattern of
+    pattern_array() from the -s / -e / -5 / -3 options (negative = the `~n` form: all but n
+    characters).  For a reverse complement the 5' and 3' ends swap."""
+    def one(ln, five, three):
+        f = max(stlen if stlen > 0 else 0, five if five > 0 else 0)
+        if edlen < 0:
+            f = max(f, ln + edlen)
+        if three < 0:
+            f = max(f, ln + three)
+        s_ = max(edlen if edlen > 0 else 0, three if three > 0 else 0)
+        if stlen < 0:
+            s_ = max(s_, ln + stlen)
+        if five < 0:
+            s_ = max(s_, ln + five)
+        return f, s_
+    cons = [one(len(p), fplen, tplen) for p in primers]
+    if rev_comp:
+        cons += [one(len(p), tplen, fplen) for p in primers]
+    return [c[0] for c in cons], [c[1] for c in cons]
+
+
 def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
     """primer_match.cc:1156-1200: coordinates handed to alignformat()."""
     recs = []
@@ -463,7 +485,8 @@ def hits_to_records(stream: Stream, hits: np.ndarray, n_primers: int):
 
 
 def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO, sqz=None):
+                 eos=EOS, device=0, index=PM_INDEX_AUTO, scan_path=PM_SCAN_AUTO, sqz=None,
+                 stlen=0, edlen=0, fplen=0, tplen=0):
     """The reference's main loop on the GPU path: returns sorted HitRecords.
     index: a -N selection; PM_INDEX_AUTO follows pick_pattern_index (exact_halves for k == 1).
     sqz = (sqz bytes, tbz table, n_chars): load the text from compress_seq's compressed
@@ -472,8 +495,9 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
     sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos,
                  scan_path=scan_path)
     try:
+        esb, eeb = pattern_constraints(primers, rev_comp, stlen, edlen, fplen, tplen)   # -s / -e / -5 / -3
         for i, p in enumerate(pats):
-            sc.add_pattern(p, i + 1)
+            sc.add_pattern(p, i + 1, esb[i], eeb[i])
         sc.init()
         if sqz is not None:
             sc.set_text_sqz(*sqz)

@@ -151,7 +151,8 @@ struct pm_ctx {
   std::vector<Pattern> pats;
   bool inited = false;
   bool index_auto = false;   // pm_create got PM_INDEX_AUTO with k > 0: resolved in pm_init
-  pm_ctx *inner = nullptr;   // exact_halves: the exact index over the 2N pattern halves
+  pm_ctx *inner = nullptr;   // exact_halves / exact_bases: the exact index over the pattern parts
+  bool inner_bases = false;  // ... exact_bases
   DevBuf d_half_rec, d_half_key, d_half_key2, d_half_ord, d_half_ord2;
   int max_len = 0;
   // symbols
@@ -515,6 +516,10 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
           const uint32_t b1 = std::min(t1, b0 + batch_tiles);
           a.tile0 = b0;
           if (edit) PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), ls));
+          if (edit && b0 == 0) {  // nominal window starts -1 .. -K (see edit_start_seeds_kernel)
+            edit_start_seeds_kernel<<<nblocks((uint64_t)n_slots * K, 256), 256, 0, ls>>>(a, K);
+            c->stats.kernel_launches++;
+          }
           kern<<<(b1 - b0) * chunks, SCAN_THREADS, smem, ls>>>(a);
           PM_CUDA(cudaGetLastError());
           c->stats.kernel_launches++;
@@ -748,12 +753,22 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
       if ((rc = c->d_half_ord2.ensure(ncand * 4))) return rc;
       if ((rc = c->d_raw.ensure(ncand * sizeof(RawHit)))) return rc;
       PM_CUDA(cudaMemsetAsync(c->d_counters + 10, 0, sizeof(unsigned long long), c->stream));
+      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
       halves_extend_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
           env, c->inner->d_keys.as<unsigned long long>(), ncand, c->inner->d_slotid.as<uint32_t>(),
-          c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>(), c->d_counters + 10);
+          c->inner_bases ? 1 : 0, c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>(),
+          c->d_counters + 10, own_lo, own_hi, c->d_raw.as<RawHit>(), c->d_counters + 4, ncand);
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches++;
       PM_CUDA(cudaMemcpyAsync(c->h_counters + 10, c->d_counters + 10, sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
+      if (c->inner_bases) {
+        n_out = c->h_counters[4];          // exact_bases: every extension is a hit
+        c->stats.n_chains = n_out;
+      } else {
       ncand = c->h_counters[10];   // from here on: the occurrences that extended
       c->stats.n_chains = ncand;
       if (ncand == 0) goto done;
@@ -768,17 +783,17 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
                                               c->d_half_key2.as<unsigned long long>(),
                                               c->d_half_ord.as<uint32_t>(), c->d_half_ord2.as<uint32_t>(), ncand,
                                               0, 64, c->stream));
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
       const uint32_t n_slots = (uint32_t)c->pats.size();
       halves_report_kernel<<<nblocks(n_slots, 128), 128, 0, c->stream>>>(
           c->d_half_key2.as<unsigned long long>(), c->d_half_ord2.as<uint32_t>(), c->d_half_rec.as<HalfRec>(),
           ncand, n_slots, K, c->opt.indels, own_lo, own_hi, c->d_raw.as<RawHit>(), c->d_counters + 4, ncand);
       PM_CUDA(cudaGetLastError());
-      c->stats.kernel_launches += 6;
+      c->stats.kernel_launches += 5;
       PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
       n_out = c->h_counters[4];
+      }
     } else if (K == 0) {
       if ((rc = c->d_hits.ensure(ncand * sizeof(pm_hit)))) return rc;
       if ((rc = c->d_sortk.ensure(ncand * 8))) return rc;
@@ -989,6 +1004,10 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
       break;
     case PM_INDEX_FILTER_BITVEC:
       if (opt->k == 0) return fail(PM_E_ARG, "filter_bitvec needs k > 0");
+      break;
+    case 7: case 8: case PM_INDEX_EXACT_BASES: case 10:      // over any of the exact indexes: same hit list
+      if (opt->k == 0) return fail(PM_E_ARG, "exact_bases needs k > 0");
+      index = PM_INDEX_EXACT_BASES;
       break;
     case 11: case 12: case PM_INDEX_EXACT_HALVES: case 14:  // over any of the exact indexes: same hit list
       if (opt->k == 0) return fail(PM_E_ARG, "exact_halves needs k > 0");
@@ -1217,6 +1236,38 @@ int pm_init(pm_ctx *c) {
     }
     // a streamed FASTA database has CharacterProducer::size() == 256 (char_io.h:96)
     if (min_length >= 8 && (cumbooldiff <= 0 || cumdiff <= 0)) c->index = PM_INDEX_EXACT_HALVES;
+  }
+  if (c->index_auto && K > 0 && ns > 0 && c->index == PM_INDEX_FILTER_BITVEC) {
+    // select.cc:131-133: exact_bases when every pattern has 6 or more constrained characters
+    int min_exact_const = 1 << 30;
+    for (const Pattern &p : c->pats) min_exact_const = std::min(min_exact_const, std::max(p.esb, p.eeb));
+    if (min_exact_const >= 6) c->index = PM_INDEX_EXACT_BASES;
+  }
+  if (K > 0)  // select.cc:84-91
+    for (const Pattern &p : c->pats)
+      if ((int)p.s.size() - std::max(p.esb, p.eeb) <= K && std::max(p.esb, p.eeb) > 0)
+        return fail(PM_E_ARG, "Number of edits >= Minimum number of inexact bases");
+  if (c->index == PM_INDEX_EXACT_BASES) {
+    // the exact index over the constrained prefix (esb >= eeb) or suffix of every pattern;
+    // inner pattern id = slot + 1 (exact_bases.cc:126-159)
+    pm_options io = c->opt;
+    io.k = 0;
+    io.indels = 0;
+    io.index = c->opt.wildcards ? PM_INDEX_SHIFT_AND : PM_INDEX_KEYWORD_TREE;
+    int rc = pm_create(&c->inner, &io);
+    if (rc) return rc;
+    c->inner_bases = true;
+    c->inner->scan_path = (c->scan_path == PM_SCAN_PLANES) ? PM_SCAN_PLANES : PM_SCAN_AUTO;
+    c->inner->stream = c->stream;
+    for (size_t i = 0; i < ns; i++) {
+      const Pattern &p = c->pats[i];
+      const int m = (int)p.s.size();
+      const int len = std::max(p.esb, p.eeb);
+      if (len <= 0 || len > m) return fail(PM_E_ARG, "exact_bases needs an exact-base constraint on every pattern");
+      const std::string part = (p.esb >= p.eeb) ? p.s.substr(0, (size_t)p.esb) : p.s.substr((size_t)(m - p.eeb));
+      if ((rc = pm_add_pattern(c->inner, part.c_str(), (uint32_t)(i + 1), 0, 0))) return rc;
+    }
+    if ((rc = pm_init(c->inner))) return rc;
   }
   if (c->index == PM_INDEX_EXACT_HALVES) {
     // the exact index over the halves: inner pattern ids 2i+1 (left), 2i+2 (right) for slot i

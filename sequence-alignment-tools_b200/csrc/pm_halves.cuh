@@ -1,4 +1,4 @@
-// pm_halves.cuh -- exact_halves semantics on the device (sm_100a).
+// pm_halves.cuh -- exact_halves and exact_bases semantics on the device (sm_100a).
 //
 // For one mismatch / edit the reference does not use filter_bitvec:
 // pick_pattern_index (select.cc:120-126) wraps its exact index in exact_halves
@@ -20,6 +20,10 @@
 //      pattern (the rule is sequential per pattern, the runs are short);
 //   4. reported (pattern, end) pairs go through the same final alignment as every
 //      other index (primer_match.cc:1132-1153).
+//
+// exact_bases (exact_bases.cc, select.cc:131-133: the automatic choice when the -s/-e/-5/-3
+// constraints are at least 6 characters) is the same machine with the constrained prefix or
+// suffix of the pattern as the exact part and without step 3: every extension is a hit.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,7 +31,7 @@
 
 namespace pm {
 
-constexpr int HALF_MAX = 40;  // longest half + k + 1 (patterns <= 64, k <= 3)
+constexpr int HALF_MAX = 72;  // longest part + k + 1 (patterns <= 64, k <= 3)
 
 struct HalfRec {
   int64_t end;      // pal.end() / par.end()
@@ -134,32 +138,41 @@ __device__ __forceinline__ bool primer_global_align(const AlignEnv &env, const u
   return true;
 }
 
-// one thread per exact half occurrence.  keys[i] = inner slot << 40 | pos;
-// inner_id[inner slot] = 2 * outer slot + 1 (left half) or + 2 (right half).
+// one thread per exact occurrence of an inner pattern.  keys[i] = inner slot << 40 | pos.
+//   bases == 0 (exact_halves): inner_id[inner slot] = 2 * outer slot + 1 (left half) or + 2
+//     (right half); the occurrences that extend are appended to rec / sortkey.
+//   bases != 0 (exact_bases, exact_bases.cc:68-124): inner_id = outer slot + 1; the exact part
+//     is the first esb characters (esb >= eeb) or the last eeb; every occurrence that extends
+//     is a hit at once (no lasthit rule): appended to out when its end lies in [own_lo, own_hi).
 __global__ void __launch_bounds__(128)
 halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ keys, uint64_t n,
-                     const uint32_t *__restrict__ inner_id, HalfRec *__restrict__ rec,
-                     unsigned long long *__restrict__ sortkey, unsigned long long *__restrict__ n_ok) {
+                     const uint32_t *__restrict__ inner_id, int bases, HalfRec *__restrict__ rec,
+                     unsigned long long *__restrict__ sortkey, unsigned long long *__restrict__ n_ok,
+                     int64_t own_lo, int64_t own_hi, RawHit *__restrict__ out, unsigned long long *__restrict__ n_out,
+                     uint64_t cap) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = keys[i];
   const uint32_t hid = inner_id[(uint32_t)(key >> 40)];
   const int64_t pos = (int64_t)(key & 0xffffffffffULL);
-  const uint32_t slot = (hid - 1) >> 1;        // outer slot
-  const bool left = (hid & 1u) != 0;           // the LEFT half matched exactly (odd inner id)
+  const uint32_t slot = bases ? hid - 1 : (hid - 1) >> 1;   // outer slot
   const uint8_t *pat = env.pat_chars + (size_t)slot * PAT_STRIDE;
-  const int m = env.plen[slot] & 0x7f, l1 = m / 2, l2 = m - l1;
-  const uint32_t esb = (uint32_t)(int)env.lconst[slot], eeb = (uint32_t)(int)env.rconst[slot];
+  const int m = env.plen[slot] & 0x7f;
+  const int esb_i = (int)env.lconst[slot], eeb_i = (int)env.rconst[slot];
+  const uint32_t esb = (uint32_t)esb_i, eeb = (uint32_t)eeb_i;
+  // the LEFT part matched exactly: odd inner id (halves), the prefix is the exact part (bases)
+  const bool left = bases ? (esb_i >= eeb_i) : ((hid & 1u) != 0);
+  const int l1 = bases ? (left ? esb_i : m - eeb_i) : m / 2, l2 = m - l1;
   HalfRec r;
   int matchlen = 0, value = 0;
   if (left) {
-    // primer_alignment_lmatch::align: text [pos, pos + |right| + k), right half from the left
+    // primer_alignment_lmatch::align: text [pos, pos + |right| + k), right part from the left
     const int buflen = l2 + env.k;
     r.ok = primer_global_align(env, env.text, env.n, pos, buflen, pat + l1, l2, 1, esb - (uint32_t)l1, eeb,
                                matchlen, value) ? 1u : 0u;
     r.end = pos + matchlen;
   } else {
-    // primer_alignment_rmatch::align: text [max(0, pos - m - k), pos - |right|), left half from the right
+    // primer_alignment_rmatch::align: text [max(0, pos - m - k), pos - |right|), left part from the right
     int64_t textstart = 0;
     const int patlen = l1 + l2 + env.k;
     if (pos > (int64_t)patlen) textstart = pos - patlen;
@@ -170,7 +183,21 @@ halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ 
     r.end = pos;
   }
   r.value = value;
-  if (!r.ok) return;   // most occurrences of a half do not extend: only the others are kept
+  if (!r.ok) return;   // most occurrences do not extend: only the others are kept
+  if (bases) {
+    if (r.end >= own_lo && r.end < own_hi) {
+      const unsigned long long at = atomicAdd(n_out, 1ULL);
+      if (at < cap) {
+        RawHit h;
+        h.end = r.end;
+        h.first = r.end;
+        h.slot = slot;
+        h.val = r.value;
+        out[at] = h;
+      }
+    }
+    return;
+  }
   const unsigned long long at = atomicAdd(n_ok, 1ULL);
   rec[at] = r;
   // exact_halves.cc:113-116: by position, then inner id DESCENDING (the right half first)

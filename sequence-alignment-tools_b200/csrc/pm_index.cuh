@@ -50,7 +50,6 @@ constexpr int PAIR_WARPS = PAIR_THREADS / 32;
 constexpr int PAIR_MAX_ND = 32;
 constexpr int PAIR_LOG_WORDS = 15;            // 2^15 words = 128 KB = 2^20 bits
 constexpr int PAIR_LMAX = 8;
-constexpr int64_t SEED_BIAS = 64;             // seeds store (nominal window start + SEED_BIAS)
 
 struct IndexArgs {
   const uint2 *pk;          // [n16] x = 2-bit codes of 16 characters, y = flags (bit0 bad, bit1 eos)
@@ -700,7 +699,7 @@ amb_seed_kernel(const ScanArgs a, const unsigned long long *__restrict__ amb, ui
         int64_t s_nominal = tc - m + 1;
         if (s_nominal < 0) s_nominal = 0;
         const unsigned long long at = atomicAdd(a.seed_n, 1ULL);
-        if (at < a.seed_cap) a.seeds[at] = ((unsigned long long)slot << 40) | (unsigned long long)s_nominal;
+        if (at < a.seed_cap) a.seeds[at] = ((unsigned long long)slot << 40) | (unsigned long long)(s_nominal + SEED_BIAS);
         else *a.seed_overflow = 1ULL;
       }
     }

@@ -42,6 +42,7 @@ constexpr int SCAN_THREADS = 128;           // 4 warps, each owns 256 words of t
 constexpr int SCAN_STRIPS = 8;              // words per lane: w = warp*256 + s*32 + lane
 constexpr int POFF_STRIDE = 64;             // offsets per pattern row (PM_MAX_PATTERN_LEN)
 constexpr int SEEDQ_CAP = 512;              // per-warp seed queue entries
+constexpr int64_t SEED_BIAS = 64;           // seeds store (nominal window start + SEED_BIAS): it can be negative
 
 struct ScanArgs {
   const uint32_t *planes;   // [n_tiles][n_planes][TILE_WT]
@@ -377,7 +378,7 @@ edit_seed_kernel(const ScanArgs a) {
 
   auto put_global = [&](unsigned long long at, uint32_t e) {
     if (at < a.seed_cap)
-      a.seeds[at] = ((unsigned long long)(slot0 + (e >> 15)) << 40) | (tile_pos + (e & 0x7fffu));
+      a.seeds[at] = ((unsigned long long)(slot0 + (e >> 15)) << 40) | (tile_pos + (e & 0x7fffu) + (unsigned long long)SEED_BIAS);
     else
       *a.seed_overflow = 1ULL;
   };
@@ -444,6 +445,20 @@ edit_seed_kernel(const ScanArgs a) {
   if (lane == 0 && a.work_count) atomicAdd(a.work_count, (unsigned long long)n_steps);
 }
 
+// An occurrence that begins with deleted pattern characters right at the start of the stream
+// has its nominal window start before position 0, where no tile position exists: those k
+// starts are seeded for every pattern unconditionally (k * n_slots seeds, once per scan).
+__global__ void __launch_bounds__(256)
+edit_start_seeds_kernel(const ScanArgs a, int K) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n_slots * (uint32_t)K) return;
+  const uint32_t slot = i / (uint32_t)K;
+  const int64_t s_nominal = -1 - (int64_t)(i % (uint32_t)K);
+  const unsigned long long at = atomicAdd(a.seed_n, 1ULL);
+  if (at < a.seed_cap) a.seeds[at] = ((unsigned long long)slot << 40) | (unsigned long long)(s_nominal + SEED_BIAS);
+  else *a.seed_overflow = 1ULL;
+}
+
 // Edit-distance scan, sparse half: one thread per seed.
 constexpr int NARROW_CLS = 8;  // classes per lane row of the shared mask table
 constexpr int VERIFY_THREADS = 128;
@@ -461,7 +476,7 @@ edit_verify_kernel(const ScanArgs a) {
        i += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned long long sd = a.seeds[i];
     const uint32_t slot = (uint32_t)(sd >> 40);
-    const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL);
+    const int64_t s_nominal = (int64_t)(sd & 0xffffffffffULL) - SEED_BIAS;
     const uint64_t *src = a.umask + (size_t)slot * a.n_cls;
     if (a.narrow) {
       uint32_t *row = s_umask[threadIdx.x];

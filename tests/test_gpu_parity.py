@@ -52,6 +52,20 @@ def test_exact_halves_golden_records_bit_exact(pkg, halves_golden, path):
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
 
 
+@pytest.mark.parametrize("path", ["auto", "planes"])
+def test_constraints_golden_records_bit_exact(pkg, constraints_golden, path):
+    """-s / -e / -5 / -3 (exact_start_bases / exact_end_bases) with -N 5 and with the automatic
+    index choice: exact_bases from 6 constrained characters on, exact_halves / filter_bitvec
+    below.  The records the reference printed."""
+    sp = pkg.PM_SCAN_AUTO if path == "auto" else pkg.PM_SCAN_PLANES
+    for case in constraints_golden["cases"]:
+        st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
+        index = pkg.PM_INDEX_AUTO if case["select"] == 0 else pkg.PM_INDEX_FILTER_BITVEC
+        got = pkg.primer_match(st, case["primers"], scan_path=sp, index=index, **case["params"],
+                               **case["constraints"])
+        assert as_tuples(got) == sorted(records_of(case)), "case %s (%s)" % (case["seed"], case["index"])
+
+
 @pytest.mark.parametrize("seed", range(3000, 3040))
 def test_exact_halves_matches_oracle_seeded(pkg, oracle, seed):
     import casegen
