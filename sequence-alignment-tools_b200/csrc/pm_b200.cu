@@ -153,6 +153,7 @@ struct pm_ctx {
   bool index_auto = false;   // pm_create got PM_INDEX_AUTO with k > 0: resolved in pm_init
   pm_ctx *inner = nullptr;   // exact_halves / exact_bases: the exact index over the pattern parts
   bool inner_bases = false;  // ... exact_bases
+  bool unordered_ok = false; // this IS such an inner context: run_scan may leave the candidates unsorted
   DevBuf d_half_rec, d_half_key, d_half_key2, d_half_ord, d_half_ord2;
   int max_len = 0;
   // symbols
@@ -594,6 +595,12 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     if (attempt == 3) return fail(PM_E_NOMEM, "candidate buffer overflow");
   }
   if (count == 0) return PM_OK;
+  if (c->unordered_ok && K == 0 && c->stats.n_ambiguous == 0) {
+    // the exact scan of an exact_halves / exact_bases inner context: every occurrence is found
+    // exactly once (one piece pair per pattern) and its consumer orders the records itself
+    *n_out = count;
+    return PM_OK;
+  }
 
   // sort by (slot, pos); edit mode emits duplicates -> unique
   int rc = c->d_keys2.ensure((size_t)count * 8);
@@ -1257,6 +1264,7 @@ int pm_init(pm_ctx *c) {
     int rc = pm_create(&c->inner, &io);
     if (rc) return rc;
     c->inner_bases = true;
+    c->inner->unordered_ok = true;
     c->inner->scan_path = (c->scan_path == PM_SCAN_PLANES) ? PM_SCAN_PLANES : PM_SCAN_AUTO;
     c->inner->stream = c->stream;
     for (size_t i = 0; i < ns; i++) {
@@ -1278,6 +1286,7 @@ int pm_init(pm_ctx *c) {
     io.index = c->opt.wildcards ? PM_INDEX_SHIFT_AND : PM_INDEX_KEYWORD_TREE;
     int rc = pm_create(&c->inner, &io);
     if (rc) return rc;
+    c->inner->unordered_ok = true;
     c->inner->scan_path = (c->scan_path == PM_SCAN_PLANES) ? PM_SCAN_PLANES : PM_SCAN_AUTO;
     c->inner->stream = c->stream;
     for (size_t i = 0; i < ns; i++) {
