@@ -175,6 +175,11 @@ int pm_set_text_device(pm_ctx *ctx, const uint8_t *d_stream, uint64_t n, int64_t
  * stream bytes are rebuilt on the device (unpack_sqz_kernel).                   */
 int pm_set_text_sqz_host(pm_ctx *ctx, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
                          uint32_t table_size, uint64_t n_chars, int64_t stream_offset);
+/* IndexedFastaFile<Normalized<...>> (select.t:29-44; char_io.t:216-283): the `.sqn` file
+ * `compress_seq -n true` writes, one index into the `.tbl` table per character; what
+ * primer_match opens first when it exists (-D 0 / -D 3).                              */
+int pm_set_text_sqn_host(pm_ctx *ctx, const uint8_t *sqn, uint64_t n_chars, const uint8_t *table,
+                         uint32_t table_size, int64_t stream_offset);
 /* bits per character of a .sqz stream with this table size (char_io.t:58-61).  */
 int pm_sqz_bits(uint32_t table_size);
 

@@ -34,7 +34,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 
 # every symbol include/pm_b200.h declares
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
-           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
+           "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
            "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path"]
 
@@ -99,6 +99,7 @@ def lib():
         L.pm_set_text_sqz_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32,
                                            C.c_uint64, C.c_int64]
         L.pm_sqz_bits.argtypes = [C.c_uint32]
+        L.pm_set_text_sqn_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_char_p, C.c_uint32, C.c_int64]
         L.pm_set_text_fasta_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
         i64pp = C.POINTER(C.POINTER(C.c_int64))
         L.pm_get_sequences.argtypes = [C.c_void_p, i64pp, i64pp, i64pp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -226,6 +227,12 @@ class Scanner:
             self._keep = a
             ptr, nb = a.ctypes.data, a.size
         _check(lib().pm_set_text_sqz_host(self._h, C.c_void_p(ptr), nb, bytes(table), len(table), n_chars, offset))
+
+    def set_text_sqn(self, sqn, table: bytes, offset: int = 0):
+        """The text as the .sqn file of compress_seq -n (one .tbl index per character)."""
+        a = np.ascontiguousarray(sqn, np.uint8)
+        self._keep = a
+        _check(lib().pm_set_text_sqn_host(self._h, C.c_void_p(a.ctypes.data), a.size, bytes(table), len(table), offset))
 
     def set_text_fasta(self, raw, uc: bool = False, fetch_chars: bool = False) -> "Stream":
         """The text as the bytes of a FASTA file (bytes, numpy uint8 array or CPU torch tensor,
@@ -499,7 +506,9 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
         for i, p in enumerate(pats):
             sc.add_pattern(p, i + 1, esb[i], eeb[i])
         sc.init()
-        if sqz is not None:
+        if sqz is not None and len(sqz) == 2:
+            sc.set_text_sqn(*sqz)        # (sqn bytes, tbl table)
+        elif sqz is not None:
             sc.set_text_sqz(*sqz)
         else:
             sc.set_text(stream.chars)

@@ -1644,12 +1644,29 @@ int pm_sqz_bits(uint32_t table_size) {  // char_io.t:58-61
   return bits;
 }
 
+static int set_text_coded(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
+                          uint32_t table_size, uint64_t n_chars, int64_t offset, int bits);
+
 int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
                          uint32_t table_size, uint64_t n_chars, int64_t offset) {
   if (!c || (!sqz && n_bytes) || !table) return fail(PM_E_ARG, "null argument");
   if (c->inner) return adopt_inner_text(c, pm_set_text_sqz_host(c->inner, sqz, n_bytes, table, table_size, n_chars, offset));
   const int bits = pm_sqz_bits(table_size);
   if (bits < 0) return bits;
+  return set_text_coded(c, sqz, n_bytes, table, table_size, n_chars, offset, bits);
+}
+
+// Normalized<> (char_io.t:216-283): the .sqn file of compress_seq -n, one table index per byte
+int pm_set_text_sqn_host(pm_ctx *c, const uint8_t *sqn, uint64_t n_chars, const uint8_t *table,
+                         uint32_t table_size, int64_t offset) {
+  if (!c || (!sqn && n_chars) || !table) return fail(PM_E_ARG, "null argument");
+  if (table_size == 0 || table_size > 256) return fail(PM_E_ARG, "character table size must be 1..256");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_sqn_host(c->inner, sqn, n_chars, table, table_size, offset));
+  return set_text_coded(c, sqn, n_chars, table, table_size, n_chars, offset, 8);
+}
+
+static int set_text_coded(pm_ctx *c, const uint8_t *sqz, uint64_t n_bytes, const uint8_t *table,
+                          uint32_t table_size, uint64_t n_chars, int64_t offset, int bits) {
   PM_CUDA(cudaSetDevice(c->opt.device));
   const uint64_t held = n_bytes * 8 / (uint64_t)bits;
   if (n_chars == 0) n_chars = held;  // the writer's padding reads as end-of-sequence characters

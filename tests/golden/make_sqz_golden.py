@@ -7,11 +7,11 @@ compiled from /root/reference by oracle/Makefile):
     make -C oracle && python tests/golden/make_sqz_golden.py
 
 For each seeded FASTA database: `compress_seq -n true -z true` writes the
-.tbz character table and the .sqz bit stream (compress_seq.cc:745-870); the
-fixture keeps both (base64) with the length of the stream (size of the .sqn file), and the records
+.tbl / .tbz character tables, the .sqn file (one table index per character) and the
+.sqz bit stream (compress_seq.cc:745-870); the fixture keeps them (base64) with the length of the stream (size of the .sqn file), and the records
 primer_match prints when it reads the database through the compressed files
-(-D 4, select.t:94-106) -- checked here to equal what it prints on the FASTA
-file itself.
+(-D 4, select.t:94-106) and through the normalised ones (-D 3) -- checked here to
+equal what it prints on the FASTA file itself.
 """
 from __future__ import annotations
 
@@ -61,9 +61,14 @@ def main():
                 continue
             subprocess.run([CSQ, "-i", path, "-n", "true", "-z", "true"], check=True, capture_output=True)
             n_chars = os.path.getsize(path + ".sqn")                    # one byte per stream character
+            via_sqn = O.run_reference(path, primers, extra=["-D", "3"], **params)   # Normalized<>
+            with open(path + ".sqn", "rb") as f:
+                sqn = f.read()
+            with open(path + ".tbl", "rb") as f:
+                tbl = f.read()
             os.unlink(path + ".sqn")                                    # leave only the compressed form
             via_sqz = O.run_reference(path, primers, extra=["-D", "4"], **params)
-            if plain != via_sqz:
+            if plain != via_sqz or plain != via_sqn:
                 raise SystemExit("reference disagrees with itself on seed %d" % seed)
             with open(path + ".tbz", "rb") as f:
                 tbz = f.read()
@@ -71,6 +76,7 @@ def main():
                 sqz = f.read()
             cases.append(dict(seed=seed, params=params, fasta=fasta, primers=primers, n_chars=n_chars,
                               tbz=base64.b64encode(tbz).decode(), sqz=base64.b64encode(sqz).decode(),
+                              tbl=base64.b64encode(tbl).decode(), sqn=base64.b64encode(sqn).decode(),
                               records=[[r.seq_index, r.seq_start, r.seq_end, r.strand, r.pattern_index,
                                         r.editdist, r.stream_start, r.stream_end, r.alignment] for r in via_sqz]))
         finally:

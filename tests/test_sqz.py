@@ -21,6 +21,8 @@ def sqz_golden():
     for c in g["cases"]:
         c["tbz_bytes"] = base64.b64decode(c["tbz"])
         c["sqz_bytes"] = base64.b64decode(c["sqz"])
+        c["tbl_bytes"] = base64.b64decode(c["tbl"])
+        c["sqn_bytes"] = base64.b64decode(c["sqn"])
     return g
 
 
@@ -31,6 +33,9 @@ def test_oracle_sqz_matches_reference_files(oracle, sqz_golden):
         assert len(st.chars) == c["n_chars"]
         assert oracle.sqz_table(st.chars) == c["tbz_bytes"]
         assert oracle.sqz_encode(st.chars, c["tbz_bytes"]) == c["sqz_bytes"]
+        # the normalised form: one table index per character (Normalized<>, char_io.t:216-283)
+        assert c["tbl_bytes"] == c["tbz_bytes"] and len(c["sqn_bytes"]) == c["n_chars"]
+        assert bytes(c["tbl_bytes"][b] for b in c["sqn_bytes"]) == st.chars.tobytes()
         dec = oracle.sqz_decode(c["sqz_bytes"], c["tbz_bytes"])
         assert dec[:c["n_chars"]].tobytes() == st.chars.tobytes()
         assert (dec[c["n_chars"]:] == 10).all()          # the writer pads with eos characters
@@ -66,6 +71,9 @@ def test_sqz_records_match_reference(pkg, built_lib, sqz_golden):
         assert as_tuples(got) == sorted(records_of(c)), "case %s" % c["seed"]
         got0 = pkg.primer_match(st, c["primers"], sqz=(sqz, c["tbz_bytes"], 0), index=n5, **c["params"])   # padding scanned too
         assert as_tuples(got0) == sorted(records_of(c))
+        sqn = np.frombuffer(c["sqn_bytes"], np.uint8)                                  # .sqn / .tbl
+        got1 = pkg.primer_match(st, c["primers"], sqz=(sqn, c["tbl_bytes"]), index=n5, **c["params"])
+        assert as_tuples(got1) == sorted(records_of(c))
 
 
 @pytest.mark.gpu
