@@ -600,7 +600,7 @@ pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *
     if (w >= w_end) return;
     const uint64_t base = w * 16;
     uint32_t b[4];
-    if (base + 16 <= n) {
+    if (base + 16 <= n && (reinterpret_cast<uintptr_t>(text) & 15) == 0) {   // an adopted device pointer may be 4-byte aligned only
       const uint4 v = __ldg(reinterpret_cast<const uint4 *>(text + base));
       b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
     } else {

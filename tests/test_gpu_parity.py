@@ -353,6 +353,34 @@ def test_full_size_properties(pkg):
     assert res[1] <= res[2]
 
 
+def test_device_pointer_with_4_byte_alignment(pkg):
+    """pm_set_text_device only asks for 4-byte alignment: a view into a larger device buffer."""
+    import torch
+    import casegen
+    rng = random.Random(21)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(20)]
+    n = 300_000
+    g = np.random.default_rng(4)
+    seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, n)].copy()
+    for j in range(50):
+        seq[1000 + j * 5000:1020 + j * 5000] = np.frombuffer(primers[j % 20].encode(), np.uint8)
+    T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
+    big = torch.zeros(len(T) + 64, dtype=torch.uint8, device="cuda")
+    out = []
+    for shift in (0, 4, 12):
+        view = big[shift:shift + len(T)]
+        view.copy_(torch.from_numpy(T))
+        sc = pkg.Scanner(k=2, indels=False)
+        for i, p in enumerate(primers):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(view)
+        out.append(sc.find_patterns())
+        sc.close()
+    assert len(out[0]) >= 50
+    assert out[1].tobytes() == out[0].tobytes() and out[2].tobytes() == out[0].tobytes()
+
+
 def test_host_pipeline_equals_device_path(pkg):
     """Pinned-host text goes through the chunked copy/pack/scan pipeline (several
     chunks at this size); the result must equal the device-resident path."""
