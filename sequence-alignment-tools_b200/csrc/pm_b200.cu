@@ -2041,7 +2041,9 @@ int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
   if (!c || (!out && len)) return fail(PM_E_ARG, "null argument");
   if (begin + len > c->n || !c->d_text) return fail(PM_E_ARG, "range outside the loaded text");
   PM_CUDA(cudaSetDevice(c->opt.device));
-  if (!c->chunks.empty() && c->chunks.back().ev) PM_CUDA(cudaStreamWaitEvent(c->stream, c->chunks.back().ev, 0));
+  const pm_ctx *owner = c->inner ? c->inner : c;   // whose pipeline brought the text in
+  if (!owner->chunks.empty() && owner->chunks.back().ev)
+    PM_CUDA(cudaStreamWaitEvent(c->stream, owner->chunks.back().ev, 0));
   PM_CUDA(cudaMemcpyAsync(out, c->d_text + begin, len, cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(cudaStreamSynchronize(c->stream));
   return PM_OK;
