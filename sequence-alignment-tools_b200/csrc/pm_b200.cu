@@ -1359,10 +1359,24 @@ int pm_init(pm_ctx *c) {
     std::vector<uint2> ents;
     std::vector<uint32_t> dist;
     if (ok) {
-      if (edit_mode) for (int d = L; d <= (P - 1) * L + K; d++) dist.push_back((uint32_t)d);
-      else for (int j = 1; j < P; j++) dist.push_back((uint32_t)(j * L));
+      // edits: the distances some piece pair can have, (pj - pi) L + e with |e| <= K and never less
+      // than L (for long pieces the ranges around L, 2L, .. leave gaps: those are not looked up)
+      if (edit_mode) {
+        for (int d = L; d <= (P - 1) * L + K; d++) {
+          bool used = false;
+          for (int g = 1; g < P && !used; g++) used = (d >= g * L - K && d <= g * L + K);
+          if (used) dist.push_back((uint32_t)d);
+        }
+      } else {
+        for (int j = 1; j < P; j++) dist.push_back((uint32_t)(j * L));
+      }
       if ((int)dist.size() > PAIR_MAX_ND) ok = false;
     }
+    auto dist_index = [&](int d) {
+      for (size_t x = 0; x < dist.size(); x++)
+        if ((int)dist[x] == d) return (uint32_t)x;
+      return 0u;
+    };
     // accept sets of a pattern character over the text codes
     auto accept4 = [&](unsigned char ch) {
       uint32_t acc = 0;
@@ -1398,7 +1412,7 @@ int pm_init(pm_ctx *c) {
             for (int e = edit_mode ? -K : 0; e <= (edit_mode ? K : 0); e++) {
               const int d = (pj - pi) * L + e;
               if (d < L) continue;
-              const uint32_t di = edit_mode ? (uint32_t)(d - L) : (uint32_t)(pj - pi - 1);
+              const uint32_t di = dist_index(d);
               const uint32_t meta = ((uint32_t)i << 10) | (di << 5) | (uint32_t)(pi * L);
               for (uint32_t x : piece_keys[pi])
                 for (uint32_t y : piece_keys[pj]) ents.push_back(make_uint2(x | (y << (2 * L)), meta));
