@@ -222,12 +222,12 @@ def test_large_pattern_set_uses_the_l2_filter(pkg, k, indels, halves):
     import casegen
     rng = random.Random(40 + k)
     primers = [casegen.rand_dna(rng, 20) for _ in range(52000)]
-    n = 1_500_000
+    n = 500_000
     g = np.random.default_rng(8)
     seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, n)].copy()
     for j in range(300):
         q = casegen.mutate(rng, primers[rng.randrange(len(primers))], rng.randint(0, k), indels)
-        at = 500 + j * 4900
+        at = 500 + j * 1600
         seq[at:at + len(q)] = np.frombuffer(q.encode(), np.uint8)
     T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
     pats = pkg.pattern_array(primers, True)
