@@ -80,6 +80,29 @@ def test_exact_halves_matches_oracle_seeded(pkg, oracle, seed):
     assert as_tuples(got) == as_tuples(want)
 
 
+@pytest.mark.parametrize("seed", range(4000, 4024))
+def test_long_primers_match_oracle(pkg, oracle, seed):
+    """Primers of 33-64 characters (bit-plane scan; the halves / exact parts of exact_halves and
+    exact_bases still go through the pair index), every index selection, with and without
+    exact-base constraints."""
+    import casegen
+    rng = random.Random(seed)
+    k = rng.choice([1, 1, 2, 3])
+    indels = rng.random() < 0.5
+    wc = rng.random() < 0.3
+    params = dict(k=k, indels=indels, wc=wc, tn=wc and rng.random() < 0.5, rev_comp=rng.random() < 0.7)
+    kw = dict(nseq=rng.choice([1, 3]), seqlen=rng.choice([400, 2500]), nprimers=rng.choice([2, 6]),
+              plen=rng.choice([(33, 40), (40, 64), (64, 64)]), k=k, indels=indels, wc=wc,
+              text_iupac=rng.choice([0, 0.01]), lower=0, repeats=rng.random() < 0.5, line=60, crlf=False)
+    fasta, primers = casegen.make_case(seed, **kw)
+    cons = dict(stlen=0, edlen=0, fplen=rng.choice([0, 0, 8, 20]), tplen=rng.choice([0, 0, 6, 12]))
+    raw = fasta.encode()
+    for index, oname in ((pkg.PM_INDEX_AUTO, "auto"), (pkg.PM_INDEX_FILTER_BITVEC, "filter_bitvec")):
+        want = oracle.primer_match(oracle.normalize_fasta(raw), primers, index=oname, **params, **cons)
+        got = pkg.primer_match(pkg.normalize_fasta(raw), primers, index=index, **params, **cons)
+        assert as_tuples(got) == as_tuples(want), oname
+
+
 def _params(seed):
     rng = random.Random(seed)
     k = rng.choice([0, 1, 2, 3])
