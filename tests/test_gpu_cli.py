@@ -82,3 +82,42 @@ def test_cli_pattern_files_and_output_file(cli, golden, tmp_path):
     assert _blocks(outf.read_text(), 4) == want
     got = _run(cli, base[:i] + ["-F", str(pfa)] + base[i + 2:])
     assert _blocks(got, 4) == want
+
+
+REF_FORMAT = "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\t%S\\t%E\\t%A\\n"
+
+
+def _records(text):
+    out = []
+    for line in text.splitlines():
+        f = line.split("\t")
+        out.append((int(f[0]), int(f[1]), int(f[2]), f[3], int(f[4]), int(f[5]), int(f[6]), int(f[7]), f[8]))
+    return sorted(out)
+
+
+def test_cli_automatic_index_and_constraints(cli, halves_golden, constraints_golden, tmp_path):
+    """The same command lines the reference got in make_halves_golden.py / make_constraints_golden.py:
+    no -N (pick_pattern_index chooses), -N 13/14 forced, and the -s / -e / -5 / -3 options."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_constraints_golden
+    n = 0
+    for gi, g in enumerate((halves_golden, constraints_golden)):
+        for case in g["cases"]:
+            fa = tmp_path / ("g%d_%s.fasta" % (gi, case["seed"]))
+            fa.write_bytes(case["fasta"].encode("latin-1"))
+            par = case["params"]
+            args = ["-i", str(fa), "-p", " ".join(case["primers"]), "-A", REF_FORMAT]
+            if par["k"] > 0:
+                args += ["-k" if par["indels"] else "-K", str(par["k"])]
+            if par["rev_comp"]:
+                args.append("-r")
+            if par["wc"]:
+                args.append("-W" if par["tn"] else "-w")
+            if case["select"]:
+                args += ["-N", str(case["select"])]
+            if "constraints" in case:
+                args += make_constraints_golden.cli_constraints(case["constraints"])
+            got = _records(_run(cli, args))
+            assert got == sorted(tuple(r) for r in case["records"]), "golden %d case %s" % (gi, case["seed"])
+            n += 1
+    assert n >= 90
