@@ -394,7 +394,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
   memset(&ia, 0, sizeof ia);
   void (*ikern)(const IndexArgs) = edit ? pair_scan_kernel<true> : pair_scan_kernel<false>;
   if (c->use_index && !edit) {
-    if (PairKernel sk = pair_sub_kernel((int)c->idx_proto.L, (int)c->idx_proto.nd)) ikern = sk;
+    const bool smem_1b = c->idx_proto.log_words2 != 0 && !c->idx_proto.b2_global;
+    if (PairKernel sk = pair_sub_kernel((int)c->idx_proto.L, (int)c->idx_proto.nd, smem_1b)) ikern = sk;
   }
   void (*ivkern)(const IndexArgs) =
       K <= 1 ? index_verify_kernel<1> : (K == 2 ? index_verify_kernel<2> : index_verify_kernel<3>);
@@ -1452,9 +1453,12 @@ int pm_init(pm_ctx *c) {
       static const size_t big_set_entries = getenv("PM_BIG_SET_ENTRIES") ? (size_t)atoll(getenv("PM_BIG_SET_ENTRIES")) : 100000;
       const bool big_set = ents.size() > big_set_entries;
       ia.b2_global = big_set ? 1u : 0u;
-      // (a shared-memory level 1b for substitution scans of 24 k - 100 k entries was measured:
-      // +7-10 % there when inlined, but the extra live state costs the headline kernel 8 %)
-      ia.log_words2 = big_set ? 22u : (edit_mode ? 14u : 0u);
+      // substitutions, 24 k .. 100 k entries: level 1 passes 2-10 % of the lookups; the 64 KB
+      // (key, distance) bitmap in the free shared memory removes most of them (+7-10 %); a kernel
+      // variant of its own (pair_scan_sub_kernel<.., B1 = true>), the plain one has no register to spare
+      static const size_t mid_set_entries = getenv("PM_MID_SET_ENTRIES") ? (size_t)atoll(getenv("PM_MID_SET_ENTRIES")) : 24000;
+      const bool sub_1b = !edit_mode && !big_set && ents.size() > mid_set_entries;
+      ia.log_words2 = big_set ? 22u : ((edit_mode || sub_1b) ? 14u : 0u);
       ia.mult2 = 0x85EBCA6Bu;
       for (size_t d = 0; d < dist.size(); d++) ia.salt2[d] = (uint32_t)(d + 1) * 0xC2B2AE35u;
       const bool have2 = ia.log_words2 != 0;

@@ -433,7 +433,11 @@ __device__ __noinline__ uint32_t pair_level1b_global(const IndexArgs &a, uint32_
 // (Moving the word-index shift and the address LEA to the FMA pipe as IMAD.HI / IMAD
 // was measured and is not worth it: the kernel sits at ~94 % of the shared-memory
 // wavefront rate and ~87 % of the ALU rate at the same time, see DESIGN.md.)
-template <int L, int ND>
+// B1: a second kernel variant that also consults the shared-memory (key, distance) bitmap
+// (level 1b) for the positions that passed level 1 -- worth it between ~24 k and 100 k
+// entries (IUPAC primer sets, a few thousand primers); kept out of the B1 = false variant,
+// whose lookup loop needs every register.
+template <int L, int ND, bool B1>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
   extern __shared__ __align__(16) uint32_t s_mem[];
@@ -470,7 +474,13 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
         hm[j] = pair_probe(t.bitmap, key, mult, salt[j], wsh, hm[j]);
       }
     }
-    if (a.b2_global) {
+    if (B1) {
+#pragma unroll
+      for (int j = 0; j < ND; j++) {
+        const uint32_t h = hm[j] & vm;
+        hm[j] = h ? pair_level1b(a, t, h, (uint32_t)j, cw[0], cw[1], cw[2]) : 0u;
+      }
+    } else if (a.b2_global) {
 #pragma unroll
       for (int j = 0; j < ND; j++) hm[j] = pair_level1b_global<L>(a, hm[j] & vm, j, cw[0], cw[1], cw[2]);
     }
@@ -481,27 +491,29 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
 }
 
 typedef void (*PairKernel)(const IndexArgs);
-template <int L>
+template <int L, bool B1>
 inline PairKernel pair_sub_kernel_nd(int nd) {
   switch (nd) {
-    case 1: return pair_scan_sub_kernel<L, 1>;
-    case 2: return pair_scan_sub_kernel<L, 2>;
-    case 3: return pair_scan_sub_kernel<L, 3>;
-    case 4: return pair_scan_sub_kernel<L, 4>;
+    case 1: return pair_scan_sub_kernel<L, 1, B1>;
+    case 2: return pair_scan_sub_kernel<L, 2, B1>;
+    case 3: return pair_scan_sub_kernel<L, 3, B1>;
+    case 4: return pair_scan_sub_kernel<L, 4, B1>;
   }
   return nullptr;
 }
-// specialised substitution kernel for (L, nd), or nullptr (the generic kernel serves)
-inline PairKernel pair_sub_kernel(int L, int nd) {
+// specialised substitution kernel for (L, nd), or nullptr (the generic kernel serves);
+// level1b: the variant that consults the shared-memory level 1b
+inline PairKernel pair_sub_kernel(int L, int nd, bool level1b) {
   switch (L) {
-    case 4: return pair_sub_kernel_nd<4>(nd);
-    case 5: return pair_sub_kernel_nd<5>(nd);
-    case 6: return pair_sub_kernel_nd<6>(nd);
-    case 7: return pair_sub_kernel_nd<7>(nd);
-    case 8: return pair_sub_kernel_nd<8>(nd);
+    case 4: return level1b ? pair_sub_kernel_nd<4, true>(nd) : pair_sub_kernel_nd<4, false>(nd);
+    case 5: return level1b ? pair_sub_kernel_nd<5, true>(nd) : pair_sub_kernel_nd<5, false>(nd);
+    case 6: return level1b ? pair_sub_kernel_nd<6, true>(nd) : pair_sub_kernel_nd<6, false>(nd);
+    case 7: return level1b ? pair_sub_kernel_nd<7, true>(nd) : pair_sub_kernel_nd<7, false>(nd);
+    case 8: return level1b ? pair_sub_kernel_nd<8, true>(nd) : pair_sub_kernel_nd<8, false>(nd);
   }
   return nullptr;
 }
+
 // Edit verifier on the packed text: the recurrence of verify_seed (pm_scan.cuh) for one
 // (slot, nominal window start) per thread.  The span t0 .. t_hi (at most m+3K+1 <= 42
 // characters) is pulled into registers first, shifted so that character t0 sits at bit 0;
