@@ -194,7 +194,9 @@ int pm_shard_overlap(pm_ctx *ctx);
  * the reference reports them in, up to ties.  *hits
  * points into pinned memory owned by the context, valid until the next call
  * on it.  Pass begin=0,end=INT64_MAX for the whole stream (what the reference
- * does).                                                                      */
+ * does).  PM_E_BOGUS (a hit whose final alignment has more than k errors, on
+ * which primer_match stops) still delivers every hit: pcr_match keeps going
+ * and skips those (pcr_match.cc:1114).                                         */
 int pm_find_patterns(pm_ctx *ctx, int64_t begin, int64_t end, const pm_hit **hits,
                      uint64_t *nhits);
 

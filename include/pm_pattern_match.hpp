@@ -92,6 +92,11 @@ class FastaStream {
     const long i = locate(pos);
     return i < 0 ? 0 : pos - key_[i];
   }
+  // FastaFile::is_subseq (fasta_io.t:203-213): [start, end) lies inside one entry
+  bool is_subseq(int64_t start, int64_t end) const {
+    const long a = locate(start + 1);
+    return a >= 0 && a == locate(end);
+  }
   unsigned long index(int64_t pos) const { const long i = locate(pos); return i < 0 ? 0 : (unsigned long)(i + 1); }
   std::string header(int64_t pos) const {
     const long i = locate(pos);
@@ -153,7 +158,7 @@ class PatternMatch {
 class b200_index : public PatternMatch {
  public:
   b200_index(int index, unsigned k, char eos, bool wc, bool tn, bool indels, int device = 0)
-      : ctx_(0), hits_(0), nhits_(0), next_(0), scanned_(false) {
+      : ctx_(0), hits_(0), nhits_(0), next_(0), scanned_(false), tolerate_bogus_(false) {
     pm_options o;
     std::memset(&o, 0, sizeof o);
     o.device = device; o.index = index; o.k = (int)k; o.indels = indels; o.wildcards = wc; o.text_n = tn;
@@ -176,8 +181,9 @@ class b200_index : public PatternMatch {
   bool find_patterns(FastaStream &, pattern_hit_vector &pas, unsigned long minka = 1) {
     if (!scanned_) {
       const int rc = pm_find_patterns(ctx_, 0, INT64_MAX, &hits_, &nhits_);
-      if (rc == PM_E_BOGUS) fatal("Bogus hit returned to primer_match main()");  // primer_match.cc:1249
-      if (rc != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+      if (rc == PM_E_BOGUS && !tolerate_bogus_)
+        fatal("Bogus hit returned to primer_match main()");  // primer_match.cc:1249
+      if (rc != PM_OK && rc != PM_E_BOGUS) fatal(std::string("Fatal error: ") + pm_last_error());
       scanned_ = true;
     }
     while (next_ < nhits_ && pas.size() < minka) {
@@ -189,6 +195,10 @@ class b200_index : public PatternMatch {
     return next_ < nhits_;
   }
   void reset() { pm_reset(ctx_); scanned_ = false; next_ = 0; batch_.clear(); }
+  // A hit whose final alignment fails (editdist > k) ends primer_match; pcr_match only
+  // skips the pairs it is part of (pcr_match.cc:1114): hand such hits out instead, the
+  // caller tests pm_hit::editdist.
+  void tolerate_bogus(bool yes) { tolerate_bogus_ = yes; }
   // the full records (alignment included) of the hits handed out by the last
   // find_patterns() call, same order as `pas`
   std::vector<const pm_hit *> &batch() { return batch_; }
@@ -198,7 +208,7 @@ class b200_index : public PatternMatch {
   pm_ctx *ctx_;
   const pm_hit *hits_;
   uint64_t nhits_, next_;
-  bool scanned_;
+  bool scanned_, tolerate_bogus_;
   std::vector<const pm_hit *> batch_;
 };
 

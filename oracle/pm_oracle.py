@@ -344,18 +344,18 @@ def auto_index(primers, k: int, lconst=None, rconst=None) -> str:
     return "filter_bitvec"
 
 
-def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
-                 eos=EOS, index="filter_bitvec", stlen=0, edlen=0, fplen=0, tplen=0):
-    """Whole path, as the reference runs it with `-N 5` for k>0 (index="filter_bitvec"), with its
-    exact_halves / exact_bases indexes (index="exact_halves" / "exact_bases"; index="auto" follows
-    pick_pattern_index), and its automatic choice for k==0 (keyword_tree, or shift_and under
-    -w/-W).  stlen / edlen / fplen / tplen = the -s / -e / -5 / -3 options.
-    Returns a sorted list of HitRecord."""
-    n = len(primers)
-    pats = pattern_array(primers, rev_comp)
-    lconst, rconst = pattern_constraints(primers, rev_comp, stlen, edlen, fplen, tplen)
+def aligned_hits(stream: Stream, pats, lconst, rconst, k=0, indels=True, wc=False, tn=False, eos=EOS,
+                 index="filter_bitvec", bogus_ok=False, exact_align=True):
+    """PatternMatch::find_patterns of the selected index followed, per hit, by the alignment
+    both command line tools make at the hit's position (primer_match.cc:1132-1153,
+    pcr_match.cc:1096-1113): [(pattern id, start, end, editdist, alignment string)] in the
+    order the index reports the hits.  end == the hit's key.  A hit whose alignment at its own
+    position fails ("bogus") makes primer_match abort; pcr_match just never pairs it
+    (pcr_match.cc:1114-1115), which bogus_ok=True stands for: such hits are left out.
+    exact_align: primer_match's exact_alignment / exact_wc_alignment for k == 0; pcr_match
+    makes an editdist_alignment there too (pcr_match.cc:1096-1100)."""
     T = stream.chars
-    recs = []
+    out = []
     if index == "auto":
         index = auto_index(pats, k, lconst, rconst)
     if k == 0:
@@ -370,7 +370,7 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
     for pos, pid, _ in hits:
         pos, pid = int(pos), int(pid)
         pat = pats[pid - 1]
-        if k == 0:
+        if k == 0 and exact_align:
             start, end, ed = pos - len(pat), pos, 0
             if wc:
                 sub, codes = exact_wc_align(T, pat, pos, tn)
@@ -383,8 +383,26 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
         else:
             al = editdist_align(T, pat, pos, pos, k, indels, wc, tn, lconst[pid - 1], rconst[pid - 1], eos)
             if al.editdist < 0 or al.editdist > k:
+                if bogus_ok:
+                    continue
                 raise AssertionError("Bogus hit (primer_match.cc:1249)")
             start, end, ed, astr = al.start, al.end, al.editdist, al.string
+        out.append((pid, start, end, ed, astr))
+    return out
+
+
+def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False,
+                 eos=EOS, index="filter_bitvec", stlen=0, edlen=0, fplen=0, tplen=0):
+    """Whole path, as the reference runs it with `-N 5` for k>0 (index="filter_bitvec"), with its
+    exact_halves / exact_bases indexes (index="exact_halves" / "exact_bases"; index="auto" follows
+    pick_pattern_index), and its automatic choice for k==0 (keyword_tree, or shift_and under
+    -w/-W).  stlen / edlen / fplen / tplen = the -s / -e / -5 / -3 options.
+    Returns a sorted list of HitRecord."""
+    n = len(primers)
+    pats = pattern_array(primers, rev_comp)
+    lconst, rconst = pattern_constraints(primers, rev_comp, stlen, edlen, fplen, tplen)
+    recs = []
+    for pid, start, end, ed, astr in aligned_hits(stream, pats, lconst, rconst, k, indels, wc, tn, eos, index):
         # primer_match.cc:1158-1179; pattern_alignment::length() is end-start+1
         idx, key = stream.locate(end)
         spe = end - key
@@ -393,6 +411,209 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
         recs.append(HitRecord(idx, sps, spe, "R" if rc else "F", pid - (n if rc else 0), ed,
                               end - (end - start + 1) + 1, end, astr))
     return sorted(recs)
+
+
+# ---------------------------------------------------------------------------
+# pcr_match: the second caller of the scan -- primer PAIRS, hits paired into amplicons
+def pcr_pattern_array(primers, rev_comp: bool):
+    """pcr_match.cc:772-784, 827, 868: pairs are (1,2), (3,4) ...; with -r the second primer of
+    every pair is reverse complemented first; ids 1..n as given, n+1..2n their reverse
+    complements (always both strands)."""
+    pr = list(primers)
+    if rev_comp:
+        pr = [reverse_comp(p) if i % 2 == 1 else p for i, p in enumerate(pr)]
+    return pr + [reverse_comp(p) for p in pr]
+
+
+def pcr_pattern_constraints(pats_fwd, stlen=0, edlen=0, fplen=0, tplen=0):
+    """pcr_match.cc:803-909: primer_match's rules, -5 and -3 swapped for the second primer of a pair."""
+    n = len(pats_fwd)
+    first, second = [0] * (2 * n), [0] * (2 * n)
+    for i, p in enumerate(pats_fwd):
+        fp, tp = (fplen, tplen) if i % 2 == 0 else (tplen, fplen)
+        f, s_ = pattern_constraints([p], True, stlen, edlen, fp, tp)
+        first[i], first[i + n], second[i], second[i + n] = f[0], f[1], s_[0], s_[1]
+    return first, second
+
+
+U64 = 1 << 64
+
+
+@dataclass(frozen=True, order=True)
+class PcrRecord:
+    """One output record of pcr_match: the arguments its alignformat() receives
+    (pcr_match.cc:1179-1196) that do not follow from the others."""
+    seq_index: int        # %f
+    start: int            # %>s  sps
+    start1: int           # %<s  sps1
+    end: int              # %>e  spe
+    end1: int             # %<e  spe1
+    stream_start: int     # %>S  ps
+    stream_start1: int    # %<S  ps1
+    stream_end: int       # %>E  pe
+    stream_end1: int      # %<E  pe1
+    pair: int             # %i   pind
+    editdist: int         # %>d
+    editdist1: int        # %<d
+    strand: str           # %>r
+    strand1: str          # %<r
+    orient: str           # %r   "F" when ppo (ind < ind1)
+    alignment: str        # %>A
+    alignment1: str       # %<A
+    ncount: int           # %N
+    amplicon: str         # %@
+
+
+def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False, eos=EOS,
+              index="auto", stlen=0, edlen=0, fplen=0, tplen=0, mindist=0, maxdist=2000,
+              betweenlen=False, allorient=False, sts_sizes=None, deviation=-1):
+    """pcr_match.cc:921-1240 with every hit in one batch (what the reference does on any
+    database whose hits it does not have to hand over in several find_patterns batches):
+    hits in position order; a hit looks for hits of its partner pattern(s) that are still
+    unprocessed -- later in the order -- and end inside its stretch window; both alignments
+    and the amplicon length decide.  sts_sizes: [(sizelb, sizeub)] per pair when the primers
+    came from a UniSTS file (-S, which implies -r); deviation = -d.  Returns the records in
+    output order."""
+    if sts_sizes is not None:
+        rev_comp = True
+    n = len(primers)
+    pats = pcr_pattern_array(primers, rev_comp)
+    lconst, rconst = pcr_pattern_constraints(pats[:n], stlen, edlen, fplen, tplen)
+    hits = aligned_hits(stream, pats, lconst, rconst, k, indels, wc, tn, eos, index, bogus_ok=True,
+                        exact_align=False)
+    hits.sort(key=lambda h: (h[2], h[0]))          # l.normalize(): by key (ties unspecified there)
+    bypid = {}
+    for i, h in enumerate(hits):
+        bypid.setdefault(h[0], []).append(i)
+    done = [False] * len(hits)
+    T = stream.chars
+    err = k if indels else 1
+    out = []
+    for i, (pid, start, pos, ed, astr) in enumerate(hits):
+        pid1 = pid2 = 0                                 # pcr_match.cc:968-997
+        if pid <= n and pid % 2 == 1:
+            pid1 = pid + 1
+        elif pid > n and (pid - n) % 2 == 0:
+            pid1 = pid - 1
+        if allorient:
+            if pid <= n:
+                if pid % 2 == 1:
+                    pid2 = pid + n + 1
+                else:
+                    pid1, pid2 = pid - 1, pid + n - 1
+            else:
+                if pid % 2 == 0:
+                    pid2 = pid - n - 1
+                else:
+                    pid1, pid2 = pid + 1, pid - n + 1
+        smax, smin = maxdist, mindist
+        if betweenlen:
+            plen = len(pats[pid1 - 1]) if pid1 else 0
+            if pid2 and len(pats[pid2 - 1]) > plen:
+                plen = len(pats[pid2 - 1])
+            smax += plen + len(pats[pid - 1])
+        if sts_sizes is not None and deviation >= 0:            # pcr_match.cc:1032-1039, unsigned compares
+            lb, ub = sts_sizes[(pid - (n if pid > n else 0) + 1) // 2 - 1]
+            if (smax % U64) > (ub + deviation) % U64:
+                smax = ub + deviation
+            if (smin % U64) < (lb - deviation) % U64:
+                smin = lb - deviation
+        smax += pos - len(pats[pid - 1]) + err
+        smin += pos - len(pats[pid - 1]) - err
+        partners = []
+        for q in (pid1, pid2):
+            if not q:
+                continue
+            for j in bypid.get(q, ()):
+                if hits[j][2] < smin:
+                    continue
+                if not done[j] and hits[j][2] > smax:
+                    break
+                if not done[j]:
+                    partners.append(j)
+        for j in partners:
+            pidb, startb, posb, edb, astrb = hits[j]
+            idx, key = stream.locate(pos)
+            idxb, keyb = stream.locate(posb)
+            spe, spe1 = pos - key, posb - keyb
+            length, length1 = pos - start + 1, posb - startb + 1      # pattern_alignment::length()
+            sps, sps1 = spe - length + 1, spe1 - length1 + 1
+            ps, ps1 = pos - length + 1, posb - length1 + 1
+            rc, rc1 = pid > n, pidb > n
+            ind, ind1 = pid - (n if rc else 0), pidb - (n if rc1 else 0)
+            pind = (ind if ind < ind1 else ind1) // 2 + 1
+            if rev_comp:
+                if ind % 2 == 0:
+                    rc = not rc
+                elif ind1 % 2 == 0:
+                    rc1 = not rc1
+            amplicon_len = (ps1 - pos) if betweenlen else (posb - ps)
+            # FastaFile::is_subseq(ps, pe1), fasta_io.t:203-213
+            same = stream.locate(ps + 1)[0] == stream.locate(posb)[0] and stream.locate(ps + 1)[0] > 0
+            if not (same and mindist <= amplicon_len <= maxdist):
+                continue
+            if sts_sizes is not None and deviation >= 0:        # pcr_match.cc:1163-1165
+                lb, ub = sts_sizes[pind - 1]
+                if not ((amplicon_len + deviation) % U64 >= lb and amplicon_len <= ub + deviation):
+                    continue
+            amp = bytes(T[ps:ps + amplicon_len]).decode("latin-1")
+            out.append(PcrRecord(idx, sps, sps1, spe, spe1, ps, ps1, pos, posb, pind, ed, edb,
+                                 "R" if rc else "F", "R" if rc1 else "F", "F" if ind < ind1 else "R",
+                                 astr, astrb, amp.count("N") + amp.count("n"), amp))
+        done[i] = True
+    return out
+
+
+PCR_REF_BIN = os.path.join(_HERE, "_ref", "pcr_match")
+PCR_REF_FORMAT = (r"%f\t%>s\t%<s\t%>e\t%<e\t%>S\t%<S\t%>E\t%<E\t%i\t%>d\t%<d\t%>r\t%<r\t%r\t%>A\t%<A"
+                  r"\t%N\t%@\n")
+
+
+def pcr_cli_args(fasta_path, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False, select=0,
+                 stlen=0, edlen=0, fplen=0, tplen=0, mindist=0, maxdist=2000, betweenlen=False,
+                 allorient=False, sts_path=None, deviation=-1):
+    """Command line of pcr_match (the reference's and the drop-in's) for these parameters;
+    sts_path: the primers are read from that UniSTS file (-S) instead of -p."""
+    args = ["-i", fasta_path] + (["-S", sts_path] if sts_path else ["-p", " ".join(primers)])
+    if deviation >= 0:
+        args += ["-d", str(deviation)]
+    if k > 0:
+        args += ["-k" if indels else "-K", str(k)]
+    if rev_comp:
+        args.append("-r")
+    if wc:
+        args.append("-W" if tn else "-w")
+    if select:
+        args += ["-N", str(select)]
+    for opt, v in (("-s", stlen), ("-e", edlen), ("-5", fplen), ("-3", tplen)):
+        if v:
+            args += [opt, ("~%d" % -v) if v < 0 else str(v)]
+    if mindist:
+        args += ["-m", str(mindist)]
+    if maxdist != 2000:
+        args += ["-M", str(maxdist)]
+    if betweenlen:
+        args.append("-b")
+    if allorient:
+        args.append("-a")
+    return args
+
+
+def parse_pcr_records(text: str):
+    recs = []
+    for line in text.splitlines():
+        f = line.split("\t")
+        recs.append(PcrRecord(*[int(x) for x in f[:12]], f[12], f[13], f[14], f[15], f[16], int(f[17]), f[18]))
+    return recs
+
+
+def run_reference_pcr(fasta_path: str, primers, fmt=PCR_REF_FORMAT, timeout=600, **params):
+    """Run the unmodified reference pcr_match; returns its stdout (fmt=None: its default format)."""
+    args = [PCR_REF_BIN] + pcr_cli_args(fasta_path, primers, **params) + (["-A", fmt] if fmt else [])
+    p = subprocess.run(args, capture_output=True, timeout=timeout)
+    if p.returncode != 0:
+        raise RuntimeError("reference failed rc=%d: %s" % (p.returncode, p.stderr.decode()[-500:]))
+    return p.stdout.decode("latin-1")
 
 
 # ---------------------------------------------------------------------------

@@ -53,23 +53,27 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_cli(force: bool = False) -> str | None:
-    src = os.path.join(CSRC, "primer_match_main.cc")
+def build_cli(force: bool = False, tool: str = "primer_match") -> str | None:
+    """bin/primer_match or bin/pcr_match: the drop-in command line tools (C++ over the C ABI)."""
+    src = os.path.join(CSRC, tool + "_main.cc")
     if not os.path.exists(src):
         return None
-    deps = [src, os.path.join(ROOT, "include", "pm_b200.h"), os.path.join(ROOT, "include", "pm_pattern_match.hpp")]
+    exe = os.path.join(os.path.dirname(CLI), tool)
+    deps = [src, os.path.join(CSRC, "pm_cli_common.hpp"), os.path.join(ROOT, "include", "pm_b200.h"),
+            os.path.join(ROOT, "include", "pm_pattern_match.hpp")]
     deps = [d for d in deps if os.path.exists(d)]
-    if not force and _newer(CLI, deps + [LIB]):
-        return CLI
-    os.makedirs(os.path.dirname(CLI), exist_ok=True)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-o", CLI, src,
+    if not force and _newer(exe, deps + [LIB]):
+        return exe
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", exe, src,
                            "-L", os.path.dirname(LIB), "-lpm_b200", "-Wl,-rpath,$ORIGIN/../lib"])
-    return CLI
+    return exe
 
 
 def build(force: bool = False, verbose: bool = False):
     build_lib(force, verbose)
     build_cli(force)
+    build_cli(force, "pcr_match")
 
 
 if __name__ == "__main__":

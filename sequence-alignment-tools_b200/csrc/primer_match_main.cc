@@ -20,9 +20,11 @@
 #include <string>
 #include <vector>
 
+#include "pm_cli_common.hpp"
 #include "pm_pattern_match.hpp"
 
 using namespace pmb200;
+using namespace pmcli;
 
 namespace {
 
@@ -61,8 +63,6 @@ void usage(const char *msg) {
                "  -G <int>                CUDA device ordinal\n";
   std::exit(1);
 }
-
-int tilde_int(const char *a) { return a[0] == '~' ? -std::atoi(a + 1) : std::atoi(a); }
 
 Options parse(int argc, char **argv) {
   Options o;
@@ -115,51 +115,6 @@ Options parse(int argc, char **argv) {
   if (o.aggregate && !o.counts) usage("Can''t use aggregate (-a) without counts (-c or -C).");
   if (o.report_interval == 0) o.report_interval = 1;
   return o;
-}
-
-// pattern_alignment::alignment_string / alignment_text / alignment_pattern
-// (pattern_alignment.h:124-197)
-char code_char(uint8_t c) {
-  switch (c) {
-    case 1: return '|';
-    case 2: return '+';
-    case 3: return '*';
-    case 4: return '^';
-    case 5: return 'v';
-    case 6: return '!';
-    default: return ' ';
-  }
-}
-
-struct Aligned {
-  std::string A, T, Q, t;
-};
-
-Aligned render(const pm_hit &h, const std::string &pat, const std::string &matching) {
-  Aligned a;
-  a.t = matching;
-  size_t tp = 0, pp = 0;
-  for (uint32_t i = 0; i < h.ncodes; i++) {
-    const uint8_t c = h.codes[i];
-    a.A += code_char(c);
-    if (c != 5) a.T += (tp < matching.size() ? matching[tp++] : ' '); else a.T += '-';
-    if (c != 4) a.Q += (pp < pat.size() ? pat[pp++] : ' '); else a.Q += '-';
-  }
-  return a;
-}
-
-void escape(std::ostream &os, const std::string &f, size_t &pos) {
-  pos++;
-  if (pos < f.size()) {
-    switch (f[pos]) {
-      case 'n': os << '\n'; break;
-      case 't': os << '\t'; break;
-      case '\\': os << '\\'; break;
-      default: os << f[pos];
-    }
-  } else {
-    os << '\\';
-  }
 }
 
 // alignformat, primer_match.cc:352-748 (the codes that do not need -S / -T / Tm)
@@ -270,30 +225,6 @@ void countformat(std::ostream &os, const std::string &f, unsigned long i, const 
   }
 }
 
-void read_words(std::istream &is, std::vector<std::string> &out) {
-  std::string w;
-  while (is >> w) out.push_back(w);
-}
-
-// fasta_entry input (sts_io / fasta_io operator>>): defline after '>', sequence = joined lines
-void read_fasta_patterns(std::istream &is, std::vector<std::string> &pats, std::vector<std::string> &defs) {
-  std::string line, seq, def;
-  bool have = false;
-  while (std::getline(is, line)) {
-    if (!line.empty() && line[line.size() - 1] == '\r') line.erase(line.size() - 1);
-    if (!line.empty() && line[0] == '>') {
-      if (have && !seq.empty()) { pats.push_back(seq); defs.push_back(def); }
-      def = line.substr(1);
-      seq.clear();
-      have = true;
-    } else if (have) {
-      for (char ch : line)
-        if (ch != ' ' && ch != '\t') seq += ch;
-    }
-  }
-  if (have && !seq.empty()) { pats.push_back(seq); defs.push_back(def); }
-}
-
 }  // namespace
 
 int main(int argc, char **argv) {
@@ -330,30 +261,11 @@ int main(int argc, char **argv) {
     const std::string &p = patterns[i - 1];
     const int len = (int)p.length();
     patarray[i] = p;
-    int first = opt.stlen > 0 ? opt.stlen : 0;
-    if (opt.fplen > first) first = opt.fplen;
-    if (opt.edlen < 0 && len + opt.edlen > first) first = len + opt.edlen;
-    if (opt.tplen < 0 && len + opt.tplen > first) first = len + opt.tplen;
-    int second = opt.edlen > 0 ? opt.edlen : 0;
-    if (opt.tplen > second) second = opt.tplen;
-    if (opt.stlen < 0 && len + opt.stlen > second) second = len + opt.stlen;
-    if (opt.fplen < 0 && len + opt.fplen > second) second = len + opt.fplen;
-    patconst[i] = std::make_pair(first, second);
+    std::pair<int, int> rev;
+    pattern_constraints(len, opt.stlen, opt.edlen, opt.fplen, opt.tplen, patconst[i], rev);
     if (opt.rev_comp) {
-      std::string rc(p.size(), ' ');
-      std::vector<char> buf(p.size() + 1);
-      pm_reverse_comp(p.c_str(), buf.data());
-      rc = buf.data();
-      patarray[i + n] = rc;
-      int f2 = opt.stlen > 0 ? opt.stlen : 0;
-      if (opt.tplen > f2) f2 = opt.tplen;
-      if (opt.edlen < 0 && len + opt.edlen > f2) f2 = len + opt.edlen;
-      if (opt.fplen < 0 && len + opt.fplen > f2) f2 = len + opt.fplen;
-      int s2 = opt.edlen > 0 ? opt.edlen : 0;
-      if (opt.fplen > s2) s2 = opt.fplen;
-      if (opt.stlen < 0 && len + opt.stlen > s2) s2 = len + opt.stlen;
-      if (opt.tplen < 0 && len + opt.tplen > s2) s2 = len + opt.tplen;
-      patconst[i + n] = std::make_pair(f2, s2);
+      patarray[i + n] = reverse_comp(p);
+      patconst[i + n] = rev;
     }
   }
 

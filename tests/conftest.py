@@ -56,6 +56,12 @@ def constraints_golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def pcr_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "pcr_match_golden.json")) as f:
+        return json.load(f)
+
+
 def records_of(case):
     return [tuple(r) for r in case["records"]]
 

@@ -1,0 +1,110 @@
+// TEST INFRASTRUCTURE ONLY -- a stand-in for libpm_b200.so that lets the host
+// logic of the command line tools (option handling, primer input, pairing of
+// hits into amplicons, output formats) run on a machine without a GPU.  It
+// implements the entry points of include/pm_b200.h the tools call and serves
+// canned data a test wrote into $PM_MOCK_DIR:
+//   stream.bin  the normalised database stream (bytes)
+//   seqs.bin    int64 n, then key[n], header offset[n], header length[n]
+//   hits.bin    pm_hit records, in the order the index reports them
+// Never built into or linked with the product; tests/test_cli_host_logic.py
+// compiles it into tests/mock/_build/.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pm_b200.h"
+
+struct pm_ctx {
+  std::vector<uint8_t> stream;
+  std::vector<int64_t> key, hoff, hlen;
+  std::vector<pm_hit> hits;
+  bool bogus = false;
+  int k = 0;
+};
+
+static std::vector<uint8_t> slurp(const char *name) {
+  const char *dir = getenv("PM_MOCK_DIR");
+  std::string path = std::string(dir ? dir : ".") + "/" + name;
+  std::vector<uint8_t> out;
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) { fprintf(stderr, "pm_mock: cannot read %s\n", path.c_str()); exit(2); }
+  uint8_t buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.insert(out.end(), buf, buf + n);
+  fclose(f);
+  return out;
+}
+
+extern "C" {
+
+const char *pm_last_error(void) { return "pm_mock"; }
+
+int pm_create(pm_ctx **ctx, const pm_options *opt) {
+  *ctx = new pm_ctx;
+  (*ctx)->k = opt->k;
+  return PM_OK;
+}
+void pm_destroy(pm_ctx *ctx) { delete ctx; }
+int pm_add_pattern(pm_ctx *, const char *, uint32_t, int, int) { return PM_OK; }
+int pm_init(pm_ctx *) { return PM_OK; }
+int pm_reset(pm_ctx *) { return PM_OK; }
+
+int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *, uint64_t, int) {
+  c->stream = slurp("stream.bin");
+  std::vector<uint8_t> s = slurp("seqs.bin");
+  int64_t n = 0;
+  memcpy(&n, s.data(), 8);
+  c->key.resize(n); c->hoff.resize(n); c->hlen.resize(n);
+  memcpy(c->key.data(), s.data() + 8, 8 * n);
+  memcpy(c->hoff.data(), s.data() + 8 + 8 * n, 8 * n);
+  memcpy(c->hlen.data(), s.data() + 8 + 16 * n, 8 * n);
+  std::vector<uint8_t> h = slurp("hits.bin");
+  c->hits.resize(h.size() / sizeof(pm_hit));
+  memcpy(c->hits.data(), h.data(), c->hits.size() * sizeof(pm_hit));
+  for (const pm_hit &x : c->hits) c->bogus |= (x.editdist < 0 || x.editdist > c->k);
+  return PM_OK;
+}
+
+int pm_get_sequences(pm_ctx *c, const int64_t **key, const int64_t **hoff, const int64_t **hlen, uint64_t *ns,
+                     uint64_t *len) {
+  *key = c->key.data(); *hoff = c->hoff.data(); *hlen = c->hlen.data();
+  *ns = c->key.size(); *len = c->stream.size();
+  return PM_OK;
+}
+
+int pm_find_patterns(pm_ctx *c, int64_t, int64_t, const pm_hit **hits, uint64_t *nhits) {
+  *hits = c->hits.data();
+  *nhits = c->hits.size();
+  return c->bogus ? PM_E_BOGUS : PM_OK;
+}
+
+int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
+  if (begin + len > c->stream.size()) return PM_E_ARG;
+  memcpy(out, c->stream.data() + begin, len);
+  return PM_OK;
+}
+
+int pm_normalize_fasta(const uint8_t *, uint64_t, int, unsigned char, uint8_t *, uint64_t *, int64_t *, int64_t *,
+                       int64_t *, uint64_t, uint64_t *) {
+  return PM_E_UNSUPPORTED;
+}
+
+// a pure host function of the product: forwarded to the real library ($PM_REAL_LIB), which
+// loads without a GPU
+int pm_reverse_comp(const char *in, char *out) {
+  typedef int (*fn_t)(const char *, char *);
+  static fn_t fn = 0;
+  if (!fn) {
+    const char *lib = getenv("PM_REAL_LIB");
+    void *h = lib ? dlopen(lib, RTLD_NOW | RTLD_LOCAL) : 0;
+    fn = h ? (fn_t)dlsym(h, "pm_reverse_comp") : 0;
+    if (!fn) { fprintf(stderr, "pm_mock: cannot load pm_reverse_comp from %s\n", lib ? lib : "(PM_REAL_LIB unset)"); exit(2); }
+  }
+  return fn(in, out);
+}
+
+}  // extern "C"

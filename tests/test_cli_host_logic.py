@@ -1,0 +1,191 @@
+"""Host logic of the command line tools without a GPU: bin/pcr_match's option handling,
+primer input (-p / -P / -F / -S), pairing of hits into amplicons and output formats,
+against the text the UNMODIFIED reference pcr_match printed (tests/golden/make_pcr_golden.py).
+
+The tools are compiled against tests/mock/pm_mock.cc, a stand-in for the C ABI that serves
+the hits the oracle computes for the case (the scan itself is what the `-m gpu` tests
+cover: tests/test_gpu_cli.py runs the same command lines on the real library)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG_NAME, ROOT
+
+MOCK = os.path.join(ROOT, "tests", "mock")
+CSRC = os.path.join(ROOT, PKG_NAME, "csrc")
+CODE_OF = {"|": 1, "+": 2, "*": 3, "^": 4, "v": 5, "!": 6}
+
+
+@pytest.fixture(scope="module")
+def mock_tools(built_lib):
+    out = os.path.join(MOCK, "_build")
+    os.makedirs(out, exist_ok=True)
+    lib = os.path.join(out, "libpm_b200.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                           "-o", lib, os.path.join(MOCK, "pm_mock.cc"), "-ldl"])
+    tools = {}
+    for tool in ("pcr_match", "primer_match"):
+        exe = os.path.join(out, tool)
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", exe,
+                               os.path.join(CSRC, tool + "_main.cc"), "-L", out, "-lpm_b200", "-Wl,-rpath," + out])
+        tools[tool] = exe
+    real = os.path.join(ROOT, PKG_NAME, "lib", "libpm_b200.so")
+    assert os.path.exists(real)
+    return tools, real
+
+
+def write_mock_inputs(d, fasta: bytes, stream, hits):
+    """stream.bin / seqs.bin / hits.bin for tests/mock/pm_mock.cc; hits = [(pid, start, end, ed, astr)]."""
+    stream.chars.astype(np.uint8).tofile(os.path.join(d, "stream.bin"))
+    hoff, hlen, at = [], [], 0
+    for h in stream.headers:
+        at = fasta.index(b">" + h.encode("latin-1"), at) + 1
+        hoff.append(at)
+        hlen.append(len(h))
+    n = len(stream.seq_key)
+    with open(os.path.join(d, "seqs.bin"), "wb") as f:
+        f.write(struct.pack("<q", n))
+        f.write(np.asarray(stream.seq_key, np.int64).tobytes())
+        f.write(np.asarray(hoff, np.int64).tobytes())
+        f.write(np.asarray(hlen, np.int64).tobytes())
+    with open(os.path.join(d, "hits.bin"), "wb") as f:
+        for pid, start, end, ed, astr in hits:
+            codes = bytes(CODE_OF[c] for c in astr)
+            f.write(struct.pack("<qqqIiiI72s", start, end, end, pid, ed, 0, len(codes), codes))
+
+
+def run_tool(exe, args, mock_dir, real_lib, stdin=None):
+    env = dict(os.environ, PM_MOCK_DIR=mock_dir, PM_REAL_LIB=real_lib)
+    p = subprocess.run([exe] + args, capture_output=True, timeout=120, env=env, input=stdin)
+    assert p.returncode == 0, p.stderr.decode()[-500:]
+    return p.stdout.decode("latin-1")
+
+
+def pcr_case_inputs(oracle, case, d):
+    par = dict(case["params"])
+    select = par.pop("select")
+    par.pop("deviation", None)
+    fasta = case["fasta"].encode("latin-1")
+    st = oracle.normalize_fasta(fasta)
+    rev_comp = par["rev_comp"] or "sts" in case
+    pats = oracle.pcr_pattern_array(case["primers"], rev_comp)
+    lc, rc = oracle.pcr_pattern_constraints(pats[:len(case["primers"])], par["stlen"], par["edlen"], par["fplen"],
+                                            par["tplen"])
+    hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"], par["wc"], par["tn"],
+                               index="auto" if select == 0 else "filter_bitvec", bogus_ok=True, exact_align=False)
+    write_mock_inputs(d, fasta, st, hits)
+    fa = os.path.join(d, "db.fasta")
+    with open(fa, "wb") as f:
+        f.write(fasta)
+    run = dict(case["params"])
+    if "sts" in case:
+        run["sts_path"] = os.path.join(d, "primers.sts")
+        with open(run["sts_path"], "w") as f:
+            f.write(case["sts"])
+    return fa, run
+
+
+def test_pcr_match_host_logic_matches_reference_output(oracle, pcr_golden, mock_tools, tmp_path):
+    import make_pcr_golden
+    tools, real = mock_tools
+    n = 0
+    for case in pcr_golden["cases"]:
+        d = str(tmp_path / ("c%d" % case["seed"]))
+        os.makedirs(d)
+        fa, run = pcr_case_inputs(oracle, case, d)
+        args = oracle.pcr_cli_args(fa, case["primers"], **run)
+        got = run_tool(tools["pcr_match"], args + ["-A", oracle.PCR_REF_FORMAT], d, real)
+        assert got == case["stdout_records"], "records, case %d" % case["seed"]
+        got = run_tool(tools["pcr_match"], args, d, real)
+        assert got == case["stdout_default"], "default format, case %d" % case["seed"]
+        fmt = make_pcr_golden.CUSTOM_FORMAT + ("%*\\n" if "sts" in case else "")
+        got = run_tool(tools["pcr_match"], args + ["-A", fmt], d, real)
+        assert got == case["stdout_custom"], "custom format, case %d" % case["seed"]
+        n += len(case["stdout_records"].splitlines())
+    assert n > 300
+
+
+def test_pcr_match_primer_files(oracle, pcr_golden, mock_tools, tmp_path):
+    """-P (words), -F (FASTA, %P = the deflines), "-" = standard input, -o appends."""
+    tools, real = mock_tools
+    case = [c for c in pcr_golden["cases"] if "sts" not in c and len(c["stdout_records"].splitlines()) > 3][0]
+    d = str(tmp_path)
+    fa, run = pcr_case_inputs(oracle, case, d)
+    base = oracle.pcr_cli_args(fa, case["primers"], **run)
+    i = base.index("-p")
+    words = "\n".join(case["primers"]) + "\n"
+    with open(os.path.join(d, "p.txt"), "w") as f:
+        f.write(words)
+    fmt = ["-A", oracle.PCR_REF_FORMAT]
+    assert run_tool(tools["pcr_match"], base[:i] + ["-P", os.path.join(d, "p.txt")] + base[i + 2:] + fmt, d,
+                    real) == case["stdout_records"]
+    assert run_tool(tools["pcr_match"], base[:i] + ["-P", "-"] + base[i + 2:] + fmt, d, real,
+                    stdin=words.encode()) == case["stdout_records"]
+    with open(os.path.join(d, "p.fa"), "w") as f:
+        f.write("".join(">primer%d of pair %d\n%s\n" % (j, j // 2, p) for j, p in enumerate(case["primers"])))
+    got = run_tool(tools["pcr_match"], base[:i] + ["-F", os.path.join(d, "p.fa")] + base[i + 2:] +
+                   ["-A", "%i %>P|%<P\\n"], d, real)
+    want = oracle.parse_pcr_records(case["stdout_records"])
+    assert len(got.splitlines()) == len(want)
+    for line, r in zip(got.splitlines(), want):
+        pair = int(line.split(" ")[0])
+        assert pair == r.pair and "of pair %d|" % (pair - 1) in line and line.endswith("of pair %d" % (pair - 1))
+    outf = os.path.join(d, "out.txt")
+    with open(outf, "w") as f:
+        f.write("kept\n")
+    run_tool(tools["pcr_match"], base + fmt + ["-o", outf], d, real)
+    assert open(outf).read() == "kept\n" + case["stdout_records"]
+
+
+def test_pcr_match_odd_number_of_primers_is_refused(mock_tools, tmp_path):
+    tools, real = mock_tools
+    env = dict(os.environ, PM_MOCK_DIR=str(tmp_path), PM_REAL_LIB=real)
+    p = subprocess.run([tools["pcr_match"], "-i", "x.fasta", "-p", "ACGTACGTACGT ACGTTTGACCA GGGTTTAAACCC"],
+                       capture_output=True, env=env)
+    assert p.returncode == 1 and b"Odd number of primers!" in p.stderr   # pcr_match.cc:768
+
+
+def _blocks(text, n):
+    lines = text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    assert len(lines) % n == 0
+    return sorted(tuple(lines[i:i + n]) for i in range(0, len(lines), n))
+
+
+def test_primer_match_host_logic_matches_reference_output(oracle, golden, mock_tools, tmp_path):
+    """bin/primer_match's formats and counts on the oracle's hits, against the reference's text
+    (records as multisets: the reference orders simultaneous hits by an unstable sort)."""
+    import make_golden
+    tools, real = mock_tools
+    checked = 0
+    for case in golden["cases"]:
+        if "stdout_default" not in case:
+            continue
+        d = str(tmp_path / ("p%s" % str(case["seed"]).replace(":", "_")))
+        os.makedirs(d)
+        par, prm = case["params"], case["primers"]
+        fasta = case["fasta"].encode("latin-1")
+        st = oracle.normalize_fasta(fasta)
+        pats = oracle.pattern_array(prm, par["rev_comp"])
+        lc, rc = oracle.pattern_constraints(prm, par["rev_comp"])
+        hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"], par["wc"], par["tn"])
+        write_mock_inputs(d, fasta, st, hits)
+        fa = os.path.join(d, "db.fasta")
+        with open(fa, "wb") as f:
+            f.write(fasta)
+        exe = tools["primer_match"]
+        got = run_tool(exe, make_golden.cli_args(fa, prm, par), d, real)
+        assert _blocks(got, 4) == _blocks(case["stdout_default"], 4), "default format, case %s" % case["seed"]
+        got = run_tool(exe, make_golden.cli_args(fa, prm, par, ["-A", "%H %f %5 %3 %l %q %p %t|%T|%Q|%A %| %^ %v %* %+ %%\\n"]),
+                       d, real)
+        assert _blocks(got, 1) == _blocks(case["stdout_custom"], 1), "custom format, case %s" % case["seed"]
+        got = run_tool(exe, make_golden.cli_args(fa, prm, par, ["-c"]), d, real)
+        assert got == case["stdout_counts"], "counts, case %s" % case["seed"]
+        got = run_tool(exe, make_golden.cli_args(fa, prm, par, ["-C", "%i\\t%p\\t%c\\t%C\\n", "-a"]), d, real)
+        assert sorted(got.split("\n")) == sorted(case["stdout_counts_agg"].split("\n")), "aggregate counts, case %s" % case["seed"]
+        checked += 1
+    assert checked >= 15

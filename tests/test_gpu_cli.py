@@ -26,6 +26,17 @@ def cli(built_lib):
     return path
 
 
+@pytest.fixture(scope="module")
+def pcr_cli(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device; the tool has no CPU fallback")
+    build = importlib.import_module(PKG_NAME + ".build")
+    path = build.build_cli(tool="pcr_match")
+    assert path and os.path.exists(path)
+    return path
+
+
 def _args(fasta_path, primers, params, extra=()):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_golden
@@ -47,6 +58,8 @@ def _blocks(text, n):
 
 
 def test_cli_output_matches_reference(cli, golden, tmp_path):
+    # every process start pays for a CUDA context (~3 s): the default format for every case, the
+    # other formats for every third; tests/test_cli_host_logic.py runs all of them on the CPU
     checked = 0
     for case in golden["cases"]:
         if "stdout_default" not in case:
@@ -56,13 +69,15 @@ def test_cli_output_matches_reference(cli, golden, tmp_path):
         prm, par = case["primers"], case["params"]
         got = _run(cli, _args(str(fa), prm, par))
         assert _blocks(got, 4) == _blocks(case["stdout_default"], 4), "default format, case %s" % case["seed"]
+        checked += 1
+        if checked % 3 != 1:
+            continue
         got = _run(cli, _args(str(fa), prm, par, ["-A", "%H %f %5 %3 %l %q %p %t|%T|%Q|%A %| %^ %v %* %+ %%\\n"]))
         assert _blocks(got, 1) == _blocks(case["stdout_custom"], 1), "custom format, case %s" % case["seed"]
         got = _run(cli, _args(str(fa), prm, par, ["-c"]))
         assert got == case["stdout_counts"], "counts, case %s" % case["seed"]
         got = _run(cli, _args(str(fa), prm, par, ["-C", "%i\\t%p\\t%c\\t%C\\n", "-a"]))
         assert sorted(got.split("\n")) == sorted(case["stdout_counts_agg"].split("\n")), "aggregate counts, case %s" % case["seed"]
-        checked += 1
     assert checked >= 15
 
 
@@ -97,12 +112,14 @@ def _records(text):
 
 def test_cli_automatic_index_and_constraints(cli, halves_golden, constraints_golden, tmp_path):
     """The same command lines the reference got in make_halves_golden.py / make_constraints_golden.py:
-    no -N (pick_pattern_index chooses), -N 13/14 forced, and the -s / -e / -5 / -3 options."""
+    no -N (pick_pattern_index chooses), -N 13/14 forced, and the -s / -e / -5 / -3 options.
+    Every third case (a process start costs ~3 s of CUDA context); test_gpu_parity.py checks all
+    of them through the C ABI in one process."""
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import make_constraints_golden
     n = 0
     for gi, g in enumerate((halves_golden, constraints_golden)):
-        for case in g["cases"]:
+        for case in g["cases"][gi::3]:
             fa = tmp_path / ("g%d_%s.fasta" % (gi, case["seed"]))
             fa.write_bytes(case["fasta"].encode("latin-1"))
             par = case["params"]
@@ -120,4 +137,32 @@ def test_cli_automatic_index_and_constraints(cli, halves_golden, constraints_gol
             got = _records(_run(cli, args))
             assert got == sorted(tuple(r) for r in case["records"]), "golden %d case %s" % (gi, case["seed"])
             n += 1
-    assert n >= 90
+    assert n >= 30
+
+
+def test_pcr_match_output_matches_reference(pcr_cli, oracle, pcr_golden, tmp_path):
+    """bin/pcr_match on the GPU library, command lines the reference got in make_pcr_golden.py:
+    records (every alignformat argument) in the reference's order, and its default output
+    format.  Every process start pays for a CUDA context, so this takes a spread of the cases
+    with records; tests/test_cli_host_logic.py runs all of them (three formats each) on the
+    oracle's hits."""
+    with_records = [c for c in pcr_golden["cases"] if c["stdout_records"]]
+    picked = with_records[::5]
+    assert len(picked) >= 10 and any("sts" in c for c in picked)
+    n = 0
+    for ci, case in enumerate(picked):
+        fa = tmp_path / ("pcr%d.fasta" % case["seed"])
+        fa.write_bytes(case["fasta"].encode("latin-1"))
+        run = dict(case["params"])
+        if "sts" in case:
+            sts = tmp_path / ("pcr%d.sts" % case["seed"])
+            sts.write_text(case["sts"])
+            run["sts_path"] = str(sts)
+        args = oracle.pcr_cli_args(str(fa), case["primers"], **run)
+        got = _run(pcr_cli, args + ["-A", oracle.PCR_REF_FORMAT])
+        assert got == case["stdout_records"], "records, case %d" % case["seed"]
+        if ci % 4 == 0:
+            got = _run(pcr_cli, args)
+            assert got == case["stdout_default"], "default format, case %d" % case["seed"]
+        n += len(case["stdout_records"].splitlines())
+    assert n > 40

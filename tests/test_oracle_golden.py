@@ -76,3 +76,20 @@ def test_oracle_with_exact_base_constraints_matches_reference_golden(oracle, con
         got = oracle.primer_match(st, case["primers"], index="auto" if case["select"] == 0 else "filter_bitvec",
                                   **case["params"], **case["constraints"])
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
+
+
+def test_oracle_pcr_match_matches_reference_golden(oracle, pcr_golden):
+    """pcr_match (primer pairs -> amplicons) over the same scan: every record the reference
+    printed, in its order; -a, -b, -m / -M, constraints, UniSTS sizes with -d."""
+    cases = pcr_golden["cases"]
+    assert len(cases) >= 60 and sum(1 for c in cases if "sts" in c) >= 10
+    n = 0
+    for case in cases:
+        st = oracle.normalize_fasta(case["fasta"].encode("latin-1"))
+        par = dict(case["params"])
+        select = par.pop("select")
+        got = oracle.pcr_match(st, case["primers"], index="auto" if select == 0 else "filter_bitvec",
+                               sts_sizes=case.get("sts_sizes"), **par)
+        assert got == oracle.parse_pcr_records(case["stdout_records"]), "case %s" % case["seed"]
+        n += len(got)
+    assert n > 300
