@@ -274,6 +274,41 @@ int pm_host_free(void *p);
  * instructions (LOP3) on `device`, in 1e12 thread-level operations per second. */
 int pm_bench_int_peak(int device, double *lop3_tera_ops);
 
+/* pcr_match's pairing of hits into amplicons (pcr_match.cc:945-1170), on the records
+ * pm_find_patterns returned for the pattern array pcr_match builds (pcr_match.cc:800-913):
+ * ids 1..n_primers the primers as given (pairs (1,2), (3,4) ...; the second of each pair
+ * reverse complemented first under -r / -S), ids n_primers+1..2*n_primers their reverse
+ * complements.  Host code; no device work.                                             */
+typedef struct pm_pcr_options {
+  int k;                /* -k / -K                                                       */
+  int indels;           /* 1: -k, 0: -K                                                  */
+  int allorient;        /* -a: every orientation of a pair, pcr_match.cc:977-997          */
+  int betweenlen;       /* -b: amplicon length measured between the primers               */
+  int deviation;        /* -d (with sizes below); < 0: none                               */
+  int reserved;
+  int64_t mindist;      /* -m                                                             */
+  int64_t maxdist;      /* -M                                                             */
+  const uint64_t *sts_sizelb; /* per pair: sts_entry::sizelb()/sizeub() of a UniSTS file  */
+  const uint64_t *sts_sizeub; /* (-S), or NULL                                            */
+} pm_pcr_options;
+
+typedef struct pm_pcr_pair {
+  uint64_t first;       /* index into `hits`: the hit that found its partner (%>x codes)  */
+  uint64_t second;      /* index into `hits`: the partner (%<x codes)                     */
+  int64_t amplicon_len; /* pcr_match.cc:1151-1157                                         */
+  uint32_t pair;        /* %i: 1-based primer pair                                        */
+  uint32_t reserved;
+} pm_pcr_pair;
+
+/* Pairs in the order pcr_match prints them.  patlen[id] = length of pattern id (index 0
+ * unused, 2*n_primers+1 entries); seq_key/n_seqs as pm_get_sequences returns them (a pair
+ * must lie inside one FASTA entry, fasta_io.t:203-213).  *pairs is allocated with malloc;
+ * release it with pm_free.                                                             */
+int pm_pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n_primers, const uint32_t *patlen,
+                 const int64_t *seq_key, uint64_t n_seqs, const pm_pcr_options *opt,
+                 pm_pcr_pair **pairs, uint64_t *npairs);
+void pm_free(void *p);
+
 /* util.cc:374-381 reverse_comp (IUPAC aware, util.cc:319-348): out must hold
  * strlen(pattern)+1 bytes.                                                    */
 int pm_reverse_comp(const char *pattern, char *out);

@@ -78,6 +78,9 @@ class FastaStream {
     return true;
   }
   std::string &raw() { return raw_; }
+  // the sequence table (stream position of each entry's first character), for pm_pcr_pairs
+  const int64_t *seq_keys() const { return key_.data(); }
+  uint64_t n_seqs() const { return key_.size(); }
   uint64_t size() const { return stream_len_; }
   // set_header_item (fasta_io.t:152-168): the entry whose key is the last <= pos-1
   long locate(int64_t pos) const {

@@ -69,6 +69,17 @@ class Stats(C.Structure):
                 ("index_entries", C.c_uint64), ("n_ambiguous", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
+class PcrOptions(C.Structure):
+    _fields_ = [("k", C.c_int), ("indels", C.c_int), ("allorient", C.c_int), ("betweenlen", C.c_int),
+                ("deviation", C.c_int), ("reserved", C.c_int), ("mindist", C.c_int64), ("maxdist", C.c_int64),
+                ("sts_sizelb", C.c_void_p), ("sts_sizeub", C.c_void_p)]
+
+
+class PcrPair(C.Structure):
+    _fields_ = [("first", C.c_uint64), ("second", C.c_uint64), ("amplicon_len", C.c_int64), ("pair", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
                       ("value", "<i4"), ("ncodes", "<u4"), ("codes", "u1", (PM_MAX_CODES,))])
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)
@@ -119,6 +130,10 @@ def lib():
                                          C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_uint64, C.POINTER(C.c_uint64)]
         L.pm_reverse_comp.argtypes = [C.c_char_p, C.c_char_p]
+        L.pm_pcr_pairs.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                   C.POINTER(PcrOptions), C.POINTER(C.POINTER(PcrPair)), C.POINTER(C.c_uint64)]
+        L.pm_free.argtypes = [C.c_void_p]
+        L.pm_free.restype = None
         L.pm_bench_int_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -267,10 +282,14 @@ class Scanner:
     def shard_overlap(self) -> int:
         return lib().pm_shard_overlap(self._h)
 
-    def find_patterns(self, begin=0, end=INT64_MAX) -> np.ndarray:
+    def find_patterns(self, begin=0, end=INT64_MAX, bogus_ok=False) -> np.ndarray:
+        """bogus_ok: PM_E_BOGUS (a hit whose own alignment has more than k errors, on which
+        primer_match stops) still delivers the hits; pcr_match goes on with them."""
         hp = C.POINTER(Hit)()
         n = C.c_uint64(0)
-        _check(lib().pm_find_patterns(self._h, begin, end, C.byref(hp), C.byref(n)))
+        rc = lib().pm_find_patterns(self._h, begin, end, C.byref(hp), C.byref(n))
+        if not (bogus_ok and rc == PM_E_BOGUS):
+            _check(rc)
         if n.value == 0:
             return np.zeros(0, HIT_DTYPE)
         buf = C.string_at(hp, n.value * C.sizeof(Hit))
@@ -514,5 +533,114 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
             sc.set_text(stream.chars)
         hits = sc.find_patterns()
         return hits_to_records(stream, hits, len(primers))
+    finally:
+        sc.close()
+
+
+# ---------------------------------------------------------------------------
+# pcr_match: primer pairs, hits paired into amplicons (pcr_match.cc)
+@dataclass(frozen=True, order=True)
+class PcrRecord:
+    """One output record of pcr_match: the positional arguments of its alignformat()
+    (pcr_match.cc:1179-1196)."""
+    seq_index: int        # %f
+    start: int            # %>s
+    start1: int           # %<s
+    end: int              # %>e
+    end1: int             # %<e
+    stream_start: int     # %>S
+    stream_start1: int    # %<S
+    stream_end: int       # %>E
+    stream_end1: int      # %<E
+    pair: int             # %i
+    editdist: int         # %>d
+    editdist1: int        # %<d
+    strand: str           # %>r
+    strand1: str          # %<r
+    orient: str           # %r
+    alignment: str        # %>A
+    alignment1: str       # %<A
+    ncount: int           # %N
+    amplicon: str         # %@
+
+
+def pcr_pattern_array(primers, rev_comp: bool):
+    """pcr_match.cc:772-784, 827, 868: pairs (1,2), (3,4) ...; -r reverse complements the second
+    primer of every pair first; ids 1..n as given, n+1..2n their reverse complements."""
+    pr = [reverse_comp(p) if (rev_comp and i % 2 == 1) else p for i, p in enumerate(primers)]
+    return pr + [reverse_comp(p) for p in pr]
+
+
+def pcr_pairs(hits: np.ndarray, n_primers: int, patlen, seq_key, k=0, indels=True, allorient=False,
+              betweenlen=False, mindist=0, maxdist=2000, sts_sizes=None, deviation=-1):
+    """pm_pcr_pairs: [(index of the first hit, index of its partner, amplicon length, pair)] in
+    the order pcr_match prints them."""
+    hits = np.ascontiguousarray(hits, HIT_DTYPE)
+    pl = np.ascontiguousarray(patlen, np.uint32)
+    keys = np.ascontiguousarray(seq_key, np.int64)
+    o = PcrOptions(k=k, indels=int(indels), allorient=int(allorient), betweenlen=int(betweenlen),
+                   deviation=deviation if sts_sizes is not None else -1, mindist=mindist, maxdist=maxdist)
+    if sts_sizes is not None:
+        lb = np.array([s[0] for s in sts_sizes], np.uint64)
+        ub = np.array([s[1] for s in sts_sizes], np.uint64)
+        o.sts_sizelb, o.sts_sizeub = lb.ctypes.data, ub.ctypes.data
+    pp = C.POINTER(PcrPair)()
+    n = C.c_uint64(0)
+    _check(lib().pm_pcr_pairs(C.c_void_p(hits.ctypes.data), len(hits), n_primers, C.c_void_p(pl.ctypes.data),
+                              C.c_void_p(keys.ctypes.data), len(keys), C.byref(o), C.byref(pp), C.byref(n)))
+    out = [(pp[i].first, pp[i].second, pp[i].amplicon_len, pp[i].pair) for i in range(n.value)]
+    lib().pm_free(pp)
+    return out
+
+
+def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=False, tn=False, eos=EOS, device=0,
+              index=PM_INDEX_AUTO, stlen=0, edlen=0, fplen=0, tplen=0, mindist=0, maxdist=2000,
+              betweenlen=False, allorient=False, sts_sizes=None, deviation=-1):
+    """pcr_match's main loop on the GPU path: the scan and the alignments of every hit
+    (pm_find_patterns), the pairing (pm_pcr_pairs), and the record each pair prints
+    (pcr_match.cc:1116-1196).  sts_sizes: [(sizelb, sizeub)] per pair for primers from a UniSTS
+    file (-S, which implies -r); deviation = -d.  Returns PcrRecords in output order."""
+    if sts_sizes is not None:
+        rev_comp = True
+    n = len(primers)
+    pats = pcr_pattern_array(primers, rev_comp)
+    sc = Scanner(k=k, indels=indels, wildcards=wc, text_n=tn, index=index, device=device, eos=eos)
+    try:
+        for i in range(n):
+            # -5 and -3 swap for the second primer of a pair (pcr_match.cc:803-808)
+            fp, tp = (fplen, tplen) if i % 2 == 0 else (tplen, fplen)
+            esb, eeb = pattern_constraints([pats[i]], True, stlen, edlen, fp, tp)
+            sc.add_pattern(pats[i], i + 1, esb[0], eeb[0])
+            sc.add_pattern(pats[i + n], i + n + 1, esb[1], eeb[1])
+        sc.init()
+        sc.set_text(stream.chars)
+        hits = sc.find_patterns(bogus_ok=True)
+        patlen = [0] + [len(p) for p in pats]
+        T = stream.chars
+        recs = []
+        for a, b, amplicon_len, pind in pcr_pairs(hits, n, patlen, stream.seq_key, k, indels, allorient, betweenlen,
+                                                  mindist, maxdist, sts_sizes, deviation):
+            h, h1 = hits[a], hits[b]
+            pid, pid1 = int(h["pattern_id"]), int(h1["pattern_id"])
+            pe, pe1 = int(h["end"]), int(h1["end"])
+            ps, ps1 = int(h["start"]), int(h1["start"])
+            idx, key = stream.locate(pe)
+            _, key1 = stream.locate(pe1)
+            spe, spe1 = pe - key, pe1 - key1
+            sps, sps1 = spe - (pe - ps), spe1 - (pe1 - ps1)
+            rc, rc1 = pid > n, pid1 > n
+            ind, ind1 = pid - (n if rc else 0), pid1 - (n if rc1 else 0)
+            if rev_comp:                                     # pcr_match.cc:1143-1149
+                if ind % 2 == 0:
+                    rc = not rc
+                elif ind1 % 2 == 0:
+                    rc1 = not rc1
+            amp = bytes(T[ps:ps + amplicon_len]).decode("latin-1") if amplicon_len > 0 else ""
+            astr = "".join(CODE_CHARS.get(int(c), " ") for c in h["codes"][:int(h["ncodes"])])
+            astr1 = "".join(CODE_CHARS.get(int(c), " ") for c in h1["codes"][:int(h1["ncodes"])])
+            recs.append(PcrRecord(idx, sps, sps1, spe, spe1, ps, ps1, pe, pe1, pind, int(h["editdist"]),
+                                  int(h1["editdist"]), "R" if rc else "F", "R" if rc1 else "F",
+                                  "F" if ind < ind1 else "R", astr, astr1, amp.count("N") + amp.count("n"), amp))
+        return recs
     finally:
         sc.close()

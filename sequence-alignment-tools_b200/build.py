@@ -36,7 +36,7 @@ def _nvcc() -> str:
 
 
 def lib_sources():
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", "pm_pcr.hpp"))]
     srcs.append(os.path.join(ROOT, "include", "pm_b200.h"))
     return srcs
 

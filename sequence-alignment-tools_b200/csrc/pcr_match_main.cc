@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -330,7 +331,7 @@ int main(int argc, char **argv) {
   for (unsigned long i = 1; i <= N1; i++) pm->add_pattern(patarray[i], i, patconst[i].first, patconst[i].second);
   pm->init(ff);
 
-  // every hit, in position order (l.normalize(), pcr_match.cc:945)
+  // every hit the scan reports
   std::vector<const pm_hit *> l;
   {
     pattern_hit_vector phv;
@@ -342,108 +343,63 @@ int main(int argc, char **argv) {
       batch.clear();
     }
   }
-  std::stable_sort(l.begin(), l.end(), [](const pm_hit *a, const pm_hit *b) {
-    return a->end != b->end ? a->end < b->end : a->pattern_id < b->pattern_id;
-  });
-  std::map<unsigned long, std::vector<size_t> > m;  // pattern id -> its hits, by position
-  for (size_t i = 0; i < l.size(); i++) m[l[i]->pattern_id].push_back(i);
-  std::vector<bool> done(l.size(), false);
+  // the pairing itself is the library's (pm_pcr_pairs, csrc/pm_pcr.hpp)
+  std::vector<pm_hit> hits;
+  hits.reserve(l.size());
+  for (const pm_hit *h : l) hits.push_back(*h);
+  std::vector<uint32_t> plen32(patlen.begin(), patlen.end());
+  std::vector<uint64_t> sizelb, sizeub;
+  for (size_t i = 1; i < stsarray.size(); i++) { sizelb.push_back(stsarray[i].sizelb); sizeub.push_back(stsarray[i].sizeub); }
+  pm_pcr_options po;
+  std::memset(&po, 0, sizeof po);
+  po.k = opt.nmismatch; po.indels = opt.indels; po.allorient = opt.allorient; po.betweenlen = opt.betweenlen;
+  po.deviation = opt.sts_pattern_file ? opt.deviation : -1;
+  po.mindist = opt.mindist; po.maxdist = opt.maxdist;
+  po.sts_sizelb = opt.sts_pattern_file ? sizelb.data() : 0;
+  po.sts_sizeub = opt.sts_pattern_file ? sizeub.data() : 0;
+  pm_pcr_pair *pairs = 0;
+  uint64_t npairs = 0;
+  if (pm_pcr_pairs(hits.data(), hits.size(), (uint32_t)n, plen32.data(), ff.seq_keys(), ff.n_seqs(), &po, &pairs,
+                   &npairs) != PM_OK)
+    fatal(std::string("Fatal error: ") + pm_last_error());
 
-  const long err = opt.indels ? opt.nmismatch : 1;
   StsEntry null_sts;
-  for (size_t hi = 0; hi < l.size(); hi++) {
-    const pm_hit &h = *l[hi];
+  for (uint64_t pi = 0; pi < npairs; pi++) {
+    const pm_hit &h = hits[pairs[pi].first];
     const unsigned long pid = h.pattern_id;
-    const long pos = (long)h.end;
-    // partner patterns, pcr_match.cc:968-997
-    unsigned long pid1 = 0, pid2 = 0;
-    if (pid <= n && pid % 2 == 1) pid1 = pid + 1;
-    else if (pid > n && (pid - n) % 2 == 0) pid1 = pid - 1;
-    if (opt.allorient) {
-      if (pid <= n) {
-        if (pid % 2 == 1) { pid2 = pid + n + 1; }
-        else { pid1 = pid - 1; pid2 = pid + n - 1; }
-      } else {
-        if (pid % 2 == 0) { pid2 = pid - n - 1; }
-        else { pid1 = pid + 1; pid2 = pid - n + 1; }
-      }
+    const pm_hit &h1 = hits[pairs[pi].second];
+    const unsigned long pidb = h1.pattern_id;
+    const long length = (long)(h.end - h.start + 1), length1 = (long)(h1.end - h1.start + 1);
+    const long pe = (long)h.end, pe1 = (long)h1.end;
+    const long spe = (long)ff.get_seq_pos(pe), spe1 = (long)ff.get_seq_pos(pe1);
+    const long sps = spe - length + 1, sps1 = spe1 - length1 + 1;
+    const long ps = pe - length + 1, ps1 = pe1 - length1 + 1;
+    bool rc = pid > n, rc1 = pidb > n;
+    const unsigned long ind = pid - (rc ? n : 0), ind1 = pidb - (rc1 ? n : 0);
+    const unsigned long pind = (ind < ind1 ? ind : ind1) / 2 + 1;
+    const StsEntry &stsref = opt.sts_pattern_file ? stsarray[pind] : null_sts;
+    if (opt.rev_comp) {
+      if (ind % 2 == 0) rc = !rc;
+      else if (ind1 % 2 == 0) rc1 = !rc1;
     }
-    // stretch window, pcr_match.cc:1019-1042 (types as there: the -d comparisons are unsigned)
-    const unsigned long pair = (pid - ((pid > n) ? n : 0) + 1) / 2;
-    long stretch_max = opt.maxdist, stretch_min = opt.mindist;
-    if (opt.betweenlen) {
-      long plen = 0;
-      if (pid1 != 0) plen = patlen[pid1];
-      if (pid2 != 0 && patlen[pid2] > plen) plen = patlen[pid2];
-      stretch_max += plen + patlen[pid];
-    }
-    if (opt.sts_pattern_file && opt.deviation >= 0) {
-      if ((unsigned long)stretch_max > stsarray[pair].sizeub + opt.deviation)
-        stretch_max = (long)(stsarray[pair].sizeub + opt.deviation);
-      if ((unsigned long)stretch_min < stsarray[pair].sizelb - opt.deviation)
-        stretch_min = (long)(stsarray[pair].sizelb - opt.deviation);
-    }
-    stretch_max += pos - patlen[pid] + err;
-    stretch_min += pos - patlen[pid] - err;
-
-    std::vector<size_t> l1;
-    for (unsigned long q : {pid1, pid2}) {
-      if (!q) continue;
-      std::map<unsigned long, std::vector<size_t> >::iterator mit = m.find(q);
-      if (mit == m.end()) continue;
-      const std::vector<size_t> &v = mit->second;
-      size_t j = 0, step = v.size();  // first hit with end >= stretch_min
-      while (step > 0) {
-        const size_t half = step / 2;
-        if ((long)l[v[j + half]]->end < stretch_min) { j += half + 1; step -= half + 1; } else { step = half; }
-      }
-      for (; j < v.size(); j++) {
-        if (done[v[j]]) continue;
-        if ((long)l[v[j]]->end > stretch_max) break;
-        l1.push_back(v[j]);
-      }
-    }
-
-    for (size_t j : l1) {
-      const pm_hit &h1 = *l[j];
-      const unsigned long pidb = h1.pattern_id;
-      const long length = (long)(h.end - h.start + 1), length1 = (long)(h1.end - h1.start + 1);
-      const long pe = (long)h.end, pe1 = (long)h1.end;
-      const long spe = (long)ff.get_seq_pos(pe), spe1 = (long)ff.get_seq_pos(pe1);
-      const long sps = spe - length + 1, sps1 = spe1 - length1 + 1;
-      const long ps = pe - length + 1, ps1 = pe1 - length1 + 1;
-      bool rc = pid > n, rc1 = pidb > n;
-      const unsigned long ind = pid - (rc ? n : 0), ind1 = pidb - (rc1 ? n : 0);
-      const unsigned long pind = (ind < ind1 ? ind : ind1) / 2 + 1;
-      const StsEntry &stsref = opt.sts_pattern_file ? stsarray[pind] : null_sts;
-      if (opt.rev_comp) {
-        if (ind % 2 == 0) rc = !rc;
-        else if (ind1 % 2 == 0) rc1 = !rc1;
-      }
-      const long amplicon_len = opt.betweenlen ? ps1 - pe : pe1 - ps;
-      if (!(ff.is_subseq(ps, pe1) && amplicon_len <= opt.maxdist && amplicon_len >= opt.mindist &&
-            (!opt.sts_pattern_file || opt.deviation < 0 ||
-             (((unsigned long)(amplicon_len + opt.deviation) >= stsref.sizelb) &&
-              (amplicon_len <= ((int)stsref.sizeub) + opt.deviation)))))
-        continue;
-      const std::string amplicon = amplicon_len > 0 ? ff.text(ps, ps + amplicon_len) : std::string();
-      unsigned long ncount = 0;
-      for (char ch : amplicon) ncount += (ch == 'N' || ch == 'n');
-      Side a, b;
-      a.s = sps; a.e = spe; a.S = ps; a.E = pe; a.d = (unsigned)h.editdist;
-      b.s = sps1; b.e = spe1; b.S = ps1; b.E = pe1; b.d = (unsigned)h1.editdist;
-      a.p = patarray[ind]; b.p = patarray[ind1];
-      if (opt.fasta_pattern_file) { a.patdef = patdefs[ind - 1]; b.patdef = patdefs[ind1 - 1]; }
-      a.q = patarray[pid]; b.q = patarray[pidb];
-      a.r = rc ? "R" : "F"; b.r = rc1 ? "R" : "F";
-      a.R = rc ? " REVCOMP" : ""; b.R = rc1 ? " REVCOMP" : "";
-      a.al = render(h, patarray[pid], ff.text(h.start, h.end));
-      b.al = render(h1, patarray[pidb], ff.text(h1.start, h1.end));
-      alignformat(*out, opt.alignformat, a, b, pind, stsref, ind < ind1, ff.header(pe), ff.short_header(pe),
-                  ff.index(pe), amplicon, ncount);
-    }
-    done[hi] = true;
+    const long amplicon_len = (long)pairs[pi].amplicon_len;
+    const std::string amplicon = amplicon_len > 0 ? ff.text(ps, ps + amplicon_len) : std::string();
+    unsigned long ncount = 0;
+    for (char ch : amplicon) ncount += (ch == 'N' || ch == 'n');
+    Side a, b;
+    a.s = sps; a.e = spe; a.S = ps; a.E = pe; a.d = (unsigned)h.editdist;
+    b.s = sps1; b.e = spe1; b.S = ps1; b.E = pe1; b.d = (unsigned)h1.editdist;
+    a.p = patarray[ind]; b.p = patarray[ind1];
+    if (opt.fasta_pattern_file) { a.patdef = patdefs[ind - 1]; b.patdef = patdefs[ind1 - 1]; }
+    a.q = patarray[pid]; b.q = patarray[pidb];
+    a.r = rc ? "R" : "F"; b.r = rc1 ? "R" : "F";
+    a.R = rc ? " REVCOMP" : ""; b.R = rc1 ? " REVCOMP" : "";
+    a.al = render(h, patarray[pid], ff.text(h.start, h.end));
+    b.al = render(h1, patarray[pidb], ff.text(h1.start, h1.end));
+    alignformat(*out, opt.alignformat, a, b, pind, stsref, ind < ind1, ff.header(pe), ff.short_header(pe),
+                ff.index(pe), amplicon, ncount);
   }
+  pm_free(pairs);
   out->flush();
   delete pm;
   return 0;

@@ -24,6 +24,7 @@
 #include "pm_index.cuh"
 #include "pm_fasta.cuh"
 #include "pm_halves.cuh"
+#include "pm_pcr.hpp"
 
 namespace {
 
@@ -2113,6 +2114,27 @@ int pm_bench_int_peak(int device, double *lop3_tera_ops) {
   *lop3_tera_ops = best;
   return PM_OK;
 }
+
+int pm_pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n_primers, const uint32_t *patlen,
+                 const int64_t *seq_key, uint64_t n_seqs, const pm_pcr_options *opt, pm_pcr_pair **pairs,
+                 uint64_t *npairs) {
+  if (!pairs || !npairs || !opt || !patlen || (nhits && !hits) || (n_seqs && !seq_key))
+    return fail(PM_E_ARG, "null argument");
+  *pairs = nullptr;
+  *npairs = 0;
+  if (n_primers == 0 || n_primers % 2 != 0) return fail(PM_E_ARG, "Odd number of primers!");  // pcr_match.cc:768
+  std::vector<pm_pcr_pair> out;
+  pcr_pairs(hits, nhits, n_primers, patlen, seq_key, n_seqs, *opt, out);
+  if (!out.empty()) {
+    *pairs = (pm_pcr_pair *)malloc(out.size() * sizeof(pm_pcr_pair));
+    if (!*pairs) return fail(PM_E_NOMEM, "out of host memory");
+    memcpy(*pairs, out.data(), out.size() * sizeof(pm_pcr_pair));
+  }
+  *npairs = out.size();
+  return PM_OK;
+}
+
+void pm_free(void *p) { free(p); }
 
 int pm_reverse_comp(const char *pattern, char *out) {
   if (!pattern || !out) return fail(PM_E_ARG, "null argument");

@@ -93,18 +93,35 @@ int pm_normalize_fasta(const uint8_t *, uint64_t, int, unsigned char, uint8_t *,
   return PM_E_UNSUPPORTED;
 }
 
-// a pure host function of the product: forwarded to the real library ($PM_REAL_LIB), which
+// pure host functions of the product: forwarded to the real library ($PM_REAL_LIB), which
 // loads without a GPU
+static void *real_symbol(const char *name) {
+  static void *h = 0;
+  const char *lib = getenv("PM_REAL_LIB");
+  if (!h && lib) h = dlopen(lib, RTLD_NOW | RTLD_LOCAL);
+  void *f = h ? dlsym(h, name) : 0;
+  if (!f) { fprintf(stderr, "pm_mock: cannot load %s from %s\n", name, lib ? lib : "(PM_REAL_LIB unset)"); exit(2); }
+  return f;
+}
+
 int pm_reverse_comp(const char *in, char *out) {
   typedef int (*fn_t)(const char *, char *);
-  static fn_t fn = 0;
-  if (!fn) {
-    const char *lib = getenv("PM_REAL_LIB");
-    void *h = lib ? dlopen(lib, RTLD_NOW | RTLD_LOCAL) : 0;
-    fn = h ? (fn_t)dlsym(h, "pm_reverse_comp") : 0;
-    if (!fn) { fprintf(stderr, "pm_mock: cannot load pm_reverse_comp from %s\n", lib ? lib : "(PM_REAL_LIB unset)"); exit(2); }
-  }
+  static fn_t fn = (fn_t)real_symbol("pm_reverse_comp");
   return fn(in, out);
+}
+
+int pm_pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n_primers, const uint32_t *patlen, const int64_t *seq_key,
+                 uint64_t n_seqs, const pm_pcr_options *opt, pm_pcr_pair **pairs, uint64_t *npairs) {
+  typedef int (*fn_t)(const pm_hit *, uint64_t, uint32_t, const uint32_t *, const int64_t *, uint64_t,
+                      const pm_pcr_options *, pm_pcr_pair **, uint64_t *);
+  static fn_t fn = (fn_t)real_symbol("pm_pcr_pairs");
+  return fn(hits, nhits, n_primers, patlen, seq_key, n_seqs, opt, pairs, npairs);
+}
+
+void pm_free(void *p) {
+  typedef void (*fn_t)(void *);
+  static fn_t fn = (fn_t)real_symbol("pm_free");
+  fn(p);
 }
 
 }  // extern "C"

@@ -189,3 +189,32 @@ def test_primer_match_host_logic_matches_reference_output(oracle, golden, mock_t
         assert sorted(got.split("\n")) == sorted(case["stdout_counts_agg"].split("\n")), "aggregate counts, case %s" % case["seed"]
         checked += 1
     assert checked >= 15
+
+
+def test_pm_pcr_pairs_on_oracle_hits(pkg, built_lib, oracle, pcr_golden):
+    """pm_pcr_pairs (host code of the library, no device) through the Python binding, on the
+    oracle's hits: the pairs behind every record the reference printed, in its order."""
+    n = 0
+    for case in pcr_golden["cases"]:
+        par = dict(case["params"])
+        select = par.pop("select")
+        st = oracle.normalize_fasta(case["fasta"].encode("latin-1"))
+        rev_comp = par["rev_comp"] or "sts" in case
+        pats = oracle.pcr_pattern_array(case["primers"], rev_comp)
+        assert pats == pkg.pcr_pattern_array(case["primers"], rev_comp)
+        lc, rc = oracle.pcr_pattern_constraints(pats[:len(case["primers"])], par["stlen"], par["edlen"], par["fplen"],
+                                                par["tplen"])
+        hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"], par["wc"], par["tn"],
+                                   index="auto" if select == 0 else "filter_bitvec", bogus_ok=True, exact_align=False)
+        arr = np.zeros(len(hits), pkg.HIT_DTYPE)
+        for i, (pid, start, end, ed, astr) in enumerate(hits):
+            arr[i]["start"], arr[i]["end"], arr[i]["first"] = start, end, end
+            arr[i]["pattern_id"], arr[i]["editdist"], arr[i]["ncodes"] = pid, ed, len(astr)
+        got = pkg.pcr_pairs(arr, len(case["primers"]), [0] + [len(p) for p in pats], st.seq_key, par["k"],
+                            par["indels"], par["allorient"], par["betweenlen"], par["mindist"], par["maxdist"],
+                            case.get("sts_sizes"), par.get("deviation", -1))
+        want = oracle.parse_pcr_records(case["stdout_records"])
+        assert [(int(arr[a]["end"]), int(arr[b]["end"]), pind, alen) for a, b, alen, pind in got] == \
+               [(r.stream_end, r.stream_end1, r.pair, len(r.amplicon)) for r in want], "case %s" % case["seed"]
+        n += len(got)
+    assert n > 300

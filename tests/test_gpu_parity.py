@@ -52,6 +52,24 @@ def test_exact_halves_golden_records_bit_exact(pkg, halves_golden, path):
         assert as_tuples(got) == sorted(records_of(case)), "case %s" % case["seed"]
 
 
+def test_pcr_match_golden_records_bit_exact(pkg, oracle, pcr_golden):
+    """pcr_match: scan + alignments on the GPU (pm_find_patterns), pairing by pm_pcr_pairs; every
+    record the reference's pcr_match printed for its 80 command lines, in its order (-a, -b,
+    -m / -M, constraints, -N 0 / 5, UniSTS sizes with -d)."""
+    import dataclasses
+    n = 0
+    for case in pcr_golden["cases"]:
+        st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
+        par = dict(case["params"])
+        select = par.pop("select")
+        got = pkg.pcr_match(st, case["primers"], index=pkg.PM_INDEX_AUTO if select == 0 else pkg.PM_INDEX_FILTER_BITVEC,
+                            sts_sizes=case.get("sts_sizes"), **par)
+        want = oracle.parse_pcr_records(case["stdout_records"])
+        assert [dataclasses.astuple(r) for r in got] == [dataclasses.astuple(r) for r in want], "case %s" % case["seed"]
+        n += len(got)
+    assert n > 300
+
+
 @pytest.mark.parametrize("path", ["auto", "planes"])
 def test_constraints_golden_records_bit_exact(pkg, constraints_golden, path):
     """-s / -e / -5 / -3 (exact_start_bases / exact_end_bases) with -N 5 and with the automatic
