@@ -128,6 +128,16 @@ int pm_create(pm_ctx **out, const pm_options *opt);
 /* delete kt                                                                   */
 void pm_destroy(pm_ctx *ctx);
 
+/* Which tool's final alignment the hits get.  They differ for exact search (k = 0) with
+ * wildcards only: primer_match makes an exact_wc_alignment (primer_match.cc:1137-1141), which
+ * asks iupac_compatible(text, pattern) (pattern_alignment.cc:79); pcr_match makes an
+ * editdist_alignment there too (pcr_match.cc:1096-1100), which asks iupac_compatible(pattern,
+ * text) (pattern_alignment.cc:317).  A hit the chosen alignment rejects has editdist > k
+ * (PM_E_BOGUS).  Default PM_ALIGN_PRIMER_MATCH.                                          */
+#define PM_ALIGN_PRIMER_MATCH 0
+#define PM_ALIGN_PCR_MATCH 1
+int pm_set_alignment_rules(pm_ctx *ctx, int rules);
+
 /* Select the device scan (before pm_init).  PM_SCAN_INDEX on patterns it cannot
  * serve makes pm_init fail with PM_E_UNSUPPORTED.                              */
 int pm_set_scan_path(pm_ctx *ctx, int path);

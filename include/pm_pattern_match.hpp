@@ -202,6 +202,10 @@ class b200_index : public PatternMatch {
   // skips the pairs it is part of (pcr_match.cc:1114): hand such hits out instead, the
   // caller tests pm_hit::editdist.
   void tolerate_bogus(bool yes) { tolerate_bogus_ = yes; }
+  // PM_ALIGN_PCR_MATCH: the alignment pcr_match makes of a hit (see pm_set_alignment_rules)
+  void alignment_rules(int rules) {
+    if (pm_set_alignment_rules(ctx_, rules) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+  }
   // the full records (alignment included) of the hits handed out by the last
   // find_patterns() call, same order as `pas`
   std::vector<const pm_hit *> &batch() { return batch_; }

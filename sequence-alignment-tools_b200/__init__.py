@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpm_b200.so")
 
 PM_OK = 0
 PM_E_ARG, PM_E_CUDA, PM_E_UNSUPPORTED, PM_E_NOMEM, PM_E_BOGUS = -1, -2, -3, -4, -5
+PM_ALIGN_PRIMER_MATCH, PM_ALIGN_PCR_MATCH = 0, 1
 PM_INDEX_AUTO, PM_INDEX_KEYWORD_TREE, PM_INDEX_SHIFT_AND, PM_INDEX_FILTER_BITVEC = 0, 3, 4, 5
 PM_INDEX_EXACT_BASES, PM_INDEX_EXACT_HALVES = 9, 13
 PM_SCAN_AUTO, PM_SCAN_PLANES, PM_SCAN_INDEX = 0, 1, 2
@@ -36,7 +37,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules"]
 
 
 class PmError(RuntimeError):
@@ -103,6 +104,7 @@ def lib():
         L.pm_destroy.restype = None
         L.pm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.pm_set_scan_path.argtypes = [C.c_void_p, C.c_int]
+        L.pm_set_alignment_rules.argtypes = [C.c_void_p, C.c_int]
         L.pm_add_pattern.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int]
         L.pm_init.argtypes = [C.c_void_p]
         L.pm_set_text_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
@@ -213,6 +215,11 @@ class Scanner:
 
     def init(self):
         _check(lib().pm_init(self._h))
+
+    def set_alignment_rules(self, rules: int):
+        """PM_ALIGN_PCR_MATCH: the alignment pcr_match makes of every hit (differs from
+        primer_match's for k = 0 with wildcards)."""
+        _check(lib().pm_set_alignment_rules(self._h, rules))
 
     def set_stream(self, cuda_stream: int):
         _check(lib().pm_set_stream(self._h, C.c_void_p(cuda_stream)))
@@ -613,6 +620,7 @@ def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=Fals
             sc.add_pattern(pats[i], i + 1, esb[0], eeb[0])
             sc.add_pattern(pats[i + n], i + n + 1, esb[1], eeb[1])
         sc.init()
+        sc.set_alignment_rules(PM_ALIGN_PCR_MATCH)
         sc.set_text(stream.chars)
         hits = sc.find_patterns(bogus_ok=True)
         patlen = [0] + [len(p) for p in pats]

@@ -328,6 +328,7 @@ int main(int argc, char **argv) {
                                       opt.device);
   // a hit whose alignment at its own position fails is simply never paired (pcr_match.cc:1114)
   pm->tolerate_bogus(true);
+  pm->alignment_rules(PM_ALIGN_PCR_MATCH);
   for (unsigned long i = 1; i <= N1; i++) pm->add_pattern(patarray[i], i, patconst[i].first, patconst[i].second);
   pm->init(ff);
 

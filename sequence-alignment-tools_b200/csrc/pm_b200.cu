@@ -155,6 +155,7 @@ struct pm_ctx {
   pm_ctx *inner = nullptr;   // exact_halves / exact_bases: the exact index over the pattern parts
   bool inner_bases = false;  // ... exact_bases
   bool unordered_ok = false; // this IS such an inner context: run_scan may leave the candidates unsorted
+  int align_rules = PM_ALIGN_PRIMER_MATCH;  // whose alignment an exact (k == 0) hit gets, pm_set_alignment_rules
   DevBuf d_half_rec, d_half_key, d_half_key2, d_half_ord, d_half_ord2;
   int max_len = 0;
   // symbols
@@ -271,7 +272,7 @@ __global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64
 // (pattern_alignment.cc:40-68) / exact_wc_alignment (pattern_alignment.cc:70-93).
 __global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *keys, uint64_t n,
                                   const uint32_t *slot_id, int64_t offset, pm_hit *hits,
-                                  unsigned long long *sortkey, unsigned long long *n_bogus) {
+                                  unsigned long long *sortkey, unsigned long long *n_bogus, int pcr_rules) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = keys[i];
@@ -286,8 +287,12 @@ __global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *
     uint8_t code = AC_EQUAL;
     if (env.wc) {
       const uint32_t tc = env.text[pos - m + j], pc = pat[j];
+      // exact_wc_alignment asks iupac_compatible(text, pattern) (pattern_alignment.cc:79), the
+      // editdist_alignment pcr_match makes at k = 0 too asks iupac_compatible(pattern, text)
+      // (pattern_alignment.cc:317); without an error to spend, that is its whole difference
+      const bool compat = pcr_rules ? compat_bit(env.compat, pc, tc) : compat_bit(env.compat, tc, pc);
       if (tc == pc) code = AC_EQUAL;
-      else if (compat_bit(env.compat, tc, pc) && (env.tn || tc != 'N')) code = AC_WC_EQUAL;
+      else if (compat && (env.tn || tc != 'N')) code = AC_WC_EQUAL;
       else { code = AC_SUBST; sub++; }
     }
     if (j < PM_MAX_CODES) out.codes[j] = code;
@@ -809,7 +814,7 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
       PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
       exact_hits_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
           env, keys, ncand, c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
-          c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
+          c->d_sortk.as<unsigned long long>(), c->d_counters + 3, c->align_rules == PM_ALIGN_PCR_MATCH);
       PM_CUDA(cudaGetLastError());
       c->stats.kernel_launches++;
       n_out = ncand;
@@ -1083,6 +1088,13 @@ void pm_destroy(pm_ctx *c) {
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->prep_stream) cudaStreamDestroy(c->prep_stream);
   delete c;
+}
+
+int pm_set_alignment_rules(pm_ctx *c, int rules) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  if (rules != PM_ALIGN_PRIMER_MATCH && rules != PM_ALIGN_PCR_MATCH) return fail(PM_E_ARG, "bad alignment rules");
+  c->align_rules = rules;
+  return PM_OK;
 }
 
 int pm_set_scan_path(pm_ctx *c, int path) {

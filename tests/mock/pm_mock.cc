@@ -52,6 +52,7 @@ void pm_destroy(pm_ctx *ctx) { delete ctx; }
 int pm_add_pattern(pm_ctx *, const char *, uint32_t, int, int) { return PM_OK; }
 int pm_init(pm_ctx *) { return PM_OK; }
 int pm_reset(pm_ctx *) { return PM_OK; }
+int pm_set_alignment_rules(pm_ctx *, int) { return PM_OK; }
 
 int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *, uint64_t, int) {
   c->stream = slurp("stream.bin");
