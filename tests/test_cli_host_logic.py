@@ -218,3 +218,46 @@ def test_pm_pcr_pairs_on_oracle_hits(pkg, built_lib, oracle, pcr_golden):
                [(r.stream_end, r.stream_end1, r.pair, len(r.amplicon)) for r in want], "case %s" % case["seed"]
         n += len(got)
     assert n > 300
+
+
+def test_primer_match_constraint_options_and_index_selections(oracle, halves_golden, constraints_golden, mock_tools,
+                                                              tmp_path):
+    """The command lines of make_halves_golden.py / make_constraints_golden.py (-N 0 / 5 / 13,
+    -s / -e / -5 / -3 with the `~n` form) through bin/primer_match on the oracle's hits: every
+    record field the reference printed."""
+    import make_constraints_golden
+    tools, real = mock_tools
+    fmt = "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\t%S\\t%E\\t%A\\n"
+    n = 0
+    for gi, g in enumerate((halves_golden, constraints_golden)):
+        for case in g["cases"]:
+            d = str(tmp_path / ("g%d_%s" % (gi, case["seed"])))
+            os.makedirs(d)
+            par, prm = case["params"], case["primers"]
+            cons = case.get("constraints", dict(stlen=0, edlen=0, fplen=0, tplen=0))
+            fasta = case["fasta"].encode("latin-1")
+            st = oracle.normalize_fasta(fasta)
+            pats = oracle.pattern_array(prm, par["rev_comp"])
+            lc, rc = oracle.pattern_constraints(prm, par["rev_comp"], **cons)
+            index = case.get("index", "exact_halves") if gi else "exact_halves"
+            hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"], par["wc"], par["tn"], index=index)
+            write_mock_inputs(d, fasta, st, hits)
+            fa = os.path.join(d, "db.fasta")
+            with open(fa, "wb") as f:
+                f.write(fasta)
+            args = ["-i", fa, "-p", " ".join(prm), "-A", fmt]
+            if par["k"] > 0:
+                args += ["-k" if par["indels"] else "-K", str(par["k"])]
+            if par["rev_comp"]:
+                args.append("-r")
+            if par["wc"]:
+                args.append("-W" if par["tn"] else "-w")
+            if case["select"]:
+                args += ["-N", str(case["select"])]
+            args += make_constraints_golden.cli_constraints(cons)
+            got = run_tool(tools["primer_match"], args, d, real)
+            recs = sorted((int(f[0]), int(f[1]), int(f[2]), f[3], int(f[4]), int(f[5]), int(f[6]), int(f[7]), f[8])
+                          for f in (line.split("\t") for line in got.splitlines()))
+            assert recs == sorted(tuple(r) for r in case["records"]), "golden %d case %s" % (gi, case["seed"])
+            n += 1
+    assert n >= 90
