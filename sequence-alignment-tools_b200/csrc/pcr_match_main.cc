@@ -122,32 +122,6 @@ Options parse(int argc, char **argv) {
   return o;
 }
 
-// sts_entry (sts_io.h:11-37, sts_io.cc:12-47): one line of a UniSTS file.  One object is
-// read into over and over, as the reference does: fields a short line does not have keep
-// the previous line's values.
-struct StsEntry {
-  std::string id, forward_primer, reverse_primer, acc, chrom, altacc, species;
-  unsigned long sizelb = 0, sizeub = 0;
-  bool read(std::istream &is) {
-    std::string line;
-    if (!std::getline(is, line)) return false;
-    std::istringstream iss(line);
-    std::string size;
-    iss >> id >> forward_primer >> reverse_primer >> size >> acc >> chrom >> altacc;
-    const std::string::size_type p = size.find("-");
-    if (p != std::string::npos) {
-      sizelb = (unsigned long)std::atoi(size.substr(0, p).c_str());
-      sizeub = (unsigned long)std::atoi(size.substr(p + 1).c_str());
-    } else {
-      sizelb = sizeub = (unsigned long)std::atoi(size.c_str());
-    }
-    std::string rest;
-    std::getline(iss, rest);
-    species = rest;
-    return true;
-  }
-};
-
 std::string spaces(long v) {  // pcr_match.cc:264-268
   std::string ret = " ";
   while (v /= 10) ret += ' ';

@@ -7,6 +7,7 @@
 
 #include <cstdlib>
 #include <iostream>
+#include <sstream>
 #include <string>
 #include <utility>
 #include <vector>
@@ -116,6 +117,45 @@ inline void read_fasta_patterns(std::istream &is, std::vector<std::string> &pats
     }
   }
   if (have && !seq.empty()) { pats.push_back(seq); defs.push_back(def); }
+}
+
+// sts_entry (sts_io.h:11-37, sts_io.cc:12-47): one line of a UniSTS file.  One object is
+// read into over and over, as the reference does: fields a short line does not have keep
+// the previous line's values.
+struct StsEntry {
+  std::string id, forward_primer, reverse_primer, acc, chrom, altacc, species;
+  unsigned long sizelb = 0, sizeub = 0;
+  bool read(std::istream &is) {
+    std::string line;
+    if (!std::getline(is, line)) return false;
+    std::istringstream iss(line);
+    std::string size;
+    iss >> id >> forward_primer >> reverse_primer >> size >> acc >> chrom >> altacc;
+    const std::string::size_type p = size.find("-");
+    if (p != std::string::npos) {
+      sizelb = (unsigned long)std::atoi(size.substr(0, p).c_str());
+      sizeub = (unsigned long)std::atoi(size.substr(p + 1).c_str());
+    } else {
+      sizelb = sizeub = (unsigned long)std::atoi(size.c_str());
+    }
+    std::string rest;
+    std::getline(iss, rest);
+    species = rest;
+    return true;
+  }
+};
+
+// the codes both tools print from an sts_entry (primer_match.cc:500-521 / 791-812, pcr_match.cc:498-549);
+// false when `code` is not one of them
+inline bool sts_code(std::ostream &os, char code, const StsEntry &sts) {
+  switch (code) {
+    case 'I': os << sts.id; return true;
+    case 'a': os << sts.acc; return true;
+    case 'O': os << sts.species; return true;
+    case '&': os << sts.altacc; return true;
+    case 'X': os << sts.chrom; return true;
+    default: return false;
+  }
 }
 
 }  // namespace pmcli

@@ -6,8 +6,8 @@
 // on the GPU through include/pm_pattern_match.hpp; there is no CPU scan.
 //
 // Not available here (the reference features outside the accelerated path):
-// -S (UniSTS input), -T (translation), -x (hash seeds), -k .N (DNA mutation
-// scoring), -D/-B/-I (database index files: the FASTA file is read whole).
+// -T (translation), -x (hash seeds), -k .N (DNA mutation scoring), -D/-B/-I
+// (database index files: the FASTA file is read whole).
 #include <getopt.h>
 #include <unistd.h>
 
@@ -30,7 +30,7 @@ namespace {
 
 struct Options {
   std::string patterns, database;
-  bool pattern_file = false, fasta_pattern_file = false;
+  bool pattern_file = false, fasta_pattern_file = false, sts_pattern_file = false;
   bool rev_comp = false, ucdict = false;
   int tplen = 0, fplen = 0, stlen = 0, edlen = 0;
   int eos_char = '\n';
@@ -48,7 +48,7 @@ void usage(const char *msg) {
   if (msg && *msg) std::cerr << msg << "\n\n";
   std::cerr << "Usage: primer_match [options]\n\n"
                "  -i <sequence-database>  FASTA database. Required.\n"
-               "  -p <sequences> | -P <file> | -F <fasta-file>   primers (\"-\" = stdin)\n"
+               "  -p <sequences> | -P <file> | -F <fasta-file> | -S <UniSTS-file>   primers (\"-\" = stdin)\n"
                "  -o <output-file>        appended to; default standard out\n"
                "  -k <n> / -K <n>         edits / substitutions permitted (0..3)\n"
                "  -r                      match reverse complements too\n"
@@ -102,7 +102,7 @@ Options parse(int argc, char **argv) {
         o.eos_char = (char)ec;
       } break;
       case 'v': case 'I': case 'B': case 'D': break;  // accepted, no effect here
-      case 'S': usage("UniSTS primer input (-S) is not available in the B200 build.");
+      case 'S': o.patterns = optarg; o.sts_pattern_file = true; o.rev_comp = true; break;  // primer_match.cc:137-141
       case 'T': usage("Translation (-T) is not available in the B200 build.");
       case 'x': usage("Exact seeds (-x) are not available in the B200 build.");
       case 'h':
@@ -121,7 +121,7 @@ Options parse(int argc, char **argv) {
 void alignformat(std::ostream &os, const std::string &f, long s, long e, long five, long three, long S, long E,
                  unsigned long i, unsigned d, const std::string &p, const std::string &P, const std::string &q,
                  const Aligned &al, const char *r, const char *R, const std::string &h, const std::string &H,
-                 unsigned long fidx) {
+                 unsigned long fidx, const StsEntry &sts) {
   unsigned mat = 0, del = 0, ins = 0, sub = 0, wcm = 0;
   for (char c : al.A) {
     switch (c) {
@@ -159,6 +159,10 @@ void alignformat(std::ostream &os, const std::string &f, long s, long e, long fi
         case 'h': os << h; break;
         case 'H': os << H; break;
         case 'f': os << fidx; break;
+        case 'L':
+          if (sts.sizeub != sts.sizelb) os << sts.sizelb << "-" << sts.sizeub;
+          else os << sts.sizelb;
+          break;
         case '%': os << "%"; break;
         case '|': os << mat; break;
         case '^': os << del; break;
@@ -183,7 +187,8 @@ void alignformat(std::ostream &os, const std::string &f, long s, long e, long fi
             start0 = end0;
           }
         } break;
-        default: os << f[pos];
+        default:
+          if (!sts_code(os, f[pos], sts)) os << f[pos];
       }
     } else if (f[pos] == '\\') {
       escape(os, f, pos);
@@ -196,7 +201,7 @@ void alignformat(std::ostream &os, const std::string &f, long s, long e, long fi
 // countformat, primer_match.cc:750-838
 void countformat(std::ostream &os, const std::string &f, unsigned long i, const std::string &p, const std::string &P,
                  const std::string &q, const char *r, const char *R, unsigned long c, const unsigned long *C,
-                 unsigned k, bool gtmax) {
+                 unsigned k, bool gtmax, const StsEntry &sts) {
   for (size_t pos = 0; pos < f.size(); pos++) {
     if (f[pos] == '%') {
       pos++;
@@ -215,7 +220,12 @@ void countformat(std::ostream &os, const std::string &f, unsigned long i, const 
           break;
         case '+': if (gtmax) os << "+"; break;
         case '%': os << "%"; break;
-        default: os << f[pos];
+        case 'L':
+          if (sts.sizeub != sts.sizelb) os << sts.sizelb << "-" << sts.sizeub;
+          else os << sts.sizelb;
+          break;
+        default:
+          if (!sts_code(os, f[pos], sts)) os << f[pos];
       }
     } else if (f[pos] == '\\') {
       escape(os, f, pos);
@@ -237,7 +247,20 @@ int main(int argc, char **argv) {
   }
 
   std::vector<std::string> patterns, patdefs;
-  if (opt.fasta_pattern_file) {
+  std::vector<StsEntry> stsarray(1);  // [(i + 1) / 2] for pattern i; index 0 wasted (primer_match.cc:955-989)
+  const StsEntry null_sts;
+  if (opt.sts_pattern_file) {  // primer_match.cc:901-916: both primers of every UniSTS line
+    std::ifstream file;
+    std::istream *is = &std::cin;
+    if (opt.patterns != "-") { file.open(opt.patterns.c_str()); is = &file; }
+    StsEntry e;
+    while (e.read(*is)) {
+      if (e.forward_primer == "") break;
+      patterns.push_back(e.forward_primer);
+      patterns.push_back(e.reverse_primer);
+      stsarray.push_back(e);
+    }
+  } else if (opt.fasta_pattern_file) {
     if (opt.patterns == "-") read_fasta_patterns(std::cin, patterns, patdefs);
     else { std::ifstream f(opt.patterns.c_str()); read_fasta_patterns(f, patterns, patdefs); }
   } else if (opt.pattern_file) {
@@ -308,7 +331,7 @@ int main(int argc, char **argv) {
         const std::string patdef = opt.fasta_pattern_file ? patdefs[ind - 1] : std::string();
         alignformat(*out, opt.alignformat, sps, spe, rc ? spe : sps, rc ? sps : spe, ps, pe, ind, ed, patarray[ind],
                     patdef, pat, al, rc ? "R" : "F", rc ? " REVCOMP" : "", ff.header(p), ff.short_header(p),
-                    ff.index(p));
+                    ff.index(p), opt.sts_pattern_file ? stsarray[(ind + 1) / 2] : null_sts);
       }
       if (opt.counts) {
         patcount[idx(pid, ed)]++;
@@ -330,8 +353,10 @@ int main(int argc, char **argv) {
       for (unsigned k = 0; k <= K; k++) { counts[k] = patcount[idx(i, k)]; total += counts[k]; }
       bool gtmax = opt.maxcount > 0 ? (bool)maxpatcount[i] : false;
       const std::string patdef = opt.fasta_pattern_file ? patdefs[i - 1] : std::string();
+      const StsEntry &sts = opt.sts_pattern_file ? stsarray[(i + 1) / 2] : null_sts;
       if (!opt.aggregate)
-        countformat(*out, opt.countformat, i, patarray[i], patdef, patarray[i], "F", "", total, counts.data(), K, gtmax);
+        countformat(*out, opt.countformat, i, patarray[i], patdef, patarray[i], "F", "", total, counts.data(), K, gtmax,
+                    sts);
       if (opt.rev_comp) {
         if (!opt.aggregate) {
           total = 0;
@@ -342,10 +367,10 @@ int main(int argc, char **argv) {
         if (opt.maxcount > 0) gtmax = gtmax || maxpatcount[i + n];
         if (!opt.aggregate)
           countformat(*out, opt.countformat, i, patarray[i], patdef, patarray[i + n], "R", " REVCOMP", total,
-                      counts.data(), K, gtmax);
+                      counts.data(), K, gtmax, sts);
       }
       if (opt.aggregate)
-        countformat(*out, opt.countformat, i, patarray[i], patdef, "", "", "", total, counts.data(), K, gtmax);
+        countformat(*out, opt.countformat, i, patarray[i], patdef, "", "", "", total, counts.data(), K, gtmax, sts);
     }
   }
   out->flush();

@@ -261,3 +261,40 @@ def test_primer_match_constraint_options_and_index_selections(oracle, halves_gol
             assert recs == sorted(tuple(r) for r in case["records"]), "golden %d case %s" % (gi, case["seed"])
             n += 1
     assert n >= 90
+
+
+def test_primer_match_unists_input(oracle, mock_tools, tmp_path):
+    """primer_match -S: primers and the %I %L %a %O %& %X codes from a UniSTS file, in the
+    alignment and the count formats (tests/golden/make_sts_golden.py)."""
+    import json
+    import make_sts_golden
+    tools, real = mock_tools
+    with open(os.path.join(ROOT, "tests", "golden", "primer_match_sts_golden.json")) as f:
+        g = json.load(f)
+    assert len(g["cases"]) >= 8
+    for case in g["cases"]:
+        d = str(tmp_path / ("s%d" % case["seed"]))
+        os.makedirs(d)
+        par, prm = case["params"], case["primers"]
+        fasta = case["fasta"].encode("latin-1")
+        st = oracle.normalize_fasta(fasta)
+        pats = oracle.pattern_array(prm, True)              # -S implies -r (primer_match.cc:137-141)
+        lc, rc = oracle.pattern_constraints(prm, True)
+        hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"])
+        write_mock_inputs(d, fasta, st, hits)
+        fa, sp = os.path.join(d, "db.fasta"), os.path.join(d, "primers.sts")
+        with open(fa, "wb") as f:
+            f.write(fasta)
+        with open(sp, "w") as f:
+            f.write(case["sts"])
+        args = make_sts_golden.sts_cli_args(fa, sp, par)
+        got = run_tool(tools["primer_match"], args + ["-A", make_sts_golden.ALIGN_FORMAT], d, real)
+        assert sorted(got.splitlines()) == sorted(case["stdout_align"].splitlines()), "case %d" % case["seed"]
+        got = run_tool(tools["primer_match"], args + ["-C", make_sts_golden.COUNT_FORMAT], d, real)
+        assert got == case["stdout_counts"], "counts, case %d" % case["seed"]
+        got = run_tool(tools["primer_match"], args + ["-C", make_sts_golden.COUNT_FORMAT, "-a"], d, real)
+        assert got == case["stdout_counts_agg"], "aggregate counts, case %d" % case["seed"]
+        with open(sp) as f:
+            got = run_tool(tools["primer_match"], ["-S", "-"] + args[args.index("-S") + 2:] + ["-i", fa, "-A",
+                           make_sts_golden.ALIGN_FORMAT], d, real, stdin=f.read().encode())
+        assert sorted(got.splitlines()) == sorted(case["stdout_align"].splitlines())
