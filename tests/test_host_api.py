@@ -71,3 +71,41 @@ def test_create_rejects_bad_options_or_missing_gpu(pkg, built_lib):
         assert b"CUDA" in built_lib.pm_last_error()
         with pytest.raises(pkg.PmError):
             pkg.Scanner(k=1)
+
+
+def _hits(pkg, rows):
+    arr = np.zeros(len(rows), pkg.HIT_DTYPE)
+    for i, (pid, start, end, ed) in enumerate(rows):
+        arr[i]["pattern_id"], arr[i]["start"], arr[i]["end"], arr[i]["first"], arr[i]["editdist"] = pid, start, end, end, ed
+    return arr
+
+
+def test_pcr_pairs_edge_cases(pkg, built_lib):
+    """pm_pcr_pairs is host code: no hits, an odd number of primers (pcr_match.cc:768), hits whose
+    own alignment failed, amplicons across two FASTA entries, -m / -M, and the rule that a hit
+    only pairs with partners that come after it."""
+    keys = np.array([1, 1001], np.int64)           # two entries: [1, 1000) and [1001, ...)
+    patlen = [0, 20, 20, 20, 20]                   # one pair, n = 2 (ids 3, 4 = reverse complements)
+    assert pkg.pcr_pairs(_hits(pkg, []), 2, patlen, keys) == []
+    with pytest.raises(pkg.PmError):
+        pkg.pcr_pairs(_hits(pkg, []), 3, patlen + [20, 20], keys)
+    fwd, rev = (1, 100, 120, 0), (2, 400, 420, 0)
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, rev]), 2, patlen, keys) == [(0, 1, 320, 1)]
+    assert pkg.pcr_pairs(_hits(pkg, [rev, fwd]), 2, patlen, keys) == [(1, 0, 320, 1)]     # input order is free
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, rev]), 2, patlen, keys, maxdist=300) == []
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, rev]), 2, patlen, keys, mindist=321) == []
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, rev]), 2, patlen, keys, betweenlen=True, maxdist=300) == [(0, 1, 280, 1)]
+    # the reverse primer's site first: nothing (id 2 starts no pair, and it had its turn before id 1 looks)
+    assert pkg.pcr_pairs(_hits(pkg, [(2, 100, 120, 0), (1, 400, 420, 0)]), 2, patlen, keys) == []
+    # the other strand: id 4 (the reverse primer as given) leads, id 3 follows
+    assert pkg.pcr_pairs(_hits(pkg, [(4, 100, 120, 0), (3, 400, 420, 0)]), 2, patlen, keys) == [(0, 1, 320, 1)]
+    # a hit with more errors than k is never paired (pcr_match.cc:1114)
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, (2, 400, 420, 2)]), 2, patlen, keys, k=1) == []
+    assert pkg.pcr_pairs(_hits(pkg, [fwd, (2, 400, 420, -1)]), 2, patlen, keys, k=1) == []
+    # an amplicon may not span two entries (fasta_io.t:203-213)
+    assert pkg.pcr_pairs(_hits(pkg, [(1, 900, 920, 0), (2, 1100, 1120, 0)]), 2, patlen, keys) == []
+    # every later partner inside the window, nearest first; -a adds the same-strand orientations
+    got = pkg.pcr_pairs(_hits(pkg, [fwd, rev, (2, 500, 520, 0), (4, 600, 620, 0)]), 2, patlen, keys)
+    assert got == [(0, 1, 320, 1), (0, 2, 420, 1)]
+    got = pkg.pcr_pairs(_hits(pkg, [fwd, rev, (2, 500, 520, 0), (4, 600, 620, 0)]), 2, patlen, keys, allorient=True)
+    assert got == [(0, 1, 320, 1), (0, 2, 420, 1), (0, 3, 520, 1)]
