@@ -447,7 +447,10 @@ def main():
             if args.indels and K:
                 kname = "pair_scan_kernel<true> + index_verify_kernel<%d>" % K
             else:
-                kname = "pair_scan_sub_kernel<%d, %d>" % (st_last["index_q"], st_last["index_nd"])
+                # third template argument: the level-1b variant (24 000 < entries <= 100 000, csrc/pm_b200.cu)
+                kname = "pair_scan_sub_kernel<%d, %d, %s>" % (
+                    st_last["index_q"], st_last["index_nd"],
+                    "true" if 24000 < st_last["index_entries"] <= 100000 else "false")
             tsrc = "ncu --set full capture prof_pairsub_r1 (profiles/README.md), bytes per base x bases"
         else:
             n_planes = 5 if not args.iupac else 16
