@@ -155,6 +155,9 @@ void alignformat(std::ostream &os, const std::string &f, long s, long e, long fi
         case 'R': os << R; break;
         case 't': os << al.t; break;
         case 'T': os << al.T; break;
+        case 'U': os << (std::string(r) == "R" ? reverse_comp(al.t) : al.t); break;  // the text in primer orientation
+        case 'F': os << -1; break;  // reading frame: -T only (default argument, primer_match.cc:378)
+        case 'n': break;            // translated bases: -T only
         case 'A': os << al.A; break;
         case 'h': os << h; break;
         case 'H': os << H; break;

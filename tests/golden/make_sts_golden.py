@@ -24,7 +24,7 @@ sys.path.insert(0, HERE)
 import pm_oracle as O  # noqa: E402
 from make_pcr_golden import make_pcr_case, sts_lines  # noqa: E402
 
-ALIGN_FORMAT = r"%f\t%s\t%e\t%r\t%i\t%d\t%S\t%E\t%A\t%I|%L|%a|%O|%&|%X\n"
+ALIGN_FORMAT = r"%f\t%s\t%e\t%r\t%i\t%d\t%S\t%E\t%A\t%I|%L|%a|%O|%&|%X|%U|%F|%n|%D\n"
 COUNT_FORMAT = r"%i %r %c ( %C ) %I|%L|%a|%O|%&|%X\n"
 
 
