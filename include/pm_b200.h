@@ -246,6 +246,9 @@ typedef struct pm_stats {
   uint64_t n_ambiguous;     /* INDEX: text characters re-examined on the raw text
                                (they match pattern symbols without being one of
                                the four text codes, e.g. a text 'R' under -w)   */
+  uint64_t host_syncs;      /* times the call waited for the device: 2 for the
+                               bit-vector and exact indexes (scan counters, then
+                               every other count together with the records)    */
   float pack_ms;            /* device time of the last pack kernel             */
   float scan_ms;            /* device time of the dense scan kernel            */
   float total_ms;           /* device time of the whole call                   */

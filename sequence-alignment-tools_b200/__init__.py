@@ -67,7 +67,7 @@ class Stats(C.Structure):
                 ("n_bogus", C.c_uint64), ("kernel_launches", C.c_uint64), ("scan_items", C.c_uint64),
                 ("scan_warp_steps", C.c_uint64), ("scan_path", C.c_uint32), ("index_q", C.c_uint32),
                 ("index_nd", C.c_uint32), ("index_pieces", C.c_uint32), ("index_lookups", C.c_uint64),
-                ("index_entries", C.c_uint64), ("n_ambiguous", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
+                ("index_entries", C.c_uint64), ("n_ambiguous", C.c_uint64), ("host_syncs", C.c_uint64), ("pack_ms", C.c_float), ("scan_ms", C.c_float), ("total_ms", C.c_float)]
 
 
 class PcrOptions(C.Structure):
@@ -232,9 +232,11 @@ class Scanner:
                 self._keep = chars
                 _check(lib().pm_set_text_device(self._h, C.c_void_p(chars.data_ptr()), n, offset))
             else:
+                self._keep = chars     # page-locked memory is read by DMA after the call returns
                 _check(lib().pm_set_text_host(self._h, C.c_void_p(chars.data_ptr()), n, offset))
             return
         a = np.ascontiguousarray(chars, np.uint8)
+        self._keep = a
         _check(lib().pm_set_text_host(self._h, C.c_void_p(a.ctypes.data), a.size, offset))
 
     def set_text_sqz(self, sqz, table: bytes, n_chars: int = 0, offset: int = 0):

@@ -135,7 +135,8 @@ struct Pattern {
 };
 
 constexpr size_t kStageBytes = 64u << 20;       // pinned staging buffer (x2)
-constexpr uint64_t kWsBudget = 2ull << 30;      // alignment workspace per batch
+constexpr uint64_t kDirectOutBytes = 64ull << 20;  // records written straight to page-locked memory up to this bound
+constexpr size_t kPoolBytes = 32u << 20;        // initial pool of the long-chain alignments
 constexpr int64_t kRightGuard = 1 << 16;
 constexpr uint64_t kAmbCap = 1u << 20;          // ambiguous text characters the index path re-examines
 constexpr int kGuardTooShort = -101;           // internal: an owned chain runs into the end of the right guard
@@ -184,6 +185,9 @@ struct pm_ctx {
   size_t ev_used = 0;
   bool pack_timed = false;
   // work buffers
+  DevBuf d_pool;   // storage of the chain alignments whose band exceeds ALIGN_BAND_MAX (bump-allocated)
+  bool out_direct = false;   // the last call wrote its records straight to h_out
+  int n_sm = 148;
   DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
@@ -239,18 +243,51 @@ AlignEnv make_env(pm_ctx *c) {
   return e;
 }
 
-// final alignment of one reported hit: primer_match.cc:1132-1153
-__global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64_t n,
-                                   uint64_t ws_stride, uint8_t *ws, const uint32_t *slot_id,
-                                   int64_t offset, pm_hit *hits, unsigned long long *sortkey,
-                                   unsigned long long *n_bogus) {
+// Device-side counters of a context (c->d_counters / c->h_counters): the tail of a call reads
+// its counts from here instead of from the host, so that one call costs one read-back.
+enum : int {
+  CTR_COUNT = 0,      // raw candidates appended by the scan kernels
+  CTR_SEEDS = 1,      // edit mode: seeds verified (all batches)
+  CTR_UNIQ = 2,       // sorted unique candidates
+  CTR_BOGUS = 3,
+  CTR_RAW = 4,        // hits after the chain alignment / exact_halves rule
+  CTR_WORK = 5,
+  CTR_SEED_N = 6,     // seeds of the current batch
+  CTR_SEED_OVF = 7,
+  CTR_AMB = 8,        // ambiguous text characters of the packed text
+  CTR_CUT = 9,        // an owned chain reaches the end of the right guard
+  CTR_HALF_OK = 10,   // exact_halves: occurrences that extended
+  CTR_FA = 11,        // [11..14] FASTA normalisation carry
+  CTR_CHAINS = 16,
+  CTR_POOL = 17,      // bytes of the long-chain pool asked for
+  CTR_NHITS = 18,     // hits written by the last tail
+  CTR_N = 32
+};
+
+__global__ void store_u64_kernel(unsigned long long *p, unsigned long long v) { *p = v; }
+
+// final alignment of one reported hit: primer_match.cc:1132-1153.  R = 0, so the band is
+// 2k+1 wide and the whole alignment lives in per-thread memory.  Threads past the hit count
+// pad the sort keys (the sort runs over `bound` items, an upper bound known to the host).
+__global__ void __launch_bounds__(64)
+final_align_kernel(const AlignEnv env, const RawHit *raw, const unsigned long long *n_ptr, uint64_t bound,
+                   const uint32_t *slot_id, int64_t offset, pm_hit *hits, unsigned long long *sortkey,
+                   unsigned long long *n_bogus, unsigned long long *n_hits) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= bound) return;
+  const uint64_t n = *n_ptr;
+  if (i == 0) *n_hits = n;
+  if (i >= n) {
+    sortkey[i] = ~0ULL;
+    return;
+  }
   const RawHit h = raw[i];
   AlignResult r;
   pm_hit out;
   memset(&out, 0, sizeof out);
-  editdist_align(env, h.slot, h.end, h.end, ws + i * ws_stride, out.codes, PM_MAX_CODES, r);
+  uint8_t best[ALIGN_LOCAL_BEST];
+  int row_a[ALIGN_BAND_MAX + 2], row_b[ALIGN_BAND_MAX + 2];
+  editdist_align_band(env, h.slot, h.end, h.end, best, row_a, row_b, out.codes, PM_MAX_CODES, r);
   out.start = r.start + offset;
   out.end = r.end + offset;
   out.first = h.first + offset;
@@ -270,11 +307,18 @@ __global__ void final_align_kernel(const AlignEnv env, const RawHit *raw, uint64
 
 // exact indexes (k == 0): every candidate is a hit.  exact_alignment
 // (pattern_alignment.cc:40-68) / exact_wc_alignment (pattern_alignment.cc:70-93).
-__global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *keys, uint64_t n,
-                                  const uint32_t *slot_id, int64_t offset, pm_hit *hits,
-                                  unsigned long long *sortkey, unsigned long long *n_bogus, int pcr_rules) {
+__global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *keys, const unsigned long long *n_ptr,
+                                  uint64_t bound, const uint32_t *slot_id, int64_t offset, pm_hit *hits,
+                                  unsigned long long *sortkey, unsigned long long *n_bogus,
+                                  unsigned long long *n_hits, int pcr_rules) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= bound) return;
+  const uint64_t n = *n_ptr;
+  if (i == 0) *n_hits = n;
+  if (i >= n) {
+    sortkey[i] = ~0ULL;
+    return;
+  }
   const unsigned long long key = keys[i];
   const uint32_t slot = (uint32_t)(key >> 40);
   const int64_t pos = (int64_t)(key & 0xffffffffffULL);
@@ -310,9 +354,20 @@ __global__ void exact_hits_kernel(const AlignEnv env, const unsigned long long *
                (unsigned long long)(out.pattern_id & 0xffffffu);
 }
 
-__global__ void gather_hits_kernel(const pm_hit *in, const uint32_t *idx, uint64_t n, pm_hit *out) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = in[idx[i]];
+// hits in sorted order, written 8 bytes per thread so that a warp writes whole lines: `out`
+// may be page-locked host memory (the records then cross PCIe once, without a count on the host)
+static_assert(sizeof(pm_hit) % 8 == 0, "pm_hit is copied in 8-byte words");
+constexpr uint32_t HIT_WORDS = sizeof(pm_hit) / 8;
+__global__ void gather_hits_kernel(const pm_hit *in, const uint32_t *idx, const unsigned long long *n_ptr,
+                                   pm_hit *out) {
+  const uint64_t n_words = *n_ptr * HIT_WORDS;
+  const unsigned long long *src = reinterpret_cast<const unsigned long long *>(in);
+  unsigned long long *dst = reinterpret_cast<unsigned long long *>(out);
+  for (uint64_t f = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; f < n_words; f += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = f / HIT_WORDS;
+    const uint32_t j = (uint32_t)(f - i * HIT_WORDS);
+    dst[f] = src[(uint64_t)idx[i] * HIT_WORDS + j];
+  }
 }
 
 __global__ void iota_kernel(uint32_t *p, uint64_t n) {
@@ -341,10 +396,14 @@ int slot_bits(size_t n_slots) {
 }
 
 // ---------------------------------------------------------------------------
-// dense scan over local candidate positions [lo, hi): fills c->d_keys (sorted,
-// unique) and returns the count.
-int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
+// dense scan over local candidate positions [lo, hi): fills c->d_keys (sorted, unique).  The
+// number of candidates is left in d_counters[CTR_UNIQ]; *n_out is that number when exact_count
+// is set (one more read-back), otherwise an upper bound (the candidates before duplicates were
+// removed), which is all the tail of pm_find_patterns needs on the host.  One host
+// synchronisation: the scan's counters (candidates, seed-list / candidate-buffer overflow).
+int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_count) {
   *n_out = 0;
+  PM_CUDA(cudaMemsetAsync(c->d_counters + CTR_UNIQ, 0, sizeof(unsigned long long), c->stream));
   if (c->n == 0 || hi <= lo || c->pats.empty()) return PM_OK;
   const size_t n_slots = c->pats.size();
   const int K = c->opt.k;
@@ -487,18 +546,32 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     if ((uint64_t)nt * chunks > 0x7fffffffull) return fail(PM_E_UNSUPPORTED, "scan grid too large");
     {
       uint32_t prev_end = 0;
-      for (const pm_ctx::Chunk &ch : c->chunks) {
+      for (size_t ci = 0; ci < c->chunks.size(); ci++) {
+        const pm_ctx::Chunk &ch = c->chunks[ci];
         const uint32_t t0 = std::max(prev_end, tile0), t1 = std::min(ch.tile_end, tile1);
         prev_end = std::max(prev_end, ch.tile_end);
         if (t1 <= t0) continue;
         if (ch.ev) PM_CUDA(cudaStreamWaitEvent(ls, ch.ev, 0));
         if (c->use_index) {
           // a verification window reaches up to 63 characters past the first piece: positions lag
-          // the packed tiles by 64 so that every window lies in words that are already packed
+          // the packed tiles by 64 so that every window lies in words that are already packed.
+          // The lag is made up by the next chunk's launch; when the range ends inside this chunk
+          // (no later chunk is visited) the positions run to the end of the range instead, after
+          // the chunks holding the words behind it have arrived.
           const int64_t lag = 64;
           int64_t pb = std::max<int64_t>(ip_lo, (int64_t)t0 * TILE_POS - (t0 ? lag : 0));
-          const int64_t pe = std::min<int64_t>(ip_hi, ch.tile_end >= c->n_tiles ? (int64_t)c->n
-                                                                               : (int64_t)t1 * TILE_POS - lag);
+          int64_t pe;
+          if (ch.tile_end >= c->n_tiles) {
+            pe = std::min<int64_t>(ip_hi, (int64_t)c->n);
+          } else if (ch.tile_end < tile1) {
+            pe = std::min<int64_t>(ip_hi, (int64_t)t1 * TILE_POS - lag);
+          } else {
+            pe = ip_hi;
+            for (size_t cj = ci + 1; cj < c->chunks.size(); cj++) {
+              if ((int64_t)c->chunks[cj - 1].tile_end * TILE_POS >= ip_hi + lag) break;
+              if (c->chunks[cj].ev) PM_CUDA(cudaStreamWaitEvent(ls, c->chunks[cj].ev, 0));
+            }
+          }
           const int64_t batch_pos = (int64_t)batch_tiles * TILE_POS;
           for (; pb < pe; pb += batch_pos) {
             ia.p_begin = pb;
@@ -542,32 +615,34 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
       if (!c->chunks.empty() && c->chunks.back().ev)
         PM_CUDA(cudaStreamWaitEvent(ls, c->chunks.back().ev, 0));
     }
-    if (c->use_index && c->idx_has_amb) {
-      // ambiguous text characters: their number is known once every chunk is packed
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 8, c->d_counters + 8, sizeof(unsigned long long),
+    const bool amb_edit = c->use_index && c->idx_has_amb && edit;
+    if (c->use_index && c->idx_has_amb && !edit) {
+      // ambiguous text characters (their number is on the device once every chunk is packed):
+      // every window around one is decided on the raw text
+      amb_sub_kernel<<<(unsigned)n_sm * 16, 256, 0, c->stream>>>(a, c->d_amb.as<unsigned long long>(),
+                                                                 c->d_counters + CTR_AMB, kAmbCap, (uint32_t)K);
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches++;
+    } else if (amb_edit) {
+      // edits: the seeds of the ambiguous characters go through the seed list in batches sized
+      // on the host (rare: IUPAC text characters under -w together with -k)
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + CTR_AMB, c->d_counters + CTR_AMB, sizeof(unsigned long long),
                               cudaMemcpyDeviceToHost, c->stream));
       PM_CUDA(cudaStreamSynchronize(c->stream));
-      const uint64_t n_amb = c->h_counters[8];
+      const uint64_t n_amb = c->h_counters[CTR_AMB];
       c->stats.n_ambiguous = n_amb;
       if (n_amb > kAmbCap) return kFallbackToPlanes;
-      if (n_amb && !edit) {
-        amb_sub_kernel<<<(unsigned)std::min<uint64_t>(n_amb, (uint64_t)n_sm * 16), 256, 0, c->stream>>>(
-            a, c->d_amb.as<unsigned long long>(), n_amb, (uint32_t)K);
+      // seeds per ambiguous character and slot: (m + 2K) / (2K + 1) + 1 alignment-end windows
+      const uint64_t per_amb = (uint64_t)n_slots * ((uint64_t)(c->max_len + 2 * K) / (2 * K + 1) + 1);
+      const uint64_t batch = std::max<uint64_t>(1, a.seed_cap / std::max<uint64_t>(1, per_amb));
+      for (uint64_t a0 = 0; a0 < n_amb; a0 += batch) {
+        const uint64_t a1 = std::min(n_amb, a0 + batch);
+        PM_CUDA(cudaMemsetAsync(c->d_counters + CTR_SEED_N, 0, sizeof(unsigned long long), c->stream));
+        amb_seed_kernel<<<(unsigned)std::min<uint64_t>(a1 - a0, (uint64_t)n_sm * 16), 256, 0, c->stream>>>(
+            a, c->d_amb.as<unsigned long long>(), a0, a1, K);
+        vkern<<<n_sm * 8, VERIFY_THREADS, 0, c->stream>>>(a);
         PM_CUDA(cudaGetLastError());
-        c->stats.kernel_launches++;
-      } else if (n_amb) {
-        // seeds per ambiguous character and slot: (m + 2K) / (2K + 1) + 1 alignment-end windows
-        const uint64_t per_amb = (uint64_t)n_slots * ((uint64_t)(c->max_len + 2 * K) / (2 * K + 1) + 1);
-        const uint64_t batch = std::max<uint64_t>(1, a.seed_cap / std::max<uint64_t>(1, per_amb));
-        for (uint64_t a0 = 0; a0 < n_amb; a0 += batch) {
-          const uint64_t a1 = std::min(n_amb, a0 + batch);
-          PM_CUDA(cudaMemsetAsync(c->d_counters + 6, 0, sizeof(unsigned long long), c->stream));
-          amb_seed_kernel<<<(unsigned)std::min<uint64_t>(a1 - a0, (uint64_t)n_sm * 16), 256, 0, c->stream>>>(
-              a, c->d_amb.as<unsigned long long>(), a0, a1, K);
-          vkern<<<n_sm * 8, VERIFY_THREADS, 0, c->stream>>>(a);
-          PM_CUDA(cudaGetLastError());
-          c->stats.kernel_launches += 2;
-        }
+        c->stats.kernel_launches += 2;
       }
     }
     PM_CUDA(cudaEventRecord(c->ev[1], c->stream));
@@ -578,16 +653,18 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
     c->stats.index_pieces = c->use_index ? (uint32_t)(K + 2) : 0;
     c->stats.index_lookups = idx_lookups;
     c->stats.index_entries = c->use_index ? c->idx_entries : 0;
-    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 8 * sizeof(unsigned long long),
+    PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, 10 * sizeof(unsigned long long),
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-    c->stats.scan_ms = ms;
-    count = c->h_counters[0];
-    c->stats.n_seeds = c->h_counters[1];
-    c->stats.scan_warp_steps = c->h_counters[5];
-    if (edit && c->h_counters[7]) {
+    c->stats.host_syncs++;
+    count = c->h_counters[CTR_COUNT];
+    c->stats.n_seeds = c->h_counters[CTR_SEEDS];
+    c->stats.scan_warp_steps = c->h_counters[CTR_WORK];
+    if (c->use_index && c->idx_has_amb) {
+      c->stats.n_ambiguous = c->h_counters[CTR_AMB];
+      if (c->h_counters[CTR_AMB] > kAmbCap) return kFallbackToPlanes;
+    }
+    if (edit && c->h_counters[CTR_SEED_OVF]) {
       // a batch produced more seeds than the list holds: smaller batches, then a larger list
       if (batch_tiles > 1) batch_tiles = std::max(1u, batch_tiles / 8);
       else if (int rc = c->d_seeds.ensure(c->d_seeds.cap * 4)) return rc;
@@ -595,7 +672,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
       continue;
     }
     if (count <= cap) break;
-    // candidate buffer too small: grow and rescan
+    // candidate buffer too small (it starts at one entry per 64 characters of text): the counter
+    // kept counting, so one more pass with a buffer of that size is enough
     int rc = c->d_keys.ensure((size_t)count * 8 + 1024);
     if (rc) return rc;
     cap = c->d_keys.cap / 8;
@@ -618,7 +696,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
                                  c->d_keys2.as<unsigned long long>(), count, 0, end_bit, c->stream);
   size_t tmp2 = 0;
   cub::DeviceSelect::Unique(nullptr, tmp2, c->d_keys2.as<unsigned long long>(),
-                            c->d_keys.as<unsigned long long>(), c->d_counters + 2, count, c->stream);
+                            c->d_keys.as<unsigned long long>(), c->d_counters + CTR_UNIQ, count, c->stream);
   tmp_bytes = std::max(tmp_bytes, tmp2);
   rc = c->d_tmp.ensure(tmp_bytes);
   if (rc) return rc;
@@ -627,44 +705,51 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
                                          c->d_keys2.as<unsigned long long>(), count, 0, end_bit,
                                          c->stream));
   c->stats.kernel_launches += 4;
-  if (edit || c->use_index) {
+  const bool has_dups = edit || c->use_index;
+  if (has_dups) {
     tb = c->d_tmp.cap;
     PM_CUDA(cub::DeviceSelect::Unique(c->d_tmp.p, tb, c->d_keys2.as<unsigned long long>(),
-                                      c->d_keys.as<unsigned long long>(), c->d_counters + 2, count,
+                                      c->d_keys.as<unsigned long long>(), c->d_counters + CTR_UNIQ, count,
                                       c->stream));
-    PM_CUDA(cudaMemcpyAsync(c->h_counters + 2, c->d_counters + 2, sizeof(unsigned long long),
-                            cudaMemcpyDeviceToHost, c->stream));
-    PM_CUDA(cudaStreamSynchronize(c->stream));
-    count = c->h_counters[2];
     c->stats.kernel_launches += 2;
+    if (exact_count) {
+      PM_CUDA(cudaMemcpyAsync(c->h_counters + CTR_UNIQ, c->d_counters + CTR_UNIQ, sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.host_syncs++;
+      count = c->h_counters[CTR_UNIQ];
+    }
   } else {
     std::swap(c->d_keys, c->d_keys2);
+    store_u64_kernel<<<1, 1, 0, c->stream>>>(c->d_counters + CTR_UNIQ, count);
+    c->stats.kernel_launches++;
   }
   *n_out = count;
   return PM_OK;
 }
 
-// sort hits by their key and leave them in c->d_hits2
-int sort_hits(pm_ctx *c, uint64_t n) {
+// sort the first d_counters[CTR_NHITS] records of c->d_hits by their key (c->d_sortk; the keys
+// behind them are padding, ~0) and write them in order to `out`: c->d_hits2, or page-locked host
+// memory.  `bound` = records + padding, the count the host knows.
+int sort_hits(pm_ctx *c, uint64_t bound, pm_hit *out) {
   int rc;
-  if ((rc = c->d_sortk2.ensure(n * 8))) return rc;
-  if ((rc = c->d_idx.ensure(n * 4))) return rc;
-  if ((rc = c->d_idx2.ensure(n * 4))) return rc;
-  if ((rc = c->d_hits2.ensure(n * sizeof(pm_hit)))) return rc;
-  iota_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(c->d_idx.as<uint32_t>(), n);
+  if ((rc = c->d_sortk2.ensure(bound * 8))) return rc;
+  if ((rc = c->d_idx.ensure(bound * 4))) return rc;
+  if ((rc = c->d_idx2.ensure(bound * 4))) return rc;
+  iota_kernel<<<nblocks(bound, 256), 256, 0, c->stream>>>(c->d_idx.as<uint32_t>(), bound);
   size_t tb = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_sortk.as<unsigned long long>(),
                                   c->d_sortk2.as<unsigned long long>(), c->d_idx.as<uint32_t>(),
-                                  c->d_idx2.as<uint32_t>(), n, 0, 64, c->stream);
+                                  c->d_idx2.as<uint32_t>(), bound, 0, 64, c->stream);
   if ((rc = c->d_tmp.ensure(tb))) return rc;
   tb = c->d_tmp.cap;
   PM_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tb, c->d_sortk.as<unsigned long long>(),
                                           c->d_sortk2.as<unsigned long long>(),
-                                          c->d_idx.as<uint32_t>(), c->d_idx2.as<uint32_t>(), n, 0,
+                                          c->d_idx.as<uint32_t>(), c->d_idx2.as<uint32_t>(), bound, 0,
                                           64, c->stream));
-  gather_hits_kernel<<<nblocks(n, 128), 128, 0, c->stream>>>(c->d_hits.as<pm_hit>(),
-                                                             c->d_idx2.as<uint32_t>(), n,
-                                                             c->d_hits2.as<pm_hit>());
+  const unsigned gb = (unsigned)std::min<uint64_t>((bound * HIT_WORDS + 255) / 256, (uint64_t)c->n_sm * 16);
+  gather_hits_kernel<<<gb, 256, 0, c->stream>>>(c->d_hits.as<pm_hit>(), c->d_idx2.as<uint32_t>(),
+                                                c->d_counters + CTR_NHITS, out);
   PM_CUDA(cudaGetLastError());
   c->stats.kernel_launches += 5;
   return PM_OK;
@@ -674,34 +759,38 @@ int pack_text(pm_ctx *c);
 
 // run_scan, falling back to the bit-plane kernels when the text holds more ambiguous
 // characters than the index path is willing to re-examine one by one
-int run_scan_any(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out) {
-  int rc = run_scan(c, lo, hi, n_out);
+int run_scan_any(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_count) {
+  int rc = run_scan(c, lo, hi, n_out, exact_count);
   if (rc != kFallbackToPlanes) return rc;
   if (c->scan_path == PM_SCAN_INDEX)
     return fail(PM_E_UNSUPPORTED, "too many ambiguous text characters for the pair-seed index scan");
   c->use_index = false;  // until the next pm_set_text_*
   const uint64_t n_amb = c->stats.n_ambiguous;
   if ((rc = pack_text(c))) return rc;
-  rc = run_scan(c, lo, hi, n_out);
+  rc = run_scan(c, lo, hi, n_out, exact_count);
   c->stats.n_ambiguous = n_amb;
   return rc;
 }
 
-int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard);
+int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard, bool to_host);
 
 // The hits whose chain head lies in [begin, end).  Chains are followed past `end` into a right
 // guard; when one is still alive at the end of the guard the scan is repeated with a guard
-// eight times as long (up to the end of the loaded text).
-int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits) {
+// eight times as long (up to the end of the loaded text).  to_host: the sorted records are
+// written to c->h_out (page-locked), otherwise to c->d_hits2.
+int find_patterns_impl(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, bool to_host) {
   int64_t guard = kRightGuard;
   for (;;) {
-    const int rc = find_patterns_guarded(c, begin, end, nhits, guard);
+    const int rc = find_patterns_guarded(c, begin, end, nhits, guard, to_host);
     if (rc != kGuardTooShort) return rc;
     guard *= 8;
   }
 }
 
-int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard) {
+// Host synchronisations of one call: the scan's counters (run_scan) and the final read-back of
+// every other count together with the hit records.  Everything in between is sized by `bound`,
+// the number of raw candidates, and reads its real counts from d_counters.
+int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits, int64_t right_guard, bool to_host) {
   *nhits = 0;
   if (!c->inited) return fail(PM_E_ARG, "pm_find_patterns before pm_init");
   if (!c->d_text && c->n) return fail(PM_E_ARG, "no text");
@@ -728,13 +817,13 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
       if (hi >= (int64_t)c->n + 1) { hi = (int64_t)c->n + 1; guarded = false; }
     }
   }
-  uint64_t ncand = 0;
+  uint64_t bound = 0;   // candidates: an upper bound on every later count
   int rc;
   if (c->inner) {
     // exact_halves: every exact occurrence of a pattern half up to the end of the range (the
     // `lasthit` rule looks back, so the scan starts where the loaded text starts)
     guarded = false;
-    rc = run_scan_any(c->inner, 0, own_hi, &ncand);
+    rc = run_scan_any(c->inner, 0, own_hi, &bound, true);
     const pm_stats &is = c->inner->stats;
     c->stats.scan_ms = is.scan_ms;
     c->stats.scan_path = is.scan_path;
@@ -747,176 +836,126 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
     c->stats.index_entries = is.index_entries;
     c->stats.n_ambiguous = is.n_ambiguous;
     c->stats.kernel_launches += is.kernel_launches;
+    c->stats.host_syncs += is.host_syncs;
   } else {
-    rc = run_scan_any(c, lo, hi, &ncand);
+    rc = run_scan_any(c, lo, hi, &bound, false);
   }
   if (rc) return rc;
-  c->stats.n_candidates = ncand;
-  if (ncand == 0) goto done;
-  {
+  c->stats.n_candidates = bound;
+  unsigned long long *const dc = c->d_counters;
+  bool have_tail = false;
+  if (bound > 0) {
+    have_tail = true;
     const AlignEnv env = make_env(c);
     const unsigned long long *keys = c->d_keys.as<unsigned long long>();
-    uint64_t n_out = 0;
+    // where the sorted records go: page-locked host memory the kernels write directly (no count
+    // needed on the host), as long as the bound is moderate
+    const bool direct = to_host && bound * sizeof(pm_hit) <= kDirectOutBytes;
+    if (direct && (rc = ensure_host_out(c, bound * sizeof(pm_hit)))) return rc;
+    if (!direct && (rc = c->d_hits2.ensure(bound * sizeof(pm_hit)))) return rc;
+    pm_hit *const out = direct ? reinterpret_cast<pm_hit *>(c->h_out) : c->d_hits2.as<pm_hit>();
+    if ((rc = c->d_hits.ensure(bound * sizeof(pm_hit)))) return rc;
+    if ((rc = c->d_sortk.ensure(bound * 8))) return rc;
+    // counters of the tail: bogus, raw hits / cut flag / halves / chains, pool, hits
+    PM_CUDA(cudaMemsetAsync(dc + CTR_BOGUS, 0, 2 * sizeof(unsigned long long), c->stream));
+    PM_CUDA(cudaMemsetAsync(dc + CTR_CUT, 0, 2 * sizeof(unsigned long long), c->stream));
+    PM_CUDA(cudaMemsetAsync(dc + CTR_CHAINS, 0, 3 * sizeof(unsigned long long), c->stream));
+    const unsigned long long *n_final = dc + CTR_RAW;   // hits that get a final alignment
     if (c->inner) {
       // extend every half occurrence over the other half, order them as exact_halves.cc:113-116
       // does, apply its lasthit rule per pattern
-      if ((rc = c->d_half_rec.ensure(ncand * sizeof(HalfRec)))) return rc;
-      if ((rc = c->d_half_key.ensure(ncand * 8))) return rc;
-      if ((rc = c->d_half_key2.ensure(ncand * 8))) return rc;
-      if ((rc = c->d_half_ord.ensure(ncand * 4))) return rc;
-      if ((rc = c->d_half_ord2.ensure(ncand * 4))) return rc;
-      if ((rc = c->d_raw.ensure(ncand * sizeof(RawHit)))) return rc;
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 10, 0, sizeof(unsigned long long), c->stream));
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
-      halves_extend_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
-          env, c->inner->d_keys.as<unsigned long long>(), ncand, c->inner->d_slotid.as<uint32_t>(),
+      if ((rc = c->d_half_rec.ensure(bound * sizeof(HalfRec)))) return rc;
+      if ((rc = c->d_half_key.ensure(bound * 8))) return rc;
+      if ((rc = c->d_half_key2.ensure(bound * 8))) return rc;
+      if ((rc = c->d_half_ord.ensure(bound * 4))) return rc;
+      if ((rc = c->d_half_ord2.ensure(bound * 4))) return rc;
+      if ((rc = c->d_raw.ensure(bound * sizeof(RawHit)))) return rc;
+      // the occurrence count is exact here (run_scan read it back); kept in the inner counters
+      const unsigned long long *n_occ = c->inner->d_counters + CTR_UNIQ;
+      store_u64_kernel<<<1, 1, 0, c->stream>>>(c->inner->d_counters + CTR_UNIQ, bound);
+      if (!c->inner_bases)   // padding of the sort below
+        PM_CUDA(cudaMemsetAsync(c->d_half_key.p, 0xff, bound * 8, c->stream));
+      halves_extend_kernel<<<nblocks(bound, 128), 128, 0, c->stream>>>(
+          env, c->inner->d_keys.as<unsigned long long>(), n_occ, bound, c->inner->d_slotid.as<uint32_t>(),
           c->inner_bases ? 1 : 0, c->d_half_rec.as<HalfRec>(), c->d_half_key.as<unsigned long long>(),
-          c->d_counters + 10, own_lo, own_hi, c->d_raw.as<RawHit>(), c->d_counters + 4, ncand);
+          dc + CTR_HALF_OK, own_lo, own_hi, c->d_raw.as<RawHit>(), dc + CTR_RAW, bound);
       PM_CUDA(cudaGetLastError());
-      c->stats.kernel_launches++;
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 10, c->d_counters + 10, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      if (c->inner_bases) {
-        n_out = c->h_counters[4];          // exact_bases: every extension is a hit
-        c->stats.n_chains = n_out;
-      } else {
-      ncand = c->h_counters[10];   // from here on: the occurrences that extended
-      c->stats.n_chains = ncand;
-      if (ncand == 0) goto done;
-      iota_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(c->d_half_ord.as<uint32_t>(), ncand);
-      size_t tb = 0;
-      cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_half_key.as<unsigned long long>(),
-                                      c->d_half_key2.as<unsigned long long>(), c->d_half_ord.as<uint32_t>(),
-                                      c->d_half_ord2.as<uint32_t>(), ncand, 0, 64, c->stream);
-      if ((rc = c->d_tmp.ensure(tb))) return rc;
-      tb = c->d_tmp.cap;
-      PM_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tb, c->d_half_key.as<unsigned long long>(),
-                                              c->d_half_key2.as<unsigned long long>(),
-                                              c->d_half_ord.as<uint32_t>(), c->d_half_ord2.as<uint32_t>(), ncand,
-                                              0, 64, c->stream));
-      const uint32_t n_slots = (uint32_t)c->pats.size();
-      halves_report_kernel<<<nblocks(n_slots, 128), 128, 0, c->stream>>>(
-          c->d_half_key2.as<unsigned long long>(), c->d_half_ord2.as<uint32_t>(), c->d_half_rec.as<HalfRec>(),
-          ncand, n_slots, K, c->opt.indels, own_lo, own_hi, c->d_raw.as<RawHit>(), c->d_counters + 4, ncand);
-      PM_CUDA(cudaGetLastError());
-      c->stats.kernel_launches += 5;
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      n_out = c->h_counters[4];
+      c->stats.kernel_launches += 2;
+      if (!c->inner_bases) {
+        // (exact_bases: every extension is a hit)
+        iota_kernel<<<nblocks(bound, 256), 256, 0, c->stream>>>(c->d_half_ord.as<uint32_t>(), bound);
+        size_t tb = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tb, c->d_half_key.as<unsigned long long>(),
+                                        c->d_half_key2.as<unsigned long long>(), c->d_half_ord.as<uint32_t>(),
+                                        c->d_half_ord2.as<uint32_t>(), bound, 0, 64, c->stream);
+        if ((rc = c->d_tmp.ensure(tb))) return rc;
+        tb = c->d_tmp.cap;
+        PM_CUDA(cub::DeviceRadixSort::SortPairs(c->d_tmp.p, tb, c->d_half_key.as<unsigned long long>(),
+                                                c->d_half_key2.as<unsigned long long>(),
+                                                c->d_half_ord.as<uint32_t>(), c->d_half_ord2.as<uint32_t>(), bound,
+                                                0, 64, c->stream));
+        const uint32_t n_slots = (uint32_t)c->pats.size();
+        halves_report_kernel<<<nblocks(n_slots, 128), 128, 0, c->stream>>>(
+            c->d_half_key2.as<unsigned long long>(), c->d_half_ord2.as<uint32_t>(), c->d_half_rec.as<HalfRec>(),
+            dc + CTR_HALF_OK, n_slots, K, c->opt.indels, own_lo, own_hi, c->d_raw.as<RawHit>(), dc + CTR_RAW, bound);
+        PM_CUDA(cudaGetLastError());
+        c->stats.kernel_launches += 5;
       }
     } else if (K == 0) {
-      if ((rc = c->d_hits.ensure(ncand * sizeof(pm_hit)))) return rc;
-      if ((rc = c->d_sortk.ensure(ncand * 8))) return rc;
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, sizeof(unsigned long long), c->stream));
-      exact_hits_kernel<<<nblocks(ncand, 128), 128, 0, c->stream>>>(
-          env, keys, ncand, c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
-          c->d_sortk.as<unsigned long long>(), c->d_counters + 3, c->align_rules == PM_ALIGN_PCR_MATCH);
+      exact_hits_kernel<<<nblocks(bound, 128), 128, 0, c->stream>>>(
+          env, keys, dc + CTR_UNIQ, bound, c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
+          c->d_sortk.as<unsigned long long>(), dc + CTR_BOGUS, dc + CTR_NHITS, c->align_rules == PM_ALIGN_PCR_MATCH);
       PM_CUDA(cudaGetLastError());
       c->stats.kernel_launches++;
-      n_out = ncand;
+      n_final = nullptr;
     } else {
-      // chains
-      if ((rc = c->d_head.ensure(ncand * 4))) return rc;
-      if ((rc = c->d_incl.ensure(ncand * 4))) return rc;
-      chain_heads_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(keys, ncand, 2 * K + 1,
-                                                                    c->d_head.as<uint32_t>());
+      // chains of candidates (filter_bitvec.cc:157-168) and their yes/no alignment
+      if ((rc = c->d_head.ensure(bound * 4))) return rc;
+      if ((rc = c->d_incl.ensure(bound * 4))) return rc;
+      if ((rc = c->d_chains.ensure(bound * sizeof(Chain)))) return rc;
+      if ((rc = c->d_raw.ensure(bound * sizeof(RawHit)))) return rc;
+      chain_heads2_kernel<<<nblocks(bound, 256), 256, 0, c->stream>>>(keys, dc + CTR_UNIQ, bound, 2 * K + 1,
+                                                                     c->d_head.as<uint32_t>());
       size_t tb = 0;
       cub::DeviceScan::InclusiveSum(nullptr, tb, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(),
-                                    ncand, c->stream);
+                                    bound, c->stream);
       if ((rc = c->d_tmp.ensure(tb))) return rc;
       tb = c->d_tmp.cap;
       PM_CUDA(cub::DeviceScan::InclusiveSum(c->d_tmp.p, tb, c->d_head.as<uint32_t>(),
-                                            c->d_incl.as<uint32_t>(), ncand, c->stream));
-      uint32_t n_chains32 = 0;
-      PM_CUDA(cudaMemcpyAsync(&n_chains32, c->d_incl.as<uint32_t>() + (ncand - 1), 4,
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      const uint64_t n_chains = n_chains32;
-      c->stats.n_chains = n_chains;
-      c->stats.kernel_launches += 3;
-      if ((rc = c->d_chains.ensure(n_chains * sizeof(Chain)))) return rc;
-      if ((rc = c->d_wsb.ensure((n_chains + 1) * 8))) return rc;
-      if ((rc = c->d_wsoff.ensure((n_chains + 1) * 8))) return rc;
-      chain_fill_kernel<<<nblocks(ncand, 256), 256, 0, c->stream>>>(
-          keys, ncand, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(), c->d_chains.as<Chain>());
-      PM_CUDA(cudaMemsetAsync(c->d_wsb.as<unsigned long long>() + n_chains, 0, 8, c->stream));
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 9, 0, sizeof(unsigned long long), c->stream));
-      chain_ws_kernel<<<nblocks(n_chains, 256), 256, 0, c->stream>>>(
-          c->d_chains.as<Chain>(), n_chains, c->d_plen.as<uint8_t>(), K, own_lo, own_hi,
-          c->d_wsb.as<unsigned long long>(), guarded ? hi : 0, c->d_counters + 9);
-      tb = 0;
-      cub::DeviceScan::ExclusiveSum(nullptr, tb, c->d_wsb.as<unsigned long long>(),
-                                    c->d_wsoff.as<unsigned long long>(), n_chains + 1, c->stream);
-      if ((rc = c->d_tmp.ensure(tb))) return rc;
-      tb = c->d_tmp.cap;
-      PM_CUDA(cub::DeviceScan::ExclusiveSum(c->d_tmp.p, tb, c->d_wsb.as<unsigned long long>(),
-                                            c->d_wsoff.as<unsigned long long>(), n_chains + 1,
-                                            c->stream));
-      c->stats.kernel_launches += 4;
-      // batches of chains whose workspace fits the budget (host walks the offsets)
-      std::vector<unsigned long long> off(n_chains + 1);
-      PM_CUDA(cudaMemcpyAsync(off.data(), c->d_wsoff.p, (n_chains + 1) * 8, cudaMemcpyDeviceToHost,
-                              c->stream));
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 9, c->d_counters + 9, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      if (guarded && c->h_counters[9]) {
-        // an owned chain reaches the end of the right guard: scan further and start over
-        *nhits = 0;
-        return kGuardTooShort;
-      }
-      if ((rc = c->d_raw.ensure(n_chains * sizeof(RawHit)))) return rc;
-      PM_CUDA(cudaMemsetAsync(c->d_counters + 3, 0, 2 * sizeof(unsigned long long), c->stream));
-      uint64_t c0 = 0;
-      while (c0 < n_chains) {
-        uint64_t c1 = c0 + 1;
-        while (c1 < n_chains && off[c1 + 1] - off[c0] <= kWsBudget) c1++;
-        const unsigned long long bytes = off[c1] - off[c0];
-        if (bytes > 0) {
-          if ((rc = c->d_ws.ensure(bytes))) return rc;
-          chain_align_kernel<<<nblocks(c1 - c0, 64), 64, 0, c->stream>>>(
-              env, c->d_chains.as<Chain>(), c0, c1, c->d_wsoff.as<unsigned long long>(), off[c0],
-              c->d_ws.as<uint8_t>(), c->d_raw.as<RawHit>(), c->d_counters + 4);
-          PM_CUDA(cudaGetLastError());
-          c->stats.kernel_launches++;
-        }
-        c0 = c1;
-      }
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 4, c->d_counters + 4, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      n_out = c->h_counters[4];
+                                            c->d_incl.as<uint32_t>(), bound, c->stream));
+      chain_fill2_kernel<<<nblocks(bound, 256), 256, 0, c->stream>>>(
+          keys, dc + CTR_UNIQ, c->d_head.as<uint32_t>(), c->d_incl.as<uint32_t>(), c->d_chains.as<Chain>(),
+          dc + CTR_CHAINS);
+      if (!c->d_pool.p && (rc = c->d_pool.ensure(kPoolBytes))) return rc;
+      TailCounts tc;
+      tc.n_cands = dc + CTR_UNIQ;
+      tc.n_chains = dc + CTR_CHAINS;
+      tc.n_raw = dc + CTR_RAW;
+      tc.n_bogus = dc + CTR_BOGUS;
+      tc.cut = dc + CTR_CUT;
+      tc.pool_used = dc + CTR_POOL;
+      chain_align2_kernel<<<nblocks(bound, 64), 64, 0, c->stream>>>(
+          env, c->d_chains.as<Chain>(), tc, bound, own_lo, own_hi, guarded ? hi : 0, c->d_pool.as<uint8_t>(),
+          (unsigned long long)c->d_pool.cap, c->d_raw.as<RawHit>());
+      PM_CUDA(cudaGetLastError());
+      c->stats.kernel_launches += 5;
     }
-    if (K > 0 && n_out) {
-      // final alignment: R = 0, buffer of at most m+k characters
-      const uint64_t stride = (align_ws_bytes(c->max_len, c->max_len + K) + 15) & ~15ull;
-      if ((rc = c->d_ws.ensure(n_out * stride))) return rc;
-      if ((rc = c->d_hits.ensure(n_out * sizeof(pm_hit)))) return rc;
-      if ((rc = c->d_sortk.ensure(n_out * 8))) return rc;
-      final_align_kernel<<<nblocks(n_out, 64), 64, 0, c->stream>>>(
-          env, c->d_raw.as<RawHit>(), n_out, stride, c->d_ws.as<uint8_t>(),
-          c->d_slotid.as<uint32_t>(), c->offset, c->d_hits.as<pm_hit>(),
-          c->d_sortk.as<unsigned long long>(), c->d_counters + 3);
+    if (n_final) {
+      final_align_kernel<<<nblocks(bound, 64), 64, 0, c->stream>>>(
+          env, c->d_raw.as<RawHit>(), n_final, bound, c->d_slotid.as<uint32_t>(), c->offset,
+          c->d_hits.as<pm_hit>(), c->d_sortk.as<unsigned long long>(), dc + CTR_BOGUS, dc + CTR_NHITS);
       PM_CUDA(cudaGetLastError());
       c->stats.kernel_launches++;
     }
-    if (n_out) {
-      if ((rc = sort_hits(c, n_out))) return rc;
-      PM_CUDA(cudaMemcpyAsync(c->h_counters + 3, c->d_counters + 3, sizeof(unsigned long long),
-                              cudaMemcpyDeviceToHost, c->stream));
-      PM_CUDA(cudaStreamSynchronize(c->stream));
-      c->stats.n_bogus = c->h_counters[3];
-    }
-    *nhits = n_out;
-    c->stats.n_hits = n_out;
+    if ((rc = sort_hits(c, bound, out))) return rc;
+    c->out_direct = direct;
   }
-done:
+  // the one read-back: every count of the tail (the records are on their way to `out` already)
+  PM_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_N * sizeof(unsigned long long),
+                          cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(cudaEventRecord(c->ev[3], c->stream));
   PM_CUDA(cudaEventSynchronize(c->ev[3]));
+  c->stats.host_syncs++;
   {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
@@ -925,6 +964,33 @@ done:
       c->stats.pack_ms = ms;
     else
       cudaGetLastError();
+  }
+  if (have_tail) {
+    const unsigned long long *h = c->h_counters;
+    if (!c->inner && K > 0) {
+      if (h[CTR_POOL] > c->d_pool.cap) {
+        // chains longer than the per-thread band (repeats) asked for more pool than there is:
+        // grow it and run the call again (the scan included: rare, and the pool stays)
+        if ((rc = c->d_pool.ensure((size_t)h[CTR_POOL] + (1u << 20)))) return rc;
+        return find_patterns_guarded(c, begin, end, nhits, right_guard, to_host);
+      }
+      if (guarded && h[CTR_CUT]) return kGuardTooShort;  // an owned chain reaches the end of the right guard
+      c->stats.n_chains = h[CTR_CHAINS];
+    }
+    if (!c->inner) c->stats.n_candidates = h[CTR_UNIQ];
+    if (c->inner) c->stats.n_chains = c->inner_bases ? h[CTR_RAW] : h[CTR_HALF_OK];
+    const uint64_t n_out = h[CTR_NHITS];
+    c->stats.n_bogus = h[CTR_BOGUS];
+    c->stats.n_hits = n_out;
+    *nhits = n_out;
+    if (to_host && !c->out_direct && n_out) {
+      // more candidates than the direct window holds: the records were sorted into device
+      // memory; copy exactly the hits
+      if ((rc = ensure_host_out(c, n_out * sizeof(pm_hit)))) return rc;
+      PM_CUDA(cudaMemcpyAsync(c->h_out, c->d_hits2.p, n_out * sizeof(pm_hit), cudaMemcpyDeviceToHost, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
+      c->stats.host_syncs++;
+    }
   }
   if (c->stats.n_bogus)
     return fail(PM_E_BOGUS, "Bogus hit returned to primer_match main()");
@@ -1044,11 +1110,13 @@ int pm_create(pm_ctx **out, const pm_options *opt) {
   c->index = index;
   c->index_auto = index_auto;
   memset(&c->stats, 0, sizeof c->stats);
-  if (cudaMalloc((void **)&c->d_counters, 16 * sizeof(unsigned long long)) != cudaSuccess ||
-      cudaMallocHost((void **)&c->h_counters, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+  if (cudaMalloc((void **)&c->d_counters, CTR_N * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMallocHost((void **)&c->h_counters, CTR_N * sizeof(unsigned long long)) != cudaSuccess) {
     delete c;
     return fail(PM_E_CUDA, "allocation of counters failed");
   }
+  cudaMemset(c->d_counters, 0, CTR_N * sizeof(unsigned long long));
+  cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, opt->device);
   for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
   cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
@@ -1073,7 +1141,7 @@ void pm_destroy(pm_ctx *c) {
                     &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab,
                     &c->d_fa_raw, &c->d_fa_map, &c->d_fa_scan, &c->d_fa_cnt, &c->d_fa_chdr, &c->d_fa_start,
                     &c->d_fa_nout, &c->d_fa_nhdr, &c->d_fa_ooff, &c->d_fa_hoff, &c->d_fa_key, &c->d_fa_hs,
-                    &c->d_fa_he, &c->d_fa_tmp, &c->d_half_rec, &c->d_half_key, &c->d_half_key2, &c->d_half_ord, &c->d_half_ord2};
+                    &c->d_fa_he, &c->d_fa_tmp, &c->d_pool, &c->d_half_rec, &c->d_half_key, &c->d_half_key2, &c->d_half_ord, &c->d_half_ord2};
   for (DevBuf *b : bufs) b->release();
   if (c->d_counters) cudaFree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -1737,7 +1805,7 @@ int pm_find_patterns_device(pm_ctx *c, int64_t begin, int64_t end, const pm_hit 
                             uint64_t *nhits) {
   if (!c || !d_hits || !nhits) return fail(PM_E_ARG, "null argument");
   *d_hits = nullptr;
-  int rc = find_patterns_impl(c, begin, end, nhits);
+  int rc = find_patterns_impl(c, begin, end, nhits, false);
   if (*nhits) *d_hits = c->d_hits2.as<pm_hit>();
   return rc;
 }
@@ -1745,15 +1813,8 @@ int pm_find_patterns_device(pm_ctx *c, int64_t begin, int64_t end, const pm_hit 
 int pm_find_patterns(pm_ctx *c, int64_t begin, int64_t end, const pm_hit **hits, uint64_t *nhits) {
   if (!c || !hits || !nhits) return fail(PM_E_ARG, "null argument");
   *hits = nullptr;
-  int rc = find_patterns_impl(c, begin, end, nhits);
-  if (*nhits) {
-    int rc2 = ensure_host_out(c, *nhits * sizeof(pm_hit));
-    if (rc2) return rc2;
-    PM_CUDA(cudaMemcpyAsync(c->h_out, c->d_hits2.p, *nhits * sizeof(pm_hit), cudaMemcpyDeviceToHost,
-                            c->stream));
-    PM_CUDA(cudaStreamSynchronize(c->stream));
-    *hits = reinterpret_cast<const pm_hit *>(c->h_out);
-  }
+  int rc = find_patterns_impl(c, begin, end, nhits, true);   // records land in c->h_out
+  if (*nhits) *hits = reinterpret_cast<const pm_hit *>(c->h_out);
   return rc;
 }
 
@@ -1773,7 +1834,7 @@ int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate
   if (begin < c->offset || lo < 0) lo = 0;
   if (end == std::numeric_limits<int64_t>::max() || hi > (int64_t)c->n + 1) hi = (int64_t)c->n + 1;
   uint64_t n = 0;
-  int rc = run_scan_any(c, lo, hi, &n);
+  int rc = run_scan_any(c, lo, hi, &n, true);
   if (rc) return rc;
   c->stats.n_candidates = n;
   if (!n) return PM_OK;

@@ -145,13 +145,14 @@ __device__ __forceinline__ bool primer_global_align(const AlignEnv &env, const u
 //     is the first esb characters (esb >= eeb) or the last eeb; every occurrence that extends
 //     is a hit at once (no lasthit rule): appended to out when its end lies in [own_lo, own_hi).
 __global__ void __launch_bounds__(128)
-halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ keys, uint64_t n,
+halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ keys,
+                     const unsigned long long *__restrict__ n_ptr, uint64_t bound,
                      const uint32_t *__restrict__ inner_id, int bases, HalfRec *__restrict__ rec,
                      unsigned long long *__restrict__ sortkey, unsigned long long *__restrict__ n_ok,
                      int64_t own_lo, int64_t own_hi, RawHit *__restrict__ out, unsigned long long *__restrict__ n_out,
                      uint64_t cap) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  if (i >= bound || i >= *n_ptr) return;   // the occurrence count stays on the device
   const unsigned long long key = keys[i];
   const uint32_t hid = inner_id[(uint32_t)(key >> 40)];
   const int64_t pos = (int64_t)(key & 0xffffffffffULL);
@@ -208,11 +209,13 @@ halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ 
 // exact_halves.cc:147-171.  own_lo / own_hi: report the hits whose end lies in there.
 __global__ void __launch_bounds__(128)
 halves_report_kernel(const unsigned long long *__restrict__ sortkey, const uint32_t *__restrict__ order,
-                     const HalfRec *__restrict__ rec, uint64_t n, uint32_t n_slots, int k, int indels,
+                     const HalfRec *__restrict__ rec, const unsigned long long *__restrict__ n_ptr,
+                     uint32_t n_slots, int k, int indels,
                      int64_t own_lo, int64_t own_hi, RawHit *__restrict__ out, unsigned long long *__restrict__ n_out,
                      uint64_t cap) {
   const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= n_slots) return;
+  const uint64_t n = *n_ptr;   // records that extended (the sorted list is padded behind them)
   // first record of this pattern: lower bound of slot << 42
   uint64_t lo = 0, hi = n;
   const unsigned long long want = (unsigned long long)slot << 42;

@@ -677,7 +677,12 @@ pack_linear_kernel(const uint8_t *__restrict__ text, uint64_t n, const uint8_t *
 //
 // substitutions: every window start x-m+1 .. x of every slot
 __global__ void __launch_bounds__(256)
-amb_sub_kernel(const ScanArgs a, const unsigned long long *__restrict__ amb, uint64_t n_amb, uint32_t k) {
+amb_sub_kernel(const ScanArgs a, const unsigned long long *__restrict__ amb,
+               const unsigned long long *__restrict__ n_amb_ptr, uint64_t amb_cap, uint32_t k) {
+  // the count is read on the device (no host round trip); a list that overflowed is not worth
+  // walking, the host falls back to the bit-plane kernels
+  uint64_t n_amb = *n_amb_ptr;
+  if (n_amb > amb_cap) return;
   for (uint64_t ai = blockIdx.x; ai < n_amb; ai += gridDim.x) {
     const int64_t x = (int64_t)amb[ai];
     for (uint32_t idx = threadIdx.x; idx < a.n_slots * 32u; idx += blockDim.x) {

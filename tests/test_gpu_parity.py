@@ -158,11 +158,15 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
     import casegen
     rng = random.Random(100 * k + 10 * indels + wc)
     n = 2 * TILE_POS + 5000
-    primers = [casegen.rand_dna(rng, rng.randint(max(8, k + 6), 32)) for _ in range(10)]
-    primers[0] = "A" * 14
+    # the pair-seed index needs k+2 pieces of at least 4 characters from every primer
+    minlen = 4 * (k + 2) if path == "index" else max(8, k + 6)
+    primers = [casegen.rand_dna(rng, rng.randint(minlen, 32)) for _ in range(10)]
+    primers[0] = "A" * max(14, minlen)
     if wc:
         primers[1] = "ACGRYACGTNACGTKMAC"
         primers[2] = "WSACGTBDHVACGT"
+        for i in (1, 2):
+            primers[i] += casegen.rand_dna(rng, max(0, minlen - len(primers[i])))
     seq = list(casegen.rand_dna(rng, n))
     seams = [1024 * j + d for j in (1, 2, 31, 32, 33, 63, 64) for d in (-20, -3, 0, 5)] + \
             [TILE_POS - 10, TILE_POS - 1, TILE_POS, 2 * TILE_POS - 7, n - 25, 3]
@@ -195,11 +199,7 @@ def test_candidates_match_oracle_across_tiles(pkg, oracle, k, indels, wc, path):
                      scan_path=pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
     for i, p in enumerate(primers):
         sc.add_pattern(p, i + 1)
-    try:
-        sc.init()
-    except pkg.PmError as ex:
-        assert path == "index" and ex.code == pkg.PM_E_UNSUPPORTED   # pieces shorter than 3 characters
-        pytest.skip("pattern pieces too short for the q-gram index")
+    sc.init()      # PM_SCAN_INDEX on patterns it cannot serve fails here: never skipped
     sc.set_text(T)
     got = sc.scan_candidates()
     assert sc.stats()["scan_path"] == (pkg.PM_SCAN_INDEX if path == "index" else pkg.PM_SCAN_PLANES)
@@ -454,3 +454,44 @@ def test_host_pipeline_equals_device_path(pkg):
         sc.close()
     assert len(out[0]) >= 140
     assert all(o.tobytes() == out[0].tobytes() for o in out[1:])
+
+
+@pytest.mark.parametrize("k", [0, 2])
+def test_range_end_inside_a_chunked_text(pkg, k):
+    """pm_find_patterns(begin, end) on a text that arrived in several chunks (pm_set_text_host
+    over 64 MiB), with `end` on / just behind tile boundaries inside the first chunk and at the
+    chunk seam: the positions just before `end` must be visited although no later chunk is."""
+    import torch
+    import casegen
+    rng = random.Random(50 + k)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(30)]
+    n = 130 * (1 << 20) + 777
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    d = lut[torch.randint(0, 4, (n,), device="cuda", generator=g, dtype=torch.uint8).long()]
+    d[0] = 10
+    d[-1] = 10
+    ends = [t * TILE_POS + e for t in (1000, 2048, 2049) for e in (0, 1, 20)]
+    for t in (1000, 2048, 2049):
+        base = t * TILE_POS
+        for j in range(60):     # dense copies from 700 before to 500 past the boundary, odd spacing
+            at = base - 700 + 21 * j
+            d[at:at + 20] = torch.tensor(list(primers[j % 30].encode()), dtype=torch.uint8, device="cuda")
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h.copy_(d)
+    torch.cuda.synchronize()
+    sc = pkg.Scanner(k=k, indels=False, scan_path=pkg.PM_SCAN_INDEX)
+    for i, p in enumerate(primers):
+        sc.add_pattern(p, i + 1)
+    sc.init()
+    sc.set_text(h)
+    whole = sc.find_patterns()
+    assert len(whole) >= 180
+    for e in ends:
+        for begin in (0, 900 * TILE_POS + 5):
+            sc.set_text(h)      # a fresh chunked upload: the scan follows the copy
+            part = sc.find_patterns(begin, e)
+            want = whole[(whole["first"] >= begin) & (whole["first"] < e)]
+            assert part.tobytes() == want.tobytes(), (e, begin)
+    sc.close()
