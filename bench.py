@@ -5,19 +5,31 @@ Metric (BASELINE.json): Gbp/s scanned, 1k 20-mer primers, k=2, both strands
 (2000 patterns), bit-exact hit lists.  One "step" = one pass of the hot path
 over one synthetic random-DNA database shard per GPU:
 
-  value  stream bytes already resident in HBM -> pack kernel -> dense scan ->
+  value  stream bytes already resident in HBM -> pack kernel -> scan ->
          chains / alignment -> sorted hit list (left on the device)
-  e2e    the same through the C ABI with HOST buffers: pinned host stream ->
-         H2D -> pack -> scan -> ... -> hit list copied back to the host
+  e2e    the same through the C ABI with HOST buffers: page-locked host copy of
+         the database (.sqz form) -> H2D -> unpack -> pack -> scan -> ... ->
+         hit records written back to host memory
 
-Weak scaling: every rank scans its own shard (a multi-genome database
-partitioned at sequence boundaries); the only communication is the NCCL
-gather of hit counts and hit records at the end of each step.
+One command covers every BASELINE.json configuration (`--config`, default
+"all": the headline in full, the others as entries of `configs`) and both
+scaling modes:
 
-`--impl reference` times the UNMODIFIED reference (oracle/_ref/primer_match,
-compiled from the reference's own sources by oracle/Makefile) on the box's
-host cores, one process per core, each on its own slice of a bounded sample of
-the same workload.
+  weak    every rank scans its own shard (a multi-genome database partitioned
+          at sequence boundaries); NCCL only sums the hit counts
+  strong  ONE database (3 Gbp for the headline) is cut with shard_plan() and the
+          documented overlap, every rank scans its piece, the hit records are
+          gathered over NCCL (all_gather of counts, then of the records) and
+          rank 0 checks the gathered list byte for byte against its own scan of
+          the whole database (`strong` object; `--scaling strong` makes it the
+          headline value)
+
+At N = 1 the CPU baseline runs the UNMODIFIED reference (oracle/_ref/primer_match)
+on windows cut out of the benchmark shard itself and the GPU hit records inside
+those windows must be identical (`parity_checked_bp`).
+
+`--impl reference` times the reference on the box's host cores, one process per
+core, each on its own slice of a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -35,26 +47,68 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 PKG = "sequence-alignment-tools_b200"
 
-N_PRIMERS = 1000
-PRIMER_LEN = 20
-K = 2
-INDELS = 0
-IUPAC = 0
-SELECT = 0
+SEQ_LEN = 50_000_000          # the synthetic database: sequences of 50 Mbp
+REF_FORMAT = "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"
+
+# BASELINE.json configs 1-4 (config 0 is the reference's own CPU case).  ref_bp: bases per
+# host core of the bounded CPU sample (sized for ~5-10 s of the reference per core).
+CONFIGS = {
+    "headline": dict(nprimers=1000, plen=20, k=2, indels=0, iupac=0, select=0, bases=3_000_000_000, ref_bp=3_000_000,
+                     metric="Gbp/s scanned, 1k 20-mer primers k=2 both strands",
+                     baseline="BASELINE.json metric; configs[2] without wildcards"),
+    "iupac_k2": dict(nprimers=1000, plen=20, k=2, indels=0, iupac=1, select=0, bases=3_000_000_000, ref_bp=1_500_000,
+                     metric="Gbp/s scanned, 1k IUPAC 20-mer primers (-w) k=2 both strands",
+                     baseline="BASELINE.json configs[2]"),
+    "edit25_k3": dict(nprimers=1000, plen=25, k=3, indels=1, iupac=0, select=0, bases=3_000_000_000, ref_bp=600_000,
+                      metric="Gbp/s scanned, 1k 25-mer primers k=3 edits both strands",
+                      baseline="BASELINE.json configs[3]"),
+    "p100_k1": dict(nprimers=100, plen=20, k=1, indels=0, iupac=0, select=0, bases=100_000_000, ref_bp=6_000_000,
+                    metric="Gbp/s scanned, 100 20-mer primers k=1 both strands, 100 Mbp",
+                    baseline="BASELINE.json configs[1]"),
+    "oligo100k_exact": dict(nprimers=100_000, plen=20, k=0, indels=0, iupac=0, select=0, bases=3_750_000_000,
+                            ref_bp=4_000_000,
+                            ref_skip="the reference's keyword_tree build grows ~n^2.5 with the pattern count (0.5 s for 2 000 "
+                                     "patterns, 2.6 s for 4 000, 15 s for 8 000, measured with oracle/_ref/primer_match): "
+                                     "200 000 patterns do not finish in bounded time",
+                            metric="Gbp/s scanned, 100k 20-mer oligos exact both strands",
+                            baseline="BASELINE.json configs[4] (keyword_tree leg), 30 Gbp / 8 GPUs per shard"),
+    "oligo100k_k1": dict(nprimers=100_000, plen=20, k=1, indels=0, iupac=0, select=5, bases=3_750_000_000,
+                         ref_bp=20_000, metric="Gbp/s scanned, 100k 20-mer oligos k=1 (-N 5) both strands",
+                         baseline="BASELINE.json configs[4] (shift_and_inexact leg), 30 Gbp / 8 GPUs per shard"),
+}
+ALL_ORDER = ["headline", "iupac_k2", "edit25_k3", "p100_k1", "oligo100k_exact", "oligo100k_k1"]
 
 
-def make_primers(seed=12345, n=None, m=None):
+def make_primers(cfg, seed=12345):
     import numpy as np
-    n = N_PRIMERS if n is None else n
-    m = PRIMER_LEN if m is None else m
+    n, m = cfg["nprimers"], cfg["plen"]
     g = np.random.default_rng(seed)
     a = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, (n, m))]
-    if IUPAC:  # one to three ambiguity codes per primer, like the reference's db/patwc.txt
+    if cfg["iupac"]:  # one to three ambiguity codes per primer, like the reference's db/patwc.txt
         codes = np.frombuffer(b"RYKMSWBDHVN", np.uint8)
         for r in a:
             for _ in range(int(g.integers(1, 4))):
                 r[int(g.integers(0, m))] = codes[int(g.integers(0, len(codes)))]
     return [bytes(r).decode() for r in a]
+
+
+def ref_cmd(cfg, fasta, pfile, fmt=REF_FORMAT):
+    ref = os.path.join(ROOT, "oracle", "_ref", "primer_match")
+    return [ref, "-i", fasta, "-P", pfile, ("-k" if cfg["indels"] else "-K"), str(cfg["k"]), "-r",
+            *(["-w"] if cfg["iupac"] else []), *(["-N", str(cfg["select"])] if cfg["select"] else []), "-A", fmt]
+
+
+def workload_text(cfg):
+    return "%d random %d-mer primers%s, k=%d %s (%s %d), both strands (-r), synthetic random-DNA database" % (
+        cfg["nprimers"], cfg["plen"], " with 1-3 IUPAC codes each (-w)" if cfg["iupac"] else "", cfg["k"],
+        "edits" if cfg["indels"] else "mismatches", "-k" if cfg["indels"] else "-K", cfg["k"])
+
+
+def index_text(cfg):
+    if cfg["select"]:
+        return "-N %d" % cfg["select"]
+    return "automatic (pick_pattern_index): " + ("exact index" if cfg["k"] == 0 else
+                                                  "exact_halves" if (cfg["k"] == 1 and cfg["plen"] >= 8) else "filter_bitvec")
 
 
 # ---------------------------------------------------------------------------
@@ -103,7 +157,6 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ---------------------------------------------------------------------------
 def visible_gpu_index(local_rank: int) -> int:
     cvd = os.environ.get("CUDA_VISIBLE_DEVICES")
     if cvd:
@@ -114,41 +167,11 @@ def visible_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
-def run_reference_sample(primers, total_bases: int, procs: int, seed: int, workdir: str):
-    """One timed pass of the unmodified reference over `total_bases` of random DNA,
-    split over `procs` processes.  Returns seconds (wall, all processes)."""
-    import numpy as np
-    ref = os.path.join(ROOT, "oracle", "_ref", "primer_match")
-    per = total_bases // procs
-    g = np.random.default_rng(seed)
-    files = []
-    pfile = os.path.join(workdir, "primers.txt")
-    with open(pfile, "w") as f:
-        f.write("\n".join(primers) + "\n")
-    for i in range(procs):
-        seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, per)]
-        path = os.path.join(workdir, "s%d_%d.fasta" % (seed, i))
-        with open(path, "wb") as f:
-            f.write(b">sample%d\n" % i)
-            body = seq.reshape(-1, 80) if per % 80 == 0 else None
-            if body is not None:
-                f.write(b"\n".join(bytes(r) for r in body))
-            else:
-                f.write(bytes(seq))
-            f.write(b"\n")
-        files.append(path)
-    t0 = time.perf_counter()
-    ps = [subprocess.Popen([ref, "-i", fp, "-P", pfile, ("-k" if INDELS else "-K"), str(K), "-r", *(["-w"] if IUPAC else []), *(["-N", str(SELECT)] if SELECT else []), "-A", "%f\\t%s\\t%e\\t%r\\t%i\\t%d\\n"],
-                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for fp in files]
-    for p in ps:
-        p.wait()
-    dt = time.perf_counter() - t0
-    for fp in files:
-        os.unlink(fp)
-    bad = [p.returncode for p in ps if p.returncode != 0]
-    if bad:
-        raise RuntimeError("reference exited with %s" % bad)
-    return dt
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def reference_available():
@@ -156,7 +179,79 @@ def reference_available():
     return os.path.exists(p) and os.access(p, os.X_OK)
 
 
-def run_oracle_sample(primers, total_bases: int, seed: int):
+# ---------------------------------------------------------------------------
+# the reference on the host cores
+def write_fasta_records(path, records):
+    """records: [(name, uint8 array of bases)]; 80 bases per line."""
+    with open(path, "wb") as f:
+        for name, seq in records:
+            f.write(b">" + name + b"\n")
+            full = len(seq) // 80 * 80
+            if full:
+                f.write(b"\n".join(bytes(r) for r in seq[:full].reshape(-1, 80)))
+                f.write(b"\n")
+            if len(seq) > full:
+                f.write(bytes(seq[full:]) + b"\n")
+
+
+REF_DEADLINE_S = 240.0
+
+
+def run_reference_files(cfg, primers, files, workdir, capture=False):
+    """One timed pass of the unmodified reference, one process per file.  Returns
+    (wall seconds over all processes, [stdout bytes per file] when capture).  The processes
+    are killed (by PID) when they exceed REF_DEADLINE_S."""
+    pfile = os.path.join(workdir, "primers_%d_%d.txt" % (cfg["nprimers"], cfg["plen"]))
+    with open(pfile, "w") as f:
+        f.write("\n".join(primers) + "\n")
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen(ref_cmd(cfg, fp, pfile), stdout=subprocess.PIPE if capture else subprocess.DEVNULL,
+                           stderr=subprocess.DEVNULL) for fp in files]
+    outs = []
+    if capture:
+        # drain the pipes concurrently (the outputs are small: a few hits per Mbp)
+        bufs = [None] * len(ps)
+
+        def drain(i, p):
+            bufs[i] = p.stdout.read()
+        ths = [threading.Thread(target=drain, args=(i, p)) for i, p in enumerate(ps)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        outs = bufs
+    for p in ps:
+        try:
+            p.wait(timeout=max(1.0, REF_DEADLINE_S - (time.perf_counter() - t0)))
+        except subprocess.TimeoutExpired:
+            for q in ps:
+                if q.poll() is None:
+                    q.kill()
+            raise RuntimeError("reference did not finish within %.0f s" % REF_DEADLINE_S)
+    dt = time.perf_counter() - t0
+    bad = [p.returncode for p in ps if p.returncode != 0]
+    if bad:
+        raise RuntimeError("reference exited with %s" % bad)
+    return dt, outs
+
+
+def run_reference_sample(cfg, primers, per_proc: int, procs: int, seed: int, workdir: str):
+    """Random DNA of the workload's shape, `per_proc` bases per process.  Returns seconds."""
+    import numpy as np
+    g = np.random.default_rng(seed)
+    files = []
+    for i in range(procs):
+        seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, per_proc)]
+        path = os.path.join(workdir, "s%d_%d.fasta" % (seed, i))
+        write_fasta_records(path, [(b"sample%d" % i, seq)])
+        files.append(path)
+    dt, _ = run_reference_files(cfg, primers, files, workdir)
+    for fp in files:
+        os.unlink(fp)
+    return dt
+
+
+def run_oracle_sample(cfg, primers, total_bases: int, seed: int):
     """Fallback CPU baseline: the oracle port (single thread)."""
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -166,69 +261,534 @@ def run_oracle_sample(primers, total_bases: int, seed: int):
     T = np.concatenate([[10], seq, [10]]).astype(np.uint8)
     st = O.Stream(T, np.array([1], np.int64), ["s"])
     t0 = time.perf_counter()
-    O.primer_match(st, primers, k=K, indels=bool(INDELS), rev_comp=True)
+    O.primer_match(st, primers, k=cfg["k"], indels=bool(cfg["indels"]), rev_comp=True, wc=bool(cfg["iupac"]))
     return time.perf_counter() - t0
 
 
-def cpu_cores():
-    try:
-        return len(os.sched_getaffinity(0))
-    except Exception:
-        return os.cpu_count() or 1
+def parse_ref_records(out: bytes):
+    """(%f, %s, %e, %r, %i, %d) records of REF_FORMAT."""
+    recs = []
+    for ln in out.decode("latin-1").splitlines():
+        p = ln.split("\t")
+        if len(p) != 6:
+            continue
+        recs.append((int(p[0]), int(p[1]), int(p[2]), p[3].strip(), int(p[4]), int(p[5])))
+    return recs
 
 
-def config_dict(args, shard_bases):
-    return {"workload": "%d random %d-mer primers%s, k=%d %s (%s %d), both strands (-r), "
-                        "synthetic random-DNA database" % (N_PRIMERS, PRIMER_LEN,
-                                                           " with 1-3 IUPAC codes each (-w)" if IUPAC else "", K,
-                                                           "edits" if INDELS else "mismatches",
-                                                           "-k" if INDELS else "-K", K),
-            "shard_bases_per_gpu": shard_bases, "patterns": 2 * N_PRIMERS,
-            "index": ("-N %d" % SELECT) if SELECT else ("automatic (pick_pattern_index): " + ("exact index" if K == 0 else "exact_halves" if (K == 1 and PRIMER_LEN >= 8) else "filter_bitvec")),
-            "l2": "inputs larger than L2 (%.1f GB stream + %.2f GB packed text per pass)" % (shard_bases / 1e9, shard_bases / 2e9),
-            "partition": "one shard per GPU, cut at sequence boundaries",
-            "host_mem": args.host_mem}
+def parity_windows(cfg, primers, d_stream, n_chars, hits, procs, per_proc, workdir, planted):
+    """The reference on `procs` windows of `per_proc` bases cut out of the benchmark shard itself
+    (some around planted primer copies, one across a sequence separator) against the GPU hit
+    records that lie inside those windows.  Returns (seconds of the reference, bp, compared, ok, detail)."""
+    import numpy as np
+    margin = 200
+    w = per_proc
+    starts = []
+    sep = SEQ_LEN if n_chars > SEQ_LEN + w else None
+    if sep is not None:
+        starts.append(max(1, sep - w // 2))                       # across a sequence separator
+    starts.append(1)                                              # the start of the database
+    for at in planted:                                            # around planted copies
+        a = max(1, min(n_chars - 1 - w, at - w // 3))
+        if all(abs(a - b) >= w for b in starts):
+            starts.append(a)
+        if len(starts) >= procs:
+            break
+    j = 0
+    while len(starts) < procs:                                    # the rest spread over the shard
+        a = 1 + (j * 7919 * 104729) % max(1, n_chars - 1 - w)
+        j += 1
+        if j > 20000 or all(abs(a - b) >= w for b in starts):
+            starts.append(a)
+    files, metas = [], []
+    for i, a in enumerate(starts):
+        b = min(n_chars - 1, a + w)
+        win = d_stream[a:b].cpu().numpy()
+        eos = np.flatnonzero(win == 10)
+        cuts = [-1] + [int(x) for x in eos] + [len(win)]
+        recs, g = [], []
+        for c0, c1 in zip(cuts, cuts[1:]):
+            if c1 - c0 - 1 > 0:
+                recs.append((b"w%d_%d" % (i, len(recs)), win[c0 + 1:c1]))
+                g.append(a + c0 + 1)                              # stream index of the record's first base
+        path = os.path.join(workdir, "win%d.fasta" % i)
+        write_fasta_records(path, recs)
+        files.append(path)
+        metas.append((a, b, g))
+    dt, outs = run_reference_files(cfg, primers, files, workdir, capture=True)
+    for fp in files:
+        os.unlink(fp)
+    npr = cfg["nprimers"]
+    want, got = set(), set()
+    for (a, b, g), out in zip(metas, outs):
+        for (f, s, e, r, i, d) in parse_ref_records(out):
+            gs, ge = s + g[f - 1], e + g[f - 1]
+            if gs >= a + margin and ge <= b - margin:
+                want.add((gs, ge, r, i, d))
+        sel = hits[(hits["start"] >= a + margin) & (hits["end"] <= b - margin)]
+        for h in sel:
+            pid = int(h["pattern_id"])
+            rc = pid > npr
+            got.add((int(h["start"]), int(h["end"]), "R" if rc else "F", pid - (npr if rc else 0), int(h["editdist"])))
+    bp = sum(b - a for a, b, _ in metas)
+    ok = want == got
+    detail = None
+    if not ok:
+        detail = {"only_reference": sorted(want - got)[:5], "only_gpu": sorted(got - want)[:5]}
+    return dt, bp, len(want), ok, detail
 
 
+# ---------------------------------------------------------------------------
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    primers = make_primers()
+    name = "headline" if args.config == "all" else args.config
+    cfg = dict(CONFIGS[name])
+    if cfg.get("ref_skip"):
+        print(json.dumps({"impl": "reference", "unavailable": "config %s: %s" % (name, cfg["ref_skip"])}))
+        return
+    primers = make_primers(cfg)
     cores = cpu_cores()
-    metric = "Gbp/s scanned, 1k 20-mer primers k=2 both strands"
     if reference_available():
         kind = "reference"
         procs = cores
-        per_proc = args.ref_bases_per_core
+        per_proc = args.ref_bases_per_core or cfg["ref_bp"]
         work = tempfile.mkdtemp(prefix="pmref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
         for w in range(args.warmup):
-            run_reference_sample(primers, max(200_000, per_proc // 8) * procs, procs, 100 + w, work)
+            run_reference_sample(cfg, primers, max(2000, per_proc // 8), procs, 100 + w, work)
         t = 0.0
         for s in range(args.steps):
-            t += run_reference_sample(primers, per_proc * procs, procs, 200 + s, work)
+            t += run_reference_sample(cfg, primers, per_proc, procs, 200 + s, work)
         total = per_proc * procs * args.steps
-        sample = "%d processes x %d bp per step, %d steps" % (procs, per_proc, args.steps)
+        sample = "%d processes x %d bp per step, %d steps (throughput of the streaming scan, not the %d bp shard)" % (
+            procs, per_proc, args.steps, cfg["bases"])
     else:
         kind = "port"
         procs = 1
-        per = 200_000
+        per = 200_000 if cfg["nprimers"] <= 1000 else 2000
         for w in range(min(args.warmup, 1)):
-            run_oracle_sample(primers, 20_000, 100 + w)
+            run_oracle_sample(cfg, primers, per // 10, 100 + w)
         t = 0.0
         for s in range(args.steps):
-            t += run_oracle_sample(primers, per, 200 + s)
+            t += run_oracle_sample(cfg, primers, per, 200 + s)
         total = per * args.steps
         sample = "oracle port, 1 thread x %d bp per step, %d steps" % (per, args.steps)
     value = total / t / 1e9
-    line = {"impl": "reference", "metric": metric, "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
+    conf = config_dict(cfg, cfg["bases"], args)
+    conf["reference_sample"] = sample
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": "Gbp/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-            "data": "synthetic", "config": config_dict(args, args.bases),
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic", "config": conf,
             "cpu_baseline": {"value": value, "unit": "Gbp/s", "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def config_dict(cfg, shard_bases, args):
+    return {"workload": workload_text(cfg), "shard_bases_per_gpu": shard_bases, "patterns": 2 * cfg["nprimers"],
+            "index": index_text(cfg), "baseline_config": cfg["baseline"],
+            "l2": "inputs larger than L2 (%.2f GB stream + %.2f GB packed text per pass)" % (shard_bases / 1e9, shard_bases / 2e9),
+            "partition": "one shard per GPU, cut at sequence boundaries (weak); one database cut by shard_plan with overlap (strong)",
+            "host_mem": args.host_mem}
+
+
+# ---------------------------------------------------------------------------
+class Bench:
+    """Everything one rank needs: the synthetic database on the device, its host copies,
+    the timing helpers."""
+
+    def __init__(self, args):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        self.np, self.torch, self.dist, self.args = np, torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.pkg = importlib.import_module(PKG)
+        self.pkg.lib()
+        self.sharding = importlib.import_module(PKG + ".sharding")
+        self.stream = torch.cuda.current_stream()
+        self.launches = 0
+        self.sqz_table = b"ACGT\n"
+        self._pats = {}
+
+    def patterns(self, name):
+        """(primers, pattern array with the reverse complements) of a configuration, cached."""
+        if name not in self._pats:
+            primers = make_primers(CONFIGS[name])
+            self._pats[name] = (primers, self.pkg.pattern_array(primers, True))
+        return self._pats[name]
+
+    # -- data ---------------------------------------------------------------
+    def make_database(self, bases, seed):
+        """eos, random ACGT in sequences of SEQ_LEN, eos: bases + 1 characters with an
+        end-of-sequence character at every multiple of SEQ_LEN (generated on the device)."""
+        torch = self.torch
+        n = bases + 1
+        gen = torch.Generator(device=self.dev)
+        gen.manual_seed(seed)
+        lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=self.dev)
+        d = torch.empty(n, dtype=torch.uint8, device=self.dev)
+        chunk = 1 << 28
+        for a in range(0, n, chunk):
+            b = min(n, a + chunk)
+            d[a:b] = lut[torch.randint(0, 4, (b - a,), device=self.dev, generator=gen, dtype=torch.uint8).long()]
+        d[0::SEQ_LEN] = 10
+        d[n - 1] = 10
+        return d
+
+    def plant(self, d, pats, k, seed, count=64, limit=None):
+        """A few exact / mutated primer copies so that the hit path is exercised."""
+        np, torch = self.np, self.torch
+        rs = np.random.default_rng(seed)
+        n = int(limit or d.numel())
+        at_list = []
+        for _ in range(count):
+            p = bytearray(pats[int(rs.integers(0, len(pats)))].encode())
+            p = bytearray(c if c in b"ACGT" else b"ACGT"[int(rs.integers(0, 4))] for c in p)
+            for _ in range(int(rs.integers(0, k + 1))):
+                p[int(rs.integers(0, len(p)))] = b"ACGT"[int(rs.integers(0, 4))]
+            at = int(rs.integers(1000, n - 1000))
+            if (at % SEQ_LEN) > SEQ_LEN - 100 or (at % SEQ_LEN) < 100:
+                continue
+            d[at:at + len(p)] = torch.tensor(list(p), dtype=torch.uint8, device=self.dev)
+            at_list.append(at)
+        return at_list
+
+    def host_copy(self, d_t):
+        """The tensor's bytes in page-locked host memory (what a pinned file reader would hold)."""
+        torch = self.torch
+        if self.args.host_mem == "wc":
+            hb = self.pkg.HostBuffer(d_t.numel(), write_combined=True)
+            torch.from_numpy(hb.array).copy_(d_t)
+            return hb
+        h = torch.empty(d_t.numel(), dtype=torch.uint8, pin_memory=True)
+        h.copy_(d_t)
+        return h
+
+    def fasta_of(self, d_stream):
+        """The FASTA file the stream came from: one record per sequence, 80 bases per line."""
+        torch = self.torch
+        n = d_stream.numel()
+        parts = []
+        bounds = list(range(0, n - 1, SEQ_LEN)) + [n - 1]
+        nl = torch.tensor([10], dtype=torch.uint8, device=self.dev)
+        for si in range(len(bounds) - 1):
+            a, b = bounds[si] + 1, bounds[si + 1]
+            if b <= a:
+                continue
+            body = d_stream[a:b]
+            full = (b - a) // 80 * 80
+            lines = torch.cat([body[:full].view(-1, 80), nl.expand(full // 80, 1)], dim=1).reshape(-1)
+            parts += [torch.tensor(list(b">synthetic%d random DNA\n" % si), dtype=torch.uint8, device=self.dev), lines]
+            if b - a > full:
+                parts += [body[full:], nl]
+        return torch.cat(parts)
+
+    # -- timing -------------------------------------------------------------
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t.tolist()]
+
+    def sum_over_ranks(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)                  # NCCL: the hit counts of all shards, summed
+        return int(t.item())
+
+    def timed(self, fn, steps, warmup):
+        """W warm-up calls, then `steps` calls between two CUDA events on the stream the
+        library launches on, bracketed by barrier + synchronize.  Returns ms (this rank)."""
+        torch = self.torch
+        for _ in range(warmup):
+            fn()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        e1.record(self.stream)
+        self.barrier()
+        return e0.elapsed_time(e1)
+
+    def scanner(self, cfg, pats):
+        sc = self.pkg.Scanner(k=cfg["k"], indels=bool(cfg["indels"]), wildcards=bool(cfg["iupac"]),
+                              device=self.local_rank, index=cfg["select"])
+        for i, p in enumerate(pats):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_stream(self.stream.cuda_stream)
+        return sc
+
+
+def kernel_name(cfg, st):
+    if st["scan_path"] != 2:
+        return ("hamming_scan_kernel<%d>" % cfg["k"]) if not cfg["indels"] else (
+            "edit_seed_kernel<%d> + edit_verify_kernel<%d>" % (cfg["k"], cfg["k"]))
+    if cfg["indels"] and cfg["k"]:
+        return "pair_scan_edit_kernel<%d, %d> + index_verify_kernel<%d>" % (st["index_q"], cfg["k"], cfg["k"])
+    ent = st["index_entries"]
+    # third template argument: the level-1b variant (24 000 < entries <= 100 000, csrc/pm_b200.cu)
+    return "pair_scan_sub_kernel<%d, %d, %s>" % (st["index_q"], st["index_nd"], "true" if 24000 < ent <= 100000 else "false")
+
+
+def roofline_of(B, cfg, sc, n_chars, n_pats, scan_ms, clocks, peaks):
+    """The dominant kernel (the scan) against both roofs; the binding one (the slower of the
+    integer pipe and HBM, per the north star) is the top-level `bound`."""
+    pkg = B.pkg
+    st = sc.stats()
+    on_index = st["scan_path"] == pkg.PM_SCAN_INDEX
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    cells = float(n_chars) * n_pats * (cfg["k"] + 1)
+    if on_index:
+        alg_bytes = n_chars * 0.5      # the scan reads the packed text once: one uint2 per 16 characters
+        # dram__bytes_read+write of one launch over 3.0e9 bases: 1504.0 + 6.3 MB (ncu --set full,
+        # profiles/README.md, prof_pairsub_r1): a constant taken from that capture, scaled by the
+        # bases of this launch -- not measured in this run
+        traffic = 0.5034 * n_chars if (not cfg["indels"] and cfg["nprimers"] <= 1000) else None
+        tsrc = "constant from the ncu --set full capture prof_pairsub_r1 (profiles/README.md): bytes per base x bases; not measured in this run"
+    else:
+        n_planes = 5 if not cfg["iupac"] else 16
+        alg_bytes = n_chars / 8.0 * n_planes * (1088.0 / 1024.0)
+        traffic, tsrc = None, None
+    hbm_ach = alg_bytes / (scan_ms * 1e-3) / 1e9
+    hbm = {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+           "algorithmic_bytes_per_base": alg_bytes / n_chars,
+           "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}
+    try:
+        ip = pkg.int_pipe_report(sc, scan_ms, B.local_rank)
+    except Exception as ex:  # diagnostic only
+        ip = {"error": str(ex)[:200]}
+    roof = {"bound": "int_pipe", "achieved": ip.get("achieved"), "peak": ip.get("peak"), "unit": "Tlop/s",
+            "frac": ip.get("frac"), "traffic": traffic, "traffic_source": tsrc,
+            "kernel": kernel_name(cfg, st), "kernel_ms": scan_ms,
+            "note": "bit-parallel integer work: the integer pipe binds (north star: the slower of the two roofs); "
+                    "the HBM view of the same kernel is under `hbm`",
+            "int_pipe": ip, "hbm": hbm, "cell_updates_per_s": cells / (scan_ms * 1e-3),
+            "scan_path": "index" if on_index else "planes"}
+    if on_index:
+        roof["index"] = {"piece_len": st["index_q"], "pieces": st["index_pieces"],
+                         "distances": st["index_nd"], "entries": st["index_entries"]}
+    return roof
+
+
+def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
+    """One configuration on this rank's shard: resident leg, end-to-end leg (.sqz host buffer),
+    and for `full` the stream / FASTA host legs.  Returns the (rank-0) result dict."""
+    np, torch, pkg, args = B.np, B.torch, B.pkg, B.args
+    cfg = dict(CONFIGS[name])
+    if args.bases and name == "headline":
+        cfg["bases"] = args.bases
+    bases = min(cfg["bases"], d_db.numel() - 1)
+    n_chars = bases + 1
+    primers, pats = B.patterns(name)
+    d_stream = d_db[:n_chars]
+    sc = B.scanner(cfg, pats)
+    scan_ms, res = [], {}
+
+    def step_resident():
+        sc.set_text(d_stream)                      # pack kernel (1 launch)
+        ptr, nh = sc.find_patterns_device()
+        st = sc.stats()
+        B.launches += 1 + st["kernel_launches"]
+        scan_ms.append(st["scan_ms"])
+        res["nh"], res["st"] = nh, st
+        res["total"] = B.sum_over_ranks(nh)
+
+    sqz_bytes = (3 * n_chars + 7) // 8
+    h_sqz_view = h_sqz.array[:sqz_bytes] if hasattr(h_sqz, "array") else h_sqz[:sqz_bytes]
+
+    def step_e2e_sqz():
+        sc.set_text_sqz(h_sqz_view, B.sqz_table, n_chars)   # H2D of the .sqz bytes + unpack + pack
+        res["hits"] = sc.find_patterns()                    # ... + the hit records written to host memory
+        B.launches += 1 + sc.stats()["kernel_launches"]
+        B.sum_over_ranks(len(res["hits"]))
+
+    sampler = ClockSampler(visible_gpu_index(B.local_rank)) if clocks_out is not None else None
+    if sampler:
+        sampler.start()
+    B.launches = 0
+    for _ in range(warmup):
+        step_resident()
+    B.launches = 0
+    scan_ms.clear()
+    ms = B.timed(step_resident, steps, 0)
+    n_launch = B.launches
+    if sampler:
+        clocks_out.update(sampler.stop())
+    mean_scan = sum(scan_ms) / max(1, len(scan_ms))
+    ms_e2e = B.timed(step_e2e_sqz, steps, min(warmup, 2))
+    hits = res["hits"]
+    legs = {}
+    if full:
+        h_stream = B.host_copy(d_stream)
+        d_fasta = B.fasta_of(d_stream)
+        h_fasta = B.host_copy(d_fasta)
+        fasta_bytes = int(d_fasta.numel())
+        del d_fasta
+
+        def step_stream():
+            sc.set_text(h_stream)
+            res["hits_stream"] = sc.find_patterns()
+            B.sum_over_ranks(len(res["hits_stream"]))
+
+        def step_fasta():
+            sc.set_text_fasta(h_fasta)
+            res["hits_fasta"] = sc.find_patterns()
+            B.sum_over_ranks(len(res["hits_fasta"]))
+
+        legs["stream"] = (B.timed(step_stream, steps, min(warmup, 2)), n_chars)
+        legs["fasta"] = (B.timed(step_fasta, steps, min(warmup, 2)), fasta_bytes)
+        assert res["hits_stream"].tobytes() == hits.tobytes() == res["hits_fasta"].tobytes(), "the three input forms disagree"
+        del h_stream, h_fasta
+    ms, ms_e2e, mean_scan = B.max_over_ranks([ms, ms_e2e, mean_scan])
+    leg_ms = {k: B.max_over_ranks([v[0]])[0] for k, v in legs.items()}
+    out = None
+    if B.rank == 0:
+        world = B.world
+        bases_total = float(n_chars) * world * steps
+        st = res["st"]
+        out = {"metric": cfg["metric"], "value": bases_total / (ms * 1e-3) / 1e9, "unit": "Gbp/s",
+               "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+               "config": config_dict(cfg, bases, args), "hits_per_step": res["total"],
+               "host_syncs_per_call": st["host_syncs"],
+               "cell_updates_per_s": float(n_chars) * world * len(pats) * (cfg["k"] + 1) / (ms / steps * 1e-3),
+               "e2e": {"value": bases_total / (ms_e2e * 1e-3) / 1e9, "unit": "Gbp/s",
+                       "h2d_bytes_per_step": int(sqz_bytes) * world,
+                       "d2h_bytes_per_step": (hits.nbytes + 256) * world, "ms_per_step": ms_e2e / steps,
+                       "h2d_gbs_per_rank": sqz_bytes / (ms_e2e / steps * 1e-3) / 1e9,
+                       "input": "pinned host buffer holding the database as compress_seq -z stores it "
+                                "(.sqz, 3 bits per character; pm_set_text_sqz_host)"},
+               "gpu_launches": n_launch}
+        if full:
+            out["e2e_stream"] = {"value": bases_total / (leg_ms["stream"] * 1e-3) / 1e9, "unit": "Gbp/s",
+                                 "h2d_bytes_per_step": n_chars * world, "ms_per_step": leg_ms["stream"] / steps,
+                                 "h2d_gbs_per_rank": n_chars / (leg_ms["stream"] / steps * 1e-3) / 1e9,
+                                 "input": "pinned host buffer holding the normalised character stream, 1 byte per character (pm_set_text_host)"}
+            out["e2e_fasta"] = {"value": bases_total / (leg_ms["fasta"] * 1e-3) / 1e9, "unit": "Gbp/s",
+                                "h2d_bytes_per_step": legs["fasta"][1] * world, "ms_per_step": leg_ms["fasta"] / steps,
+                                "h2d_gbs_per_rank": legs["fasta"][1] / (leg_ms["fasta"] / steps * 1e-3) / 1e9,
+                                "input": "pinned host buffer holding the FASTA file (80 bases per line), normalised on the "
+                                         "device chunk by chunk while the copy runs (pm_set_text_fasta_host); pack and scan follow"}
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        out["roofline"] = roofline_of(B, cfg, sc, n_chars, len(pats), mean_scan, clocks_out or {}, peaks)
+    res["cfg"], res["primers"], res["n_chars"] = cfg, primers, n_chars
+    sc.close()
+    return out, res
+
+
+def cpu_baseline_leg(B, res, d_db, planted, line, per_proc=None):
+    """N = 1, rank 0: the reference on windows of the shard, GPU records compared inside them."""
+    cfg, primers, n_chars = res["cfg"], res["primers"], res["n_chars"]
+    cores = cpu_cores()
+    if cfg.get("ref_skip"):
+        line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": "not run: " + cfg["ref_skip"]}
+        return True
+    try:
+        if reference_available():
+            work = tempfile.mkdtemp(prefix="pmref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            per = per_proc or cfg["ref_bp"]
+            per = min(per, max(1000, (n_chars - 2) // (2 * cores)))
+            dt, bp, compared, ok, detail = parity_windows(cfg, primers, d_db, n_chars, res["hits"], cores, per, work, planted)
+            line["cpu_baseline"] = {"value": bp / dt / 1e9, "unit": "Gbp/s", "cores": cores, "kind": "reference",
+                                    "sample": "%d processes x %d bp windows of the benchmark shard itself, %.1f s" % (cores, per, dt)}
+            line["parity_checked_bp"] = bp
+            line["parity_records_compared"] = compared
+            line["parity_ok"] = ok
+            if not ok:
+                line["parity_detail"] = detail
+            return ok
+        dt = run_oracle_sample(cfg, primers, 200_000 if cfg["nprimers"] <= 1000 else 2000, 300)
+        line["cpu_baseline"] = {"value": (200_000 if cfg["nprimers"] <= 1000 else 2000) / dt / 1e9, "unit": "Gbp/s",
+                                "cores": 1, "kind": "port", "sample": "oracle port, %.1f s" % dt}
+    except Exception as ex:
+        line["cpu_baseline"] = {"error": str(ex)[:300]}
+    return True
+
+
+def strong_scaling(B, cfg_name, steps, warmup):
+    """ONE database of cfg.bases, cut with shard_plan + overlap; every rank scans its piece
+    (resident and from its .sqz host shard) and the hit records are gathered over NCCL.  Rank 0
+    then scans the whole database alone and compares byte for byte."""
+    np, torch, pkg, args, dist = B.np, B.torch, B.pkg, B.args, B.dist
+    cfg = dict(CONFIGS[cfg_name])
+    if args.bases and cfg_name == "headline":
+        cfg["bases"] = args.bases
+    bases = cfg["bases"]
+    n_chars = bases + 1
+    primers, pats = B.patterns(cfg_name)
+    d_db = B.make_database(bases, 777)           # the same database on every rank
+    B.plant(d_db, pats, cfg["k"], 778)
+    sc = B.scanner(cfg, pats)
+    plan = B.sharding.shard_plan(n_chars, B.world, sc.shard_overlap())
+    sh = plan[B.rank]
+    lo = sh.load_lo & ~15                        # a .sqz shard starts on a byte boundary of the bit stream
+    d_shard = d_db[lo:sh.load_hi]
+    h_sqz = B.host_copy(pkg.sqz_encode_torch(d_shard, B.sqz_table))
+    nsh = int(d_shard.numel())
+    sqz_bytes = (3 * nsh + 7) // 8
+    h_view = h_sqz.array[:sqz_bytes] if hasattr(h_sqz, "array") else h_sqz[:sqz_bytes]
+    item = pkg.HIT_DTYPE.itemsize
+    res = {}
+
+    def step_resident():
+        sc.set_text(d_shard, offset=lo)
+        ptr, nh = sc.find_patterns_device(sh.begin, sh.end)
+        counts, recs = B.sharding.gather_hits_device(ptr, nh, item, dist if B.world > 1 else None, B.dev)
+        res["counts"], res["recs"] = counts, recs
+
+    def step_e2e():
+        sc.set_text_sqz(h_view, B.sqz_table, nsh, offset=lo)
+        ptr, nh = sc.find_patterns_device(sh.begin, sh.end)
+        counts, recs = B.sharding.gather_hits_device(ptr, nh, item, dist if B.world > 1 else None, B.dev)
+        res["host"] = recs.cpu() if B.rank == 0 else None      # the gathered records on rank 0's host
+
+    ms = B.timed(step_resident, steps, warmup)
+    ms_e2e = B.timed(step_e2e, steps, min(warmup, 2))
+    ms, ms_e2e = B.max_over_ranks([ms, ms_e2e])
+    gathered = res["recs"].cpu().numpy().tobytes()
+    parity = None
+    if B.rank == 0:
+        sc.set_text(d_db)
+        whole = sc.find_patterns()
+        parity = (whole.tobytes() == gathered) and (res["host"].numpy().tobytes() == gathered)
+    sc.close()
+    del d_db, h_sqz
+    torch.cuda.empty_cache()
+    if B.rank != 0:
+        return None
+    return {"database_bases": bases, "shards": B.world, "overlap": plan[0].load_hi - plan[0].end if B.world > 1 else 0,
+            "left_overlap_chars": (plan[-1].begin - plan[-1].load_lo) if B.world > 1 else 0,
+            "value": n_chars * steps / (ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms / steps,
+            "e2e": {"value": n_chars * steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": ms_e2e / steps,
+                    "input": "every rank's shard as a .sqz host buffer; gathered records copied to rank 0's host"},
+            "hits": sum(res["counts"]), "hits_per_rank": res["counts"],
+            "gather": "NCCL all_gather_into_tensor of the counts, then of the hit records (padded to the largest count)",
+            "parity": "gathered hit list byte-equal to rank 0's scan of the whole database" if parity else "MISMATCH against the whole-database scan",
+            "parity_ok": bool(parity)}
 
 
 def main():
@@ -237,297 +797,80 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--bases", type=int, default=3_000_000_000, help="database shard per GPU")
-    ap.add_argument("--indels", type=int, default=0, help="1: -k (edits) instead of -K")
-    ap.add_argument("--iupac", type=int, default=0, help="1: IUPAC wildcard primers (db/patwc.txt style), scanned with -w")
-    ap.add_argument("--k", type=int, default=K, help="errors allowed (headline: 2)")
-    ap.add_argument("--plen", type=int, default=PRIMER_LEN, help="primer length (headline: 20)")
-    ap.add_argument("--nprimers", type=int, default=N_PRIMERS, help="primers before reverse complements (headline: 1000)")
-    ap.add_argument("--N", type=int, default=0, dest="select",
-                    help="primer_match -N: pattern index (0 automatic, 5 filter_bitvec, 13 exact_halves)")
+    ap.add_argument("--config", default="all", choices=["all"] + ALL_ORDER,
+                    help="BASELINE.json configuration; all = the headline in full + the others under `configs`")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="strong: ONE database partitioned over the ranks with overlap, hit records gathered over NCCL")
+    ap.add_argument("--bases", type=int, default=0, help="override the headline's database shard per GPU")
     ap.add_argument("--host-mem", default="wc", choices=["pinned", "wc"],
                     help="host buffers of the end-to-end legs: torch pinned memory, or write-combined pages (pm_host_alloc)")
-    ap.add_argument("--cpu-bases-per-core", type=int, default=3_000_000)
-    ap.add_argument("--ref-bases-per-core", type=int, default=4_000_000)
+    ap.add_argument("--ref-bases-per-core", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block of a multi-GPU run")
     args = ap.parse_args()
-    globals().update(K=args.k, PRIMER_LEN=args.plen, N_PRIMERS=args.nprimers, INDELS=args.indels, IUPAC=args.iupac,
-                     SELECT=args.select)
     if args.impl == "reference":
         return main_reference(args)
 
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    pkg = importlib.import_module(PKG)
-    pkg.lib()
-
-    primers = make_primers()
-    pats = pkg.pattern_array(primers, True)
-    n = args.bases
-    # synthetic shard: eos, random ACGT in sequences of 50 Mbp, eos  (generated on the device,
-    # then copied to pinned host memory for the end-to-end leg)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
-    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
-    d_stream = torch.empty(n + 2, dtype=torch.uint8, device=dev)
-    chunk = 1 << 28
-    for a in range(0, n, chunk):
-        b = min(n, a + chunk)
-        d_stream[1 + a:1 + b] = lut[torch.randint(0, 4, (b - a,), device=dev, generator=gen, dtype=torch.uint8).long()]
-    d_stream[0] = 10
-    d_stream[n + 1] = 10
-    seq_len = 50_000_000
-    d_stream[seq_len::seq_len] = 10     # sequence separators
-    # plant a few exact / mutated primer copies so that the hit path is exercised
-    rs = np.random.default_rng(99 + rank)
-    for j in range(64):
-        p = bytearray(pats[int(rs.integers(0, len(pats)))].encode())
-        p = bytearray(c if c in b"ACGT" else b"ACGT"[int(rs.integers(0, 4))] for c in p)
-        for _ in range(int(rs.integers(0, K + 1))):
-            p[int(rs.integers(0, len(p)))] = b"ACGT"[int(rs.integers(0, 4))]
-        at = int(rs.integers(1000, n - 1000))
-        d_stream[at:at + len(p)] = torch.tensor(list(p), dtype=torch.uint8, device=dev)
-    def host_copy(d_t):
-        """The tensor's bytes in page-locked host memory (what a pinned file reader would hold)."""
-        if args.host_mem == "wc":
-            hb = pkg.HostBuffer(d_t.numel(), write_combined=True)
-            torch.from_numpy(hb.array).copy_(d_t)
-            return hb
-        h = torch.empty(d_t.numel(), dtype=torch.uint8, pin_memory=True)
-        h.copy_(d_t)
-        return h
-
-    h_stream = host_copy(d_stream)
-    # the same database as compress_seq -z would store it (.tbz table + .sqz bit stream,
-    # 3 bits per character for A C G T eos): what primer_match opens when the files exist
-    sqz_table = b"ACGT\n"
-    d_sqz = pkg.sqz_encode_torch(d_stream, sqz_table)
-    h_sqz = host_copy(d_sqz)
-    del d_sqz
-    # ... and as the FASTA file it came from: one record per sequence, 80 bases per line
-    parts = []
-    bounds = [0] + list(range(seq_len, n + 1, seq_len)) + [n + 1]
-    nl = torch.tensor([10], dtype=torch.uint8, device=dev)
-    for si in range(len(bounds) - 1):
-        a, b = bounds[si] + 1, bounds[si + 1]          # bases of this sequence: d_stream[a:b]
-        if b <= a:
-            continue
-        body = d_stream[a:b]
-        full = (b - a) // 80 * 80
-        lines = torch.cat([body[:full].view(-1, 80), nl.expand(full // 80, 1)], dim=1).reshape(-1)
-        parts += [torch.tensor(list(b">synthetic%d random DNA\n" % si), dtype=torch.uint8, device=dev), lines]
-        if b - a > full:
-            parts += [body[full:], nl]
-    d_fasta = torch.cat(parts)
-    h_fasta = host_copy(d_fasta)
-    del d_fasta, parts
+    B = Bench(args)
+    torch, pkg = B.torch, B.pkg
+    main_name = "headline" if args.config == "all" else args.config
+    names = ALL_ORDER if args.config == "all" else [args.config]
+    bases_max = max((args.bases if (args.bases and n == "headline") else CONFIGS[n]["bases"]) for n in names)
+    d_db = B.make_database(bases_max, 1234 + B.rank)
+    main_cfg = CONFIGS[main_name]
+    main_bases = args.bases if (args.bases and main_name == "headline") else main_cfg["bases"]
+    # planted primer copies of every configuration (before the host copies are made)
+    planted = {}
+    for nm in names:
+        nb = args.bases if (args.bases and nm == "headline") else CONFIGS[nm]["bases"]
+        planted[nm] = B.plant(d_db, B.patterns(nm)[1], CONFIGS[nm]["k"], 99 + B.rank + 17 * len(planted), limit=min(nb, bases_max))
+    h_sqz = B.host_copy(pkg.sqz_encode_torch(d_db, B.sqz_table))
     torch.cuda.synchronize()
 
-    sc = pkg.Scanner(k=K, indels=bool(args.indels), wildcards=bool(args.iupac), device=local_rank, index=args.select)
-    for i, p in enumerate(pats):
-        sc.add_pattern(p, i + 1)
-    sc.init()
-    stream = torch.cuda.current_stream()
-    sc.set_stream(stream.cuda_stream)
-
-    launches = {"n": 0}
-    scan_ms = []
-
-    def step_resident():
-        sc.set_text(d_stream)                      # pack kernel (1 launch)
-        ptr, nh = sc.find_patterns_device()
-        st = sc.stats()
-        launches["n"] += 1 + st["kernel_launches"]
-        scan_ms.append(st["scan_ms"])
-        return nh, st
-
-    def step_e2e(source):
-        if source == "sqz":
-            sc.set_text_sqz(h_sqz, sqz_table, n + 2)   # H2D of the .sqz bytes + unpack + pack
-        elif source == "fasta":
-            sc.set_text_fasta(h_fasta)             # H2D of the file + normalisation on the device + pack
-        else:
-            sc.set_text(h_stream)                  # H2D of the stream from pinned memory + pack
-        hits = sc.find_patterns()                  # ... + D2H of the hit list
-        st = sc.stats()
-        launches["n"] += 1 + st["kernel_launches"]
-        return hits, st
-
-    def gather_counts(nh):
-        if world == 1:
-            return nh
-        t = torch.tensor([nh], dtype=torch.int64, device=dev)
-        dist.all_reduce(t)                      # NCCL: the hit counts of all shards, summed
-        return int(t.item())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        nh, st = step_resident()
-        gather_counts(nh)
-    launches["n"] = 0
-    scan_ms.clear()
-    sampler = ClockSampler(visible_gpu_index(local_rank))
-    sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    total_hits = 0
-    for _ in range(args.steps):
-        nh, st = step_resident()
-        total_hits = gather_counts(nh)
-    e1.record(stream)
-    barrier()
-    clocks = sampler.stop()
-    ms = e0.elapsed_time(e1)
-    n_launch = launches["n"]
-    mean_scan_ms = sum(scan_ms) / max(1, len(scan_ms))
-
-    # end-to-end legs: host buffers in, hit list out.  "e2e" reads the database in the
-    # reference's compressed form, "e2e_stream" as the plain character stream.
-    e2e_ms, d2h, hit_sets = {}, 0, {}
-    for source in ("sqz", "stream", "fasta"):
-        for _ in range(min(args.warmup, 2)):
-            step_e2e(source)
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2.record(stream)
-        for _ in range(args.steps):
-            hits, st = step_e2e(source)
-            d2h = hits.nbytes + 64
-            gather_counts(len(hits))
-        e3.record(stream)
-        barrier()
-        e2e_ms[source] = e2.elapsed_time(e3)
-        hit_sets[source] = hits.tobytes()
-    assert hit_sets["sqz"] == hit_sets["stream"] == hit_sets["fasta"], "the three input forms disagree"
-    ms_e2e, ms_e2e_stream, ms_e2e_fasta = e2e_ms["sqz"], e2e_ms["stream"], e2e_ms["fasta"]
-
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e, mean_scan_ms, ms_e2e_stream, ms_e2e_fasta], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, mean_scan_ms, ms_e2e_stream, ms_e2e_fasta = (float(x) for x in t.tolist())
-
-    if rank == 0:
-        bases_total = float(n + 2) * world * args.steps
-        value = bases_total / (ms * 1e-3) / 1e9
-        e2e = bases_total / (ms_e2e * 1e-3) / 1e9
-        e2e_stream = bases_total / (ms_e2e_stream * 1e-3) / 1e9
-        e2e_fasta = bases_total / (ms_e2e_fasta * 1e-3) / 1e9
-        # roofline of the dominant kernel (the dense scan), per launch
-        peaks = {}
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                peaks = json.load(f)
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        st_last = sc.stats()
-        on_index = st_last["scan_path"] == pkg.PM_SCAN_INDEX
-        cells = float(n + 2) * len(pats) * (K + 1)
-        if on_index:
-            # pair_scan_kernel reads the packed text once: one uint2 (codes, flags) per 16 characters
-            alg_bytes = (n + 2) * 0.5
-            # dram__bytes_read+write of one launch over 3.0e9 bases: 1504.0 + 6.3 MB
-            # (ncu --set full, profiles/README.md, prof_pairsub_r1), scaled to this launch's bases
-            traffic = None if args.indels else 0.5034 * (n + 2)
-            if args.indels and K:
-                kname = "pair_scan_kernel<true> + index_verify_kernel<%d>" % K
-            else:
-                # third template argument: the level-1b variant (24 000 < entries <= 100 000, csrc/pm_b200.cu)
-                kname = "pair_scan_sub_kernel<%d, %d, %s>" % (
-                    st_last["index_q"], st_last["index_nd"],
-                    "true" if 24000 < st_last["index_entries"] <= 100000 else "false")
-            tsrc = "ncu --set full capture prof_pairsub_r1 (profiles/README.md), bytes per base x bases"
-        else:
-            n_planes = 5 if not args.iupac else 16
-            alg_bytes = (n + 2) / 8.0 * n_planes * (1088.0 / 1024.0)      # planes read once per launch
-            # (268 Mbp: 567.6 MB with 4 pattern chunks), scaled to this launch's bases
-            traffic = None if args.indels else 2.115 * (n + 2)
-            kname = ("hamming_scan_kernel<%d>" % K) if not args.indels else ("edit_seed_kernel<%d> + edit_verify_kernel<%d>" % (K, K))
-            tsrc = "ncu --set full capture prof_hamming_r1b (profiles/README.md), bytes per base x bases"
-        hbm_achieved = alg_bytes / (mean_scan_ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": hbm_achieved / hbm_peak, "traffic": traffic,
-                "traffic_source": tsrc,
-                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s",
-                "kernel": kname,
-                "kernel_ms": mean_scan_ms,
-                "algorithmic_bytes_per_base": alg_bytes / (n + 2),
-                "note": "the scan is integer-pipe bound, not HBM bound (north star: the slower of the two): see int_pipe",
-                "cell_updates_per_s": cells / (mean_scan_ms * 1e-3),
-                "scan_path": "index" if on_index else "planes"}
-        if on_index:
-            roof["index"] = {"piece_len": st_last["index_q"], "pieces": st_last["index_pieces"],
-                             "distances": st_last["index_nd"], "entries": st_last["index_entries"]}
-        if on_index and not args.indels and K > 0 and st_last["index_pieces"] == K + 2:
-            # the pipe that actually binds pair_scan_sub_kernel: shared-memory wavefronts.  One level-1
-            # lookup is one lane of an LDS; 32 lanes hitting 32 random banks take 3.76 wavefronts
-            # (l1tex__data_pipe_lsu_wavefronts_mem_shared / smsp__sass_inst_executed_op_shared_ld of the
-            # ncu capture prof_pairsub_r1); an SM retires one wavefront per clock.
-            wf = st_last["index_lookups"] * 3.76 / 32.0
-            sm_clock = (clocks.get("sm_mhz") or 1965) * 1e6
-            lsu_peak = 148 * sm_clock
-            roof["smem_wavefronts"] = {"unit": "Gwavefront/s", "achieved": wf / (mean_scan_ms * 1e-3) / 1e9,
-                                       "peak": lsu_peak / 1e9, "frac": wf / (mean_scan_ms * 1e-3) / lsu_peak,
-                                       "wavefronts_per_warp_lds": 3.76,
-                                       "note": "ncu (profiles/README.md): l1tex data pipe 93.9 % busy incl. queue traffic"}
-        try:
-            ip = pkg.int_pipe_report(sc, mean_scan_ms, local_rank)
-            roof["int_pipe"] = ip
-        except Exception as ex:  # diagnostic only
-            roof["int_pipe"] = {"error": str(ex)[:200]}
-        line = {"metric": "Gbp/s scanned, 1k 20-mer primers k=2 both strands", "value": value, "unit": "Gbp/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-                "data": "synthetic", "config": config_dict(args, n),
-                "hits_per_step": total_hits, "clocks": clocks,
-                "e2e": {"value": e2e, "unit": "Gbp/s", "h2d_bytes_per_step": int(h_sqz.numel()) * world,
-                        "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps,
-                        "input": "pinned host buffer holding the database as compress_seq -z stores it "
-                                 "(.sqz, 3 bits per character; pm_set_text_sqz_host)"},
-                "e2e_stream": {"value": e2e_stream, "unit": "Gbp/s", "h2d_bytes_per_step": (n + 2) * world,
-                               "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_stream / args.steps,
-                               "input": "pinned host buffer holding the normalised character stream, "
-                                        "1 byte per character (pm_set_text_host)"},
-                "e2e_fasta": {"value": e2e_fasta, "unit": "Gbp/s", "h2d_bytes_per_step": int(h_fasta.numel()) * world,
-                              "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e_fasta / args.steps,
-                              "input": "pinned host buffer holding the FASTA file (80 bases per line), normalised "
-                                       "on the device chunk by chunk while the copy runs (pm_set_text_fasta_host); pack and scan follow"},
-                "gpu_launches": n_launch, "roofline": roof}
-        if not args.no_cpu_baseline and world == 1:
-            cores = cpu_cores()
-            try:
-                if reference_available():
-                    work = tempfile.mkdtemp(prefix="pmref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-                    per = args.cpu_bases_per_core
-                    dt = run_reference_sample(primers, per * cores, cores, 300, work)
-                    line["cpu_baseline"] = {"value": per * cores / dt / 1e9, "unit": "Gbp/s", "cores": cores,
-                                            "kind": "reference",
-                                            "sample": "%d processes x %d bp of the same workload, %.1f s" % (cores, per, dt)}
-                else:
-                    dt = run_oracle_sample(primers, 200_000, 300)
-                    line["cpu_baseline"] = {"value": 200_000 / dt / 1e9, "unit": "Gbp/s", "cores": 1, "kind": "port",
-                                            "sample": "oracle port, 200000 bp, %.1f s" % dt}
-            except Exception as ex:
-                line["cpu_baseline"] = {"error": str(ex)[:200]}
+    clocks = {}
+    line, res = measure_config(B, main_name, d_db, h_sqz, args.steps, args.warmup, full=True, clocks_out=clocks)
+    ok = True
+    if B.rank == 0:
+        line = {**{"metric": line.pop("metric"), "value": line.pop("value"), "unit": line.pop("unit"),
+                   "n_gpus": B.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": line.pop("ms_per_step"),
+                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+                   "data": "synthetic"}, **line, "clocks": clocks}
+        if not args.no_cpu_baseline and B.world == 1:
+            ok = cpu_baseline_leg(B, res, d_db, planted[main_name], line)
+    # the other BASELINE configurations: short runs on the same shard
+    if len(names) > 1:
+        others = {}
+        for nm in names[1:]:
+            steps = max(1, min(args.steps, 2))
+            o, r = measure_config(B, nm, d_db, h_sqz, steps, min(args.warmup, 2), full=False)
+            if B.rank == 0:
+                if not args.no_cpu_baseline and B.world == 1:
+                    ok = cpu_baseline_leg(B, r, d_db, planted[nm], o) and ok
+                others[nm] = o
+        if B.rank == 0:
+            line["configs"] = others
+    del d_db, h_sqz
+    torch.cuda.empty_cache()
+    # strong scaling: one database, partitioned with overlap, hit records gathered
+    if B.world > 1 and not args.no_strong:
+        s = strong_scaling(B, main_name, args.steps, args.warmup)
+        if B.rank == 0:
+            line["strong"] = s
+            ok = ok and s["parity_ok"]
+            if args.scaling == "strong":
+                line["weak_value"] = line["value"]
+                line["value"], line["ms_per_step"], line["scaling"] = s["value"], s["ms_per_step"], "strong"
+                line["e2e_weak"] = line["e2e"]
+                line["e2e"] = {**s["e2e"], "h2d_bytes_per_step": int(3 * (main_bases + 1) / 8),
+                               "d2h_bytes_per_step": s["hits"] * pkg.HIT_DTYPE.itemsize}
+    if B.rank == 0:
         print(json.dumps(line))
-    sc.close()
-    if world > 1:
-        dist.destroy_process_group()
+        if not ok:
+            print("bench.py: PARITY FAILED (see parity_ok / strong.parity in the line)", file=sys.stderr)
+    if B.world > 1:
+        B.dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -75,3 +75,40 @@ def gather_hits(local: np.ndarray, dist=None):
     parts = [np.frombuffer(b.cpu().numpy().tobytes()[:c * item], dtype=local.dtype) for b, c in zip(bufs, counts)]
     out = np.concatenate(parts)
     return out[np.lexsort((out["pattern_id"], out["first"]))]
+
+
+class _DeviceBytes:
+    """A device pointer as a CUDA-array-interface object (so that torch can wrap it)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 3}
+
+
+def gather_hits_device(d_ptr: int, n_hits: int, item_bytes: int, dist, device=None):
+    """The hit lists of all ranks, as they lie on the devices (pm_find_patterns_device),
+    gathered over NCCL without a detour through the host.  Returns (counts, records): a
+    uint8 device tensor holding the records of rank 0, rank 1, ... back to back.  The
+    shards of shard_plan() own disjoint, ascending ranges of `first`, and every rank's list
+    is sorted by (first, pattern_id): the concatenation in rank order is the sorted list of
+    the whole database.  Two collectives: the counts, then the records padded to the largest
+    count (all_gather_into_tensor)."""
+    import torch
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    nbytes = n_hits * item_bytes
+    local = torch.as_tensor(_DeviceBytes(d_ptr, nbytes), device=dev) if nbytes else torch.empty(0, dtype=torch.uint8, device=dev)
+    if world == 1:
+        return [n_hits], local
+    cnt = torch.tensor([n_hits], dtype=torch.int64, device=dev)
+    counts_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, cnt)
+    counts = [int(x) for x in counts_t.tolist()]
+    mx = max(counts)
+    if mx == 0:
+        return counts, torch.empty(0, dtype=torch.uint8, device=dev)
+    send = torch.zeros(mx * item_bytes, dtype=torch.uint8, device=dev)
+    send[:nbytes] = local
+    recv = torch.empty(world * mx * item_bytes, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    parts = [recv[r * mx * item_bytes: r * mx * item_bytes + counts[r] * item_bytes] for r in range(world)]
+    return counts, torch.cat(parts)
