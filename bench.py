@@ -464,6 +464,31 @@ class Bench:
             at_list.append(at)
         return at_list
 
+    def plant_dense(self, d, pats, k, seed, count, limit=None):
+        """`count` primer copies (up to k substitutions each) at evenly spread positions, written with
+        one scatter: the hit-dense shape of a genome whose repeats contain primer sites."""
+        torch = self.torch
+        n = int(limit or d.numel())
+        m = len(pats[0])
+        g = torch.Generator(device=self.dev)
+        g.manual_seed(seed)
+        pm_ = torch.tensor([list(p.encode()) for p in pats if len(p) == m], dtype=torch.uint8, device=self.dev)
+        lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=self.dev)
+        pm_ = torch.where(((pm_ == 65) | (pm_ == 67) | (pm_ == 71) | (pm_ == 84)), pm_, torch.full_like(pm_, 65))
+        step = max(m + 8, (n - 4000) // count)
+        pos = 2000 + torch.arange(count, device=self.dev, dtype=torch.int64) * step
+        pos = pos[(pos % SEQ_LEN > 200) & (pos % SEQ_LEN < SEQ_LEN - 200) & (pos < n - 200)]
+        which = torch.randint(0, pm_.shape[0], (pos.numel(),), device=self.dev, generator=g)
+        copies = pm_[which].clone()
+        for _ in range(k):      # up to k substitutions (a drawn base may equal the original)
+            col = torch.randint(0, m, (pos.numel(),), device=self.dev, generator=g)
+            base = lut[torch.randint(0, 4, (pos.numel(),), device=self.dev, generator=g)]
+            hit = torch.rand(pos.numel(), device=self.dev, generator=g) < 0.5
+            rows = torch.arange(pos.numel(), device=self.dev)[hit]
+            copies[rows, col[hit]] = base[hit]
+        d[(pos[:, None] + torch.arange(m, device=self.dev)[None, :]).reshape(-1)] = copies.reshape(-1)
+        return int(pos.numel())
+
     def host_copy(self, d_t):
         """The tensor's bytes in page-locked host memory (what a pinned file reader would hold)."""
         torch = self.torch

@@ -464,6 +464,16 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
   }
   void (*ivkern)(const IndexArgs) =
       K <= 1 ? index_verify_kernel<1> : (K == 2 ? index_verify_kernel<2> : index_verify_kernel<3>);
+  if (c->use_index && edit) {
+    // the kernel specialised for (piece length, k) and the verifier that reads its seeds;
+    // PM_EDIT_GENERIC=1 keeps the run-time kernel pair (for A/B measurements)
+    static const bool generic = getenv("PM_EDIT_GENERIC") && atoi(getenv("PM_EDIT_GENERIC")) != 0;
+    PairKernel ek = generic ? nullptr : pair_edit_kernel((int)c->idx_proto.L, K);
+    if (ek && c->n < (1ull << (SEED_POS_BITS - 1))) {
+      ikern = ek;
+      ivkern = K <= 1 ? index_verify_lv_kernel<1> : (K == 2 ? index_verify_lv_kernel<2> : index_verify_lv_kernel<3>);
+    }
+  }
   size_t ismem = 0;
   if (c->use_index) {
     ia = c->idx_proto;
@@ -657,6 +667,11 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
                             cudaMemcpyDeviceToHost, c->stream));
     PM_CUDA(cudaStreamSynchronize(c->stream));
     c->stats.host_syncs++;
+    {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+      c->stats.scan_ms = ms;
+    }
     count = c->h_counters[CTR_COUNT];
     c->stats.n_seeds = c->h_counters[CTR_SEEDS];
     c->stats.scan_warp_steps = c->h_counters[CTR_WORK];

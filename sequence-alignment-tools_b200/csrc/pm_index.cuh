@@ -42,6 +42,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pm_scan.cuh"
+#include "pm_lv.cuh"
 
 namespace pm {
 
@@ -398,6 +399,254 @@ pair_scan_kernel(const __grid_constant__ IndexArgs a) {
   pair_cta_finish<EDIT>(a, t);
 }
 
+typedef void (*PairKernel)(const IndexArgs);
+
+// ---------------------------------------------------------------------------
+// Edit scan with compile-time piece length and error count.  The distances a piece pair can
+// have are known at compile time (EditDist), so the lookup loop is straight-line code over
+// shifted windows shared between positions and distances (block by block, to stay inside 64
+// registers): 7 instructions per lookup instead of 10.  Level 1b is not asked inline -- there
+// it ran as a divergent per-lane loop with 9 of 32 lanes busy, a third of the old kernel's
+// instructions (profiles/README.md, r2_before_edit25_scan) -- but by stage A, one queued
+// record per lane.  Seeds carry the index of their first piece: index_verify_lv_kernel
+// extends from that anchor (pm_lv.cuh).
+template <int L, int K>
+struct EditDist {
+  static constexpr int P = K + 2;
+  static constexpr int DMAX = (P - 1) * L + K;
+  __host__ __device__ static constexpr bool used(int d) {
+    if (d < L || d > DMAX) return false;
+    for (int g = 1; g < P; g++)
+      if (d >= g * L - K && d <= g * L + K) return true;
+    return false;
+  }
+  // position of d in the ascending list of used distances (IndexArgs::dist)
+  __host__ __device__ static constexpr int index(int d) {
+    int n = 0;
+    for (int x = L; x < d; x++) n += used(x) ? 1 : 0;
+    return n;
+  }
+};
+
+constexpr int SEED_POS_BITS = 39;   // edit seeds of the index path: slot << 42 | piece index << 39 | biased start
+
+// Stage A of the edit scan: one queued record per lane = (word of the chunk, distance index,
+// 16-bit mask of the word's positions that passed level 1).  Every set position first asks
+// level 1b (the shared-memory bitmap keyed by (pair key, distance)), then walks its bucket of the
+// exact table; matches become seeds (slot, piece index, nominal start).
+template <int L>
+__device__ __forceinline__ void pair_stage_a_edit(const IndexArgs &a, const uint32_t *bitmap2, int64_t w_base,
+                                                  bool valid, uint32_t rec, uint32_t lane) {
+  const int64_t w = w_base + (int64_t)(rec >> 21);
+  const uint32_t di = (rec >> 16) & 31u;
+  uint32_t hm = valid ? (rec & 0xffffu) : 0u;
+  constexpr uint32_t L2 = 2u * L;
+  constexpr uint32_t maskL = (1u << L2) - 1u;
+  const uint32_t d2 = 2u * a.dist[valid ? di : 0u];
+  const uint32_t salt2 = a.salt2[valid ? di : 0u], wsh2 = 32u - a.log_words2;
+  uint32_t c0 = 0, c1 = 0, c2 = 0;
+  if (valid) { c0 = pk_codes(a, w); c1 = pk_codes(a, w + 1); c2 = pk_codes(a, w + 2); }
+  uint32_t e0 = 0, e1 = 0, key = 0;
+  int64_t p = 0;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (;;) {
+    if (!__any_sync(0xffffffffu, (hm != 0u) || (e0 < e1))) break;
+    if (e0 >= e1 && hm) {  // next set position of the word: level 1b, then its bucket
+      const int b = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const uint32_t i2 = 2u * (uint32_t)(15 - b);
+      const uint32_t v0 = __funnelshift_r(c0, c1, i2), v1 = __funnelshift_r(c1, c2, i2), v2 = c2 >> i2;
+      const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
+      key = (v0 & maskL) | ((hi & maskL) << L2);
+      const uint32_t idx2 = key * a.mult2 + salt2;
+      const uint32_t wrd = bitmap2[idx2 >> wsh2];
+      if ((wrd >> (idx2 & 31u)) & 1u) {
+        const uint32_t h = pair_hash2(key, di, a.log_buckets);
+        e0 = __ldg(a.bucket + h);
+        e1 = __ldg(a.bucket + h + 1);
+        p = (w << 4) + (15 - b);
+      }
+    }
+    bool found = false;
+    uint32_t meta = 0;
+    if (e0 < e1) {
+      const uint2 ent = __ldg(a.entries + e0);
+      ++e0;
+      meta = ent.y;
+      found = (ent.x == key) && (((meta >> 5) & 31u) == di);
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, found);
+    if (bal == 0u) continue;
+    const uint32_t slot = meta >> 10, off = meta & 31u;
+    const int64_t s = p - (int64_t)off + SEED_BIAS;  // nominal window start, biased
+    const uint32_t rank = __popc(bal & lt), cnt = __popc(bal);
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(a.seed_n, (unsigned long long)cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (found) {
+      const unsigned long long at = base + rank;
+      if (at < a.seed_cap)
+        a.seeds[at] = ((unsigned long long)slot << (SEED_POS_BITS + 3)) | ((unsigned long long)(off / L) << SEED_POS_BITS) |
+                      (unsigned long long)s;
+      else *a.seed_overflow = 1ULL;
+    }
+  }
+}
+
+constexpr int EDIT_DBLOCK = 8;     // distances handled per block of shifted windows
+constexpr int EDIT_QCAP = 256;     // 4-byte records per warp: the queues' kilobyte per warp
+
+// One chunk the slow way (run-time distance loop, stage A after every distance): only for a chunk
+// whose records did not fit the queue -- text that repeats a piece pair of some pattern over and over.
+template <int L>
+__device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const uint32_t *bitmap, const uint32_t *bitmap2,
+                                                      int64_t w_base, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t vm,
+                                                      uint32_t lane) {
+  uint32_t n_queued = 0;
+  const uint32_t wsh = 32u - a.log_words;
+  constexpr uint32_t maskL = (1u << (2 * L)) - 1u, maskHi = maskL << (2 * L);
+  for (uint32_t di = 0; di < a.nd; ++di) {
+    const uint32_t s = 2u * (a.dist[di] - L);  // < 64
+    const bool hiw = s >= 32u;
+    const uint32_t y0 = hiw ? c1 : c0, y1 = hiw ? c2 : c1, y2 = hiw ? 0u : c2;
+    const uint32_t X0 = __funnelshift_r(y0, y1, s), X1 = __funnelshift_r(y1, y2, s);
+    uint32_t hm = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+      hm = pair_probe(bitmap, (__funnelshift_r(X0, X1, 2 * i) & maskHi) | (__funnelshift_r(c0, c1, 2 * i) & maskL), a.mult, 0u, wsh, hm);
+    hm &= vm;
+    if (__any_sync(0xffffffffu, hm != 0u)) {
+      n_queued += __popc(__ballot_sync(0xffffffffu, hm != 0u));
+      pair_stage_a_edit<L>(a, bitmap2, w_base, hm != 0u, (lane << 21) | (di << 16) | hm, lane);
+    }
+  }
+  return n_queued;
+}
+
+template <int L, int K>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  using ED = EditDist<L, K>;
+  PairCta t;
+  pair_cta_init(a, s_mem, t);
+  const uint32_t wsh = 32u - a.log_words;
+  constexpr uint32_t maskL = (1u << (2 * L)) - 1u;
+  constexpr uint32_t mask2L = (L >= 8) ? 0xffffffffu : ((1u << (4 * L)) - 1u);
+  constexpr uint32_t maskHi = mask2L & ~maskL;
+  constexpr int NB = (ED::DMAX - L + 1 + EDIT_DBLOCK - 1) / EDIT_DBLOCK;
+  const uint32_t mult = a.mult;
+  const uint32_t warp = threadIdx.x >> 5;
+  uint32_t *queue = reinterpret_cast<uint32_t *>(t.q.qa);   // this warp's kilobyte: EDIT_QCAP records
+  const uint32_t lane_tag = t.lane << 21;
+
+  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    int64_t w;
+    uint32_t cw[5], vm;
+    pair_load_words(a, t, c, w, cw[0], cw[1], cw[2], vm);
+    cw[3] = cw[4] = 0u;
+    uint32_t av[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) av[i] = __funnelshift_r(cw[0], cw[1], 2 * i) & maskL;
+    uint32_t na = 0;        // records queued for this chunk (warp-uniform); > EDIT_QCAP: overflow
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      // windows G[tt] = text from character (d_lo - L + tt): bits [2L, 4L) hold the piece at distance
+      // d_lo + (tt - i) from position i
+      const int d_lo = L + b * EDIT_DBLOCK;
+      uint32_t G[16 + EDIT_DBLOCK - 1];
+#pragma unroll
+      for (int tt = 0; tt < 16 + EDIT_DBLOCK - 1; tt++) {
+        const int q = d_lo - L + tt;
+        G[tt] = (q < 48) ? __funnelshift_r(cw[q >> 4], cw[(q >> 4) + 1], 2 * (q & 15)) : 0u;
+      }
+#pragma unroll
+      for (int dd = 0; dd < EDIT_DBLOCK; dd++) {
+        const int d = d_lo + dd;
+        if (!ED::used(d)) continue;
+        uint32_t hm = 0u;
+#pragma unroll
+        for (int i = 0; i < 16; i++) hm = pair_probe(t.bitmap, (G[i + dd] & maskHi) | av[i], mult, 0u, wsh, hm);
+        hm &= vm;
+        // queue (lane, distance, positions): no stage A here, the lookups stay straight-line code
+        const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);
+        const uint32_t at = na + __popc(bal & t.lt);
+        if (hm && at < (uint32_t)EDIT_QCAP) queue[at] = lane_tag | ((uint32_t)ED::index(d) << 16) | hm;
+        na += __popc(bal);
+      }
+    }
+    const int64_t w_base = w - t.lane;
+    if (na > (uint32_t)EDIT_QCAP) {
+      t.n_queued += pair_edit_chunk_slow<L>(a, t.bitmap, t.bitmap2, w_base, cw[0], cw[1], cw[2], vm, t.lane);
+    } else {
+      t.n_queued += na;
+      __syncwarp();
+      for (uint32_t r0 = 0; r0 < na; r0 += 32u) {
+        const bool valid = r0 + t.lane < na;
+        const uint32_t rec = valid ? queue[r0 + t.lane] : 0u;
+        pair_stage_a_edit<L>(a, t.bitmap2, w_base, valid, rec, t.lane);
+      }
+      __syncwarp();
+    }
+  }
+  if (t.lane == 0 && a.work_count) atomicAdd(a.work_count, t.n_queued);
+}
+
+template <int K>
+inline PairKernel pair_edit_kernel_l(int L) {
+  switch (L) {
+    case 4: return pair_scan_edit_kernel<4, K>;
+    case 5: return pair_scan_edit_kernel<5, K>;
+    case 6: if (K <= 2) return pair_scan_edit_kernel<6, (K <= 2 ? K : 1)>; break;
+    case 7: if (K <= 2) return pair_scan_edit_kernel<7, (K <= 2 ? K : 1)>; break;
+    case 8: if (K <= 1) return pair_scan_edit_kernel<8, 1>; break;
+  }
+  return nullptr;
+}
+// specialised edit kernel for (L, K), or nullptr
+inline PairKernel pair_edit_kernel(int L, int K) {
+  switch (K) {
+    case 1: return pair_edit_kernel_l<1>(L);
+    case 2: return pair_edit_kernel_l<2>(L);
+    case 3: return pair_edit_kernel_l<3>(L);
+  }
+  return nullptr;
+}
+
+// Edit verifier of pair_scan_edit_kernel's seeds: one seed per thread, furthest-reaching
+// extension from the seed's first piece (pm_lv.cuh) on the packed text.
+template <int K>
+__global__ void __launch_bounds__(128)
+index_verify_lv_kernel(const __grid_constant__ IndexArgs a) {
+  unsigned long long count = *a.seed_n;
+  if (count > a.seed_cap) count = a.seed_cap;
+  const int L = (int)a.L;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long sd = a.seeds[i];
+    const uint32_t slot = (uint32_t)(sd >> (SEED_POS_BITS + 3));
+    const int pi = (int)((sd >> SEED_POS_BITS) & 7ULL);
+    const int64_t s_nom = (int64_t)(sd & ((1ULL << SEED_POS_BITS) - 1ULL)) - SEED_BIAS;
+    LvCtx t;
+    t.m = (int)(a.plen[slot] & 0x7fu);
+    t.lenmask = (t.m >= 32) ? ~0ULL : ((1ULL << (2 * t.m)) - 1ULL);
+    const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
+    const ulonglong2 acc01 = __ldg(accp), acc23 = __ldg(accp + 1);
+    t.acc[0] = acc01.x; t.acc[1] = acc01.y; t.acc[2] = acc23.x; t.acc[3] = acc23.y;
+    const int64_t s0 = s_nom - K;
+    const int64_t wb = s0 >> 4;   // arithmetic shift: s0 may be negative near the start
+    const uint32_t sh = 2u * (uint32_t)(s0 & 15);
+    const uint2 p0 = pk_load(a, wb), p1 = pk_load(a, wb + 1), p2 = pk_load(a, wb + 2), p3 = pk_load(a, wb + 3);
+    t.c[0] = __funnelshift_r(p0.x, p1.x, sh); t.c[1] = __funnelshift_r(p1.x, p2.x, sh); t.c[2] = __funnelshift_r(p2.x, p3.x, sh);
+    t.f[0] = __funnelshift_r(p0.y, p1.y, sh); t.f[1] = __funnelshift_r(p1.y, p2.y, sh); t.f[2] = __funnelshift_r(p2.y, p3.y, sh);
+    const uint32_t ends = lv_verify<K>(t, pi * L, L);
+#pragma unroll
+    for (int d = -K; d <= K; d++)
+      if ((ends >> (d + K)) & 1u) index_emit(a, slot, s_nom + t.m + d);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.seed_count) atomicAdd(a.seed_count, count);
+}
+
 // level 1b for large pattern sets (substitutions): level 1 passes a sizeable fraction of the
 // positions there; ask the L2-resident (key, distance) table before anything is queued.  The
 // 16 loads of a lane are independent, so their latencies overlap.  Kept out of line: its 32
@@ -490,7 +739,6 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
   pair_cta_finish<false>(a, t);
 }
 
-typedef void (*PairKernel)(const IndexArgs);
 template <int L, bool B1>
 inline PairKernel pair_sub_kernel_nd(int nd) {
   switch (nd) {
