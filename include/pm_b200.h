@@ -138,6 +138,13 @@ void pm_destroy(pm_ctx *ctx);
 #define PM_ALIGN_PCR_MATCH 1
 int pm_set_alignment_rules(pm_ctx *ctx, int rules);
 
+/* CharacterProducer::size() of the database the index will scan (before pm_init): 256 for a
+ * streamed FASTA file (the default), the size of the character table for a .sqn / .sqz
+ * database.  pick_pattern_index consults it when it chooses exact_halves for k == 1: primers
+ * of at least 12 characters when the alphabet has fewer than 10, of at least 8 otherwise
+ * (select.cc:120-123).  Only PM_INDEX_AUTO depends on it.                                */
+int pm_set_alphabet_size(pm_ctx *ctx, int size);
+
 /* Select the device scan (before pm_init).  PM_SCAN_INDEX on patterns it cannot
  * serve makes pm_init fail with PM_E_UNSUPPORTED.                              */
 int pm_set_scan_path(pm_ctx *ctx, int path);

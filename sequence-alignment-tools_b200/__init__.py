@@ -37,7 +37,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size"]
 
 
 class PmError(RuntimeError):
@@ -105,6 +105,7 @@ def lib():
         L.pm_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.pm_set_scan_path.argtypes = [C.c_void_p, C.c_int]
         L.pm_set_alignment_rules.argtypes = [C.c_void_p, C.c_int]
+        L.pm_set_alphabet_size.argtypes = [C.c_void_p, C.c_int]
         L.pm_add_pattern.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int]
         L.pm_init.argtypes = [C.c_void_p]
         L.pm_set_text_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int64]
@@ -220,6 +221,10 @@ class Scanner:
         """PM_ALIGN_PCR_MATCH: the alignment pcr_match makes of every hit (differs from
         primer_match's for k = 0 with wildcards)."""
         _check(lib().pm_set_alignment_rules(self._h, rules))
+
+    def set_alphabet_size(self, size: int):
+        """CharacterProducer::size() of the database (select.cc:120-123); before init()."""
+        _check(lib().pm_set_alphabet_size(self._h, size))
 
     def set_stream(self, cuda_stream: int):
         _check(lib().pm_set_stream(self._h, C.c_void_p(cuda_stream)))

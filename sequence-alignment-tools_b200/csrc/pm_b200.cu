@@ -157,6 +157,7 @@ struct pm_ctx {
   bool inner_bases = false;  // ... exact_bases
   bool unordered_ok = false; // this IS such an inner context: run_scan may leave the candidates unsorted
   int align_rules = PM_ALIGN_PRIMER_MATCH;  // whose alignment an exact (k == 0) hit gets, pm_set_alignment_rules
+  int alphabet_size = 256;   // CharacterProducer::size() of the database, pm_set_alphabet_size
   DevBuf d_half_rec, d_half_key, d_half_key2, d_half_ord, d_half_ord2;
   int max_len = 0;
   // symbols
@@ -199,6 +200,7 @@ struct pm_ctx {
   bool index_ok = false;         // resolved in pm_init: the patterns can use the pair index
   bool idx_has_amb = false;      // some text byte would be ambiguous (wildcards): pack lists them
   bool idx_dna_fast = false;     // text codes are (byte >> 1) & 3 for A, C, G, T: table-free pack
+  bool idx_edit_special = false; // edits: pair_scan_edit_kernel<L, K> + index_verify_lv_kernel<K> serve (else the run-time pair)
   DevBuf d_amb;
   int idx_q = 0;                 // piece length L of the pair index
   DevBuf d_pk, d_bucket, d_entries, d_pacc, d_umask4, d_lin, d_bitmap, d_bitmap2;
@@ -467,9 +469,10 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
   if (c->use_index && edit) {
     // the kernel specialised for (piece length, k) and the verifier that reads its seeds;
     // PM_EDIT_GENERIC=1 keeps the run-time kernel pair (for A/B measurements)
-    static const bool generic = getenv("PM_EDIT_GENERIC") && atoi(getenv("PM_EDIT_GENERIC")) != 0;
-    PairKernel ek = generic ? nullptr : pair_edit_kernel((int)c->idx_proto.L, K);
-    if (ek && c->n < (1ull << (SEED_POS_BITS - 1))) {
+    PairKernel ek = c->idx_edit_special ? pair_edit_kernel((int)c->idx_proto.L, K) : nullptr;
+    if (c->n >= (1ull << (SEED_POS_BITS - 1)))
+      return fail(PM_E_UNSUPPORTED, "shard longer than 2^38 characters for the edit scan of the pair index");
+    if (ek) {
       ikern = ek;
       ivkern = K <= 1 ? index_verify_lv_kernel<1> : (K == 2 ? index_verify_lv_kernel<2> : index_verify_lv_kernel<3>);
     }
@@ -1180,6 +1183,14 @@ int pm_set_alignment_rules(pm_ctx *c, int rules) {
   return PM_OK;
 }
 
+int pm_set_alphabet_size(pm_ctx *c, int size) {
+  if (!c) return fail(PM_E_ARG, "null context");
+  if (c->inited) return fail(PM_E_ARG, "pm_set_alphabet_size after pm_init");
+  if (size < 1 || size > 256) return fail(PM_E_ARG, "alphabet size must be 1..256");
+  c->alphabet_size = size;
+  return PM_OK;
+}
+
 int pm_set_scan_path(pm_ctx *c, int path) {
   if (!c) return fail(PM_E_ARG, "null context");
   if (c->inited) return fail(PM_E_ARG, "pm_set_scan_path after pm_init");
@@ -1338,8 +1349,11 @@ int pm_init(pm_ctx *c) {
       cumdiff += ex - len / 2;
       cumbooldiff += (ex - len / 2 >= 0) ? 1 : 0;
     }
-    // a streamed FASTA database has CharacterProducer::size() == 256 (char_io.h:96)
-    if (min_length >= 8 && (cumbooldiff <= 0 || cumdiff <= 0)) c->index = PM_INDEX_EXACT_HALVES;
+    // select.cc:120-123: the alphabet size of the database decides how long the shortest primer
+    // has to be.  A streamed FASTA database has CharacterProducer::size() == 256 (char_io.h:96),
+    // a .sqn / .sqz database the size of its character table (pm_set_alphabet_size).
+    const long need = (c->alphabet_size < 10) ? 12 : 8;
+    if (min_length >= need && (cumbooldiff <= 0 || cumdiff <= 0)) c->index = PM_INDEX_EXACT_HALVES;
   }
   if (c->index_auto && K > 0 && ns > 0 && c->index == PM_INDEX_FILTER_BITVEC) {
     // select.cc:131-133: exact_bases when every pattern has 6 or more constrained characters
@@ -1549,6 +1563,10 @@ int pm_init(pm_ctx *c) {
       static const size_t big_set_entries = getenv("PM_BIG_SET_ENTRIES") ? (size_t)atoll(getenv("PM_BIG_SET_ENTRIES")) : 100000;
       const bool big_set = ents.size() > big_set_entries;
       ia.b2_global = big_set ? 1u : 0u;
+      // the edit kernel specialised on (L, k) reads level 1 through the bijective index when the keys fit
+      static const bool edit_generic = getenv("PM_EDIT_GENERIC") && atoi(getenv("PM_EDIT_GENERIC")) != 0;
+      c->idx_edit_special = edit_mode && !edit_generic && pair_edit_kernel(L, K) != nullptr;
+      ia.l1_bij = (c->idx_edit_special && 4 * L <= 20 && ia.log_words == 15) ? 1u : 0u;
       // substitutions, 24 k .. 100 k entries: level 1 passes 2-10 % of the lookups; the 64 KB
       // (key, distance) bitmap in the free shared memory removes most of them (+7-10 %); a kernel
       // variant of its own (pair_scan_sub_kernel<.., B1 = true>), the plain one has no register to spare
@@ -1563,8 +1581,17 @@ int pm_init(pm_ctx *c) {
       std::vector<uint32_t> hs(ents.size());
       for (size_t x = 0; x < ents.size(); x++) {
         const uint32_t di = (ents[x].y >> 5) & 31u;
-        const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
-        bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
+        if (ia.l1_bij) {
+          // pair keys of at most 20 bits (L <= 5) against the 2^20 bits of level 1: an odd multiplier
+          // mod 2^20 is a bijection, so a text key only ever meets the bit of the SAME key -- no
+          // hash collisions (a non-injective hash costs 3x the false positives here: the key space
+          // is no larger than the table, profiles/README.md)
+          const uint32_t v = (ents[x].x * ia.mult) & 0xfffffu;
+          bitmap[v >> 5] |= 1u << (31u - (v & 31u));
+        } else {
+          const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
+          bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
+        }
         if (have2) {
           const uint32_t idx2 = ents[x].x * ia.mult2 + ia.salt2[di];
           bitmap2[idx2 >> (32 - ia.log_words2)] |= 1u << (idx2 & 31u);

@@ -62,6 +62,8 @@ struct IndexArgs {
   uint32_t L;               // piece length
   uint32_t nd;              // distances
   uint32_t mult;            // odd multiplier of the level-1 hash
+  uint32_t l1_bij;          // level 1 indexed by (key * mult) mod 2^20, a bijection of keys of <= 20 bits
+                            // (the edit kernels with L <= 5); else by the hash key * mult + salt
   uint32_t dist[PAIR_MAX_ND];
   uint32_t salt[PAIR_MAX_ND];
   // level 1b: a second bitmap keyed by (pair key, distance), consulted only for the positions
@@ -356,6 +358,15 @@ __device__ __forceinline__ uint32_t pair_probe(const uint32_t *bitmap, uint32_t 
   return __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);
 }
 
+// the same through the bijective index of short keys (IndexArgs::l1_bij): v = key * mult mod 2^20,
+// word v >> 5, bit 31 - (v & 31).  Two multiplies (FMA pipe, which has room) keep the ALU count:
+// the word index comes from key * (mult << 12), the rotation from key * mult.
+__device__ __forceinline__ uint32_t pair_probe_bij(const uint32_t *bitmap, uint32_t key, uint32_t mult, uint32_t mult_hi,
+                                                   uint32_t hm) {
+  const uint32_t wrd = bitmap[(key * mult_hi) >> 17];
+  return __funnelshift_l(__funnelshift_l(wrd, wrd, key * mult), hm, 1);
+}
+
 // Generic kernel: run-time piece length and distance set, one distance after the other.
 // Serves the edit scans (13-19 distances: they are bound by the shared-memory wavefront
 // rate of the lookups themselves -- a variant sharing the shifted windows between the
@@ -512,8 +523,10 @@ __device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const 
     const uint32_t X0 = __funnelshift_r(y0, y1, s), X1 = __funnelshift_r(y1, y2, s);
     uint32_t hm = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++)
-      hm = pair_probe(bitmap, (__funnelshift_r(X0, X1, 2 * i) & maskHi) | (__funnelshift_r(c0, c1, 2 * i) & maskL), a.mult, 0u, wsh, hm);
+    for (int i = 0; i < 16; i++) {
+      const uint32_t key = (__funnelshift_r(X0, X1, 2 * i) & maskHi) | (__funnelshift_r(c0, c1, 2 * i) & maskL);
+      hm = (4 * L <= 20) ? pair_probe_bij(bitmap, key, a.mult, a.mult << 12, hm) : pair_probe(bitmap, key, a.mult, 0u, wsh, hm);
+    }
     hm &= vm;
     if (__any_sync(0xffffffffu, hm != 0u)) {
       n_queued += __popc(__ballot_sync(0xffffffffu, hm != 0u));
@@ -566,7 +579,10 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
         if (!ED::used(d)) continue;
         uint32_t hm = 0u;
 #pragma unroll
-        for (int i = 0; i < 16; i++) hm = pair_probe(t.bitmap, (G[i + dd] & maskHi) | av[i], mult, 0u, wsh, hm);
+        for (int i = 0; i < 16; i++) {
+          const uint32_t key = (G[i + dd] & maskHi) | av[i];
+          hm = (4 * L <= 20) ? pair_probe_bij(t.bitmap, key, mult, mult << 12, hm) : pair_probe(t.bitmap, key, mult, 0u, wsh, hm);
+        }
         hm &= vm;
         // queue (lane, distance, positions): no stage A here, the lookups stay straight-line code
         const uint32_t bal = __ballot_sync(0xffffffffu, hm != 0u);

@@ -54,7 +54,18 @@ int pm_init(pm_ctx *) { return PM_OK; }
 int pm_reset(pm_ctx *) { return PM_OK; }
 int pm_set_alignment_rules(pm_ctx *, int) { return PM_OK; }
 
-int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *, uint64_t, int) {
+int pm_set_alphabet_size(pm_ctx *, int) { return PM_OK; }
+int pm_host_alloc(uint64_t bytes, int, void **out) { *out = malloc(bytes ? bytes : 1); return *out ? PM_OK : PM_E_NOMEM; }
+int pm_host_free(void *p) { free(p); return PM_OK; }
+
+static int load_canned(pm_ctx *c);
+// whatever form the database arrives in, the canned stream / sequence table / hits are served
+int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *, uint64_t, int) { return load_canned(c); }
+int pm_set_text_host(pm_ctx *c, const uint8_t *, uint64_t, int64_t) { return load_canned(c); }
+int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *, uint64_t, const uint8_t *, uint32_t, uint64_t, int64_t) { return load_canned(c); }
+int pm_set_text_sqn_host(pm_ctx *c, const uint8_t *, uint64_t, const uint8_t *, uint32_t, int64_t) { return load_canned(c); }
+
+static int load_canned(pm_ctx *c) {
   c->stream = slurp("stream.bin");
   std::vector<uint8_t> s = slurp("seqs.bin");
   int64_t n = 0;
