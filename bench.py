@@ -76,6 +76,9 @@ CONFIGS = {
                          ref_bp=20_000, metric="Gbp/s scanned, 100k 20-mer oligos k=1 (-N 5) both strands",
                          baseline="BASELINE.json configs[4] (shift_and_inexact leg), 30 Gbp / 8 GPUs per shard"),
 }
+# not a BASELINE configuration: the 20-mer edit scan (A/B runs of tools/run_config.py)
+CONFIGS["edit20_k2"] = dict(nprimers=1000, plen=20, k=2, indels=1, iupac=0, select=0, bases=3_000_000_000, ref_bp=600_000,
+                            metric="Gbp/s scanned, 1k 20-mer primers k=2 edits both strands", baseline="(none)")
 ALL_ORDER = ["headline", "iupac_k2", "edit25_k3", "p100_k1", "oligo100k_exact", "oligo100k_k1"]
 
 

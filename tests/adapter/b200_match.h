@@ -162,10 +162,16 @@ class b200_match : public PatternMatch {
       scanned_ = true;
       next_ = 0;
     }
+    int64_t frontier = 0;
     while (next_ < nhits_ && phs.size() < minka) {
       const pm_hit &h = hits_[next_++];
       phs.push_back((FILE_POSITION_TYPE)h.end, std::make_pair(plit_[h.pattern_id], (unsigned char)h.value));
+      if (h.end > frontier) frontier = h.end;
     }
+    // the reference's indexes leave the producer at their scan frontier, behind every hit they
+    // report: a StreamedFastaFile only knows the sequences it has read past (get_seq_pos /
+    // get_header_data, fasta_io.t:163-215), so it is moved there before the caller looks them up
+    if (frontier > (int64_t)cp.pos()) cp.pos((FILE_POSITION_TYPE)frontier);
     return next_ < nhits_;
   }
   void reset() {

@@ -84,6 +84,39 @@ def test_reference_main_through_the_adapter_on_the_mock(adapter, oracle, golden,
     assert checked >= 15
 
 
+def test_adapter_moves_the_producer_to_the_scan_frontier(adapter, oracle, tmp_path):
+    """A database longer than the adapter's prefix probe, several sequences, exact search: the
+    reference's main() does not read the text for an exact_alignment, so the sequence index and
+    header of a hit in a later sequence are only right when find_patterns has moved the producer
+    past it (what the reference's own indexes do by scanning)."""
+    import casegen
+    real = os.path.join(ROOT, PKG_NAME, "lib", "libpm_b200.so")
+    for seed, k in ((71, 0), (72, 2)):
+        fasta_text, primers = casegen.make_case(seed, nseq=5, seqlen=12000, nprimers=8, plen=(18, 22), k=k, indels=True)
+        par = dict(k=k, indels=True, wc=False, tn=False, rev_comp=True)
+        fasta = fasta_text.encode()
+        d = str(tmp_path / ("f%d" % seed))
+        os.makedirs(d)
+        st = oracle.normalize_fasta(fasta)
+        pats = oracle.pattern_array(primers, True)
+        lc, rc = oracle.pattern_constraints(primers, True)
+        hits = oracle.aligned_hits(st, pats, lc, rc, k, True, False, False)
+        assert len(st.chars) > 20000 and any(h[2] > 18000 for h in hits)
+        from test_cli_host_logic import write_mock_inputs as wmi
+        wmi(d, fasta, st, hits)
+        fa = os.path.join(d, "db.fasta")
+        with open(fa, "wb") as f:
+            f.write(fasta)
+        ref = os.path.join(ROOT, "oracle", "_ref", "primer_match")
+        if not os.path.exists(ref):
+            pytest.skip("needs oracle/_ref/primer_match")
+        args = _golden_args(fa, primers, par, ["-A", oracle.REF_FORMAT])
+        want = subprocess.run([ref] + args, capture_output=True, timeout=300).stdout.decode("latin-1")
+        env = dict(os.environ, PM_MOCK_DIR=d, PM_REAL_LIB=real)
+        got = _run(adapter["primer_match_b200_mock"], args, env)
+        assert sorted(got.splitlines()) == sorted(want.splitlines()) and len(want.splitlines()) >= 5
+
+
 def test_reference_pcr_match_through_the_adapter_on_the_mock(adapter, oracle, pcr_golden, tmp_path):
     real = os.path.join(ROOT, PKG_NAME, "lib", "libpm_b200.so")
     n = 0

@@ -13,7 +13,7 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="headline", choices=bench.ALL_ORDER)
+    ap.add_argument("--config", default="headline", choices=list(bench.CONFIGS))
     ap.add_argument("--bases", type=int, default=1_000_000_000)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
