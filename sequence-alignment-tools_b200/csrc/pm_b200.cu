@@ -497,7 +497,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
     ia.hi = hi;
     ia.k = (uint32_t)K;
     ismem = ((size_t)4 << ia.log_words) + (size_t)PAIR_WARPS * 2 * PAIR_QCAP * 8 +
-            ((ia.log_words2 && !ia.b2_global) ? ((size_t)4 << ia.log_words2) : 0);
+            ((ia.log_words2 && !ia.b2_global) ? ((size_t)4 << ia.log_words2) : 0) +
+            (size_t)PAIR_WARPS * 32 * sizeof(uint16_t);   // staging rows of the edit kernels' stage A
     PM_CUDA(cudaFuncSetAttribute(ikern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ismem));
   }
   void (*kern)(const ScanArgs) = nullptr;
@@ -1619,6 +1620,18 @@ int pm_init(pm_ctx *c) {
               um4[i * 4 + cc] |= 1u << j;
             }
         }
+      }
+      {
+        // plain patterns: every character accepts exactly one text code (the edit verifier then
+        // compares codes with one XOR)
+        bool plain = true;
+        for (size_t i = 0; i < ns && plain; i++)
+          for (int j = 0; j < (int)c->pats[i].s.size() && plain; j++) {
+            int n_acc = 0;
+            for (int cc = 0; cc < 4; cc++) n_acc += (int)((pacc[i * 4 + cc] >> (2 * j)) & 1ull);
+            plain = (n_acc == 1);
+          }
+        ia.plain_patterns = plain ? 1u : 0u;
       }
       const Up iups[] = {{&c->d_bucket, bucket.data(), bucket.size() * 4},
                          {&c->d_entries, sorted.data(), sorted.size() * 8},

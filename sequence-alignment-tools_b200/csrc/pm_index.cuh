@@ -62,6 +62,7 @@ struct IndexArgs {
   uint32_t L;               // piece length
   uint32_t nd;              // distances
   uint32_t mult;            // odd multiplier of the level-1 hash
+  uint32_t plain_patterns;  // every pattern character accepts exactly one text code (no IUPAC symbols)
   uint32_t l1_bij;          // level 1 indexed by (key * mult) mod 2^20, a bijection of keys of <= 20 bits
                             // (the edit kernels with L <= 5); else by the hash key * mult + salt
   uint32_t dist[PAIR_MAX_ND];
@@ -441,50 +442,47 @@ struct EditDist {
 
 constexpr int SEED_POS_BITS = 39;   // edit seeds of the index path: slot << 42 | piece index << 39 | biased start
 
-// Stage A of the edit scan: one queued record per lane = (word of the chunk, distance index,
-// 16-bit mask of the word's positions that passed level 1).  Every set position first asks
-// level 1b (the shared-memory bitmap keyed by (pair key, distance)), then walks its bucket of the
-// exact table; matches become seeds (slot, piece index, nominal start).
+// Stage A of the edit scan, in two steps so that neither waits for the other's stragglers:
+//   A1  one queued record per lane = (lane that owns the word, distance index, 16-bit mask of the
+//       word's positions that passed level 1).  Every set position asks level 1b (the shared-memory
+//       bitmap keyed by (pair key, distance)); what passes is compacted across the warp into a
+//       32-entry staging row (lane, position, distance);
+//   A2  32 staged entries at a time: one (position, distance) per lane walks its bucket of the
+//       exact table in L2; matches become seeds (slot, piece index, nominal start).
+// The text words of a record's lane come from that lane's registers (shuffle), not from memory.
 template <int L>
-__device__ __forceinline__ void pair_stage_a_edit(const IndexArgs &a, const uint32_t *bitmap2, int64_t w_base,
-                                                  bool valid, uint32_t rec, uint32_t lane) {
-  const int64_t w = w_base + (int64_t)(rec >> 21);
-  const uint32_t di = (rec >> 16) & 31u;
-  uint32_t hm = valid ? (rec & 0xffffu) : 0u;
+__device__ __forceinline__ uint32_t pair_edit_key(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t b, uint32_t d2) {
   constexpr uint32_t L2 = 2u * L;
   constexpr uint32_t maskL = (1u << L2) - 1u;
-  const uint32_t d2 = 2u * a.dist[valid ? di : 0u];
-  const uint32_t salt2 = a.salt2[valid ? di : 0u], wsh2 = 32u - a.log_words2;
-  uint32_t c0 = 0, c1 = 0, c2 = 0;
-  if (valid) { c0 = pk_codes(a, w); c1 = pk_codes(a, w + 1); c2 = pk_codes(a, w + 2); }
+  const uint32_t i2 = 2u * (15u - b);
+  const uint32_t v0 = __funnelshift_r(c0, c1, i2), v1 = __funnelshift_r(c1, c2, i2), v2 = c2 >> i2;
+  const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
+  return (v0 & maskL) | ((hi & maskL) << L2);
+}
+
+template <int L>
+__device__ __forceinline__ void pair_edit_a2(const IndexArgs &a, int64_t w_base, uint32_t cw0, uint32_t cw1,
+                                             uint32_t cw2, bool valid, uint32_t ent, uint32_t lane) {
+  const uint32_t src = (ent >> 9) & 31u, b = (ent >> 5) & 15u, di = ent & 31u;
+  const uint32_t c0 = __shfl_sync(0xffffffffu, cw0, src), c1 = __shfl_sync(0xffffffffu, cw1, src),
+                 c2 = __shfl_sync(0xffffffffu, cw2, src);
   uint32_t e0 = 0, e1 = 0, key = 0;
-  int64_t p = 0;
+  if (valid) {
+    key = pair_edit_key<L>(c0, c1, c2, b, 2u * a.dist[di]);
+    const uint32_t h = pair_hash2(key, di, a.log_buckets);
+    e0 = __ldg(a.bucket + h);
+    e1 = __ldg(a.bucket + h + 1);
+  }
+  const int64_t p = ((w_base + (int64_t)src) << 4) + (15 - (int)b);
   const uint32_t lt = (1u << lane) - 1u;
-  for (;;) {
-    if (!__any_sync(0xffffffffu, (hm != 0u) || (e0 < e1))) break;
-    if (e0 >= e1 && hm) {  // next set position of the word: level 1b, then its bucket
-      const int b = __ffs(hm) - 1;
-      hm &= hm - 1;
-      const uint32_t i2 = 2u * (uint32_t)(15 - b);
-      const uint32_t v0 = __funnelshift_r(c0, c1, i2), v1 = __funnelshift_r(c1, c2, i2), v2 = c2 >> i2;
-      const uint32_t hi = (d2 >= 32u) ? __funnelshift_r(v1, v2, d2) : __funnelshift_r(v0, v1, d2);
-      key = (v0 & maskL) | ((hi & maskL) << L2);
-      const uint32_t idx2 = key * a.mult2 + salt2;
-      const uint32_t wrd = bitmap2[idx2 >> wsh2];
-      if ((wrd >> (idx2 & 31u)) & 1u) {
-        const uint32_t h = pair_hash2(key, di, a.log_buckets);
-        e0 = __ldg(a.bucket + h);
-        e1 = __ldg(a.bucket + h + 1);
-        p = (w << 4) + (15 - b);
-      }
-    }
+  while (__any_sync(0xffffffffu, e0 < e1)) {
     bool found = false;
     uint32_t meta = 0;
     if (e0 < e1) {
-      const uint2 ent = __ldg(a.entries + e0);
+      const uint2 en = __ldg(a.entries + e0);
       ++e0;
-      meta = ent.y;
-      found = (ent.x == key) && (((meta >> 5) & 31u) == di);
+      meta = en.y;
+      found = (en.x == key) && (((meta >> 5) & 31u) == di);
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, found);
     if (bal == 0u) continue;
@@ -504,16 +502,57 @@ __device__ __forceinline__ void pair_stage_a_edit(const IndexArgs &a, const uint
   }
 }
 
+// A1 over 32 records (one per lane); `stage` = this warp's 32 staging entries, n_staged how many
+// wait there (warp-uniform, < 32 on entry and on return).
+template <int L>
+__device__ __forceinline__ void pair_edit_a1(const IndexArgs &a, const uint32_t *bitmap2, uint16_t *stage,
+                                             uint32_t &n_staged, int64_t w_base, uint32_t cw0, uint32_t cw1, uint32_t cw2,
+                                             bool valid, uint32_t rec, uint32_t lane) {
+  const uint32_t src = (rec >> 21) & 31u, di = (rec >> 16) & 31u;
+  uint32_t hm = valid ? (rec & 0xffffu) : 0u;
+  const uint32_t c0 = __shfl_sync(0xffffffffu, cw0, src), c1 = __shfl_sync(0xffffffffu, cw1, src),
+                 c2 = __shfl_sync(0xffffffffu, cw2, src);
+  const uint32_t d2 = 2u * a.dist[valid ? di : 0u];
+  const uint32_t salt2 = a.salt2[valid ? di : 0u], wsh2 = 32u - a.log_words2;
+  const uint32_t lt = (1u << lane) - 1u;
+  while (__any_sync(0xffffffffu, hm != 0u)) {
+    bool pass = false;
+    uint32_t ent = 0;
+    if (hm) {
+      const uint32_t b = (uint32_t)(__ffs(hm) - 1);
+      hm &= hm - 1;
+      const uint32_t idx2 = pair_edit_key<L>(c0, c1, c2, b, d2) * a.mult2 + salt2;
+      pass = (bitmap2[idx2 >> wsh2] >> (idx2 & 31u)) & 1u;
+      ent = (src << 9) | (b << 5) | di;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (bal == 0u) continue;
+    const uint32_t at = n_staged + __popc(bal & lt), total = n_staged + __popc(bal);
+    if (pass && at < 32u) stage[at] = (uint16_t)ent;
+    if (total >= 32u) {     // a full row: A2 takes it, the rest of this round starts the next row
+      __syncwarp();
+      const uint32_t e = stage[lane];
+      __syncwarp();
+      pair_edit_a2<L>(a, w_base, cw0, cw1, cw2, true, e, lane);
+      if (pass && at >= 32u) stage[at - 32u] = (uint16_t)ent;
+      n_staged = total - 32u;
+    } else {
+      n_staged = total;
+    }
+  }
+}
+
 constexpr int EDIT_DBLOCK = 8;     // distances handled per block of shifted windows
+
 constexpr int EDIT_QCAP = 256;     // 4-byte records per warp: the queues' kilobyte per warp
 
 // One chunk the slow way (run-time distance loop, stage A after every distance): only for a chunk
 // whose records did not fit the queue -- text that repeats a piece pair of some pattern over and over.
 template <int L>
 __device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const uint32_t *bitmap, const uint32_t *bitmap2,
-                                                      int64_t w_base, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t vm,
-                                                      uint32_t lane) {
-  uint32_t n_queued = 0;
+                                                      uint16_t *stage, int64_t w_base, uint32_t c0, uint32_t c1,
+                                                      uint32_t c2, uint32_t vm, uint32_t lane) {
+  uint32_t n_queued = 0, n_staged = 0;
   const uint32_t wsh = 32u - a.log_words;
   constexpr uint32_t maskL = (1u << (2 * L)) - 1u, maskHi = maskL << (2 * L);
   for (uint32_t di = 0; di < a.nd; ++di) {
@@ -530,9 +569,13 @@ __device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const 
     hm &= vm;
     if (__any_sync(0xffffffffu, hm != 0u)) {
       n_queued += __popc(__ballot_sync(0xffffffffu, hm != 0u));
-      pair_stage_a_edit<L>(a, bitmap2, w_base, hm != 0u, (lane << 21) | (di << 16) | hm, lane);
+      pair_edit_a1<L>(a, bitmap2, stage, n_staged, w_base, c0, c1, c2, hm != 0u, (lane << 21) | (di << 16) | hm, lane);
     }
   }
+  __syncwarp();
+  const uint32_t e = (lane < n_staged) ? stage[lane] : 0u;
+  __syncwarp();
+  pair_edit_a2<L>(a, w_base, c0, c1, c2, lane < n_staged, e, lane);
   return n_queued;
 }
 
@@ -551,6 +594,9 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
   const uint32_t mult = a.mult;
   const uint32_t warp = threadIdx.x >> 5;
   uint32_t *queue = reinterpret_cast<uint32_t *>(t.q.qa);   // this warp's kilobyte: EDIT_QCAP records
+  // the staging rows of A1 / A2 lie behind level 1b (the host sizes the shared memory for them)
+  uint16_t *stage = reinterpret_cast<uint16_t *>(s_mem + (1u << a.log_words) + PAIR_WARPS * 2 * PAIR_QCAP * 2 +
+                                                 (1u << a.log_words2)) + warp * 32;
   const uint32_t lane_tag = t.lane << 21;
 
   for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
@@ -593,16 +639,20 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
     }
     const int64_t w_base = w - t.lane;
     if (na > (uint32_t)EDIT_QCAP) {
-      t.n_queued += pair_edit_chunk_slow<L>(a, t.bitmap, t.bitmap2, w_base, cw[0], cw[1], cw[2], vm, t.lane);
+      t.n_queued += pair_edit_chunk_slow<L>(a, t.bitmap, t.bitmap2, stage, w_base, cw[0], cw[1], cw[2], vm, t.lane);
     } else {
       t.n_queued += na;
       __syncwarp();
+      uint32_t n_staged = 0;
       for (uint32_t r0 = 0; r0 < na; r0 += 32u) {
         const bool valid = r0 + t.lane < na;
         const uint32_t rec = valid ? queue[r0 + t.lane] : 0u;
-        pair_stage_a_edit<L>(a, t.bitmap2, w_base, valid, rec, t.lane);
+        pair_edit_a1<L>(a, t.bitmap2, stage, n_staged, w_base, cw[0], cw[1], cw[2], valid, rec, t.lane);
       }
       __syncwarp();
+      const uint32_t e = (t.lane < n_staged) ? stage[t.lane] : 0u;
+      __syncwarp();
+      pair_edit_a2<L>(a, w_base, cw[0], cw[1], cw[2], t.lane < n_staged, e, t.lane);
     }
   }
   if (t.lane == 0 && a.work_count) atomicAdd(a.work_count, t.n_queued);
@@ -644,11 +694,9 @@ index_verify_lv_kernel(const __grid_constant__ IndexArgs a) {
     const int pi = (int)((sd >> SEED_POS_BITS) & 7ULL);
     const int64_t s_nom = (int64_t)(sd & ((1ULL << SEED_POS_BITS) - 1ULL)) - SEED_BIAS;
     LvCtx t;
-    t.m = (int)(a.plen[slot] & 0x7fu);
-    t.lenmask = (t.m >= 32) ? ~0ULL : ((1ULL << (2 * t.m)) - 1ULL);
     const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
     const ulonglong2 acc01 = __ldg(accp), acc23 = __ldg(accp + 1);
-    t.acc[0] = acc01.x; t.acc[1] = acc01.y; t.acc[2] = acc23.x; t.acc[3] = acc23.y;
+    lv_set_pattern(t, (int)(a.plen[slot] & 0x7fu), acc01.x, acc01.y, acc23.x, acc23.y, (int)a.plain_patterns);
     const int64_t s0 = s_nom - K;
     const int64_t wb = s0 >> 4;   // arithmetic shift: s0 may be negative near the start
     const uint32_t sh = 2u * (uint32_t)(s0 & 15);

@@ -51,7 +51,9 @@ constexpr int LV_NONE = -64;   // "diagonal not reached"
 struct LvCtx {
   uint32_t c[3], f[3];
   uint64_t acc[4];     // bit 2j: pattern character j accepts text code 0 / 1 / 2 / 3
-  uint64_t lenmask;    // bits 2j, j < m
+  uint64_t lenmask;    // bits below 2m
+  uint64_t pcodes;     // plain patterns (every character accepts exactly one code): the 2-bit codes
+  int plain;           // ... and the flag; lv_mis then is an XOR instead of four masked selects
   int m;
 };
 
@@ -62,6 +64,10 @@ PM_HD inline uint64_t lv_mis(const LvCtx &t, int fd, int K) {
   const uint64_t codes = (uint64_t)PM_FSR(t.c[0], t.c[1], sh) | ((uint64_t)PM_FSR(t.c[1], t.c[2], sh) << 32);
   const uint64_t flags = (uint64_t)PM_FSR(t.f[0], t.f[1], sh) | ((uint64_t)PM_FSR(t.f[1], t.f[2], sh) << 32);
   constexpr uint64_t M5 = 0x5555555555555555ULL;
+  if (t.plain) {
+    const uint64_t x = codes ^ t.pcodes;
+    return (((x | (x >> 1)) | flags) & M5 & t.lenmask) | ~t.lenmask;
+  }
   const uint64_t lo = codes & M5, hi = (codes >> 1) & M5;
   const uint64_t match = (~(hi | lo) & t.acc[0]) | (lo & ~hi & t.acc[1]) | (hi & ~lo & t.acc[2]) | (hi & lo & t.acc[3]);
   return ((~match | flags) & M5 & t.lenmask) | ~t.lenmask;   // positions past the pattern stop every extension
@@ -83,10 +89,44 @@ PM_HD inline int lv_lce_bwd(uint64_t mis, int j) {   // pattern positions j, j-1
 // length L, at text position s_nom + a): bit (d + K) of the result <=> an occurrence with
 // <= K errors ends behind text position s_nom + m + d - 1, i.e. candidate position
 // s_nom + m + d.  K is a template parameter so that the diagonal arrays stay in registers.
+PM_HD inline void lv_set_pattern(LvCtx &t, int m, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, int plain) {
+  t.m = m;
+  t.lenmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1ULL);
+  t.acc[0] = a0; t.acc[1] = a1; t.acc[2] = a2; t.acc[3] = a3;
+  t.plain = plain;
+  t.pcodes = (a1 | a3) | ((a2 | a3) << 1);
+}
+
 template <int K>
 PM_HD inline uint32_t lv_verify(const LvCtx &t, int a, int L) {
   const int m = t.m;
   constexpr int ND = 2 * K + 1;
+  // the mismatch vectors of the 2K+1 diagonals (every loop below has compile-time bounds, so
+  // the vectors and the furthest-reaching rows stay in registers)
+  uint64_t mis[ND];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < ND; i++) mis[i] = lv_mis(t, i - K, K);
+  // q-gram filter (q = 3): K errors cut the pattern into at most K+1 runs of matches, each on one
+  // of these diagonals, and destroy at most 3K of its m-2 triples of consecutive characters; the
+  // others match as a whole on some diagonal.  Random seeds fail here, before any extension.
+  {
+    uint64_t any3 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < ND; i++) {
+      const uint64_t nm = ~mis[i];
+      any3 |= nm & (nm >> 2) & (nm >> 4);
+    }
+#if defined(__CUDA_ARCH__)
+    const int n3 = __popcll(any3 & 0x5555555555555555ULL);
+#else
+    const int n3 = __builtin_popcountll(any3 & 0x5555555555555555ULL);
+#endif
+    if (n3 < m - 2 - 3 * K) return 0u;
+  }
   // walls: end-of-sequence characters of the window (flag bit 2i+1 of character i, window
   // offset i <-> text position s_nom - K + i)
   constexpr uint32_t ODD = 0xAAAAAAAAu;
@@ -130,33 +170,6 @@ PM_HD inline uint32_t lv_verify(const LvCtx &t, int a, int L) {
       }
     }
   }
-  // the mismatch vectors of the 2K+1 diagonals (every loop below has compile-time bounds, so
-  // the vectors and the furthest-reaching rows stay in registers)
-  uint64_t mis[ND];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-  for (int i = 0; i < ND; i++) mis[i] = lv_mis(t, i - K, K);
-  // q-gram filter (q = 3): K errors cut the pattern into at most K+1 runs of matches, each on one
-  // of these diagonals, and destroy at most 3K of its m-2 triples of consecutive characters; the
-  // others match as a whole on some diagonal.  Random seeds fail here, before any extension.
-  {
-    uint64_t any3 = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < ND; i++) {
-      const uint64_t nm = ~mis[i];
-      any3 |= nm & (nm >> 2) & (nm >> 4);
-    }
-#if defined(__CUDA_ARCH__)
-    const int n3 = __popcll(any3 & 0x5555555555555555ULL);
-#else
-    const int n3 = __builtin_popcountll(any3 & 0x5555555555555555ULL);
-#endif
-    if (n3 < m - 2 - 3 * K) return 0u;
-  }
-
   // ---- left: pattern[0, a) reversed against the text going left from the anchor ----------
   // state: j' pattern characters and x' = j' + d' text characters consumed; reversed diagonal
   // d' is the forward diagonal -d'.  x' <= lw; no deletion at x' == lw (see the header).

@@ -100,12 +100,11 @@ int main(int argc, char **argv) {
     };
     for (int p = 0; p < npat; p++) {
       LvCtx t;
-      t.m = m;
-      t.lenmask = (m >= 32) ? ~0ULL : ((1ULL << (2 * m)) - 1ULL);
-      for (int c = 0; c < 4; c++) t.acc[c] = 0;
+      uint64_t acc[4] = {0, 0, 0, 0};
       for (int j = 0; j < m; j++)
         for (const char *tc = "ACGT"; *tc; ++tc)
-          if (pmatch(pats[p][j], (uint8_t)*tc)) t.acc[code_of((uint8_t)*tc)] |= 1ULL << (2 * j);
+          if (pmatch(pats[p][j], (uint8_t)*tc)) acc[code_of((uint8_t)*tc)] |= 1ULL << (2 * j);
+      lv_set_pattern(t, m, acc[0], acc[1], acc[2], acc[3], wc ? 0 : 1);   // what the host passes: plain patterns without -w
       // pair seeds: pieces pi < pj exact at text distance (pj - pi) L + e, |e| <= K, never < L
       for (long pos = 1; pos < n; pos++) {
         for (int pi = 0; pi < P; pi++) {
