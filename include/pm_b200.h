@@ -283,6 +283,21 @@ int pm_get_sequences(pm_ctx *ctx, const int64_t **seq_key, const int64_t **hdr_o
                      const int64_t **hdr_len, uint64_t *n_seqs, uint64_t *stream_len);
 int pm_get_text(pm_ctx *ctx, uint64_t begin, uint64_t len, uint8_t *out);
 
+/* pick_fasta_file (select.t:23-190) and the reader in one call: opens `database` the way
+ * primer_match does for its -D value `dbind` -- 0: <db>.sqn if it exists, else <db>.sqz, else
+ * <db>.seq, else the FASTA file itself; 1: the FASTA file; 2: <db>.seq; 3: <db>.sqn + <db>.tbl;
+ * 4: <db>.sqz + <db>.tbz (the files compress_seq writes, with <db>.idb / <db>.hdr for the sequence
+ * index) -- and reads it with a few threads into a ring of page-locked chunk buffers while the copy
+ * engine moves the chunks that are full and the device normalises / unpacks / packs them: the
+ * pinned, double-buffered host reader of the input path (replaces MapFileChars / BufferedFileChars,
+ * char_io.h:150-190).  The file never sits in host memory as a whole.  pm_get_sequences and
+ * pm_get_header serve what FastaFile::get_seq_pos / get_header_data serve (fasta_io.t:163-215).
+ * Call after pm_init.  PM_READER_THREADS (environment) sets the reader threads (default 6).      */
+int pm_set_text_database(pm_ctx *ctx, const char *database, int dbind, int upper_case);
+/* Header line of sequence i (0-based, without '>' and the line end); valid until the next
+ * pm_set_text_* call.                                                                         */
+int pm_get_header(pm_ctx *ctx, uint64_t i, const char **text, uint64_t *len);
+
 /* Page-locked host buffers for the database (the pinned reader side of the input
  * path): pm_set_text_host / _sqz_host / _fasta_host read such memory directly by DMA.
  * write_combined != 0 asks for write-combined pages: right for a buffer the CPU only

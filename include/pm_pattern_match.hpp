@@ -27,57 +27,49 @@ inline void fatal(const std::string &msg) {
   std::exit(1);
 }
 
-// The CharacterProducer of this library: a FASTA database as StreamedFastaFile
-// presents it (fasta_io.t:448-751), with the header index FastaFile<H> keeps
-// (fasta_io.t:140-215).  The raw file is read into host memory; the normalised
-// stream is built on the device when an index adopts the stream (b200_index::init
-// -> pm_set_text_fasta_host) and only the sequence table comes back.  Without a
-// device (normalise_on_host) the stream is built by pm_normalize_fasta.
+// The CharacterProducer of this library: a sequence database as pick_fasta_file opens it
+// (select.t:23-190) -- the FASTA file itself (StreamedFastaFile, fasta_io.t:448-751) or the
+// .seq / .sqn / .sqz files of compress_seq (IndexedFastaFile) -- with the header index FastaFile<H>
+// keeps (fasta_io.t:140-215).  The file is read by the library's own reader (pm_set_text_database:
+// a ring of page-locked chunk buffers feeding the copy engine) when an index adopts the database
+// (b200_index::init); the stream is built on the device and only the sequence table comes back.
 class FastaStream {
  public:
-  FastaStream() : ctx_(0), stream_len_(0), upper_case_(false), eos_('\n') {}
-  bool load(const std::string &filename, bool upper_case, unsigned char eos) {
-    std::ifstream f(filename.c_str(), std::ios::binary);
-    if (!f) return false;
-    f.seekg(0, std::ios::end);
-    const std::streamoff n = f.tellg();
-    f.seekg(0);
-    raw_.resize((size_t)n);
-    if (n) f.read(&raw_[0], n);
+  FastaStream() : ctx_(0), stream_len_(0), dbind_(0), upper_case_(false), eos_('\n') {}
+  // the database and how to open it (-D: 0 automatic, 1 FASTA, 2 .seq, 3 .sqn, 4 .sqz)
+  bool load(const std::string &database, bool upper_case, unsigned char eos, int dbind = 0) {
+    std::ifstream f(database.c_str(), std::ios::binary);
+    std::ifstream g((database + ".idb").c_str(), std::ios::binary);
+    if (!f && !g) return false;
+    database_ = database;
     upper_case_ = upper_case;
     eos_ = eos;
+    dbind_ = dbind;
     return true;
   }
-  bool normalise_on_host() {
-    size_t nh = 2;
-    for (char ch : raw_) nh += (ch == '>');
-    chars_.resize(raw_.size() + 4);
-    key_.resize(nh);
-    hoff_.resize(nh);
-    hlen_.resize(nh);
-    uint64_t len = 0, ns = 0;
-    if (pm_normalize_fasta((const uint8_t *)raw_.data(), raw_.size(), upper_case_, eos_, chars_.data(), &len,
-                           key_.data(), hoff_.data(), hlen_.data(), nh, &ns) != PM_OK)
-      return false;
-    chars_.resize(len);
-    key_.resize(ns);
-    stream_len_ = len;
-    return true;
+  // CharacterProducer::size() as pick_pattern_index sees it (select.cc:120-123): 256 for the raw
+  // FASTA file, the size of the character table for a .sqn / .sqz database
+  int alphabet_size() const {
+    int kind = dbind_;
+    if (kind == 0) kind = exists(database_ + ".sqn") ? 3 : (exists(database_ + ".sqz") ? 4 : (exists(database_ + ".seq") ? 2 : 1));
+    if (kind != 3 && kind != 4) return 256;
+    std::ifstream t((database_ + (kind == 3 ? ".tbl" : ".tbz")).c_str(), std::ios::binary);
+    if (!t) return 256;
+    t.seekg(0, std::ios::end);
+    const long n = (long)t.tellg();
+    return (n >= 1 && n <= 256) ? (int)n : 256;
   }
-  // hand the raw bytes to the device and keep its sequence table
+  // hand the database to the device and keep its sequence table
   bool normalise_on_device(pm_ctx *ctx) {
-    if (pm_set_text_fasta_host(ctx, (const uint8_t *)raw_.data(), raw_.size(), upper_case_) != PM_OK) return false;
+    if (pm_set_text_database(ctx, database_.c_str(), dbind_, upper_case_) != PM_OK) return false;
     const int64_t *k = 0, *o = 0, *l = 0;
     uint64_t ns = 0, len = 0;
     if (pm_get_sequences(ctx, &k, &o, &l, &ns, &len) != PM_OK) return false;
     key_.assign(k, k + ns);
-    hoff_.assign(o, o + ns);
-    hlen_.assign(l, l + ns);
     stream_len_ = len;
     ctx_ = ctx;
     return true;
   }
-  std::string &raw() { return raw_; }
   // the sequence table (stream position of each entry's first character), for pm_pcr_pairs
   const int64_t *seq_keys() const { return key_.data(); }
   uint64_t n_seqs() const { return key_.size(); }
@@ -103,8 +95,11 @@ class FastaStream {
   unsigned long index(int64_t pos) const { const long i = locate(pos); return i < 0 ? 0 : (unsigned long)(i + 1); }
   std::string header(int64_t pos) const {
     const long i = locate(pos);
-    if (i < 0) return "";
-    return raw_.substr((size_t)hoff_[i], (size_t)(hlen_[i] > 0 ? hlen_[i] : 0));
+    if (i < 0 || !ctx_) return "";
+    const char *t = 0;
+    uint64_t n = 0;
+    if (pm_get_header(ctx_, (uint64_t)i, &t, &n) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
+    return std::string(t, (size_t)n);
   }
   std::string short_header(int64_t pos) const {  // first word, fasta_io.t:118-126
     const std::string h = header(pos);
@@ -115,8 +110,7 @@ class FastaStream {
   std::string text(int64_t a, int64_t b) const {
     if (a < 0) a = 0;
     if (b > (int64_t)stream_len_) b = (int64_t)stream_len_;
-    if (a >= b) return std::string();
-    if (!ctx_) return std::string((const char *)chars_.data() + a, (size_t)(b - a));
+    if (a >= b || !ctx_) return std::string();
     std::string out((size_t)(b - a), '\0');
     if (pm_get_text(ctx_, (uint64_t)a, (uint64_t)(b - a), (uint8_t *)&out[0]) != PM_OK)
       fatal(std::string("Fatal error: ") + pm_last_error());
@@ -124,11 +118,12 @@ class FastaStream {
   }
 
  private:
-  std::string raw_;
-  std::vector<uint8_t> chars_;
-  std::vector<int64_t> key_, hoff_, hlen_;
+  static bool exists(const std::string &p) { std::ifstream f(p.c_str(), std::ios::binary); return (bool)f; }
+  std::string database_;
+  std::vector<int64_t> key_;
   pm_ctx *ctx_;
   uint64_t stream_len_;
+  int dbind_;
   bool upper_case_;
   unsigned char eos_;
 };
@@ -178,6 +173,7 @@ class b200_index : public PatternMatch {
     return id;
   }
   void init(FastaStream &cp) {
+    if (pm_set_alphabet_size(ctx_, cp.alphabet_size()) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
     if (pm_init(ctx_) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());
     if (!cp.normalise_on_device(ctx_)) fatal(std::string("Fatal error: ") + pm_last_error());
   }

@@ -37,7 +37,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size", "pm_set_text_database", "pm_get_header"]
 
 
 class PmError(RuntimeError):
@@ -118,6 +118,8 @@ def lib():
         i64pp = C.POINTER(C.POINTER(C.c_int64))
         L.pm_get_sequences.argtypes = [C.c_void_p, i64pp, i64pp, i64pp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.pm_get_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.pm_set_text_database.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+        L.pm_get_header.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.pm_host_alloc.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
         L.pm_host_free.argtypes = [C.c_void_p]
         L.pm_shard_overlap.argtypes = [C.c_void_p]
@@ -286,6 +288,23 @@ class Scanner:
         headers = [bytes(view[op[i]:op[i] + max(lp[i], 0)]).decode("latin-1") for i in range(n)]
         chars = self.get_text(0, sl.value) if fetch_chars else None
         return Stream(chars, key, headers)
+
+    def set_text_database(self, database: str, dbind: int = 0, uc: bool = False) -> "Stream":
+        """The text read from a database on disk the way primer_match opens it for -D `dbind`
+        (pick_fasta_file): the FASTA file, or compress_seq's .seq / .sqn / .sqz, through the library's
+        own reader (ring of page-locked chunk buffers).  Returns the Stream with the sequence table."""
+        _check(lib().pm_set_text_database(self._h, database.encode(), dbind, int(uc)))
+        kp, op, lp = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        ns, sl = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().pm_get_sequences(self._h, C.byref(kp), C.byref(op), C.byref(lp), C.byref(ns), C.byref(sl)))
+        n = ns.value
+        key = np.array([kp[i] for i in range(n)], np.int64)
+        headers = []
+        for i in range(n):
+            tp, tl = C.c_void_p(), C.c_uint64(0)
+            _check(lib().pm_get_header(self._h, i, C.byref(tp), C.byref(tl)))
+            headers.append(C.string_at(tp, tl.value).decode("latin-1") if tl.value else "")
+        return Stream(None, key, headers)
 
     def get_text(self, begin: int, length: int) -> np.ndarray:
         out = np.zeros(length, np.uint8)

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "lib", "libpm_b200.so")
 CLI = os.path.join(HERE, "bin", "primer_match")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def _newer(target: str, sources) -> bool:
@@ -36,7 +36,7 @@ def _nvcc() -> str:
 
 
 def lib_sources():
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", "pm_pcr.hpp"))]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", "pm_pcr.hpp", "pm_reader.hpp"))]
     srcs.append(os.path.join(ROOT, "include", "pm_b200.h"))
     return srcs
 

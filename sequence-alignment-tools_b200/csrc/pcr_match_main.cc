@@ -47,7 +47,7 @@ struct Options {
   std::string alignformat =
       ">%h\\n %>T %>s ... %l ... %<e %<T\\n %>A  %!>s    %!l    %!<e  %<A\\n %>Q %>r%!>s    %!l    %!<e%<r %<Q %a%R\\n";
   bool wc = false, tn = false, indels = true;
-  int node = 0, device = 0;
+  int node = 0, device = 0, dbind = 0;
   int maxdist = 2000, mindist = 0, deviation = -1;
   int stlen = 0, edlen = 0, fplen = 0, tplen = 0;
   unsigned long report_interval = 1000;
@@ -111,7 +111,11 @@ Options parse(int argc, char **argv) {
       case 'b': o.betweenlen = true; break;
       case 'r': o.rev_comp = true; break;
       case 'a': o.allorient = true; break;
-      case 'v': case 'V': case 'B': case 'D': break;  // accepted, no effect here
+      case 'D':
+        o.dbind = std::atoi(optarg);
+        if (o.dbind < 0 || o.dbind > 4) usage("Invalid integer for fasta database indexing (-D).");
+        break;
+      case 'v': case 'V': case 'B': break;  // accepted, no effect here (the library has its own reader)
       case 'x': usage("Exact seeds (-x) are not available in the B200 build.");
       case 'h':
       default: usage(0);
@@ -295,7 +299,7 @@ int main(int argc, char **argv) {
   }
 
   FastaStream ff;
-  if (!ff.load(opt.database, false, (unsigned char)opt.eos_char))
+  if (!ff.load(opt.database, false, (unsigned char)opt.eos_char, opt.dbind))
     fatal("Fatal error: can't read sequence database " + opt.database);
 
   b200_index *pm = pick_pattern_index(opt.node, opt.nmismatch, opt.wc, opt.tn, opt.indels, (char)opt.eos_char,

@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <sys/stat.h>
 #include <algorithm>
 #include <cmath>
 #include <limits>
@@ -25,6 +26,7 @@
 #include "pm_fasta.cuh"
 #include "pm_halves.cuh"
 #include "pm_pcr.hpp"
+#include "pm_reader.hpp"
 
 namespace {
 
@@ -172,6 +174,11 @@ struct pm_ctx {
   DevBuf d_fa_raw, d_fa_map, d_fa_scan, d_fa_cnt, d_fa_chdr, d_fa_start, d_fa_nout, d_fa_nhdr, d_fa_ooff, d_fa_hoff,
       d_fa_key, d_fa_hs, d_fa_he, d_fa_tmp;
   std::vector<int64_t> seq_key, seq_hdr_off, seq_hdr_len;  // sequence table of the last FASTA text
+  std::string hdr_blob;                 // header lines (gathered from the device, or <db>.hdr)
+  std::vector<unsigned long long> hdr_blob_off;
+  bool hdr_ready = false, hdr_from_file = false;
+  int db_kind = 0;                      // pm_set_text_database: 1 FASTA, 2 .seq, 3 .sqn, 4 .sqz
+  pm::ChunkReader *reader = nullptr;    // ... and its reader (kept until the next text: its buffers are DMA sources)
   const uint8_t *d_text = nullptr;
   uint64_t n = 0;
   int64_t offset = 0;
@@ -1151,6 +1158,8 @@ void pm_destroy(pm_ctx *c) {
   c->inner = nullptr;
   cudaSetDevice(c->opt.device);
   cudaDeviceSynchronize();
+  delete c->reader;
+  c->reader = nullptr;
   DevBuf *bufs[] = {&c->d_symmask, &c->d_poff,   &c->d_plen,   &c->d_patchars, &c->d_lconst,
                     &c->d_rconst,  &c->d_compat, &c->d_cls,    &c->d_umask,    &c->d_piece,
                     &c->d_slotid,  &c->d_text_own, &c->d_planes, &c->d_keys,   &c->d_keys2,
@@ -1562,12 +1571,14 @@ int pm_init(pm_ctx *c) {
       // measured crossover (1 Gbp, 2000-20000 primers): below ~100 k entries the queue stages cope with
       // level 1's false positives faster than 16 extra L2 loads per word do
       static const size_t big_set_entries = getenv("PM_BIG_SET_ENTRIES") ? (size_t)atoll(getenv("PM_BIG_SET_ENTRIES")) : 100000;
-      const bool big_set = ents.size() > big_set_entries;
-      ia.b2_global = big_set ? 1u : 0u;
       // the edit kernel specialised on (L, k) reads level 1 through the bijective index when the keys fit
       static const bool edit_generic = getenv("PM_EDIT_GENERIC") && atoi(getenv("PM_EDIT_GENERIC")) != 0;
       c->idx_edit_special = edit_mode && !edit_generic && pair_edit_kernel(L, K) != nullptr;
       ia.l1_bij = (c->idx_edit_special && 4 * L <= 20 && ia.log_words == 15) ? 1u : 0u;
+      // (that kernel asks level 1b from its queued stage, one L2 round trip per question if the table
+      // were global: it keeps the shared-memory table until that is half full)
+      const bool big_set = c->idx_edit_special ? ents.size() > ((size_t)1 << 18) : ents.size() > big_set_entries;
+      ia.b2_global = big_set ? 1u : 0u;
       // substitutions, 24 k .. 100 k entries: level 1 passes 2-10 % of the lookups; the 64 KB
       // (key, distance) bitmap in the free shared memory removes most of them (+7-10 %); a kernel
       // variant of its own (pair_scan_sub_kernel<.., B1 = true>), the plain one has no register to spare
@@ -1703,8 +1714,12 @@ static int unpack_groups(pm_ctx *c, uint32_t bits, uint64_t n_bytes, uint64_t g0
   return PM_OK;
 }
 
+// src: the bytes in host memory, or (src == nullptr) `reader`, which delivers them chunk by chunk
+// from a file through its ring of page-locked buffers (chunk size = this pipeline's)
+static uint64_t stream_chunk_bytes(uint32_t bits) { return bits ? (24ull << 20) : (64ull << 20); }
+
 static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t bits, uint64_t n,
-                     int64_t offset) {
+                     int64_t offset, pm::ChunkReader *reader = nullptr) {
   int rc = c->d_text_own.ensure(n + 64);
   if (rc) return rc;
   c->d_text = c->d_text_own.as<uint8_t>();
@@ -1719,10 +1734,12 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
   }
   cudaPointerAttributes at;
   bool pinned = false;
-  if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
+  if (reader) pinned = true;
+  else if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
     pinned = (at.type == cudaMemoryTypeHost);
   else
     cudaGetLastError();
+  if (!c->inited && reader) return fail(PM_E_ARG, "pm_set_text_database before pm_init");
   if (!c->inited) {  // not the reference's call order: plain copy now, pack in pm_init
     PM_CUDA(cudaMemcpyAsync(d_dst, src, n_bytes, cudaMemcpyHostToDevice, c->stream));
     if (bits && (rc = unpack_groups(c, bits, n_bytes, 0, (n + 15) / 16, c->stream))) return rc;
@@ -1739,14 +1756,20 @@ static int stream_in(pm_ctx *c, const uint8_t *src, uint64_t n_bytes, uint32_t b
       if (!c->stage[i]) PM_CUDA(cudaMallocHost(&c->stage[i], kStageBytes));
   // constant chunks: what is left to do when the last byte has arrived is one chunk's
   // unpack + pack + scan, so small chunks keep the tail short (a chunk costs ~6 launches)
-  const uint64_t chunk_bytes = bits ? (24ull << 20) : (64ull << 20);
+  const uint64_t chunk_bytes = stream_chunk_bytes(bits);
   uint64_t done = 0, groups_done = 0;
   uint32_t tiles_done = 0;
   int which = 0;
   while (done < n_bytes) {
     uint64_t take = std::min<uint64_t>(chunk_bytes, n_bytes - done);
-    if (n_bytes - done - take < chunk_bytes / 4) take = n_bytes - done;  // no tiny last chunk
-    if (pinned) {
+    if (!reader && n_bytes - done - take < chunk_bytes / 4) take = n_bytes - done;  // no tiny last chunk
+    if (reader) {
+      uint64_t got = 0;
+      const uint8_t *p = reader->acquire(done / chunk_bytes, &got);
+      if (!p || got < take) return fail(PM_E_ARG, "read error on the database file");
+      PM_CUDA(cudaMemcpyAsync(d_dst + done, p, take, cudaMemcpyHostToDevice, c->copy_stream));
+      reader->release(done / chunk_bytes, c->copy_stream);
+    } else if (pinned) {
       PM_CUDA(cudaMemcpyAsync(d_dst + done, src + done, take, cudaMemcpyHostToDevice, c->copy_stream));
     } else {
       for (uint64_t o = 0; o < take; o += kStageBytes) {
@@ -2002,13 +2025,29 @@ int pm_normalize_fasta(const uint8_t *raw, uint64_t n, int upper_case, unsigned 
 }
 
 // The same on the device (pm_fasta.cuh): raw FASTA bytes in host memory -> stream in HBM.
-int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int upper_case) {
-  if (!c || (!raw && n_raw)) return fail(PM_E_ARG, "null argument");
-  if (!c->inited) return fail(PM_E_ARG, "pm_set_text_fasta_host before pm_init");
-  if (c->inner) return adopt_inner_text(c, pm_set_text_fasta_host(c->inner, raw, n_raw, upper_case));
+constexpr uint64_t kFastaChunk = (uint64_t)FA_THREADS * FA_SEG * 2048;   // 64 MiB of raw bytes, whole blocks
+
+// raw: the bytes of the file in host memory, or (raw == nullptr) `reader`, which delivers them in
+// chunks of kFastaChunk through its ring of page-locked buffers
+static int set_text_fasta_impl(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int upper_case, pm::ChunkReader *reader) {
   if (n_raw >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "file longer than 2^40 bytes");
   PM_CUDA(cudaSetDevice(c->opt.device));
+  c->hdr_ready = false;
+  c->hdr_from_file = false;
   const unsigned char eos = c->opt.eos;
+  std::vector<uint8_t> whole;   // reader + a file that has to take the host path
+  if (reader && n_raw) {
+    uint64_t got = 0;
+    const uint8_t *p0 = reader->acquire(0, &got);
+    if (!p0) return fail(PM_E_ARG, "read error on the database file");
+    raw = p0;   // the first chunk: the prefix walk below reads at most 16 KB of it
+    if (n_raw < 16384) {
+      whole.assign(p0, p0 + n_raw);
+      reader->release(0, c->copy_stream);
+      raw = whole.data();
+      reader = nullptr;
+    }
+  }
   // host prefix: everything up to the first stream character (first-header rule)
   std::vector<uint8_t> pre;
   std::vector<int64_t> pk, po, pl;
@@ -2030,6 +2069,19 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
                      po.data(), pl.data(), pk.size(), &pre_seqs, true, &r0);
       if (r0 >= std::min<uint64_t>(n_raw, 16384)) all = true;  // no stream character in the first 16 KB
     }
+    if (all && reader) {
+      // (no stream character in the first 16 KB: the whole file through host memory)
+      whole.resize(n_raw);
+      for (uint64_t j = 0; j < reader->n_chunks(); j++) {
+        uint64_t got = 0;
+        const uint8_t *pj = reader->acquire(j, &got);
+        if (!pj) return fail(PM_E_ARG, "read error on the database file");
+        memcpy(whole.data() + j * reader->chunk_bytes(), pj, got);
+        reader->release(j, c->copy_stream);
+      }
+      raw = whole.data();
+      reader = nullptr;
+    }
     if (all) {
       std::vector<uint8_t> full(n_raw + 4);
       std::vector<int64_t> k2(n_raw / 2 + 4), o2(n_raw / 2 + 4), l2(n_raw / 2 + 4);
@@ -2047,7 +2099,7 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
   // normalises chunk j (summary -> scan of the state maps -> counts -> two exclusive sums ->
   // write); the state / stream length / header count after a chunk are carried on the device
   // (d_counters[11..13]), so the host does not wait between chunks.
-  const uint64_t kChunk = (uint64_t)FA_THREADS * FA_SEG * 2048;   // 64 MiB of raw bytes, whole blocks
+  const uint64_t kChunk = kFastaChunk;
   const uint64_t n_seg_max = std::min<uint64_t>(kChunk, n_raw - r0 + FA_SEG) / FA_SEG + 1;
   const uint64_t hdr_cap = std::min<uint64_t>(n_raw / 32 + 1024, 1ull << 27);
   int rc;
@@ -2084,7 +2136,8 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
   PM_CUDA(cudaGetLastError());
   cudaPointerAttributes pat_;
   bool pinned = false;
-  if (cudaPointerGetAttributes(&pat_, raw) == cudaSuccess) pinned = (pat_.type == cudaMemoryTypeHost);
+  if (reader) pinned = true;
+  else if (cudaPointerGetAttributes(&pat_, raw) == cudaSuccess) pinned = (pat_.type == cudaMemoryTypeHost);
   else cudaGetLastError();
   if (!pinned)
     for (int i = 0; i < 2; i++)
@@ -2094,9 +2147,17 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
   const uint8_t *d_raw = d_raw_w;
   uint8_t *d_stream = c->d_text_own.as<uint8_t>();
   c->ev_used = 0;
-  for (uint64_t a0 = r0; a0 < n_raw; a0 += kChunk) {
-    const uint64_t a1 = std::min(n_raw, a0 + kChunk);
-    if (pinned) {
+  // chunks end on multiples of kChunk (the reader's chunks); the first one starts behind the prefix
+  for (uint64_t a0 = r0, a1 = 0; a0 < n_raw; a0 = a1) {
+    a1 = std::min(n_raw, (a0 / kChunk + 1) * kChunk);
+    if (reader) {
+      const uint64_t j = a0 / kChunk;
+      uint64_t got = 0;
+      const uint8_t *pj = reader->acquire(j, &got);
+      if (!pj || j * kChunk + got < a1) return fail(PM_E_ARG, "read error on the database file");
+      PM_CUDA(cudaMemcpyAsync(d_raw_w + a0, pj + (a0 - j * kChunk), a1 - a0, cudaMemcpyHostToDevice, cs));
+      reader->release(j, cs);
+    } else if (pinned) {
       PM_CUDA(cudaMemcpyAsync(d_raw_w + a0, raw + a0, a1 - a0, cudaMemcpyHostToDevice, cs));
     } else {
       for (uint64_t o = a0; o < a1; o += kStageBytes) {
@@ -2173,6 +2234,148 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int up
     c->seq_hdr_len[i] = c->seq_hdr_len[i] - c->seq_hdr_off[i] - 1;  // hend - hstart - 1 (fasta_io.t:548)
   c->d_text = d_stream;
   return set_text_common(c, n, 0);   // prep stream is drained: pack on the main stream
+}
+
+int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, int upper_case) {
+  if (!c || (!raw && n_raw)) return fail(PM_E_ARG, "null argument");
+  if (!c->inited) return fail(PM_E_ARG, "pm_set_text_fasta_host before pm_init");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_fasta_host(c->inner, raw, n_raw, upper_case));
+  return set_text_fasta_impl(c, raw, n_raw, upper_case, nullptr);
+}
+
+static bool file_exists(const std::string &path) {
+  struct stat st;
+  return stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+static bool slurp_file(const std::string &path, std::string *out) {
+  FILE *f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  out->clear();
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+  fclose(f);
+  return true;
+}
+
+// pick_fasta_file (select.t:23-190) + the reader: the database is opened the way primer_match
+// opens it for this -D value and read through the ring of page-locked chunk buffers.
+int pm_set_text_database(pm_ctx *c, const char *database, int dbind, int upper_case) {
+  if (!c || !database) return fail(PM_E_ARG, "null argument");
+  if (!c->inited) return fail(PM_E_ARG, "pm_set_text_database before pm_init");
+  if (c->inner) return adopt_inner_text(c, pm_set_text_database(c->inner, database, dbind, upper_case));
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  const std::string db(database);
+  int kind = dbind;   // 1 raw FASTA, 2 .seq, 3 .sqn, 4 .sqz
+  if (dbind == 0) kind = file_exists(db + ".sqn") ? 3 : (file_exists(db + ".sqz") ? 4 : (file_exists(db + ".seq") ? 2 : 1));
+  if (kind < 1 || kind > 4) return fail(PM_E_ARG, "database selection (-D) must be 0..4");
+  static const int n_threads = getenv("PM_READER_THREADS") ? std::max(1, atoi(getenv("PM_READER_THREADS"))) : 6;
+  std::string err;
+  c->db_kind = kind;
+  delete c->reader;
+  c->reader = new pm::ChunkReader();
+  pm::ChunkReader &rd = *c->reader;
+  if (kind == 1) {
+    if (!rd.open(db, kFastaChunk, n_threads, n_threads + 2, &err)) return fail(PM_E_ARG, err);
+    return set_text_fasta_impl(c, nullptr, rd.size(), upper_case, &rd);
+  }
+  // indexed databases of compress_seq: the stream (.seq), its table indices (.sqn + .tbl) or the
+  // bit stream (.sqz + .tbz); sequence starts and header offsets in <db>.idb, headers in <db>.hdr
+  std::string idb, table;
+  if (!slurp_file(db + ".idb", &idb) || idb.size() < 8)
+    return fail(PM_E_ARG, "cannot read " + db + ".idb (compress_seq's binary sequence index)");
+  uint64_t n_ent = 0;
+  memcpy(&n_ent, idb.data(), 8);
+  if (n_ent < 1 || idb.size() < 8 + n_ent * 16) return fail(PM_E_ARG, db + ".idb is truncated");
+  c->seq_key.clear();
+  c->seq_hdr_off.clear();
+  c->seq_hdr_len.clear();
+  for (uint64_t i = 0; i + 1 < n_ent; i++) {   // the last entry is the end marker
+    int64_t key = 0, hoff = 0, hnext = 0;
+    memcpy(&key, idb.data() + 8 + i * 16, 8);
+    memcpy(&hoff, idb.data() + 8 + i * 16 + 8, 8);
+    memcpy(&hnext, idb.data() + 8 + (i + 1) * 16 + 8, 8);
+    c->seq_key.push_back(key);
+    c->seq_hdr_off.push_back(hoff);
+    c->seq_hdr_len.push_back(hnext - hoff - 1);   // without the newline
+  }
+  if (!slurp_file(db + ".hdr", &c->hdr_blob)) return fail(PM_E_ARG, "cannot read " + db + ".hdr");
+  c->hdr_ready = true;
+  c->hdr_from_file = true;
+  const std::string path = db + (kind == 2 ? ".seq" : (kind == 3 ? ".sqn" : ".sqz"));
+  uint32_t bits = 0;
+  if (kind != 2) {
+    if (!slurp_file(db + (kind == 3 ? ".tbl" : ".tbz"), &table) || table.empty() || table.size() > 256)
+      return fail(PM_E_ARG, "cannot read the character table of " + db);
+    bits = (kind == 3) ? 8u : (uint32_t)pm_sqz_bits((uint32_t)table.size());
+    uint8_t tab[256];
+    memset(tab, 0, sizeof tab);
+    memcpy(tab, table.data(), table.size());
+    if (int rc = c->d_sqztab.ensure(256)) return rc;
+    PM_CUDA(cudaMemcpyAsync(c->d_sqztab.p, tab, 256, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  if (!rd.open(path, stream_chunk_bytes(bits), n_threads, n_threads + 2, &err)) return fail(PM_E_ARG, err);
+  const uint64_t n_bytes = rd.size();
+  const uint64_t n_chars = bits ? n_bytes * 8 / bits : n_bytes;   // the writer's padding reads as end-of-sequence characters
+  if (n_chars >= (1ull << 40)) return fail(PM_E_UNSUPPORTED, "database longer than 2^40 characters");
+  return stream_in(c, nullptr, n_bytes, bits, n_chars, 0, &rd);
+}
+
+// header line of sequence i (0-based; the text behind '>' without the line end): FastaFile's
+// get_header_data (fasta_io.t:163-191).  For a FASTA database the header bytes are gathered from
+// the raw file on the device once and kept; for an indexed database they come from <db>.hdr.
+__global__ void gather_ranges_kernel(const uint8_t *src, const long long *off, const long long *len,
+                                     const unsigned long long *out_off, uint64_t n, uint8_t *out) {
+  const uint64_t i = blockIdx.x;
+  if (i >= n) return;
+  const long long l = len[i];
+  for (long long x = threadIdx.x; x < l; x += blockDim.x) out[out_off[i] + x] = src[off[i] + x];
+}
+
+int pm_get_header(pm_ctx *c, uint64_t i, const char **text, uint64_t *len) {
+  if (!c || !text || !len) return fail(PM_E_ARG, "null argument");
+  pm_ctx *o = c->inner ? c->inner : c;   // whose pipeline brought the text in
+  if (i >= o->seq_key.size()) return fail(PM_E_ARG, "sequence index out of range");
+  if (!o->hdr_ready) {
+    // FASTA text normalised on the device: the headers lie in the raw bytes there
+    PM_CUDA(cudaSetDevice(o->opt.device));
+    if (!o->d_fa_raw.p) return fail(PM_E_ARG, "headers are available for FASTA / indexed databases only");
+    const size_t n = o->seq_key.size();
+    std::vector<unsigned long long> ooff(n + 1, 0);
+    std::vector<long long> hl(n);
+    for (size_t x = 0; x < n; x++) {
+      hl[x] = std::max<long long>(0, o->seq_hdr_len[x]);
+      ooff[x + 1] = ooff[x] + (unsigned long long)hl[x];
+    }
+    DevBuf d_off, d_len, d_ooff, d_out;
+    int rc;
+    if ((rc = d_off.ensure(n * 8 + 8)) || (rc = d_len.ensure(n * 8 + 8)) || (rc = d_ooff.ensure((n + 1) * 8)) ||
+        (rc = d_out.ensure(ooff[n] + 8)))
+      return rc;
+    PM_CUDA(cudaMemcpyAsync(d_off.p, o->seq_hdr_off.data(), n * 8, cudaMemcpyHostToDevice, o->stream));
+    PM_CUDA(cudaMemcpyAsync(d_len.p, hl.data(), n * 8, cudaMemcpyHostToDevice, o->stream));
+    PM_CUDA(cudaMemcpyAsync(d_ooff.p, ooff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, o->stream));
+    if (n) gather_ranges_kernel<<<(unsigned)n, 64, 0, o->stream>>>(o->d_fa_raw.as<uint8_t>(), d_off.as<long long>(),
+                                                                   d_len.as<long long>(), d_ooff.as<unsigned long long>(),
+                                                                   n, d_out.as<uint8_t>());
+    o->hdr_blob.assign((size_t)ooff[n], '\0');
+    if (ooff[n]) PM_CUDA(cudaMemcpyAsync(&o->hdr_blob[0], d_out.p, ooff[n], cudaMemcpyDeviceToHost, o->stream));
+    PM_CUDA(cudaStreamSynchronize(o->stream));
+    o->hdr_blob_off.assign(ooff.begin(), ooff.end());
+    d_off.release(); d_len.release(); d_ooff.release(); d_out.release();
+    o->hdr_ready = true;
+  }
+  if (o->hdr_from_file) {
+    const int64_t a = o->seq_hdr_off[i], l = std::max<int64_t>(0, o->seq_hdr_len[i]);
+    if (a < 0 || (uint64_t)(a + l) > o->hdr_blob.size()) return fail(PM_E_ARG, "header index outside <db>.hdr");
+    *text = o->hdr_blob.data() + a;
+    *len = (uint64_t)l;
+  } else {
+    *text = o->hdr_blob.data() + o->hdr_blob_off[i];
+    *len = o->hdr_blob_off[i + 1] - o->hdr_blob_off[i];
+  }
+  return PM_OK;
 }
 
 int pm_get_sequences(pm_ctx *c, const int64_t **seq_key, const int64_t **hdr_off, const int64_t **hdr_len,

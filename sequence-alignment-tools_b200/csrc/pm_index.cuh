@@ -596,7 +596,7 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
   uint32_t *queue = reinterpret_cast<uint32_t *>(t.q.qa);   // this warp's kilobyte: EDIT_QCAP records
   // the staging rows of A1 / A2 lie behind level 1b (the host sizes the shared memory for them)
   uint16_t *stage = reinterpret_cast<uint16_t *>(s_mem + (1u << a.log_words) + PAIR_WARPS * 2 * PAIR_QCAP * 2 +
-                                                 (1u << a.log_words2)) + warp * 32;
+                                                 (a.b2_global ? 0u : t.n_words2)) + warp * 32;
   const uint32_t lane_tag = t.lane << 21;
 
   for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {

@@ -40,7 +40,7 @@ struct Options {
   std::string countformat = "%i %r %q %c%+ ( %C )\\n";
   bool alignments = true, counts = false, aggregate = false;
   bool wc = false, tn = false, indels = true;
-  int node = 0, device = 0;
+  int node = 0, device = 0, dbind = 0;
   std::string outfile;
 };
 
@@ -101,7 +101,11 @@ Options parse(int argc, char **argv) {
         if (!std::sscanf(optarg, "%i", &ec)) usage("Invalid end-of-sequence specification.\n");
         o.eos_char = (char)ec;
       } break;
-      case 'v': case 'I': case 'B': case 'D': break;  // accepted, no effect here
+      case 'D':   // primer_match.cc:246-247, 278
+        o.dbind = std::atoi(optarg);
+        if (o.dbind < 0 || o.dbind > 4) usage("Invalid integer for fasta database indexing (-D).");
+        break;
+      case 'v': case 'I': case 'B': break;  // accepted, no effect here (the library has its own reader)
       case 'S': o.patterns = optarg; o.sts_pattern_file = true; o.rev_comp = true; break;  // primer_match.cc:137-141
       case 'T': usage("Translation (-T) is not available in the B200 build.");
       case 'x': usage("Exact seeds (-x) are not available in the B200 build.");
@@ -296,7 +300,7 @@ int main(int argc, char **argv) {
   }
 
   FastaStream ff;
-  if (!ff.load(opt.database, opt.ucdict, (unsigned char)opt.eos_char))
+  if (!ff.load(opt.database, opt.ucdict, (unsigned char)opt.eos_char, opt.dbind))
     fatal("Fatal error: can't read sequence database " + opt.database);
 
   b200_index *kt = pick_pattern_index(opt.node, opt.nmismatch, opt.wc, opt.tn, opt.indels, (char)opt.eos_char,

@@ -22,6 +22,7 @@ struct pm_ctx {
   std::vector<uint8_t> stream;
   std::vector<int64_t> key, hoff, hlen;
   std::vector<pm_hit> hits;
+  std::vector<uint8_t> raw;   // the database file (for the header lines)
   bool bogus = false;
   int k = 0;
 };
@@ -64,6 +65,23 @@ int pm_set_text_fasta_host(pm_ctx *c, const uint8_t *, uint64_t, int) { return l
 int pm_set_text_host(pm_ctx *c, const uint8_t *, uint64_t, int64_t) { return load_canned(c); }
 int pm_set_text_sqz_host(pm_ctx *c, const uint8_t *, uint64_t, const uint8_t *, uint32_t, uint64_t, int64_t) { return load_canned(c); }
 int pm_set_text_sqn_host(pm_ctx *c, const uint8_t *, uint64_t, const uint8_t *, uint32_t, int64_t) { return load_canned(c); }
+
+int pm_set_text_database(pm_ctx *c, const char *database, int, int) {
+  c->raw.clear();
+  if (FILE *f = fopen(database, "rb")) {
+    uint8_t buf[65536];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) c->raw.insert(c->raw.end(), buf, buf + n);
+    fclose(f);
+  }
+  return load_canned(c);
+}
+int pm_get_header(pm_ctx *c, uint64_t i, const char **text, uint64_t *len) {
+  if (i >= c->key.size() || (uint64_t)(c->hoff[i] + c->hlen[i]) > c->raw.size()) return PM_E_ARG;
+  *text = (const char *)c->raw.data() + c->hoff[i];
+  *len = (uint64_t)(c->hlen[i] > 0 ? c->hlen[i] : 0);
+  return PM_OK;
+}
 
 static int load_canned(pm_ctx *c) {
   c->stream = slurp("stream.bin");

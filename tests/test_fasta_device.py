@@ -102,3 +102,47 @@ def test_large_file_pinned_and_pageable(pkg, built_lib):
         assert got.chars.tobytes() == want.chars.tobytes()
         assert got.seq_key.tolist() == want.seq_key.tolist()
         assert got.headers == want.headers
+
+
+@pytest.mark.gpu
+def test_database_reader_equals_memory_path(pkg, built_lib, tmp_path):
+    """pm_set_text_database: a FASTA file of several reader chunks (> 64 MiB) read through the ring of
+    page-locked buffers gives the stream, sequence table, headers and hits of the in-memory path."""
+    import random
+    import numpy as np
+    import casegen
+    rng = random.Random(12)
+    primers = [casegen.rand_dna(rng, 20) for _ in range(50)]
+    g = np.random.default_rng(6)
+    parts = []
+    total = 0
+    i = 0
+    while total < 150 * (1 << 20):
+        n = int(g.integers(2_000_000, 30_000_000))
+        seq = np.frombuffer(b"ACGT", np.uint8)[g.integers(0, 4, n)].copy()
+        for j in range(20):
+            at = int(g.integers(0, n - 30))
+            seq[at:at + 20] = np.frombuffer(primers[(i + j) % 50].encode(), np.uint8)
+        body = seq[:n // 70 * 70].reshape(-1, 70)
+        lines = np.concatenate([body, np.full((body.shape[0], 1), 10, np.uint8)], axis=1).reshape(-1)
+        parts += [np.frombuffer(b">chr%d synthetic %d\n" % (i, n), np.uint8), lines]
+        total += n
+        i += 1
+    raw = np.concatenate(parts)
+    path = tmp_path / "big.fasta"
+    raw.tofile(str(path))
+    out = {}
+    for how in ("memory", "reader"):
+        sc = pkg.Scanner(k=1, indels=False, index=pkg.PM_INDEX_FILTER_BITVEC)
+        for j, p in enumerate(pkg.pattern_array(primers, True)):
+            sc.add_pattern(p, j + 1)
+        sc.init()
+        st = sc.set_text_fasta(raw) if how == "memory" else sc.set_text_database(str(path), 1)
+        hits = sc.find_patterns()
+        n_stream = sc.stats()["text_len"]
+        head = sc.get_text(0, 100000).tobytes()
+        tail = sc.get_text(n_stream - 100000, 100000).tobytes()
+        out[how] = (st.seq_key.tolist(), st.headers, hits.tobytes(), n_stream, head, tail)
+        sc.close()
+    assert len(out["memory"][0]) == i and len(out["memory"][2]) > 100 * 120
+    assert out["reader"] == out["memory"]

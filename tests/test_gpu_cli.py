@@ -166,3 +166,33 @@ def test_pcr_match_output_matches_reference(pcr_cli, oracle, pcr_golden, tmp_pat
             assert got == case["stdout_default"], "default format, case %d" % case["seed"]
         n += len(case["stdout_records"].splitlines())
     assert n > 40
+
+
+def test_cli_opens_the_database_like_pick_fasta_file(cli, golden, tmp_path):
+    """-D: the FASTA file itself (1), or the .sqn (3) / .sqz (4) database the reference's compress_seq
+    wrote next to it, or whichever exists (0) -- read by the library's own reader; the text must be
+    the one the reference printed for the FASTA file (coordinates and headers do not depend on the
+    form of the database)."""
+    csq = os.path.join(ROOT, "oracle", "_ref", "compress_seq")
+    if not os.path.exists(csq):
+        pytest.skip("needs oracle/_ref/compress_seq")
+    checked = 0
+    for case in golden["cases"]:
+        if "stdout_default" not in case or case["params"]["wc"]:
+            continue
+        checked += 1
+        if checked % 4 != 1:
+            continue
+        d = tmp_path / ("db%d" % checked)
+        d.mkdir()
+        fa = d / "db.fasta"
+        fa.write_bytes(case["fasta"].encode("latin-1"))
+        prm, par = case["primers"], case["params"]
+        want = _blocks(case["stdout_default"], 4)
+        assert _blocks(_run(cli, _args(str(fa), prm, par, ["-D", "1"])), 4) == want, "FASTA, case %s" % case["seed"]
+        p = subprocess.run([csq, "-i", str(fa), "-z", "true", "-n", "true"], capture_output=True, timeout=120)
+        assert p.returncode == 0 and (d / "db.fasta.sqz").exists() and (d / "db.fasta.idb").exists()
+        for dbind in ("4", "3", "0"):
+            got = _run(cli, _args(str(fa), prm, par, ["-D", dbind]))
+            assert _blocks(got, 4) == want, "-D %s, case %s" % (dbind, case["seed"])
+    assert checked >= 8
