@@ -79,6 +79,10 @@ CONFIGS = {
 # not a BASELINE configuration: the 20-mer edit scan (A/B runs of tools/run_config.py)
 CONFIGS["edit20_k2"] = dict(nprimers=1000, plen=20, k=2, indels=1, iupac=0, select=0, bases=3_000_000_000, ref_bp=600_000,
                             metric="Gbp/s scanned, 1k 20-mer primers k=2 edits both strands", baseline="(none)")
+# the headline workload on a database whose repeats contain primer sites: 10^6 planted copies per Gbp
+CONFIGS["hit_dense"] = dict(nprimers=1000, plen=20, k=2, indels=0, iupac=0, select=0, bases=1_000_000_000, ref_bp=1_000_000,
+                            metric="Gbp/s scanned, 1k 20-mer primers k=2 both strands, 10^6 hits per Gbp",
+                            baseline="(none: the headline workload, hit-dense database)", dense=1_000_000)
 ALL_ORDER = ["headline", "iupac_k2", "edit25_k3", "p100_k1", "oligo100k_exact", "oligo100k_k1"]
 
 
@@ -414,6 +418,18 @@ class Bench:
         assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        # this rank's threads (and with them the pages of its page-locked buffers, first touch) on
+        # the CPUs next to its GPU: NVML knows them
+        self.affinity = None
+        self.all_cpus = os.sched_getaffinity(0)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(visible_gpu_index(self.local_rank))
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            self.affinity = {"cpus": len(os.sched_getaffinity(0)), "set_by": "nvmlDeviceSetCpuAffinity"}
+        except Exception as ex:
+            self.affinity = {"error": str(ex)[:100]}
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.pkg = importlib.import_module(PKG)
@@ -642,7 +658,9 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
         res["total"] = B.sum_over_ranks(nh)
 
     sqz_bytes = (3 * n_chars + 7) // 8
-    h_sqz_view = h_sqz.array[:sqz_bytes] if hasattr(h_sqz, "array") else h_sqz[:sqz_bytes]
+    h_sqz_view = None
+    if h_sqz is not None:
+        h_sqz_view = h_sqz.array[:sqz_bytes] if hasattr(h_sqz, "array") else h_sqz[:sqz_bytes]
 
     def step_e2e_sqz():
         sc.set_text_sqz(h_sqz_view, B.sqz_table, n_chars)   # H2D of the .sqz bytes + unpack + pack
@@ -663,7 +681,12 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
     if sampler:
         clocks_out.update(sampler.stop())
     mean_scan = sum(scan_ms) / max(1, len(scan_ms))
-    ms_e2e = B.timed(step_e2e_sqz, steps, min(warmup, 2))
+    if h_sqz_view is not None:
+        ms_e2e = B.timed(step_e2e_sqz, steps, min(warmup, 2))
+    else:   # no host leg: the hit records of the resident text, for the parity check
+        sc.set_text(d_stream)
+        res["hits"] = sc.find_patterns()
+        ms_e2e = 0.0
     hits = res["hits"]
     legs = {}
     if full:
@@ -699,7 +722,8 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
                "config": config_dict(cfg, bases, args), "hits_per_step": res["total"],
                "host_syncs_per_call": st["host_syncs"],
                "cell_updates_per_s": float(n_chars) * world * len(pats) * (cfg["k"] + 1) / (ms / steps * 1e-3),
-               "e2e": {"value": bases_total / (ms_e2e * 1e-3) / 1e9, "unit": "Gbp/s",
+               "tail_ms_per_step": st["total_ms"] - st["scan_ms"],
+               "e2e": None if h_sqz_view is None else {"value": bases_total / (ms_e2e * 1e-3) / 1e9, "unit": "Gbp/s",
                        "h2d_bytes_per_step": int(sqz_bytes) * world,
                        "d2h_bytes_per_step": (hits.nbytes + 256) * world, "ms_per_step": ms_e2e / steps,
                        "h2d_gbs_per_rank": sqz_bytes / (ms_e2e / steps * 1e-3) / 1e9,
@@ -731,6 +755,10 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
 def cpu_baseline_leg(B, res, d_db, planted, line, per_proc=None):
     """N = 1, rank 0: the reference on windows of the shard, GPU records compared inside them."""
     cfg, primers, n_chars = res["cfg"], res["primers"], res["n_chars"]
+    try:
+        os.sched_setaffinity(0, B.all_cpus)       # the reference gets every host core, not only the GPU's neighbours
+    except Exception:
+        pass
     cores = cpu_cores()
     if cfg.get("ref_skip"):
         line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": cores, "kind": "reference", "sample": "not run: " + cfg["ref_skip"]}
@@ -862,7 +890,7 @@ def main():
         line = {**{"metric": line.pop("metric"), "value": line.pop("value"), "unit": line.pop("unit"),
                    "n_gpus": B.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": line.pop("ms_per_step"),
                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
-                   "data": "synthetic"}, **line, "clocks": clocks}
+                   "data": "synthetic"}, **line, "clocks": clocks, "cpu_affinity": B.affinity}
         if not args.no_cpu_baseline and B.world == 1:
             ok = cpu_baseline_leg(B, res, d_db, planted[main_name], line)
     # the other BASELINE configurations: short runs on the same shard
@@ -879,6 +907,19 @@ def main():
             line["configs"] = others
     del d_db, h_sqz
     torch.cuda.empty_cache()
+    if args.config == "all":
+        # the hit-dense database: 10^6 primer sites per Gbp (a genome whose repeats contain primer sites)
+        cfg = CONFIGS["hit_dense"]
+        d_dense = B.make_database(cfg["bases"], 4321 + B.rank)
+        n_planted = B.plant_dense(d_dense, B.patterns("hit_dense")[1], cfg["k"], 77 + B.rank, cfg["dense"])
+        o, r = measure_config(B, "hit_dense", d_dense, None, max(1, min(args.steps, 2)), min(args.warmup, 2), full=False)
+        if B.rank == 0:
+            o["planted_copies"] = n_planted
+            if not args.no_cpu_baseline and B.world == 1:
+                ok = cpu_baseline_leg(B, r, d_dense, [], o) and ok
+            line["configs"]["hit_dense"] = o
+        del d_dense
+        torch.cuda.empty_cache()
     # strong scaling: one database, partitioned with overlap, hit records gathered
     if B.world > 1 and not args.no_strong:
         s = strong_scaling(B, main_name, args.steps, args.warmup)

@@ -298,6 +298,11 @@ int pm_set_text_database(pm_ctx *ctx, const char *database, int dbind, int upper
  * pm_set_text_* call.                                                                         */
 int pm_get_header(pm_ctx *ctx, uint64_t i, const char **text, uint64_t *len);
 
+/* Characters of n ranges [begin[i], begin[i] + len[i]) of the loaded stream, concatenated into
+ * `out`: one gather on the device and one copy, for the alignment buffers a tool prints next to a
+ * batch of hits (pm_get_text costs a round trip per range).                                     */
+int pm_gather_text(pm_ctx *ctx, const int64_t *begin, const int64_t *len, uint64_t n, uint8_t *out);
+
 /* Page-locked host buffers for the database (the pinned reader side of the input
  * path): pm_set_text_host / _sqz_host / _fasta_host read such memory directly by DMA.
  * write_combined != 0 asks for write-combined pages: right for a buffer the CPU only

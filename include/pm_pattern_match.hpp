@@ -106,11 +106,33 @@ class FastaStream {
     const size_t p = h.find_first_of(" \t");
     return p == std::string::npos ? h : h.substr(0, p);
   }
+  // the texts of a batch of hits in one round trip: text(a, b) below then serves them from memory
+  void prefetch_texts(const std::vector<const pm_hit *> &batch) {
+    pre_begin_.clear(); pre_off_.clear(); pre_.clear();
+    if (!ctx_ || batch.empty()) return;
+    std::vector<int64_t> len;
+    int64_t total = 0;
+    for (const pm_hit *h : batch) {
+      int64_t a = h->start < 0 ? 0 : h->start, b = h->end > (int64_t)stream_len_ ? (int64_t)stream_len_ : h->end;
+      if (b < a) b = a;
+      pre_begin_.push_back(a);
+      len.push_back(b - a);
+      pre_off_.push_back(total);
+      total += b - a;
+    }
+    pre_off_.push_back(total);
+    pre_.resize((size_t)total);
+    if (pm_gather_text(ctx_, pre_begin_.data(), len.data(), batch.size(), (uint8_t *)(total ? &pre_[0] : 0)) != PM_OK)
+      fatal(std::string("Fatal error: ") + pm_last_error());
+  }
   // characters [a, b) of the stream (the text primer_match prints next to an alignment)
-  std::string text(int64_t a, int64_t b) const {
+  std::string text(int64_t a, int64_t b, long batch_index = -1) const {
     if (a < 0) a = 0;
     if (b > (int64_t)stream_len_) b = (int64_t)stream_len_;
     if (a >= b || !ctx_) return std::string();
+    if (batch_index >= 0 && (size_t)batch_index + 1 < pre_off_.size() && pre_begin_[batch_index] == a &&
+        pre_off_[batch_index + 1] - pre_off_[batch_index] == b - a)
+      return pre_.substr((size_t)pre_off_[batch_index], (size_t)(b - a));
     std::string out((size_t)(b - a), '\0');
     if (pm_get_text(ctx_, (uint64_t)a, (uint64_t)(b - a), (uint8_t *)&out[0]) != PM_OK)
       fatal(std::string("Fatal error: ") + pm_last_error());
@@ -120,7 +142,8 @@ class FastaStream {
  private:
   static bool exists(const std::string &p) { std::ifstream f(p.c_str(), std::ios::binary); return (bool)f; }
   std::string database_;
-  std::vector<int64_t> key_;
+  std::vector<int64_t> key_, pre_begin_, pre_off_;
+  std::string pre_;
   pm_ctx *ctx_;
   uint64_t stream_len_;
   int dbind_;

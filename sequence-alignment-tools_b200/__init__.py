@@ -37,7 +37,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size", "pm_set_text_database", "pm_get_header"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size", "pm_set_text_database", "pm_get_header", "pm_gather_text"]
 
 
 class PmError(RuntimeError):
@@ -118,6 +118,7 @@ def lib():
         i64pp = C.POINTER(C.POINTER(C.c_int64))
         L.pm_get_sequences.argtypes = [C.c_void_p, i64pp, i64pp, i64pp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.pm_get_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.pm_gather_text.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pm_set_text_database.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         L.pm_get_header.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.pm_host_alloc.argtypes = [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]

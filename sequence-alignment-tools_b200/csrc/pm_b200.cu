@@ -1599,7 +1599,7 @@ int pm_init(pm_ctx *c) {
           // hash collisions (a non-injective hash costs 3x the false positives here: the key space
           // is no larger than the table, profiles/README.md)
           const uint32_t v = (ents[x].x * ia.mult) & 0xfffffu;
-          bitmap[v >> 5] |= 1u << (31u - (v & 31u));
+          bitmap[v >> 5] |= 1u << (31u - (ents[x].x & 31u));   // pair_probe_bij: bit chosen by the key itself
         } else {
           const uint32_t idx = pair_hash1(ents[x].x, ia.mult, ia.salt[di]);
           bitmap[idx >> (32 - ia.log_words)] |= 1u << (31u - (idx & 31u));
@@ -2091,6 +2091,10 @@ static int set_text_fasta_impl(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, in
       c->seq_key.assign(k2.begin(), k2.begin() + ns);
       c->seq_hdr_off.assign(o2.begin(), o2.begin() + ns);
       c->seq_hdr_len.assign(l2.begin(), l2.begin() + ns);
+      // the raw bytes go to the device as well: pm_get_header gathers the header lines from there
+      if (int rc2 = c->d_fa_raw.ensure(n_raw + 64)) return rc2;
+      PM_CUDA(cudaMemcpyAsync(c->d_fa_raw.p, raw, n_raw, cudaMemcpyHostToDevice, c->stream));
+      PM_CUDA(cudaStreamSynchronize(c->stream));
       return stream_in(c, full.data(), len, 0, len, 0);
     }
     pre.assign(tmp.begin(), tmp.begin() + pre_len);
@@ -2147,6 +2151,8 @@ static int set_text_fasta_impl(pm_ctx *c, const uint8_t *raw, uint64_t n_raw, in
   const uint8_t *d_raw = d_raw_w;
   uint8_t *d_stream = c->d_text_own.as<uint8_t>();
   c->ev_used = 0;
+  // the bytes in front of the first chunk (the first header line lives there; pm_get_header reads it)
+  if (r0) PM_CUDA(cudaMemcpyAsync(d_raw_w, raw, r0, cudaMemcpyHostToDevice, cs));
   // chunks end on multiples of kChunk (the reader's chunks); the first one starts behind the prefix
   for (uint64_t a0 = r0, a1 = 0; a0 < n_raw; a0 = a1) {
     a1 = std::min(n_raw, (a0 / kChunk + 1) * kChunk);
@@ -2398,6 +2404,38 @@ int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
     PM_CUDA(cudaStreamWaitEvent(c->stream, owner->chunks.back().ev, 0));
   PM_CUDA(cudaMemcpyAsync(out, c->d_text + begin, len, cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(cudaStreamSynchronize(c->stream));
+  return PM_OK;
+}
+
+// characters of n ranges of the loaded stream, concatenated: one gather on the device and one copy
+// (the alignment buffers a tool prints next to its hits)
+int pm_gather_text(pm_ctx *c, const int64_t *begin, const int64_t *len, uint64_t n, uint8_t *out) {
+  if (!c || (n && (!begin || !len || !out))) return fail(PM_E_ARG, "null argument");
+  if (!n) return PM_OK;
+  if (!c->d_text) return fail(PM_E_ARG, "no text");
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  std::vector<unsigned long long> ooff(n + 1, 0);
+  for (uint64_t i = 0; i < n; i++) {
+    if (begin[i] < 0 || len[i] < 0 || (uint64_t)(begin[i] + len[i]) > c->n) return fail(PM_E_ARG, "range outside the loaded text");
+    ooff[i + 1] = ooff[i] + (unsigned long long)len[i];
+  }
+  const pm_ctx *owner = c->inner ? c->inner : c;
+  if (!owner->chunks.empty() && owner->chunks.back().ev)
+    PM_CUDA(cudaStreamWaitEvent(c->stream, owner->chunks.back().ev, 0));
+  DevBuf d_off, d_len, d_ooff, d_out;
+  int rc;
+  if ((rc = d_off.ensure(n * 8)) || (rc = d_len.ensure(n * 8)) || (rc = d_ooff.ensure((n + 1) * 8)) ||
+      (rc = d_out.ensure(ooff[n] + 8)))
+    return rc;
+  PM_CUDA(cudaMemcpyAsync(d_off.p, begin, n * 8, cudaMemcpyHostToDevice, c->stream));
+  PM_CUDA(cudaMemcpyAsync(d_len.p, len, n * 8, cudaMemcpyHostToDevice, c->stream));
+  PM_CUDA(cudaMemcpyAsync(d_ooff.p, ooff.data(), (n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+  gather_ranges_kernel<<<(unsigned)std::min<uint64_t>(n, 1u << 30), 32, 0, c->stream>>>(
+      c->d_text, d_off.as<long long>(), d_len.as<long long>(), d_ooff.as<unsigned long long>(), n, d_out.as<uint8_t>());
+  PM_CUDA(cudaGetLastError());
+  if (ooff[n]) PM_CUDA(cudaMemcpyAsync(out, d_out.p, ooff[n], cudaMemcpyDeviceToHost, c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  d_off.release(); d_len.release(); d_ooff.release(); d_out.release();
   return PM_OK;
 }
 

@@ -359,13 +359,14 @@ __device__ __forceinline__ uint32_t pair_probe(const uint32_t *bitmap, uint32_t 
   return __funnelshift_l(__funnelshift_l(wrd, wrd, idx), hm, 1);
 }
 
-// the same through the bijective index of short keys (IndexArgs::l1_bij): v = key * mult mod 2^20,
-// word v >> 5, bit 31 - (v & 31).  Two multiplies (FMA pipe, which has room) keep the ALU count:
-// the word index comes from key * (mult << 12), the rotation from key * mult.
-__device__ __forceinline__ uint32_t pair_probe_bij(const uint32_t *bitmap, uint32_t key, uint32_t mult, uint32_t mult_hi,
-                                                   uint32_t hm) {
-  const uint32_t wrd = bitmap[(key * mult_hi) >> 17];
-  return __funnelshift_l(__funnelshift_l(wrd, wrd, key * mult), hm, 1);
+// the same through the bijective index of short keys (IndexArgs::l1_bij): word = top 15 bits of
+// (key * mult mod 2^20), bit 31 - (key & 31).  For a fixed value of the key's low five bits the
+// word index is a bijection of the other fifteen (odd multiplier), so no two keys share a bit;
+// the rotation takes the key itself: LOP3 key, IMAD, SHF + LOP3 address, LDS, 2 x SHF per lookup.
+__device__ __forceinline__ uint32_t pair_probe_bij(const uint32_t *bitmap, uint32_t key, uint32_t mult_hi, uint32_t hm) {
+  const uint32_t off = ((key * mult_hi) >> 15) & 0x1fffcu;   // byte offset of the word
+  const uint32_t wrd = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bitmap) + off);
+  return __funnelshift_l(__funnelshift_l(wrd, wrd, key), hm, 1);
 }
 
 // Generic kernel: run-time piece length and distance set, one distance after the other.
@@ -564,7 +565,7 @@ __device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const 
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t key = (__funnelshift_r(X0, X1, 2 * i) & maskHi) | (__funnelshift_r(c0, c1, 2 * i) & maskL);
-      hm = (4 * L <= 20) ? pair_probe_bij(bitmap, key, a.mult, a.mult << 12, hm) : pair_probe(bitmap, key, a.mult, 0u, wsh, hm);
+      hm = (4 * L <= 20) ? pair_probe_bij(bitmap, key, a.mult << 12, hm) : pair_probe(bitmap, key, a.mult, 0u, wsh, hm);
     }
     hm &= vm;
     if (__any_sync(0xffffffffu, hm != 0u)) {
@@ -627,7 +628,7 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           const uint32_t key = (G[i + dd] & maskHi) | av[i];
-          hm = (4 * L <= 20) ? pair_probe_bij(t.bitmap, key, mult, mult << 12, hm) : pair_probe(t.bitmap, key, mult, 0u, wsh, hm);
+          hm = (4 * L <= 20) ? pair_probe_bij(t.bitmap, key, mult << 12, hm) : pair_probe(t.bitmap, key, mult, 0u, wsh, hm);
         }
         hm &= vm;
         // queue (lane, distance, positions): no stage A here, the lookups stay straight-line code
@@ -679,35 +680,79 @@ inline PairKernel pair_edit_kernel(int L, int K) {
   return nullptr;
 }
 
-// Edit verifier of pair_scan_edit_kernel's seeds: one seed per thread, furthest-reaching
-// extension from the seed's first piece (pm_lv.cuh) on the packed text.
+// Edit verifier of pair_scan_edit_kernel's seeds (pm_lv.cuh).  Every seed goes through the q-gram
+// filter, one seed per lane; the few that pass wait in a per-warp queue until 32 are there and
+// are then extended from their first piece with all lanes busy (a warp running the extension for
+// one lane in 32 was half of this kernel's instructions, profiles/README.md).
+__device__ __forceinline__ void lv_load_seed(const IndexArgs &a, unsigned long long sd, int K, LvCtx &t, uint32_t &slot,
+                                             int &pi, int64_t &s_nom) {
+  slot = (uint32_t)(sd >> (SEED_POS_BITS + 3));
+  pi = (int)((sd >> SEED_POS_BITS) & 7ULL);
+  s_nom = (int64_t)(sd & ((1ULL << SEED_POS_BITS) - 1ULL)) - SEED_BIAS;
+  const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
+  const ulonglong2 acc01 = __ldg(accp), acc23 = __ldg(accp + 1);
+  lv_set_pattern(t, (int)(a.plen[slot] & 0x7fu), acc01.x, acc01.y, acc23.x, acc23.y, (int)a.plain_patterns);
+  const int64_t s0 = s_nom - K;
+  const int64_t wb = s0 >> 4;   // arithmetic shift: s0 may be negative near the start
+  const uint32_t sh = 2u * (uint32_t)(s0 & 15);
+  const uint2 p0 = pk_load(a, wb), p1 = pk_load(a, wb + 1), p2 = pk_load(a, wb + 2), p3 = pk_load(a, wb + 3);
+  t.c[0] = __funnelshift_r(p0.x, p1.x, sh); t.c[1] = __funnelshift_r(p1.x, p2.x, sh); t.c[2] = __funnelshift_r(p2.x, p3.x, sh);
+  t.f[0] = __funnelshift_r(p0.y, p1.y, sh); t.f[1] = __funnelshift_r(p1.y, p2.y, sh); t.f[2] = __funnelshift_r(p2.y, p3.y, sh);
+}
+
 template <int K>
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void lv_extend_seed(const IndexArgs &a, bool valid, unsigned long long sd) {
+  if (!valid) return;
+  LvCtx t;
+  uint32_t slot;
+  int pi;
+  int64_t s_nom;
+  lv_load_seed(a, sd, K, t, slot, pi, s_nom);
+  const uint32_t ends = lv_verify<K>(t, pi * (int)a.L, (int)a.L);
+#pragma unroll
+  for (int d = -K; d <= K; d++)
+    if ((ends >> (d + K)) & 1u) index_emit(a, slot, s_nom + t.m + d);
+}
+
+constexpr int VERIFY_LV_THREADS = 128;
+template <int K>
+__global__ void __launch_bounds__(VERIFY_LV_THREADS)
 index_verify_lv_kernel(const __grid_constant__ IndexArgs a) {
+  __shared__ unsigned long long s_q[VERIFY_LV_THREADS / 32][64];
   unsigned long long count = *a.seed_n;
   if (count > a.seed_cap) count = a.seed_cap;
-  const int L = (int)a.L;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned long long sd = a.seeds[i];
-    const uint32_t slot = (uint32_t)(sd >> (SEED_POS_BITS + 3));
-    const int pi = (int)((sd >> SEED_POS_BITS) & 7ULL);
-    const int64_t s_nom = (int64_t)(sd & ((1ULL << SEED_POS_BITS) - 1ULL)) - SEED_BIAS;
-    LvCtx t;
-    const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
-    const ulonglong2 acc01 = __ldg(accp), acc23 = __ldg(accp + 1);
-    lv_set_pattern(t, (int)(a.plen[slot] & 0x7fu), acc01.x, acc01.y, acc23.x, acc23.y, (int)a.plain_patterns);
-    const int64_t s0 = s_nom - K;
-    const int64_t wb = s0 >> 4;   // arithmetic shift: s0 may be negative near the start
-    const uint32_t sh = 2u * (uint32_t)(s0 & 15);
-    const uint2 p0 = pk_load(a, wb), p1 = pk_load(a, wb + 1), p2 = pk_load(a, wb + 2), p3 = pk_load(a, wb + 3);
-    t.c[0] = __funnelshift_r(p0.x, p1.x, sh); t.c[1] = __funnelshift_r(p1.x, p2.x, sh); t.c[2] = __funnelshift_r(p2.x, p3.x, sh);
-    t.f[0] = __funnelshift_r(p0.y, p1.y, sh); t.f[1] = __funnelshift_r(p1.y, p2.y, sh); t.f[2] = __funnelshift_r(p2.y, p3.y, sh);
-    const uint32_t ends = lv_verify<K>(t, pi * L, L);
-#pragma unroll
-    for (int d = -K; d <= K; d++)
-      if ((ends >> (d + K)) & 1u) index_emit(a, slot, s_nom + t.m + d);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  unsigned long long *q = s_q[warp];
+  uint32_t nq = 0;   // warp-uniform
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + warp * 32u; i0 < count; i0 += stride) {
+    const unsigned long long i = i0 + lane;
+    bool pass = false;
+    unsigned long long sd = 0;
+    if (i < count) {
+      sd = a.seeds[i];
+      LvCtx t;
+      uint32_t slot;
+      int pi;
+      int64_t s_nom;
+      lv_load_seed(a, sd, K, t, slot, pi, s_nom);
+      pass = lv_prefilter<K>(t);
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (bal == 0u) continue;
+    if (pass) q[nq + __popc(bal & lt)] = sd;
+    nq += __popc(bal);
+    if (nq >= 32u) {
+      __syncwarp();
+      const unsigned long long s2 = q[nq - 32u + lane];
+      __syncwarp();
+      nq -= 32u;
+      lv_extend_seed<K>(a, true, s2);
+    }
   }
+  __syncwarp();
+  lv_extend_seed<K>(a, lane < nq, lane < nq ? q[lane] : 0ULL);
   if (blockIdx.x == 0 && threadIdx.x == 0 && a.seed_count) atomicAdd(a.seed_count, count);
 }
 

@@ -97,6 +97,28 @@ PM_HD inline void lv_set_pattern(LvCtx &t, int m, uint64_t a0, uint64_t a1, uint
   t.pcodes = (a1 | a3) | ((a2 | a3) << 1);
 }
 
+// The q-gram filter alone: false <=> no occurrence with <= K errors can run through this window
+// (what lv_verify decides first).  The verify kernel asks it for every seed and runs lv_verify,
+// whose cost a random seed never reaches, only for the few that pass, 32 of them at a time.
+template <int K>
+PM_HD inline bool lv_prefilter(const LvCtx &t) {
+  constexpr int ND = 2 * K + 1;
+  uint64_t any3 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < ND; i++) {
+    const uint64_t nm = ~lv_mis(t, i - K, K);
+    any3 |= nm & (nm >> 2) & (nm >> 4);
+  }
+#if defined(__CUDA_ARCH__)
+  const int n3 = __popcll(any3 & 0x5555555555555555ULL);
+#else
+  const int n3 = __builtin_popcountll(any3 & 0x5555555555555555ULL);
+#endif
+  return n3 >= t.m - 2 - 3 * K;
+}
+
 template <int K>
 PM_HD inline uint32_t lv_verify(const LvCtx &t, int a, int L) {
   const int m = t.m;

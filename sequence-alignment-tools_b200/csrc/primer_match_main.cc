@@ -8,6 +8,7 @@
 // Not available here (the reference features outside the accelerated path):
 // -T (translation), -x (hash seeds), -k .N (DNA mutation scoring), -D/-B/-I
 // (database index files: the FASTA file is read whole).
+#include <time.h>
 #include <getopt.h>
 #include <unistd.h>
 
@@ -244,7 +245,15 @@ void countformat(std::ostream &os, const std::string &f, unsigned long i, const 
 
 }  // namespace
 
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 int main(int argc, char **argv) {
+  const double t_start = now_s();
+  const bool timing = getenv("PM_TIMING") != 0;   // stage times to stderr
   Options opt = parse(argc, argv);
   std::ostream *out = &std::cout;
   std::ofstream ofs;
@@ -306,7 +315,10 @@ int main(int argc, char **argv) {
   b200_index *kt = pick_pattern_index(opt.node, opt.nmismatch, opt.wc, opt.tn, opt.indels, (char)opt.eos_char,
                                       opt.device);
   for (unsigned long i = 1; i <= N1; i++) kt->add_pattern(patarray[i], i, patconst[i].first, patconst[i].second);
+  const double t_ctx = now_s();
   kt->init(ff);
+  const double t_init = now_s();
+  double t_first = 0;
 
   const unsigned K = (unsigned)opt.nmismatch;
   std::vector<unsigned long> patcount(opt.counts ? N1 * (K + 1) : 0, 0);
@@ -316,7 +328,9 @@ int main(int argc, char **argv) {
   pattern_hit_vector l;
   bool more;
   while ((more = kt->find_patterns(ff, l, opt.report_interval)) || !l.empty()) {
+    if (t_first == 0) t_first = now_s();
     std::vector<const pm_hit *> &batch = kt->batch();
+    if (opt.alignments && !(K == 0 && !opt.wc)) ff.prefetch_texts(batch);   // one round trip for the batch's texts
     for (size_t hi = 0; hi < l.size(); hi++) {
       const pm_hit &h = *batch[hi];
       const unsigned long pid = h.pattern_id;
@@ -333,7 +347,7 @@ int main(int argc, char **argv) {
         const std::string &pat = patarray[pid];
         // matching_text: the pattern itself for exact_alignment (pattern_alignment.cc:25-43),
         // the text under the alignment otherwise
-        std::string matching = (K == 0 && !opt.wc) ? pat : ff.text(h.start, h.end);
+        std::string matching = (K == 0 && !opt.wc) ? pat : ff.text(h.start, h.end, (long)hi);
         const Aligned al = render(h, pat, matching);
         const std::string patdef = opt.fasta_pattern_file ? patdefs[ind - 1] : std::string();
         alignformat(*out, opt.alignformat, sps, spe, rc ? spe : sps, rc ? sps : spe, ps, pe, ind, ed, patarray[ind],
@@ -381,6 +395,15 @@ int main(int argc, char **argv) {
     }
   }
   out->flush();
+  if (timing) {
+    const double t_end = now_s();
+    if (t_first == 0) t_first = t_end;
+    std::fprintf(stderr,
+                 "PM_TIMING {\"context_s\": %.4f, \"init_and_read_s\": %.4f, \"scan_s\": %.4f, \"output_s\": %.4f, "
+                 "\"total_s\": %.4f, \"stream_chars\": %llu}\n",
+                 t_ctx - t_start, t_init - t_ctx, t_first - t_init, t_end - t_first, t_end - t_start,
+                 (unsigned long long)ff.size());
+  }
   delete kt;
   return 0;
 }

@@ -35,6 +35,10 @@ CASES = [
     dict(seed=6, n=2_500_000, nseq=2, nprimers=100, plen=20, k=0, indels=False, wc=False, tn=False, select=0),
     dict(seed=7, n=1_000_000, nseq=3, nprimers=60, plen=20, k=1, indels=True, wc=False, tn=False, select=5),
     dict(seed=8, n=800_000, nseq=2, nprimers=30, plen=18, k=2, indels=True, wc=True, tn=True, select=0),
+    # hit-dense: primer sites in tandem repeats (runs of copies 20-26 apart, so that chains of candidates
+    # touch and overlap), thousands of hits per 100 kbp
+    dict(seed=9, n=600_000, nseq=2, nprimers=40, plen=20, k=2, indels=False, wc=False, tn=False, select=0, dense=4000),
+    dict(seed=10, n=400_000, nseq=2, nprimers=30, plen=20, k=2, indels=True, wc=False, tn=False, select=0, dense=2000),
 ]
 
 
@@ -59,6 +63,19 @@ def large_case(c):
         q = casegen.mutate(rng, q, rng.randint(0, c["k"]), c["indels"])
         at = rng.randrange(100, n - 100)
         seq[at:at + len(q)] = np.frombuffer(q.encode(), np.uint8)
+    if c.get("dense"):                            # tandem repeats of primer sites
+        left = c["dense"]
+        while left > 0:
+            run = min(left, rng.randint(5, 60))
+            at = rng.randrange(100, n - 100 - 30 * run)
+            p = primers[rng.randrange(len(primers))]
+            if rng.random() < 0.5:
+                p = p[::-1].translate(str.maketrans("ACGT", "TGCA"))
+            for _ in range(run):
+                q = casegen.mutate(rng, p, rng.randint(0, c["k"]), c["indels"])
+                seq[at:at + len(q)] = np.frombuffer(q.encode(), np.uint8)
+                at += len(q) + rng.randint(0, 6)
+            left -= run
     for _ in range(6):                            # runs of N
         at, ln = rng.randrange(0, n - 5000), rng.choice([1, 7, 300, 4000])
         seq[at:at + ln] = ord("N")
@@ -91,7 +108,15 @@ def main():
         raise SystemExit("oracle/_ref/primer_match missing: run `make -C oracle` first")
     tmp = tempfile.mkdtemp()
     out_cases = []
+    out = os.path.join(HERE, "large_golden.json")
+    have = {}
+    if os.path.exists(out) and "--all" not in sys.argv:      # keep what is there, add the new cases
+        with open(out) as f:
+            have = {e["case"]["seed"]: e for e in json.load(f)["cases"]}
     for c in CASES:
+        if c["seed"] in have and have[c["seed"]]["case"] == c:
+            out_cases.append(have[c["seed"]])
+            continue
         fasta, primers = large_case(c)
         path = os.path.join(tmp, "large%d.fasta" % c["seed"])
         with open(path, "wb") as f:
@@ -101,7 +126,6 @@ def main():
         out_cases.append(dict(case=c, records=[[r.seq_index, r.seq_start, r.seq_end, r.strand, r.pattern_index,
                                                 r.editdist, r.stream_start, r.stream_end, r.alignment] for r in recs]))
         print("case %d: %d records" % (c["seed"], len(recs)), flush=True)
-    out = os.path.join(HERE, "large_golden.json")
     with open(out, "w") as f:
         json.dump(dict(generator="tests/golden/make_large_golden.py", cases=out_cases), f, indent=0)
     print("wrote", out)

@@ -118,6 +118,15 @@ int pm_get_text(pm_ctx *c, uint64_t begin, uint64_t len, uint8_t *out) {
   return PM_OK;
 }
 
+int pm_gather_text(pm_ctx *c, const int64_t *begin, const int64_t *len, uint64_t n, uint8_t *out) {
+  for (uint64_t i = 0; i < n; i++) {
+    if (begin[i] < 0 || (uint64_t)(begin[i] + len[i]) > c->stream.size()) return PM_E_ARG;
+    memcpy(out, c->stream.data() + begin[i], (size_t)len[i]);
+    out += len[i];
+  }
+  return PM_OK;
+}
+
 int pm_normalize_fasta(const uint8_t *, uint64_t, int, unsigned char, uint8_t *, uint64_t *, int64_t *, int64_t *,
                        int64_t *, uint64_t, uint64_t *) {
   return PM_E_UNSUPPORTED;
