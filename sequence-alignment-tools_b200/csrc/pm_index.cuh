@@ -294,6 +294,12 @@ __device__ __forceinline__ void pair_load_words(const IndexArgs &a, const PairCt
   if (base + 16 > a.p_end) vm &= (a.p_end <= base) ? 0u : (0xffffu << (uint32_t)(base + 16 - a.p_end));
 }
 
+// the words of a later chunk towards L2 (no register is held: the kernels sit at their register cap)
+__device__ __forceinline__ void pair_prefetch_words(const IndexArgs &a, const PairCta &t, int64_t chunk) {
+  const int64_t w = t.w_begin + (chunk << 5) + t.lane;
+  if (chunk < t.n_chunks && (uint64_t)w < a.n16) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + w));
+}
+
 // level 1b (edits): the shared bits of level 1 say "some distance"; keep the positions whose
 // (key, distance) bit is set as well.  Divergent, only for lanes with a hit.
 __device__ __forceinline__ uint32_t pair_level1b(const IndexArgs &a, const PairCta &t, uint32_t hm, uint32_t di,
@@ -604,6 +610,7 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
     int64_t w;
     uint32_t cw[5], vm;
     pair_load_words(a, t, c, w, cw[0], cw[1], cw[2], vm);
+    pair_prefetch_words(a, t, c + (int64_t)gridDim.x * (blockDim.x >> 5));
     cw[3] = cw[4] = 0u;
     uint32_t av[16];
 #pragma unroll
@@ -812,10 +819,12 @@ pair_scan_sub_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
   for (int j = 0; j < ND; j++) salt[j] = a.salt[j];
 
-  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+  const int64_t c_step = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += c_step) {
     int64_t w;
     uint32_t cw[4], vm;
     pair_load_words(a, t, c, w, cw[0], cw[1], cw[2], vm);
+    pair_prefetch_words(a, t, c + c_step);   // the next chunk's words on their way from HBM to L2 under the lookups
     cw[3] = 0u;
     uint32_t G[NG];
 #pragma unroll
