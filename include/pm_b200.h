@@ -89,7 +89,7 @@ typedef struct pm_options {
 #define PM_SCAN_PLANES 1
 #define PM_SCAN_INDEX 2
 
-#define PM_MAX_K 3
+#define PM_MAX_K 5   /* k <= 3: pair-seed index scan; 4, 5: bit-plane kernels */
 #define PM_MAX_PATTERN_LEN 64
 #define PM_MAX_CODES 72 /* >= PM_MAX_PATTERN_LEN + PM_MAX_K + 1 */
 

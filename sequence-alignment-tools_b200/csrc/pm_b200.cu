@@ -514,14 +514,18 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
     switch (K) {
       case 1: kern = edit_seed_kernel<1>; vkern = edit_verify_kernel<1>; break;
       case 2: kern = edit_seed_kernel<2>; vkern = edit_verify_kernel<2>; break;
-      default: kern = edit_seed_kernel<3>; vkern = edit_verify_kernel<3>; break;
+      case 3: kern = edit_seed_kernel<3>; vkern = edit_verify_kernel<3>; break;
+      case 4: kern = edit_seed_kernel<4>; vkern = edit_verify_kernel<4>; break;
+      default: kern = edit_seed_kernel<5>; vkern = edit_verify_kernel<5>; break;
     }
   } else {
     switch (K) {
       case 0: kern = hamming_scan_kernel<0>; break;
       case 1: kern = hamming_scan_kernel<1>; break;
       case 2: kern = hamming_scan_kernel<2>; break;
-      default: kern = hamming_scan_kernel<3>; break;
+      case 3: kern = hamming_scan_kernel<3>; break;
+      case 4: kern = hamming_scan_kernel<4>; break;
+      default: kern = hamming_scan_kernel<5>; break;
     }
   }
   PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1091,7 +1095,7 @@ const char *pm_version(void) { return "pm_b200 0.1 (sm_100a)"; }
 int pm_create(pm_ctx **out, const pm_options *opt) {
   if (!out || !opt) return fail(PM_E_ARG, "null argument");
   *out = nullptr;
-  if (opt->k < 0 || opt->k > PM_MAX_K) return fail(PM_E_UNSUPPORTED, "k out of range (0..3)");
+  if (opt->k < 0 || opt->k > PM_MAX_K) return fail(PM_E_UNSUPPORTED, "k out of range (0..5)");
   int index = opt->index;
   bool index_auto = false;
   if (index == PM_INDEX_AUTO) {
@@ -1428,7 +1432,7 @@ int pm_init(pm_ctx *c) {
     const uint32_t symbits = (c->n_sym >= 32) ? 0xffffffffu : ((1u << c->n_sym) - 1u);
     uint32_t code_mask[4] = {0, 0, 0, 0};  // symbols matched by a text character of that code
     int n_codes = 0;
-    bool ok = c->max_len <= 32 && ns > 0 && ns < (1u << 22);
+    bool ok = c->max_len <= 32 && ns > 0 && ns < (1u << 22) && K <= 3;   // k = 4, 5: the bit-plane kernels
     // DNA: code = (byte >> 1) & 3 for the bytes A, C, T, G (0, 1, 2, 3), which the pack kernel
     // computes without its table (pack_linear_kernel's fast path)
     bool dna_codes = wc;

@@ -737,6 +737,18 @@ index_verify_lv_kernel(const __grid_constant__ IndexArgs a) {
     const unsigned long long i = i0 + lane;
     bool pass = false;
     unsigned long long sd = 0;
+    if (i + stride < count) {
+      // the next seed's text words and accept masks towards L2 while this one is filtered (a seed's
+      // window is 32 bytes somewhere in the packed text: HBM latency, and nothing else to hide it)
+      const unsigned long long nx = a.seeds[i + stride];
+      const int64_t s0n = (int64_t)(nx & ((1ULL << SEED_POS_BITS) - 1ULL)) - SEED_BIAS - K;
+      const int64_t wn = s0n >> 4;
+      if (wn >= 0 && (uint64_t)(wn + 3) < a.n16) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + wn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pk + wn + 3));
+      }
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pacc + (uint32_t)(nx >> (SEED_POS_BITS + 3))));
+    }
     if (i < count) {
       sd = a.seeds[i];
       LvCtx t;

@@ -192,6 +192,24 @@ template <> struct Counter<3> {
   static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[3]) { return b[2] & ~b[0]; }
 };
 
+// K = 4, 5: a plain saturating 3-bit binary counter (states 0..7, 7 absorbs): a ripple add of the
+// mismatch bit and an OR of the overflow.  Three times the logic of the K <= 3 encodings; these
+// error counts only run on this (general) path.
+template <int K> struct CounterSat3 {
+  static constexpr int NB = 3;
+  static __device__ __forceinline__ void step(uint32_t (&b)[3], uint32_t nx) {
+    const uint32_t c0 = b[0] & nx, c1 = b[1] & c0, ov = b[2] & c1;
+    b[0] = (b[0] ^ nx) | ov;
+    b[1] = (b[1] ^ c0) | ov;
+    b[2] = (b[2] ^ c1) | ov;
+  }
+  static __device__ __forceinline__ uint32_t dead(const uint32_t (&b)[3]) {
+    return K == 4 ? (b[2] & (b[1] | b[0])) : (b[2] & b[1]);   // count > K
+  }
+};
+template <> struct Counter<4> : CounterSat3<4> {};
+template <> struct Counter<5> : CounterSat3<5> {};
+
 constexpr uint32_t PLEN_SHARE = 0x80u;  // plen flag: first 4 characters equal the previous slot's
 
 // Substitutions-only scan.  FIRST_CHECK = group of 4 characters after which the

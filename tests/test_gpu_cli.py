@@ -170,13 +170,15 @@ def test_pcr_match_output_matches_reference(pcr_cli, oracle, pcr_golden, tmp_pat
 
 def test_cli_opens_the_database_like_pick_fasta_file(cli, golden, tmp_path):
     """-D: the FASTA file itself (1), or the .sqn (3) / .sqz (4) database the reference's compress_seq
-    wrote next to it, or whichever exists (0) -- read by the library's own reader; the text must be
-    the one the reference printed for the FASTA file (coordinates and headers do not depend on the
-    form of the database)."""
+    wrote next to it, or whichever exists (0) -- read by the library's own reader.  The expectation
+    is what the UNMODIFIED reference prints for the same -D on the same files (run here: a
+    compressed database is not the same text as its FASTA file -- compress_seq upper-cases it -- and
+    its small alphabet changes the automatic index choice, select.cc:120-123)."""
     csq = os.path.join(ROOT, "oracle", "_ref", "compress_seq")
-    if not os.path.exists(csq):
-        pytest.skip("needs oracle/_ref/compress_seq")
-    checked = 0
+    ref = os.path.join(ROOT, "oracle", "_ref", "primer_match")
+    if not (os.path.exists(csq) and os.path.exists(ref)):
+        pytest.skip("needs oracle/_ref/compress_seq and oracle/_ref/primer_match")
+    checked = differ = 0
     for case in golden["cases"]:
         if "stdout_default" not in case or case["params"]["wc"]:
             continue
@@ -193,6 +195,11 @@ def test_cli_opens_the_database_like_pick_fasta_file(cli, golden, tmp_path):
         p = subprocess.run([csq, "-i", str(fa), "-z", "true", "-n", "true"], capture_output=True, timeout=120)
         assert p.returncode == 0 and (d / "db.fasta.sqz").exists() and (d / "db.fasta.idb").exists()
         for dbind in ("4", "3", "0"):
-            got = _run(cli, _args(str(fa), prm, par, ["-D", dbind]))
-            assert _blocks(got, 4) == want, "-D %s, case %s" % (dbind, case["seed"])
-    assert checked >= 8
+            args = _args(str(fa), prm, par, ["-D", dbind])
+            r = subprocess.run([ref] + args, capture_output=True, timeout=300)
+            assert r.returncode == 0
+            want_d = _blocks(r.stdout.decode("latin-1"), 4)
+            differ += want_d != want
+            got = _run(cli, args)
+            assert _blocks(got, 4) == want_d, "-D %s, case %s" % (dbind, case["seed"])
+    assert checked >= 8 and differ >= 1
