@@ -81,7 +81,7 @@ class _DeviceBytes:
     """A device pointer as a CUDA-array-interface object (so that torch can wrap it)."""
 
     def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, True), "version": 3}
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
 def gather_hits_device(d_ptr: int, n_hits: int, item_bytes: int, dist, device=None):

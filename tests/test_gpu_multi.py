@@ -24,6 +24,14 @@ def _free_port():
 
 
 def _worker(rank, world, port, q):
+    try:
+        _work(rank, world, port, q)
+    except Exception as ex:     # the parent must not wait for a worker that died
+        import traceback
+        q.put(("error", rank, traceback.format_exc()[-1500:]))
+
+
+def _work(rank, world, port, q):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     import random
@@ -60,7 +68,8 @@ def _worker(rank, world, port, q):
         sc.init()
         plan = sharding.shard_plan(n + 1, world, sc.shard_overlap())
         sh = plan[rank]
-        sc.set_text(d[sh.load_lo:sh.load_hi], offset=sh.load_lo)
+        lo = sh.load_lo & ~3                     # pm_set_text_device wants a 4-byte aligned pointer
+        sc.set_text(d[lo:sh.load_hi], offset=lo)
         ptr, nh = sc.find_patterns_device(sh.begin, sh.end)
         counts, recs = sharding.gather_hits_device(ptr, nh, pkg.HIT_DTYPE.itemsize, dist, dev)
         gathered = recs.cpu().numpy().tobytes()
@@ -90,7 +99,11 @@ def test_shards_over_gpus_gathered_over_nccl_equal_the_whole_scan(built_lib):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = q.get(timeout=600)
+    results = q.get(timeout=400)
+    if results and results[0] == "error":
+        for p in procs:
+            p.kill()
+        pytest.fail("rank %d: %s" % (results[1], results[2]))
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
