@@ -853,6 +853,7 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
     // exact_halves: every exact occurrence of a pattern half up to the end of the range (the
     // `lasthit` rule looks back, so the scan starts where the loaded text starts)
     guarded = false;
+    memset(&c->inner->stats, 0, offsetof(pm_stats, pack_ms));   // the inner context's counters of THIS call
     rc = run_scan_any(c->inner, 0, own_hi, &bound, true);
     const pm_stats &is = c->inner->stats;
     c->stats.scan_ms = is.scan_ms;

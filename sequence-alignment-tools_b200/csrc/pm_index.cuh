@@ -369,9 +369,12 @@ __device__ __forceinline__ uint32_t pair_probe(const uint32_t *bitmap, uint32_t 
 // (key * mult mod 2^20), bit 31 - (key & 31).  For a fixed value of the key's low five bits the
 // word index is a bijection of the other fifteen (odd multiplier), so no two keys share a bit;
 // the rotation takes the key itself: LOP3 key, IMAD, SHF + LOP3 address, LDS, 2 x SHF per lookup.
-__device__ __forceinline__ uint32_t pair_probe_bij(const uint32_t *bitmap, uint32_t key, uint32_t mult_hi, uint32_t hm) {
-  const uint32_t off = ((key * mult_hi) >> 15) & 0x1fffcu;   // byte offset of the word
-  const uint32_t wrd = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(bitmap) + off);
+__device__ __forceinline__ uint32_t pair_probe_bij(uint32_t bitmap_saddr, uint32_t key, uint32_t mult_hi, uint32_t hm) {
+  // address = base + 4 * word as ONE multiply-add (FMA pipe; the ALU pipe is the one that binds):
+  // written in PTX because the compiler turns the C expression into shift + mask + add
+  uint32_t addr, wrd;
+  asm("mad.lo.u32 %0, %1, 4, %2;" : "=r"(addr) : "r"((key * mult_hi) >> 17), "r"(bitmap_saddr));
+  asm("ld.shared.u32 %0, [%1];" : "=r"(wrd) : "r"(addr));
   return __funnelshift_l(__funnelshift_l(wrd, wrd, key), hm, 1);
 }
 
@@ -571,7 +574,7 @@ __device__ __noinline__ uint32_t pair_edit_chunk_slow(const IndexArgs &a, const 
 #pragma unroll
     for (int i = 0; i < 16; i++) {
       const uint32_t key = (__funnelshift_r(X0, X1, 2 * i) & maskHi) | (__funnelshift_r(c0, c1, 2 * i) & maskL);
-      hm = (4 * L <= 20) ? pair_probe_bij(bitmap, key, a.mult << 12, hm) : pair_probe(bitmap, key, a.mult, 0u, wsh, hm);
+      hm = (4 * L <= 20) ? pair_probe_bij((uint32_t)__cvta_generic_to_shared(bitmap), key, a.mult << 12, hm) : pair_probe(bitmap, key, a.mult, 0u, wsh, hm);
     }
     hm &= vm;
     if (__any_sync(0xffffffffu, hm != 0u)) {
@@ -605,6 +608,7 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
   uint16_t *stage = reinterpret_cast<uint16_t *>(s_mem + (1u << a.log_words) + PAIR_WARPS * 2 * PAIR_QCAP * 2 +
                                                  (a.b2_global ? 0u : t.n_words2)) + warp * 32;
   const uint32_t lane_tag = t.lane << 21;
+  const uint32_t bitmap_saddr = (uint32_t)__cvta_generic_to_shared(t.bitmap);
 
   for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; c < t.n_chunks; c += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     int64_t w;
@@ -635,7 +639,7 @@ pair_scan_edit_kernel(const __grid_constant__ IndexArgs a) {
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           const uint32_t key = (G[i + dd] & maskHi) | av[i];
-          hm = (4 * L <= 20) ? pair_probe_bij(t.bitmap, key, mult << 12, hm) : pair_probe(t.bitmap, key, mult, 0u, wsh, hm);
+          hm = (4 * L <= 20) ? pair_probe_bij(bitmap_saddr, key, mult << 12, hm) : pair_probe(t.bitmap, key, mult, 0u, wsh, hm);
         }
         hm &= vm;
         // queue (lane, distance, positions): no stage A here, the lookups stay straight-line code
