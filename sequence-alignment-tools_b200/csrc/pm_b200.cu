@@ -530,9 +530,12 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
   }
   PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+  // candidate buffer: one entry per 64 characters of the scanned range (a genome whose repeats hold
+  // primer sites gives ~1 hit per kbp), at least 2^20; more than that costs one repeated scan
   uint64_t cap = c->d_keys.cap / 8;
-  if (cap < (1u << 20)) {
-    int rc = c->d_keys.ensure((size_t)(1u << 20) * 8);
+  const uint64_t want_cap = std::max<uint64_t>(1u << 20, (uint64_t)(q_hi - q_lo) / 64);
+  if (cap < want_cap) {
+    int rc = c->d_keys.ensure((size_t)want_cap * 8);
     if (rc) return rc;
     cap = c->d_keys.cap / 8;
   }
