@@ -710,6 +710,21 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
         legs["fasta"] = (B.timed(step_fasta, steps, min(warmup, 2)), fasta_bytes)
         assert res["hits_stream"].tobytes() == hits.tobytes() == res["hits_fasta"].tobytes(), "the three input forms disagree"
         del h_stream, h_fasta
+    copy_gbs = None
+    if full and h_sqz_view is not None:
+        # the host-to-device copy alone, all ranks at once: what the uplinks give this rank while its
+        # neighbours copy too (the end-to-end legs are bound by it; the ratio says how close they come)
+        h_t = torch.from_numpy(h_sqz_view) if not hasattr(h_sqz_view, "is_pinned") else h_sqz_view
+        d_tmp = torch.empty(int(sqz_bytes), dtype=torch.uint8, device=B.dev)
+
+        def step_copy():
+            d_tmp.copy_(h_t, non_blocking=True)
+        try:
+            ms_copy = B.timed(step_copy, steps, 1)
+            copy_gbs = sqz_bytes * steps / (ms_copy * 1e-3) / 1e9
+        except Exception:
+            copy_gbs = None
+        del d_tmp
     ms, ms_e2e, mean_scan = B.max_over_ranks([ms, ms_e2e, mean_scan])
     leg_ms = {k: B.max_over_ranks([v[0]])[0] for k, v in legs.items()}
     out = None
@@ -727,6 +742,7 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
                        "h2d_bytes_per_step": int(sqz_bytes) * world,
                        "d2h_bytes_per_step": (hits.nbytes + 256) * world, "ms_per_step": ms_e2e / steps,
                        "h2d_gbs_per_rank": sqz_bytes / (ms_e2e / steps * 1e-3) / 1e9,
+                       "h2d_copy_only_gbs_this_rank": copy_gbs,
                        "input": "pinned host buffer holding the database as compress_seq -z stores it "
                                 "(.sqz, 3 bits per character; pm_set_text_sqz_host)"},
                "gpu_launches": n_launch}

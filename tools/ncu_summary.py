@@ -47,7 +47,7 @@ def launches(path):
         a[1] += v
 
     def own(k):
-        return ("pm::" in k or "<unnamed>::" in k or "cub::" in k) and "lop3_peak" not in k and "at::" not in k
+        return ("pm::" in k or "<unnamed>::" in k or "cub::" in k or k.startswith("void CUB_")) and "lop3_peak" not in k and "at::" not in k and "at_cuda" not in k
     tot = sum(t for k, (n, t) in agg.items() if own(k))
     print("| kernel | launches | total ms | share of the library's own kernels |")
     print("|---|---|---|---|")
