@@ -131,10 +131,26 @@ __host__ __device__ __forceinline__ uint32_t pair_hash2(uint32_t key, uint32_t d
   return ((key + di * 0x9E3779B1u) * 0x85EBCA6Bu) >> (32u - log_buckets);
 }
 
-// substitutions: mismatches of the whole window of `slot` starting at s
-__device__ __forceinline__ void pair_verify_window(const IndexArgs &a, uint32_t slot, int64_t s) {
+// one slot of the candidate list for every lane that has one: a single atomic per warp (all 32 lanes
+// call this together)
+__device__ __forceinline__ void index_emit_warp(const IndexArgs &a, bool has, uint32_t slot, int64_t pos) {
+  has = has && pos >= a.lo && pos < a.hi;
+  const uint32_t bal = __ballot_sync(0xffffffffu, has);
+  if (bal == 0u) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  unsigned long long base = 0;
+  if (lane == (uint32_t)(__ffs(bal) - 1)) base = atomicAdd(a.count, (unsigned long long)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  if (has) {
+    const unsigned long long at = base + __popc(bal & ((1u << lane) - 1u));
+    if (at < a.cap) a.out[at] = ((unsigned long long)slot << 40) | (unsigned long long)pos;
+  }
+}
+
+// substitutions: mismatches of the whole window of `slot` starting at s; true: a candidate at *pos
+__device__ __forceinline__ bool pair_verify_window(const IndexArgs &a, uint32_t slot, int64_t s, int64_t *pos) {
   const uint32_t m = a.plen[slot] & 0x7fu;
-  if (s < 0 || (uint64_t)(s + m) > a.n) return;
+  if (s < 0 || (uint64_t)(s + m) > a.n) return false;
   uint64_t codes, flags;
   pk_window(a, s, codes, flags);
   const ulonglong2 *accp = reinterpret_cast<const ulonglong2 *>(a.pacc + slot);
@@ -146,7 +162,8 @@ __device__ __forceinline__ void pair_verify_window(const IndexArgs &a, uint32_t 
   const uint64_t lo = codes & M5, hi = (codes >> 1) & M5;
   const uint64_t match = (~(hi | lo) & acc.x) | (lo & ~hi & acc.y) | (hi & ~lo & acc.z) | (hi & lo & acc.w);
   const uint64_t mis = (~match | flags) & M5 & lenmask;
-  if (__popcll(mis) <= (int)a.k && (flags & ~M5 & lenmask) == 0) index_emit(a, slot, s + m);
+  *pos = s + m;
+  return __popcll(mis) <= (int)a.k && (flags & ~M5 & lenmask) == 0;
 }
 
 // Level 2 and verification run as two warp-wide stages fed from per-warp queues in
@@ -166,8 +183,12 @@ struct PairQueues {
 
 template <bool EDIT>
 __device__ __forceinline__ void pair_stage_b(const IndexArgs &a, bool valid, unsigned long long rec) {
-  if (EDIT || !valid) return;
-  pair_verify_window(a, (uint32_t)(rec & 0x3fffffu), (int64_t)(rec >> 22) - SEED_BIAS);
+  if (EDIT) return;
+  // (called by all 32 lanes: candidates are appended with one atomic per warp)
+  const uint32_t slot = (uint32_t)(rec & 0x3fffffu);
+  int64_t pos = 0;
+  const bool hit = valid && pair_verify_window(a, slot, (int64_t)(rec >> 22) - SEED_BIAS, &pos);
+  index_emit_warp(a, hit, slot, pos);
 }
 
 template <bool EDIT>
