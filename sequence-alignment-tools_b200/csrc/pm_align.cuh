@@ -72,7 +72,9 @@ PM_HD inline int64_t align_textstart(int64_t e1, int m, int k) {
   return (e1 > (int64_t)m + k) ? e1 - m - k : 0;  // pattern_alignment.cc:137-139
 }
 
-// codes (if not null) receives the alignment codes in pattern order.
+// The plain statement of the dynamic programme over the full (m+1) x (buflen+1) matrix.  The
+// kernels run the banded form below; this one stays as what tools/align_band_check.cc compares it
+// with.  codes (if not null) receives the alignment codes in pattern order.
 PM_HD inline void editdist_align(const AlignEnv &env, uint32_t slot, int64_t e1, int64_t e2,
                                       uint8_t *ws, uint8_t *codes, int max_codes, AlignResult &r) {
   const int m = env.plen[slot] & 0x7f;
@@ -381,61 +383,13 @@ PM_HD inline void editdist_align_band(const AlignEnv &env, uint32_t slot, int64_
 
 #if defined(__CUDACC__)
 // ---------------------------------------------------------------------------
-// keys are sorted (slot << 40 | pos) and unique.  head[i] = 1 if candidate i
-// starts a chain (filter_bitvec.cc:157-168: the chain continues while the next
-// candidate of the pattern is at most 2k+1 past the previous one).
-__global__ void chain_heads_kernel(const unsigned long long *keys, uint64_t n, int gap,
-                                   uint32_t *head) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t h = 1;
-  if (i > 0) {
-    const unsigned long long a = keys[i - 1], b = keys[i];
-    if ((a >> 40) == (b >> 40) && (b & 0xffffffffffULL) - (a & 0xffffffffffULL) <= (unsigned long long)gap)
-      h = 0;
-  }
-  head[i] = h;
-}
-
+// Chains of candidates: keys are sorted (slot << 40 | pos) and unique; a chain continues while the
+// next candidate of the pattern is at most 2k+1 past the previous one (filter_bitvec.cc:157-168).
 struct Chain {
   int64_t first, last;  // candidate positions (local to the shard)
   uint32_t slot;
   uint32_t pad;
 };
-
-// chain_id[i] = inclusive prefix sum of head - 1
-__global__ void chain_fill_kernel(const unsigned long long *keys, uint64_t n, const uint32_t *head,
-                                  const uint32_t *chain_incl, Chain *chains) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t c = chain_incl[i] - 1;
-  const unsigned long long key = keys[i];
-  if (head[i]) {
-    chains[c].first = (int64_t)(key & 0xffffffffffULL);
-    chains[c].slot = (uint32_t)(key >> 40);
-    chains[c].pad = 0;
-  }
-  if (i + 1 == n || head[i + 1]) chains[c].last = (int64_t)(key & 0xffffffffffULL);
-}
-
-// workspace size per chain (0 for chains this call does not own)
-// guard_end > 0: the scanned window ends there although the text goes on; an owned chain whose
-// last candidate lies within 2k+1 of it may continue past the window (*cut is set).
-__global__ void chain_ws_kernel(const Chain *chains, uint64_t n, const uint8_t *plen, int k,
-                                int64_t own_lo, int64_t own_hi, unsigned long long *ws_bytes,
-                                int64_t guard_end, unsigned long long *cut) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Chain c = chains[i];
-  unsigned long long b = 0;
-  if (c.first >= own_lo && c.first < own_hi) {
-    if (guard_end > 0 && c.last + (2 * k + 1) >= guard_end) *cut = 1ULL;
-    const int m = plen[c.slot] & 0x7f;
-    const int64_t buflen = c.last - align_textstart(c.first, m, k);
-    b = (align_ws_bytes(m, buflen) + 15ull) & ~15ull;
-  }
-  ws_bytes[i] = b;
-}
 
 struct RawHit {
   int64_t end;       // pa.end() of the chain alignment
@@ -444,28 +398,8 @@ struct RawHit {
   int32_t val;
 };
 
-// one thread per chain in [c0, c1): yes/no alignment over [first, last]
-__global__ void chain_align_kernel(const AlignEnv env, const Chain *chains, uint64_t c0, uint64_t c1,
-                                   const unsigned long long *ws_off, unsigned long long ws_base,
-                                   uint8_t *ws, RawHit *hits, unsigned long long *n_hits) {
-  const uint64_t i = c0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c1) return;
-  const unsigned long long off = ws_off[i];
-  if (ws_off[i + 1] == off) return;  // not owned
-  const Chain c = chains[i];
-  AlignResult r;
-  editdist_align(env, c.slot, c.first, c.last, ws + (off - ws_base), nullptr, 0, r);
-  if (r.ok == 1) {
-    const unsigned long long at = atomicAdd(n_hits, 1ULL);
-    RawHit h;
-    h.end = r.end; h.first = c.first; h.slot = c.slot; h.val = r.val;
-    hits[at] = h;
-  }
-}
-
-
 // ---------------------------------------------------------------------------
-// The same tail with every count left on the device: the host only knows an upper bound
+// The tail with every count left on the device: the host only knows an upper bound
 // (`bound` = candidates before duplicates were removed) and sizes buffers and grids by it.
 struct TailCounts {
   const unsigned long long *n_cands;   // sorted unique candidates

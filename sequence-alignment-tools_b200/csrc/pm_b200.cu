@@ -196,7 +196,7 @@ struct pm_ctx {
   DevBuf d_pool;   // storage of the chain alignments whose band exceeds ALIGN_BAND_MAX (bump-allocated)
   bool out_direct = false;   // the last call wrote its records straight to h_out
   int n_sm = 148;
-  DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_wsb, d_wsoff, d_ws, d_raw, d_hits, d_hits2,
+  DevBuf d_keys, d_keys2, d_head, d_incl, d_chains, d_raw, d_hits, d_hits2,
       d_sortk, d_sortk2, d_idx, d_idx2, d_tmp, d_cands, d_seeds;
   double seed_rate = 0;  // expected piece occurrences per base on uniform ACGT text
   double idx_seed_rate = 0;  // same for the pair index (pair occurrences)
@@ -1171,8 +1171,8 @@ void pm_destroy(pm_ctx *c) {
   DevBuf *bufs[] = {&c->d_symmask, &c->d_poff,   &c->d_plen,   &c->d_patchars, &c->d_lconst,
                     &c->d_rconst,  &c->d_compat, &c->d_cls,    &c->d_umask,    &c->d_piece,
                     &c->d_slotid,  &c->d_text_own, &c->d_planes, &c->d_keys,   &c->d_keys2,
-                    &c->d_head,    &c->d_incl,   &c->d_chains, &c->d_wsb,      &c->d_wsoff,
-                    &c->d_ws,      &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
+                    &c->d_head,    &c->d_incl,   &c->d_chains,
+                    &c->d_raw,    &c->d_hits,   &c->d_hits2,    &c->d_sortk,
                     &c->d_sortk2,  &c->d_idx,    &c->d_idx2,   &c->d_tmp,      &c->d_cands, &c->d_seeds, &c->d_pk,
                     &c->d_bucket,  &c->d_entries, &c->d_pacc,  &c->d_umask4,   &c->d_lin, &c->d_bitmap, &c->d_bitmap2, &c->d_amb, &c->d_sqz, &c->d_sqztab,
                     &c->d_fa_raw, &c->d_fa_map, &c->d_fa_scan, &c->d_fa_cnt, &c->d_fa_chdr, &c->d_fa_start,

@@ -495,3 +495,43 @@ def test_range_end_inside_a_chunked_text(pkg, k):
             want = whole[(whole["first"] >= begin) & (whole["first"] < e)]
             assert part.tobytes() == want.tobytes(), (e, begin)
     sc.close()
+
+
+@pytest.mark.parametrize("k", [2, 3])
+def test_edit_scan_dense_chunks_take_the_slow_path(pkg, oracle, k):
+    """Text that repeats a piece pair of some pattern over and over (poly-A against a poly-A primer,
+    a dinucleotide repeat against its primer): every lane of a chunk has level-1 hits at every
+    distance, the per-warp record queue of pair_scan_edit_kernel overflows and the chunk is redone by
+    its slow path.  Raw candidates against the oracle's recurrence."""
+    import casegen
+    rng = random.Random(700 + k)
+    m = 4 * (k + 2) + 5
+    primers = ["A" * m, ("AC" * 20)[:m], casegen.rand_dna(rng, m), casegen.rand_dna(rng, m)]
+    n = 40_000
+    seq = list(casegen.rand_dna(rng, n))
+    seq[3_000:9_000] = "A" * 6_000
+    seq[15_000:19_000] = list(("AC" * 2_000))
+    seq[19_000:19_600] = "A" * 600            # the two repeats next to each other
+    for at in (25_000, 30_010, 35_555):
+        q = casegen.mutate(rng, primers[2], k, True)
+        seq[at:at + len(q)] = list(q)
+    seq[8_990] = "N"
+    st = pkg.normalize_fasta((">r\n" + "".join(seq[:20_000]) + "\n>s\n" + "".join(seq[20_000:]) + "\n").encode())
+    T = st.chars
+    want = sorted({(int(b), int(a)) for a, b, _ in oracle.wm_scan(T, primers, k, True, False, False)})
+    sc = pkg.Scanner(k=k, indels=True, index=pkg.PM_INDEX_FILTER_BITVEC, scan_path=pkg.PM_SCAN_INDEX)
+    for i, p in enumerate(primers):
+        sc.add_pattern(p, i + 1)
+    sc.init()
+    sc.set_text(T)
+    got = sorted((int(b), int(a)) for a, b in sc.scan_candidates())
+    stats = sc.stats()
+    hits = sc.find_patterns()
+    sc.close()
+    assert stats["scan_path"] == pkg.PM_SCAN_INDEX and len(want) > 9_000
+    assert got == want
+    # ... and the hit list against the oracle's (chains thousands of candidates long: the pool path)
+    recs = pkg.hits_to_records(st, hits, len(primers))
+    ref = oracle.primer_match(oracle.normalize_fasta((">r\n" + "".join(seq[:20_000]) + "\n>s\n" + "".join(seq[20_000:]) + "\n").encode()),
+                              primers, k=k, indels=True, rev_comp=False)
+    assert as_tuples(recs) == as_tuples(ref)
