@@ -129,6 +129,10 @@ struct DevBuf {
   }
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
+// a buffer that lives for one call (freed on every way out of the function)
+struct LocalBuf : DevBuf {
+  ~LocalBuf() { release(); }
+};
 
 struct Pattern {
   std::string s;
@@ -2362,7 +2366,7 @@ int pm_get_header(pm_ctx *c, uint64_t i, const char **text, uint64_t *len) {
       hl[x] = std::max<long long>(0, o->seq_hdr_len[x]);
       ooff[x + 1] = ooff[x] + (unsigned long long)hl[x];
     }
-    DevBuf d_off, d_len, d_ooff, d_out;
+    LocalBuf d_off, d_len, d_ooff, d_out;
     int rc;
     if ((rc = d_off.ensure(n * 8 + 8)) || (rc = d_len.ensure(n * 8 + 8)) || (rc = d_ooff.ensure((n + 1) * 8)) ||
         (rc = d_out.ensure(ooff[n] + 8)))
@@ -2377,7 +2381,6 @@ int pm_get_header(pm_ctx *c, uint64_t i, const char **text, uint64_t *len) {
     if (ooff[n]) PM_CUDA(cudaMemcpyAsync(&o->hdr_blob[0], d_out.p, ooff[n], cudaMemcpyDeviceToHost, o->stream));
     PM_CUDA(cudaStreamSynchronize(o->stream));
     o->hdr_blob_off.assign(ooff.begin(), ooff.end());
-    d_off.release(); d_len.release(); d_ooff.release(); d_out.release();
     o->hdr_ready = true;
   }
   if (o->hdr_from_file) {
@@ -2430,7 +2433,7 @@ int pm_gather_text(pm_ctx *c, const int64_t *begin, const int64_t *len, uint64_t
   const pm_ctx *owner = c->inner ? c->inner : c;
   if (!owner->chunks.empty() && owner->chunks.back().ev)
     PM_CUDA(cudaStreamWaitEvent(c->stream, owner->chunks.back().ev, 0));
-  DevBuf d_off, d_len, d_ooff, d_out;
+  LocalBuf d_off, d_len, d_ooff, d_out;
   int rc;
   if ((rc = d_off.ensure(n * 8)) || (rc = d_len.ensure(n * 8)) || (rc = d_ooff.ensure((n + 1) * 8)) ||
       (rc = d_out.ensure(ooff[n] + 8)))
@@ -2443,7 +2446,6 @@ int pm_gather_text(pm_ctx *c, const int64_t *begin, const int64_t *len, uint64_t
   PM_CUDA(cudaGetLastError());
   if (ooff[n]) PM_CUDA(cudaMemcpyAsync(out, d_out.p, ooff[n], cudaMemcpyDeviceToHost, c->stream));
   PM_CUDA(cudaStreamSynchronize(c->stream));
-  d_off.release(); d_len.release(); d_ooff.release(); d_out.release();
   return PM_OK;
 }
 
