@@ -547,7 +547,11 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
   // edit mode: the seed list of one batch of tiles (dense kernel -> verify kernel)
   uint32_t batch_tiles = nt;
   if (edit) {
-    int rc = c->d_seeds.ensure((size_t)(64u << 20) * 8);
+    // 2^26 entries unless PM_SEED_LIST_ENTRIES says otherwise (a smaller list on a small GPU share;
+    // a batch that does not fit is cut into smaller batches, then the list grows)
+    size_t seed_entries = (size_t)64u << 20;
+    if (const char *e = getenv("PM_SEED_LIST_ENTRIES")) seed_entries = (size_t)std::max(1024ll, atoll(e));
+    int rc = c->d_seeds.ensure(seed_entries * 8);
     if (rc) return rc;
     const double per_tile = std::max(1.0, (c->use_index ? c->idx_seed_rate : c->seed_rate) * (double)TILE_POS);
     const double fit = (double)(c->d_seeds.cap / 8) / (2.0 * per_tile);
@@ -556,7 +560,8 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
   // first-piece positions the index path has to visit: a window starts at most 31 characters earlier
   const int64_t ip_lo = q_lo, ip_hi = std::min<int64_t>((int64_t)c->n, q_hi + 32);
   uint64_t idx_lookups = 0;
-  for (int attempt = 0; attempt < 4; attempt++) {
+  const int kAttempts = 10;
+  for (int attempt = 0; attempt < kAttempts; attempt++) {
     idx_lookups = 0;
     ia.out = c->d_keys.as<unsigned long long>();
     ia.cap = cap;
@@ -705,7 +710,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
       // a batch produced more seeds than the list holds: smaller batches, then a larger list
       if (batch_tiles > 1) batch_tiles = std::max(1u, batch_tiles / 8);
       else if (int rc = c->d_seeds.ensure(c->d_seeds.cap * 4)) return rc;
-      if (attempt == 3) return fail(PM_E_NOMEM, "seed list overflow");
+      if (attempt == kAttempts - 1) return fail(PM_E_NOMEM, "seed list overflow");
       continue;
     }
     if (count <= cap) break;
@@ -714,7 +719,7 @@ int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_coun
     int rc = c->d_keys.ensure((size_t)count * 8 + 1024);
     if (rc) return rc;
     cap = c->d_keys.cap / 8;
-    if (attempt == 3) return fail(PM_E_NOMEM, "candidate buffer overflow");
+    if (attempt == kAttempts - 1) return fail(PM_E_NOMEM, "candidate buffer overflow");
   }
   if (count == 0) return PM_OK;
   if (c->unordered_ok && K == 0 && c->stats.n_ambiguous == 0) {

@@ -535,3 +535,65 @@ def test_edit_scan_dense_chunks_take_the_slow_path(pkg, oracle, k):
     ref = oracle.primer_match(oracle.normalize_fasta((">r\n" + "".join(seq[:20_000]) + "\n>s\n" + "".join(seq[20_000:]) + "\n").encode()),
                               primers, k=k, indels=True, rev_comp=False)
     assert as_tuples(recs) == as_tuples(ref)
+
+
+@pytest.mark.parametrize("k", [0, 1])
+def test_candidate_buffer_grows_on_a_tandem_repeat(pkg, oracle, k):
+    """Every position of an (ACGT)n text ends an occurrence of one of the four rotations of
+    (ACGT)5: 1.2 M candidates against a buffer that starts at 2^20 entries.  The scan counts past
+    the end of the buffer, the buffer grows to the count and the scan runs once more."""
+    unit = "ACGT"
+    primers = [(unit[r:] + unit[:r]) * 5 for r in range(4)]
+    n = 1_200_000
+    st = pkg.normalize_fasta((">t\n" + unit * (n // 4) + "\n").encode())
+    T = st.chars
+    raw = oracle.exact_scan(T, primers, False, False) if k == 0 else oracle.wm_scan(T, primers, k, False, False, False)
+    want = np.array(sorted((int(b), int(a)) for a, b, _ in raw), dtype=np.int64)
+    sc = pkg.Scanner(k=k, indels=False, index=_n5(pkg, dict(k=k)), scan_path=pkg.PM_SCAN_INDEX)
+    for i, p in enumerate(primers):
+        sc.add_pattern(p, i + 1)
+    sc.init()
+    sc.set_text(T)
+    cands = sc.scan_candidates()
+    got = np.array(sorted((int(b), int(a)) for a, b in cands), dtype=np.int64)
+    hits = sc.find_patterns()
+    sc.close()
+    assert len(want) > (1 << 20)
+    assert got.shape == want.shape and (got == want).all()
+    # occurrences of a rotation lie 4 apart, further than the 2k+1 a chain bridges: one hit per candidate
+    assert len(hits) == len(want)
+    assert (np.diff(hits["first"].astype(np.int64)) >= 0).all()
+    assert int((hits["editdist"] != 0).sum()) == 0
+
+
+def test_seed_list_overflow_is_retried(pkg, oracle, monkeypatch):
+    """A seed list far too small for the text (PM_SEED_LIST_ENTRIES): the scan is cut into smaller
+    batches, then the list grows, and the candidates are those of the oracle's recurrence."""
+    import casegen
+    monkeypatch.setenv("PM_SEED_LIST_ENTRIES", "1024")
+    rng = random.Random(811)
+    k = 2
+    m = 21
+    primers = ["A" * m, casegen.rand_dna(rng, m), casegen.rand_dna(rng, m)]
+    seq = list(casegen.rand_dna(rng, 90_000))
+    seq[10_000:14_000] = "A" * 4_000
+    seq[70_000:71_000] = "A" * 1_000
+    for at in (5_000, 40_000, 80_000):
+        q = casegen.mutate(rng, primers[1], k, True)
+        seq[at:at + len(q)] = list(q)
+    st = pkg.normalize_fasta((">r\n" + "".join(seq) + "\n").encode())
+    T = st.chars
+    want = sorted({(int(b), int(a)) for a, b, _ in oracle.wm_scan(T, primers, k, True, False, False)})
+    for path in (pkg.PM_SCAN_INDEX, pkg.PM_SCAN_PLANES):
+        sc = pkg.Scanner(k=k, indels=True, index=pkg.PM_INDEX_FILTER_BITVEC, scan_path=path)
+        for i, p in enumerate(primers):
+            sc.add_pattern(p, i + 1)
+        sc.init()
+        sc.set_text(T)
+        got = sorted((int(b), int(a)) for a, b in sc.scan_candidates())
+        n_seeds = sc.stats()["n_seeds"]
+        sc.close()
+        assert got == want, path
+        # the 4 000 poly-A positions lie in one tile, the smallest batch: more seeds than the
+        # list held at the start, it had to grow
+        assert n_seeds > 2 * 1024, (path, n_seeds)
