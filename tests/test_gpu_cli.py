@@ -203,3 +203,39 @@ def test_cli_opens_the_database_like_pick_fasta_file(cli, golden, tmp_path):
             got = _run(cli, args)
             assert _blocks(got, 4) == want_d, "-D %s, case %s" % (dbind, case["seed"])
     assert checked >= 8 and differ >= 1
+
+
+def test_cli_uppercase_maxcount_and_eos_options(cli, golden, tmp_path):
+    """-u (primers and database upper-cased), -M (a primer stops being reported once it has that
+    many hits; the counts carry a '+'), -E (another end-of-sequence character): the same command
+    line on the UNMODIFIED reference (oracle/_ref/primer_match, run here) and on the drop-in tool."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "primer_match")
+    if not os.path.exists(ref):
+        pytest.skip("needs oracle/_ref/primer_match")
+    variants = (["-u"], ["-c", "-M", "2"], ["-C", "%i %r %p %+ %c", "-a", "-M", "1"],
+                ["-c", "-M", "1", "-A", "%h %s %e %i\n"], ["-E", "36"])
+    checked = with_hits = 0
+    for case in golden["cases"]:
+        if "stdout_default" not in case or case["params"]["wc"]:
+            continue
+        checked += 1
+        if checked % 3 != 1:
+            continue
+        d = tmp_path / ("c%d" % checked)
+        d.mkdir()
+        fa = d / "db.fasta"
+        txt = case["fasta"]
+        mixed = "\n".join(l if l.startswith(">") else "".join(c.lower() if i % 3 == 0 else c for i, c in enumerate(l))
+                          for l in txt.split("\n"))
+        for extra in variants:
+            lower = extra == ["-u"]
+            fa.write_bytes((mixed if lower else txt).encode("latin-1"))
+            prm = [p.lower() for p in case["primers"]] if lower else case["primers"]
+            args = _args(str(fa), prm, case["params"], extra)
+            r = subprocess.run([ref] + args, capture_output=True, timeout=300)
+            assert r.returncode == 0
+            want = sorted(r.stdout.decode("latin-1").split("\n"))
+            got = sorted(_run(cli, args).split("\n"))
+            with_hits += len(want) > 3
+            assert got == want, "%s, case %s" % (extra, case["seed"])
+    assert checked >= 8 and with_hits >= 5
