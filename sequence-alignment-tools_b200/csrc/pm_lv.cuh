@@ -130,6 +130,11 @@ PM_HD inline uint32_t lv_verify(const LvCtx &t, int a, int L) {
 #pragma unroll
 #endif
   for (int i = 0; i < ND; i++) mis[i] = lv_mis(t, i - K, K);
+  // The seed's claim itself: the index keys on the 2-bit codes alone, and a flagged character (one
+  // that matches nothing, an end of sequence) carries an arbitrary code that can complete a piece
+  // by accident.  An anchor that is not an exact match is no anchor; a real occurrence has two
+  // pieces that are, and is seeded by those.
+  if ((mis[K] >> (2 * a)) & ((1ULL << (2 * L)) - 1ULL)) return 0u;
   // q-gram filter (q = 3): K errors cut the pattern into at most K+1 runs of matches, each on one
   // of these diagonals, and destroy at most 3K of its m-2 triples of consecutive characters; the
   // others match as a whole on some diagonal.  Random seeds fail here, before any extension.

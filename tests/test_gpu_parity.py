@@ -597,3 +597,44 @@ def test_seed_list_overflow_is_retried(pkg, oracle, monkeypatch):
         # the 4 000 poly-A positions lie in one tile, the smallest batch: more seeds than the
         # list held at the start, it had to grow
         assert n_seeds > 2 * 1024, (path, n_seeds)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3])
+def test_edit_seeds_through_flagged_characters_are_rejected(pkg, oracle, k):
+    """The pair index keys on 2-bit codes; an end-of-sequence or N character carries an arbitrary
+    code and can complete a piece by accident (found by tools/fuzz_vs_reference.py: a sequence that
+    begins with a primer minus its first character -- the reference reports nothing there, the
+    deletion would fall into the column behind the end of sequence).  Sequences that begin or end
+    with every primer minus a character, N in place of primer characters: candidates of the
+    oracle's recurrence, exactly."""
+    import casegen
+    rng = random.Random(900 + k)
+    m = 4 * (k + 2) + rng.randrange(0, 4)
+    core = casegen.rand_dna(rng, m - 1)
+    primers = [c + core for c in "ACGT"] + [core + c for c in "ACGT"]
+    seqs = []
+    for i in range(400):
+        body = casegen.rand_dna(rng, rng.randrange(20, 60))
+        kind = i % 4
+        if kind == 0:
+            s = core + body                      # first character of the primer missing at the start
+        elif kind == 1:
+            s = body + core                      # last character missing at the end
+        elif kind == 2:
+            s = body + "N" + core + body         # an N where the first character would be
+        else:
+            s = body + core + "N" + body
+        seqs.append(s)
+    fasta = "".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(seqs))
+    st = pkg.normalize_fasta(fasta.encode())
+    T = st.chars
+    want = sorted({(int(b), int(a)) for a, b, _ in oracle.wm_scan(T, primers, k, True, False, False)})
+    sc = pkg.Scanner(k=k, indels=True, index=pkg.PM_INDEX_FILTER_BITVEC, scan_path=pkg.PM_SCAN_INDEX)
+    for i, p in enumerate(primers):
+        sc.add_pattern(p, i + 1)
+    sc.init()
+    sc.set_text(T)
+    got = sorted((int(b), int(a)) for a, b in sc.scan_candidates())
+    sc.close()
+    assert len(want) > 400
+    assert got == want

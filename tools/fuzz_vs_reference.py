@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Differential campaign: seeded random databases and primer sets (tests/golden/casegen.py, the
+generator of the goldens) through the UNMODIFIED reference binary (oracle/_ref/primer_match) and
+through the GPU library on both scan paths; every record compared.  Not part of the test suite: a
+way to spend spare GPU minutes looking for parity bugs beyond the committed goldens.
+
+    python tools/fuzz_vs_reference.py --first 10000 --count 2000 > gpurun_out/fuzz.json
+"""
+import argparse
+import importlib
+import json
+import os
+import random
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--first", type=int, default=10000)
+    ap.add_argument("--count", type=int, default=500)
+    ap.add_argument("--seconds", type=float, default=600.0)
+    a = ap.parse_args()
+    import casegen
+    import make_golden
+    import pm_oracle as O
+    from conftest import as_tuples
+    pkg = importlib.import_module("sequence-alignment-tools_b200")
+    tmp = tempfile.mkdtemp()
+    t0 = time.time()
+    done = skipped = records = 0
+    failures = []
+    by_kind = {}
+    for seed in range(a.first, a.first + a.count):
+        if time.time() - t0 > a.seconds:
+            break
+        params, kw = make_golden.case_params(seed)
+        rng = random.Random(seed * 7 + 1)
+        select = rng.choice([None, None, 0])       # -N 5, or the reference's automatic choice
+        if rng.random() < 0.1:
+            params["k"] = kw["k"] = rng.choice([4, 5])
+        if rng.random() < 0.3:                       # longer databases: several tiles' worth of rows
+            kw["seqlen"] = rng.choice([5000, 20000])
+        fasta, primers = casegen.make_case(seed, **kw)
+        path = os.path.join(tmp, "f.fasta")
+        with open(path, "w", newline="") as f:
+            f.write(fasta)
+        try:
+            want = O.run_reference(path, primers, select=select, **params)
+        except RuntimeError:
+            skipped += 1                             # the reference aborts on this input
+            continue
+        kind = "k%d%s%s%s" % (params["k"], "e" if params["indels"] else "s", "w" if params["wc"] else "",
+                              "-auto" if select == 0 else "")
+        index = pkg.PM_INDEX_AUTO if (select == 0 or params["k"] == 0) else pkg.PM_INDEX_FILTER_BITVEC
+        st = pkg.normalize_fasta(fasta.encode("latin-1"))
+        for sp_name, sp in (("auto", pkg.PM_SCAN_AUTO), ("planes", pkg.PM_SCAN_PLANES)):
+            try:
+                got = as_tuples(pkg.primer_match(st, primers, scan_path=sp, index=index, **params))
+                ok = got == as_tuples(want)
+                why = None if ok else "records differ: %d against %d" % (len(got), len(want))
+            except Exception as e:   # noqa: BLE001
+                ok, why = False, "%s: %s" % (type(e).__name__, e)
+            if not ok:
+                failures.append(dict(seed=seed, path=sp_name, kind=kind, select=select, why=why))
+        done += 1
+        records += len(want)
+        by_kind[kind] = by_kind.get(kind, 0) + 1
+    print(json.dumps(dict(first=a.first, cases=done, reference_aborts=skipped, records=records,
+                          seconds=round(time.time() - t0, 1), failures=failures, by_kind=by_kind)))
+
+
+if __name__ == "__main__":
+    main()

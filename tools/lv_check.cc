@@ -108,9 +108,11 @@ int main(int argc, char **argv) {
       // pair seeds: pieces pi < pj exact at text distance (pj - pi) L + e, |e| <= K, never < L
       for (long pos = 1; pos < n; pos++) {
         for (int pi = 0; pi < P; pi++) {
+          // the index keys on the 2-bit codes alone: a flagged character (N, end of sequence) carries
+          // an arbitrary code and can complete a piece by accident -- such a seed must verify to nothing
           bool okA = true;
           for (int x = 0; x < L && okA; x++)
-            okA = pos + x < n && flag_at(pos + x) == 0 && pmatch(pats[p][pi * L + x], T[pos + x]);
+            okA = pos + x < n && pmatch(pats[p][pi * L + x], (uint8_t)"ACTG"[code_at(pos + x)]);
           if (!okA) continue;
           bool paired = false;
           for (int pj = pi + 1; pj < P && !paired; pj++)
@@ -119,7 +121,7 @@ int main(int argc, char **argv) {
               if (d < L) continue;
               bool okB = true;
               for (int x = 0; x < L && okB; x++)
-                okB = pos + d + x < n && flag_at(pos + d + x) == 0 && pmatch(pats[p][pj * L + x], T[pos + d + x]);
+                okB = pos + d + x < n && pmatch(pats[p][pj * L + x], (uint8_t)"ACTG"[code_at(pos + d + x)]);
               paired = okB;
             }
           if (!paired) continue;
