@@ -208,7 +208,10 @@ int pm_shard_overlap(pm_ctx *ctx);
  * alignment of primer_match.cc:1132-1153.  Reports the hits whose FIRST raw
  * candidate position (pm_candidate.pos of the head of its chain) lies in
  * [begin, end) of the global stream, sorted by (first, pattern_id): the order
- * the reference reports them in, up to ties.  *hits
+ * the reference reports them in, up to hits that begin at one position (pm_hit_order
+ * settles those).  The hits of exact_halves / exact_bases (first = end there) come in the
+ * order of the half / exact-part occurrences they grew from, which is the reference's
+ * (exact_halves.cc:113-116, exact_bases.cc:68-124).  *hits
  * points into pinned memory owned by the context, valid until the next call
  * on it.  Pass begin=0,end=INT64_MAX for the whole stream (what the reference
  * does).  PM_E_BOGUS (a hit whose final alignment has more than k errors, on
@@ -226,6 +229,20 @@ int pm_find_patterns_device(pm_ctx *ctx, int64_t begin, int64_t end, const pm_hi
  * (pattern_id, pos).  For tests and for callers that do their own filtering.  */
 int pm_scan_candidates(pm_ctx *ctx, int64_t begin, int64_t end, const pm_candidate **cands,
                        uint64_t *ncands);
+
+/* The raw candidates of the last pm_find_patterns / pm_find_patterns_device call on this
+ * context (every candidate of the scanned range, sorted by (pattern_id, pos)): what
+ * shift_and_inexact handed filter_bitvec (filter_bitvec.cc:89).  PM_E_UNSUPPORTED for the
+ * exact_halves / exact_bases indexes, whose hits do not come from such a list.  *cands is
+ * owned by the context, valid until the next call on it.                                  */
+int pm_last_candidates(pm_ctx *ctx, const pm_candidate **cands, uint64_t *ncands);
+
+/* The order in which filter_bitvec::find_patterns reports `hits` (filter_bitvec.cc:89-141):
+ * the candidates as shift_and_inexact emits them (position, then pattern), std::sort on the
+ * position alone, chains taken in that order.  order[i] = index into hits of the i-th hit
+ * reported; hits without a chain in `cands` follow in their given order.  Host code.       */
+int pm_hit_order(const pm_hit *hits, uint64_t nhits, const pm_candidate *cands, uint64_t ncands, int k,
+                 uint64_t *order);
 
 /* PatternMatch::reset (pattern_match.h:136): forget the text.                 */
 int pm_reset(pm_ctx *ctx);
@@ -330,6 +347,13 @@ typedef struct pm_pcr_options {
   int64_t maxdist;      /* -M                                                             */
   const uint64_t *sts_sizelb; /* per pair: sts_entry::sizelb()/sizeub() of a UniSTS file  */
   const uint64_t *sts_sizeub; /* (-S), or NULL                                            */
+  /* The raw candidates behind the hits (pm_last_candidates), or NULL.  The reference leaves
+   * hits that end at one position in the order two std::sort calls on position alone leave
+   * them -- filter_bitvec.cc:91 on the candidates, pcr_match.cc:958 on the hits -- and a hit
+   * only pairs with partners that come later, so that order is part of its answer.  With the
+   * candidates pm_pcr_pairs reproduces both sorts; without them the first is taken as stable. */
+  const pm_candidate *cands;
+  uint64_t ncands;
 } pm_pcr_options;
 
 typedef struct pm_pcr_pair {

@@ -221,6 +221,12 @@ class b200_index : public PatternMatch {
   // skips the pairs it is part of (pcr_match.cc:1114): hand such hits out instead, the
   // caller tests pm_hit::editdist.
   void tolerate_bogus(bool yes) { tolerate_bogus_ = yes; }
+  // the raw candidates behind the hits of the last find_patterns (none for exact_halves / exact_bases)
+  void last_candidates(const pm_candidate **cands, uint64_t *n) {
+    *cands = 0;
+    *n = 0;
+    if (pm_last_candidates(ctx_, cands, n) != PM_OK) { *cands = 0; *n = 0; }
+  }
   // PM_ALIGN_PCR_MATCH: the alignment pcr_match makes of a hit (see pm_set_alignment_rules)
   void alignment_rules(int rules) {
     if (pm_set_alignment_rules(ctx_, rules) != PM_OK) fatal(std::string("Fatal error: ") + pm_last_error());

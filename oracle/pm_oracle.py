@@ -345,7 +345,7 @@ def auto_index(primers, k: int, lconst=None, rconst=None) -> str:
 
 
 def aligned_hits(stream: Stream, pats, lconst, rconst, k=0, indels=True, wc=False, tn=False, eos=EOS,
-                 index="filter_bitvec", bogus_ok=False, exact_align=True):
+                 index="filter_bitvec", bogus_ok=False, exact_align=True, keep_bogus=False):
     """PatternMatch::find_patterns of the selected index followed, per hit, by the alignment
     both command line tools make at the hit's position (primer_match.cc:1132-1153,
     pcr_match.cc:1096-1113): [(pattern id, start, end, editdist, alignment string)] in the
@@ -366,6 +366,11 @@ def aligned_hits(stream: Stream, pats, lconst, rconst, k=0, indels=True, wc=Fals
         hits = exact_bases(T, pats, k, indels, lconst, rconst, wc, tn, eos)
     else:
         cands = wm_scan(T, pats, k, indels, wc, tn, eos)
+        if len(cands) > 16:
+            # filter_bitvec.cc:91: l.normalize() -- std::sort by position on the candidates as
+            # shift_and_inexact reports them (position, then pattern): equal positions come out
+            # in the order introsort leaves them, and chains are taken in that order
+            cands = np.array(std_sort_by_key([tuple(r) for r in cands.tolist()], lambda r: r[0]), np.int64).reshape(-1, 3)
         hits = filter_chains(T, pats, cands, k, indels, wc, tn, lconst, rconst, eos)
     for pos, pid, _ in hits:
         pos, pid = int(pos), int(pid)
@@ -384,6 +389,8 @@ def aligned_hits(stream: Stream, pats, lconst, rconst, k=0, indels=True, wc=Fals
             al = editdist_align(T, pat, pos, pos, k, indels, wc, tn, lconst[pid - 1], rconst[pid - 1], eos)
             if al.editdist < 0 or al.editdist > k:
                 if bogus_ok:
+                    if keep_bogus:      # pcr_match: stays in the list (and in its sort), never pairs
+                        out.append((pid, pos, pos, -1, ""))
                     continue
                 raise AssertionError("Bogus hit (primer_match.cc:1249)")
             start, end, ed, astr = al.start, al.end, al.editdist, al.string
@@ -414,6 +421,120 @@ def primer_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=F
 
 
 # ---------------------------------------------------------------------------
+def std_sort_by_key(items, key):
+    """std::sort of libstdc++ (bits/stl_algo.h: introsort with median-of-three pivots down to
+    ranges of 16, then one insertion sort) on a comparison that looks at the key alone
+    (sortedvector.t:38-44, :502-504).  The reference leaves hits with equal positions in whatever
+    order this leaves them, and pcr_match's pairing depends on that order (a hit only pairs with
+    partners that come later), so the order is part of the reference's answer."""
+    v = list(items)
+    n = len(v)
+    if n < 2:
+        return v
+    k = [key(x) for x in v]
+
+    def swap(i, j):
+        v[i], v[j] = v[j], v[i]
+        k[i], k[j] = k[j], k[i]
+
+    def linear_insert(last):           # __unguarded_linear_insert
+        val, kv = v[last], k[last]
+        nxt = last - 1
+        while kv < k[nxt]:
+            v[last], k[last] = v[nxt], k[nxt]
+            last = nxt
+            nxt -= 1
+        v[last], k[last] = val, kv
+
+    def insertion_sort(first, last):   # __insertion_sort
+        for i in range(first + 1, last):
+            if k[i] < k[first]:
+                val, kv = v[i], k[i]
+                v[first + 1:i + 1] = v[first:i]
+                k[first + 1:i + 1] = k[first:i]
+                v[first], k[first] = val, kv
+            else:
+                linear_insert(i)
+
+    def heap_sort(first, last):        # __partial_sort(first, last, last): make_heap + sort_heap
+        def adjust(hole, length, val, kv):
+            top = hole
+            child = hole
+            while child < (length - 1) // 2:
+                child = 2 * (child + 1)
+                if k[first + child] < k[first + child - 1]:
+                    child -= 1
+                v[first + hole], k[first + hole] = v[first + child], k[first + child]
+                hole = child
+            if (length & 1) == 0 and child == (length - 2) // 2:
+                child = 2 * (child + 1)
+                v[first + hole], k[first + hole] = v[first + child - 1], k[first + child - 1]
+                hole = child - 1
+            parent = (hole - 1) // 2
+            while hole > top and k[first + parent] < kv:
+                v[first + hole], k[first + hole] = v[first + parent], k[first + parent]
+                hole = parent
+                parent = (hole - 1) // 2
+            v[first + hole], k[first + hole] = val, kv
+        length = last - first
+        if length >= 2:
+            parent = (length - 2) // 2
+            while True:
+                adjust(parent, length, v[first + parent], k[first + parent])
+                if parent == 0:
+                    break
+                parent -= 1
+        while last - first > 1:
+            last -= 1
+            val, kv = v[last], k[last]
+            v[last], k[last] = v[first], k[first]
+            adjust(0, last - first, val, kv)
+
+    def introsort(first, last, depth):
+        while last - first > 16:
+            if depth == 0:
+                heap_sort(first, last)
+                return
+            depth -= 1
+            mid = first + (last - first) // 2
+            a, b, c = first + 1, mid, last - 1       # __move_median_to_first(first, a, b, c)
+            if k[a] < k[b]:
+                if k[b] < k[c]:
+                    swap(first, b)
+                elif k[a] < k[c]:
+                    swap(first, c)
+                else:
+                    swap(first, a)
+            elif k[a] < k[c]:
+                swap(first, a)
+            elif k[b] < k[c]:
+                swap(first, c)
+            else:
+                swap(first, b)
+            lo, hi = first + 1, last                 # __unguarded_partition(first + 1, last, first)
+            while True:
+                while k[lo] < k[first]:
+                    lo += 1
+                hi -= 1
+                while k[first] < k[hi]:
+                    hi -= 1
+                if not lo < hi:
+                    break
+                swap(lo, hi)
+                lo += 1
+            introsort(lo, last, depth)
+            last = lo
+
+    introsort(0, n, 2 * (n.bit_length() - 1))
+    if n > 16:                                       # __final_insertion_sort
+        insertion_sort(0, 16)
+        for i in range(16, n):
+            linear_insert(i)
+    else:
+        insertion_sort(0, n)
+    return v
+
+
 # pcr_match: the second caller of the scan -- primer PAIRS, hits paired into amplicons
 def pcr_pattern_array(primers, rev_comp: bool):
     """pcr_match.cc:772-784, 827, 868: pairs are (1,2), (3,4) ...; with -r the second primer of
@@ -480,8 +601,8 @@ def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=Fals
     pats = pcr_pattern_array(primers, rev_comp)
     lconst, rconst = pcr_pattern_constraints(pats[:n], stlen, edlen, fplen, tplen)
     hits = aligned_hits(stream, pats, lconst, rconst, k, indels, wc, tn, eos, index, bogus_ok=True,
-                        exact_align=False)
-    hits.sort(key=lambda h: (h[2], h[0]))          # l.normalize(): by key (ties unspecified there)
+                        exact_align=False, keep_bogus=True)
+    hits = std_sort_by_key(hits, lambda h: h[2])    # l.normalize() (pcr_match.cc:958): std::sort on the key alone
     bypid = {}
     for i, h in enumerate(hits):
         bypid.setdefault(h[0], []).append(i)
@@ -490,6 +611,9 @@ def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=Fals
     err = k if indels else 1
     out = []
     for i, (pid, start, pos, ed, astr) in enumerate(hits):
+        if ed < 0:                                      # its own alignment fails for every partner (pcr_match.cc:1114)
+            done[i] = True
+            continue
         pid1 = pid2 = 0                                 # pcr_match.cc:968-997
         if pid <= n and pid % 2 == 1:
             pid1 = pid + 1
@@ -529,7 +653,7 @@ def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=Fals
                     continue
                 if not done[j] and hits[j][2] > smax:
                     break
-                if not done[j]:
+                if not done[j] and hits[j][3] >= 0:
                     partners.append(j)
         for j in partners:
             pidb, startb, posb, edb, astrb = hits[j]

@@ -37,7 +37,7 @@ CODE_CHARS = {1: "|", 2: "+", 3: "*", 4: "^", 5: "v", 6: "!"}
 EXPORTS = ["pm_last_error", "pm_version", "pm_create", "pm_destroy", "pm_set_stream", "pm_add_pattern",
            "pm_init", "pm_set_text_host", "pm_set_text_device", "pm_set_text_sqz_host", "pm_set_text_sqn_host", "pm_sqz_bits", "pm_set_text_fasta_host", "pm_get_sequences", "pm_get_text", "pm_host_alloc", "pm_host_free", "pm_shard_overlap", "pm_find_patterns",
            "pm_find_patterns_device", "pm_scan_candidates", "pm_reset", "pm_get_stats",
-           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size", "pm_set_text_database", "pm_get_header", "pm_gather_text"]
+           "pm_normalize_fasta", "pm_reverse_comp", "pm_bench_int_peak", "pm_set_scan_path", "pm_pcr_pairs", "pm_free", "pm_set_alignment_rules", "pm_set_alphabet_size", "pm_set_text_database", "pm_get_header", "pm_gather_text", "pm_last_candidates", "pm_hit_order"]
 
 
 class PmError(RuntimeError):
@@ -73,7 +73,7 @@ class Stats(C.Structure):
 class PcrOptions(C.Structure):
     _fields_ = [("k", C.c_int), ("indels", C.c_int), ("allorient", C.c_int), ("betweenlen", C.c_int),
                 ("deviation", C.c_int), ("reserved", C.c_int), ("mindist", C.c_int64), ("maxdist", C.c_int64),
-                ("sts_sizelb", C.c_void_p), ("sts_sizeub", C.c_void_p)]
+                ("sts_sizelb", C.c_void_p), ("sts_sizeub", C.c_void_p), ("cands", C.c_void_p), ("ncands", C.c_uint64)]
 
 
 class PcrPair(C.Structure):
@@ -83,6 +83,7 @@ class PcrPair(C.Structure):
 
 HIT_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("first", "<i8"), ("pattern_id", "<u4"), ("editdist", "<i4"),
                       ("value", "<i4"), ("ncodes", "<u4"), ("codes", "u1", (PM_MAX_CODES,))])
+CAND_DTYPE = np.dtype([("pos", "<i8"), ("pattern_id", "<u4"), ("reserved", "<u4")])
 assert HIT_DTYPE.itemsize == C.sizeof(Hit)
 
 _lib = None
@@ -128,6 +129,8 @@ def lib():
                                        C.POINTER(C.c_uint64)]
         L.pm_find_patterns_device.argtypes = [C.c_void_p, C.c_int64, C.c_int64,
                                               C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.pm_last_candidates.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Candidate)), C.POINTER(C.c_uint64)]
+        L.pm_hit_order.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
         L.pm_scan_candidates.argtypes = [C.c_void_p, C.c_int64, C.c_int64,
                                          C.POINTER(C.POINTER(Candidate)), C.POINTER(C.c_uint64)]
         L.pm_reset.argtypes = [C.c_void_p]
@@ -344,6 +347,19 @@ class Scanner:
             out[i, 0] = cp[i].pos
             out[i, 1] = cp[i].pattern_id
         return out
+
+    def last_candidates(self):
+        """pm_last_candidates: the raw candidates behind the hits of the last find_patterns as a
+        structured array (pos, pattern_id, reserved), or None for exact_halves / exact_bases."""
+        cp = C.POINTER(Candidate)()
+        n = C.c_uint64(0)
+        rc = lib().pm_last_candidates(self._h, C.byref(cp), C.byref(n))
+        if rc == PM_E_UNSUPPORTED:
+            return None
+        _check(rc)
+        if not n.value:
+            return np.zeros(0, CAND_DTYPE)
+        return np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_uint8)), (n.value * C.sizeof(Candidate),)).view(CAND_DTYPE).copy()
 
     def stats(self) -> dict:
         s = Stats()
@@ -606,7 +622,7 @@ def pcr_pattern_array(primers, rev_comp: bool):
 
 
 def pcr_pairs(hits: np.ndarray, n_primers: int, patlen, seq_key, k=0, indels=True, allorient=False,
-              betweenlen=False, mindist=0, maxdist=2000, sts_sizes=None, deviation=-1):
+              betweenlen=False, mindist=0, maxdist=2000, sts_sizes=None, deviation=-1, cands=None):
     """pm_pcr_pairs: [(index of the first hit, index of its partner, amplicon length, pair)] in
     the order pcr_match prints them."""
     hits = np.ascontiguousarray(hits, HIT_DTYPE)
@@ -618,6 +634,9 @@ def pcr_pairs(hits: np.ndarray, n_primers: int, patlen, seq_key, k=0, indels=Tru
         lb = np.array([s[0] for s in sts_sizes], np.uint64)
         ub = np.array([s[1] for s in sts_sizes], np.uint64)
         o.sts_sizelb, o.sts_sizeub = lb.ctypes.data, ub.ctypes.data
+    if cands is not None and len(cands):
+        cands = np.ascontiguousarray(cands, CAND_DTYPE)
+        o.cands, o.ncands = cands.ctypes.data, len(cands)
     pp = C.POINTER(PcrPair)()
     n = C.c_uint64(0)
     _check(lib().pm_pcr_pairs(C.c_void_p(hits.ctypes.data), len(hits), n_primers, C.c_void_p(pl.ctypes.data),
@@ -650,11 +669,12 @@ def pcr_match(stream: Stream, primers, k=0, indels=True, rev_comp=False, wc=Fals
         sc.set_alignment_rules(PM_ALIGN_PCR_MATCH)
         sc.set_text(stream.chars)
         hits = sc.find_patterns(bogus_ok=True)
+        cands = sc.last_candidates()
         patlen = [0] + [len(p) for p in pats]
         T = stream.chars
         recs = []
         for a, b, amplicon_len, pind in pcr_pairs(hits, n, patlen, stream.seq_key, k, indels, allorient, betweenlen,
-                                                  mindist, maxdist, sts_sizes, deviation):
+                                                  mindist, maxdist, sts_sizes, deviation, cands):
             h, h1 = hits[a], hits[b]
             pid, pid1 = int(h["pattern_id"]), int(h1["pattern_id"])
             pe, pe1 = int(h["end"]), int(h1["end"])

@@ -316,8 +316,8 @@ int main(int argc, char **argv) {
     pattern_hit_vector phv;
     while (pm->find_patterns(ff, phv, 1ul << 20) || !phv.empty()) {
       std::vector<const pm_hit *> &batch = pm->batch();
-      for (const pm_hit *h : batch)
-        if (h->pattern_id && h->editdist >= 0 && h->editdist <= opt.nmismatch) l.push_back(h);
+      for (const pm_hit *h : batch)   // every hit: one whose own alignment failed still takes part in the sort
+        if (h->pattern_id) l.push_back(h);
       phv.clear();
       batch.clear();
     }
@@ -336,6 +336,8 @@ int main(int argc, char **argv) {
   po.mindist = opt.mindist; po.maxdist = opt.maxdist;
   po.sts_sizelb = opt.sts_pattern_file ? sizelb.data() : 0;
   po.sts_sizeub = opt.sts_pattern_file ? sizeub.data() : 0;
+  // the candidates behind the hits (filter_bitvec only): the order of hits that end at one position
+  pm->last_candidates(&po.cands, &po.ncands);
   pm_pcr_pair *pairs = 0;
   uint64_t npairs = 0;
   if (pm_pcr_pairs(hits.data(), hits.size(), (uint32_t)n, plen32.data(), ff.seq_keys(), ff.n_seqs(), &po, &pairs,

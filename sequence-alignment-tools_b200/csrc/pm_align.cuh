@@ -396,6 +396,8 @@ struct RawHit {
   int64_t first;     // chain head (ordering / ownership)
   uint32_t slot;
   int32_t val;
+  uint64_t ord;      // exact_halves / exact_bases: the order the reference reports the hit in (position of
+                     // the exact part's occurrence, then its inner id); unused for chains
 };
 
 // ---------------------------------------------------------------------------
@@ -473,7 +475,7 @@ chain_align2_kernel(const AlignEnv env, const Chain *chains, TailCounts tc, uint
   if (r.ok == 1) {
     const unsigned long long at = atomicAdd(tc.n_raw, 1ULL);
     RawHit h;
-    h.end = r.end; h.first = c.first; h.slot = c.slot; h.val = r.val;
+    h.end = r.end; h.first = c.first; h.slot = c.slot; h.val = r.val; h.ord = 0;
     hits[at] = h;
   }
 }

@@ -181,6 +181,8 @@ struct pm_ctx {
   std::string hdr_blob;                 // header lines (gathered from the device, or <db>.hdr)
   std::vector<unsigned long long> hdr_blob_off;
   bool hdr_ready = false, hdr_from_file = false;
+  uint64_t last_uniq = 0;               // candidates of the last pm_find_patterns (d_keys), for pm_last_candidates
+  std::vector<pm_candidate> h_cands;
   int db_kind = 0;                      // pm_set_text_database: 1 FASTA, 2 .seq, 3 .sqn, 4 .sqz
   pm::ChunkReader *reader = nullptr;    // ... and its reader (kept until the next text: its buffers are DMA sources)
   const uint8_t *d_text = nullptr;
@@ -285,7 +287,7 @@ __global__ void store_u64_kernel(unsigned long long *p, unsigned long long v) { 
 __global__ void __launch_bounds__(64)
 final_align_kernel(const AlignEnv env, const RawHit *raw, const unsigned long long *n_ptr, uint64_t bound,
                    const uint32_t *slot_id, int64_t offset, pm_hit *hits, unsigned long long *sortkey,
-                   unsigned long long *n_bogus, unsigned long long *n_hits) {
+                   unsigned long long *n_bogus, unsigned long long *n_hits, int use_ord) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= bound) return;
   const uint64_t n = *n_ptr;
@@ -313,9 +315,12 @@ final_align_kernel(const AlignEnv env, const RawHit *raw, const unsigned long lo
   // so traceback order already is left-to-right.
   if (r.editdist < 0 || r.editdist > env.k) atomicAdd(n_bogus, 1ULL);
   hits[i] = out;
-  // order: (first, pattern id); first < 2^40, id < 2^24
-  sortkey[i] = ((unsigned long long)(out.first & 0xffffffffffLL) << 24) |
-               (unsigned long long)(out.pattern_id & 0xffffffu);
+  // order: (first, pattern id); first < 2^40, id < 2^24 -- the order filter_bitvec reports its chains
+  // in, up to hits that begin at one position.  exact_halves / exact_bases: the order of the
+  // occurrences they extend (RawHit::ord).
+  sortkey[i] = use_ord ? h.ord
+                       : (((unsigned long long)(out.first & 0xffffffffffLL) << 24) |
+                          (unsigned long long)(out.pattern_id & 0xffffffu));
 }
 
 // exact indexes (k == 0): every candidate is a hit.  exact_alignment
@@ -416,6 +421,7 @@ int slot_bits(size_t n_slots) {
 // synchronisation: the scan's counters (candidates, seed-list / candidate-buffer overflow).
 int run_scan(pm_ctx *c, int64_t lo, int64_t hi, uint64_t *n_out, bool exact_count) {
   *n_out = 0;
+  c->last_uniq = 0;
   PM_CUDA(cudaMemsetAsync(c->d_counters + CTR_UNIQ, 0, sizeof(unsigned long long), c->stream));
   if (c->n == 0 || hi <= lo || c->pats.empty()) return PM_OK;
   const size_t n_slots = c->pats.size();
@@ -986,7 +992,8 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
     if (n_final) {
       final_align_kernel<<<nblocks(bound, 64), 64, 0, c->stream>>>(
           env, c->d_raw.as<RawHit>(), n_final, bound, c->d_slotid.as<uint32_t>(), c->offset,
-          c->d_hits.as<pm_hit>(), c->d_sortk.as<unsigned long long>(), dc + CTR_BOGUS, dc + CTR_NHITS);
+          c->d_hits.as<pm_hit>(), c->d_sortk.as<unsigned long long>(), dc + CTR_BOGUS, dc + CTR_NHITS,
+          c->inner ? 1 : 0);
       PM_CUDA(cudaGetLastError());
       c->stats.kernel_launches++;
     }
@@ -999,6 +1006,7 @@ int find_patterns_guarded(pm_ctx *c, int64_t begin, int64_t end, uint64_t *nhits
   PM_CUDA(cudaEventRecord(c->ev[3], c->stream));
   PM_CUDA(cudaEventSynchronize(c->ev[3]));
   c->stats.host_syncs++;
+  c->last_uniq = (bound > 0 && !c->inner) ? c->h_counters[CTR_UNIQ] : 0;
   {
     float ms = 0;
     cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]);
@@ -1944,6 +1952,40 @@ int pm_scan_candidates(pm_ctx *c, int64_t begin, int64_t end, const pm_candidate
   PM_CUDA(cudaStreamSynchronize(c->stream));
   *cands = reinterpret_cast<const pm_candidate *>(c->h_out);
   *ncands = n;
+  return PM_OK;
+}
+
+int pm_last_candidates(pm_ctx *c, const pm_candidate **cands, uint64_t *ncands) {
+  if (!c || !cands || !ncands) return fail(PM_E_ARG, "null argument");
+  *cands = nullptr;
+  *ncands = 0;
+  if (!c->inited) return fail(PM_E_ARG, "pm_last_candidates before pm_init");
+  if (c->inner)
+    return fail(PM_E_UNSUPPORTED, "the hits of exact_halves / exact_bases do not come from a candidate list");
+  const uint64_t n = c->last_uniq;
+  if (!n) return PM_OK;
+  PM_CUDA(cudaSetDevice(c->opt.device));
+  int rc;
+  if ((rc = c->d_cands.ensure(n * sizeof(pm_candidate)))) return rc;
+  keys_to_cands_kernel<<<nblocks(n, 256), 256, 0, c->stream>>>(
+      c->d_keys.as<unsigned long long>(), n, c->d_slotid.as<uint32_t>(), c->offset,
+      c->d_cands.as<pm_candidate>());
+  PM_CUDA(cudaGetLastError());
+  c->h_cands.resize(n);
+  PM_CUDA(cudaMemcpyAsync(c->h_cands.data(), c->d_cands.p, n * sizeof(pm_candidate), cudaMemcpyDeviceToHost,
+                          c->stream));
+  PM_CUDA(cudaStreamSynchronize(c->stream));
+  *cands = c->h_cands.data();
+  *ncands = n;
+  return PM_OK;
+}
+
+int pm_hit_order(const pm_hit *hits, uint64_t nhits, const pm_candidate *cands, uint64_t ncands, int k,
+                 uint64_t *order) {
+  if ((nhits && (!hits || !order)) || (ncands && !cands)) return fail(PM_E_ARG, "null argument");
+  std::vector<uint64_t> o;
+  hit_order(hits, nhits, cands, ncands, k, o);
+  for (uint64_t i = 0; i < nhits; i++) order[i] = o[i];
   return PM_OK;
 }
 

@@ -194,6 +194,8 @@ halves_extend_kernel(const AlignEnv env, const unsigned long long *__restrict__ 
         h.first = r.end;
         h.slot = slot;
         h.val = r.value;
+        // exact_bases.cc:68-124: the occurrences of the exact parts in (position, pattern) order
+        h.ord = ((unsigned long long)pos << 24) | (unsigned long long)((slot + 1u) & 0xffffffu);
         out[at] = h;
       }
     }
@@ -238,6 +240,11 @@ halves_report_kernel(const unsigned long long *__restrict__ sortkey, const uint3
           h.first = r.end;
           h.slot = slot;
           h.val = r.value;
+          // exact_halves.cc:113-116: half occurrences by position, then inner id DESCENDING
+          // (inner id = 2 * slot + 1 for the left half, + 2 for the right half)
+          const unsigned long long sk = sortkey[i];
+          const unsigned long long hid = 2ull * slot + ((sk & 1ull) ? 1ull : 2ull);
+          h.ord = (((sk >> 1) & 0xffffffffffULL) << 24) | (0xffffffull - (hid & 0xffffffull));
           out[at] = h;
         }
       }

@@ -29,17 +29,66 @@ inline long pcr_locate(const int64_t *seq_key, uint64_t n_seqs, int64_t pos) {
   return lo - 1;
 }
 
+// element of the reference's sortedvector: compared by its key alone (sortedvector.t:38-44), so
+// std::sort leaves equal keys in whatever order introsort leaves them -- the same order here,
+// because it is the same std::sort on the same sequence of keys
+struct KeyIdx {
+  long key;
+  uint64_t idx;
+  bool operator<(const KeyIdx &o) const { return key < o.key; }
+};
+
+// filter_bitvec::find_patterns' order of reporting (filter_bitvec.cc:89-141), see pm_hit_order
+inline void hit_order(const pm_hit *hits, uint64_t nhits, const pm_candidate *cands, uint64_t ncands, int k,
+                      std::vector<uint64_t> &order) {
+  order.clear();
+  order.reserve(nhits);
+  std::vector<bool> placed(nhits, false);
+  if (cands && ncands && k > 0) {
+    std::vector<std::pair<long, uint32_t> > emitted(ncands);   // (position, pattern): shift_and_inexact.cc:315-333
+    for (uint64_t i = 0; i < ncands; i++) emitted[i] = std::make_pair((long)cands[i].pos, cands[i].pattern_id);
+    std::sort(emitted.begin(), emitted.end());
+    std::vector<KeyIdx> c(ncands);
+    for (uint64_t i = 0; i < ncands; i++) { c[i].key = emitted[i].first; c[i].idx = emitted[i].second; }
+    std::sort(c.begin(), c.end());                             // l.normalize(), filter_bitvec.cc:91
+    std::map<std::pair<uint32_t, long>, uint64_t> by_head;     // (pattern, first candidate) -> hit
+    for (uint64_t i = 0; i < nhits; i++) by_head[std::make_pair(hits[i].pattern_id, (long)hits[i].first)] = i;
+    std::vector<bool> done(ncands, false);
+    for (uint64_t i = 0; i < ncands; i++) {
+      if (done[i]) continue;
+      const uint32_t pid = (uint32_t)c[i].idx;
+      const long firstpos = c[i].key;
+      long pos = firstpos;
+      done[i] = true;
+      for (uint64_t j = i + 1; j < ncands && (done[j] || c[j].key <= pos + 2 * k + 1); j++)
+        if (!done[j] && (uint32_t)c[j].idx == pid) { pos = c[j].key; done[j] = true; }
+      std::map<std::pair<uint32_t, long>, uint64_t>::iterator it = by_head.find(std::make_pair(pid, firstpos));
+      if (it != by_head.end() && !placed[it->second]) { order.push_back(it->second); placed[it->second] = true; }
+    }
+  }
+  for (uint64_t i = 0; i < nhits; i++)
+    if (!placed[i]) order.push_back(i);
+}
+
 inline void pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n, const uint32_t *patlen, const int64_t *seq_key,
                       uint64_t n_seqs, const pm_pcr_options &opt, std::vector<pm_pcr_pair> &out) {
-  // l.normalize() (pcr_match.cc:945): by hit key; a hit whose own alignment failed is never paired (1114)
-  std::vector<uint64_t> l;
-  for (uint64_t i = 0; i < nhits; i++) {
+  // the hits in the order find_patterns reports them, then l.normalize() (pcr_match.cc:958): std::sort
+  // on the hit key alone.  A hit whose own alignment failed stays in the list (it takes part in
+  // the sort) and is never paired (pcr_match.cc:1114).
+  std::vector<uint64_t> order;
+  hit_order(hits, nhits, opt.cands, opt.ncands, opt.k, order);
+  std::vector<KeyIdx> sorted;
+  for (uint64_t i : order) {
     const pm_hit &h = hits[i];
-    if (h.pattern_id >= 1 && h.pattern_id <= 2 * n && h.editdist >= 0 && h.editdist <= opt.k) l.push_back(i);
+    if (h.pattern_id >= 1 && h.pattern_id <= 2 * n) { KeyIdx e; e.key = (long)h.end; e.idx = i; sorted.push_back(e); }
   }
-  std::stable_sort(l.begin(), l.end(), [&](uint64_t a, uint64_t b) {
-    return hits[a].end != hits[b].end ? hits[a].end < hits[b].end : hits[a].pattern_id < hits[b].pattern_id;
-  });
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<uint64_t> l(sorted.size());
+  std::vector<bool> bogus(sorted.size(), false);
+  for (size_t i = 0; i < sorted.size(); i++) {
+    l[i] = sorted[i].idx;
+    bogus[i] = !(hits[l[i]].editdist >= 0 && hits[l[i]].editdist <= opt.k);
+  }
   std::map<uint32_t, std::vector<size_t> > m;  // pattern id -> positions in l
   for (size_t i = 0; i < l.size(); i++) m[hits[l[i]].pattern_id].push_back(i);
   std::vector<bool> done(l.size(), false);
@@ -47,6 +96,7 @@ inline void pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n, const uint
   std::vector<size_t> l1;
   for (size_t hi = 0; hi < l.size(); hi++) {
     const pm_hit &h = hits[l[hi]];
+    if (bogus[hi]) { done[hi] = true; continue; }
     const unsigned long pid = h.pattern_id;
     const long pos = (long)h.end;
     // partner patterns, pcr_match.cc:968-997
@@ -94,7 +144,7 @@ inline void pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n, const uint
       for (; j < v.size(); j++) {
         if (done[v[j]]) continue;  // already had its turn (its key reads 0 in the reference)
         if ((long)hits[l[v[j]]].end > stretch_max) break;
-        l1.push_back(v[j]);
+        if (!bogus[v[j]]) l1.push_back(v[j]);
       }
     }
     for (size_t j : l1) {

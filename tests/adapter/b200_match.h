@@ -28,6 +28,8 @@ class b200_match : public PatternMatch {
   std::vector<pattern_list::const_iterator> plit_;
   const pm_hit *hits_;
   uint64_t nhits_, next_;
+  std::vector<uint64_t> order_;   // the hits in the order filter_bitvec would report them (pm_hit_order)
+  int k_;
   bool loaded_, scanned_;
   unsigned char eos_;
   void *host_;       // page-locked copy of the database file
@@ -129,7 +131,7 @@ class b200_match : public PatternMatch {
 
  public:
   b200_match(int index, unsigned k, char eos, bool wc, bool tn, bool indels, int alphabet_size, bool pcr_rules)
-      : hits_(0), nhits_(0), next_(0), loaded_(false), scanned_(false), eos_((unsigned char)eos), host_(0) {
+      : hits_(0), nhits_(0), next_(0), k_((int)k), loaded_(false), scanned_(false), eos_((unsigned char)eos), host_(0) {
     pm_options o = {0, index, (int)k, indels ? 1 : 0, wc ? 1 : 0, tn ? 1 : 0, (unsigned char)eos};
     if (const char *d = getenv("PM_B200_DEVICE")) o.device = atoi(d);
     if (pm_create(&ctx_, &o)) die("pm_create");
@@ -161,10 +163,18 @@ class b200_match : public PatternMatch {
       if (rc != PM_OK && rc != PM_E_BOGUS) die("pm_find_patterns");   // a bogus hit is the caller's to judge
       scanned_ = true;
       next_ = 0;
+      // hits that end at one position: the callers sort by position alone (std::sort), so the
+      // order they are handed over in is part of the answer (pcr_match pairs a hit only with
+      // partners that come later)
+      const pm_candidate *cands = 0;
+      uint64_t ncands = 0;
+      if (pm_last_candidates(ctx_, &cands, &ncands) != PM_OK) { cands = 0; ncands = 0; }
+      order_.assign(nhits_, 0);
+      if (nhits_ && pm_hit_order(hits_, nhits_, cands, ncands, k_, order_.data())) die("pm_hit_order");
     }
     int64_t frontier = 0;
     while (next_ < nhits_ && phs.size() < minka) {
-      const pm_hit &h = hits_[next_++];
+      const pm_hit &h = hits_[order_[next_++]];
       phs.push_back((FILE_POSITION_TYPE)h.end, std::make_pair(plit_[h.pattern_id], (unsigned char)h.value));
       if (h.end > frontier) frontier = h.end;
     }

@@ -62,6 +62,12 @@ def pcr_golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def pcr_ties_golden():
+    with open(os.path.join(ROOT, "tests", "golden", "pcr_ties_golden.json")) as f:
+        return json.load(f)
+
+
 def records_of(case):
     return [tuple(r) for r in case["records"]]
 

@@ -157,6 +157,19 @@ int pm_pcr_pairs(const pm_hit *hits, uint64_t nhits, uint32_t n_primers, const u
   return fn(hits, nhits, n_primers, patlen, seq_key, n_seqs, opt, pairs, npairs);
 }
 
+// the hits of hits.bin already come in the order the index reports them
+int pm_last_candidates(pm_ctx *, const pm_candidate **cands, uint64_t *n) {
+  *cands = 0;
+  *n = 0;
+  return PM_E_UNSUPPORTED;
+}
+
+int pm_hit_order(const pm_hit *hits, uint64_t nhits, const pm_candidate *cands, uint64_t ncands, int k, uint64_t *order) {
+  typedef int (*fn_t)(const pm_hit *, uint64_t, const pm_candidate *, uint64_t, int, uint64_t *);
+  static fn_t fn = (fn_t)real_symbol("pm_hit_order");
+  return fn(hits, nhits, cands, ncands, k, order);
+}
+
 void pm_free(void *p) {
   typedef void (*fn_t)(void *);
   static fn_t fn = (fn_t)real_symbol("pm_free");

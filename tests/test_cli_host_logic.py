@@ -75,7 +75,8 @@ def pcr_case_inputs(oracle, case, d):
     lc, rc = oracle.pcr_pattern_constraints(pats[:len(case["primers"])], par["stlen"], par["edlen"], par["fplen"],
                                             par["tplen"])
     hits = oracle.aligned_hits(st, pats, lc, rc, par["k"], par["indels"], par["wc"], par["tn"],
-                               index="auto" if select == 0 else "filter_bitvec", bogus_ok=True, exact_align=False)
+                               index="auto" if select == 0 else "filter_bitvec", bogus_ok=True, exact_align=False,
+                               keep_bogus=True)
     write_mock_inputs(d, fasta, st, hits)
     fa = os.path.join(d, "db.fasta")
     with open(fa, "wb") as f:
@@ -106,6 +107,19 @@ def test_pcr_match_host_logic_matches_reference_output(oracle, pcr_golden, mock_
         assert got == case["stdout_custom"], "custom format, case %d" % case["seed"]
         n += len(case["stdout_records"].splitlines())
     assert n > 300
+
+
+def test_pcr_match_host_logic_orders_simultaneous_hits_like_the_reference(oracle, pcr_ties_golden, mock_tools, tmp_path):
+    """pm_pcr_pairs runs the std::sort the reference runs (csrc/pm_pcr.hpp): the 15 cases in which
+    hits of different primers end at one position and the order decides the pairs."""
+    tools, real = mock_tools
+    for case in pcr_ties_golden["cases"]:
+        d = str(tmp_path / ("t%d" % case["seed"]))
+        os.makedirs(d)
+        fa, run = pcr_case_inputs(oracle, case, d)
+        args = oracle.pcr_cli_args(fa, case["primers"], **run)
+        got = run_tool(tools["pcr_match"], args + ["-A", oracle.PCR_REF_FORMAT], d, real)
+        assert got == case["stdout_records"], "records, case %d" % case["seed"]
 
 
 def test_pcr_match_primer_files(oracle, pcr_golden, mock_tools, tmp_path):

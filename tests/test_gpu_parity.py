@@ -70,6 +70,24 @@ def test_pcr_match_golden_records_bit_exact(pkg, oracle, pcr_golden):
     assert n > 300
 
 
+def test_pcr_match_orders_simultaneous_hits_like_the_reference(pkg, oracle, pcr_ties_golden):
+    """Hits of different primers that end at one position: pm_last_candidates + pm_pcr_pairs
+    reproduce the order the reference's two std::sort calls leave them in (and with it which of
+    two partners finds the other).  The records the reference printed, in its order."""
+    import dataclasses
+    n = 0
+    for case in pcr_ties_golden["cases"]:
+        st = pkg.normalize_fasta(case["fasta"].encode("latin-1"))
+        par = dict(case["params"])
+        select = par.pop("select")
+        got = pkg.pcr_match(st, case["primers"], index=pkg.PM_INDEX_AUTO if select == 0 else pkg.PM_INDEX_FILTER_BITVEC,
+                            **par)
+        want = oracle.parse_pcr_records(case["stdout_records"])
+        assert [dataclasses.astuple(r) for r in got] == [dataclasses.astuple(r) for r in want], "case %s" % case["seed"]
+        n += len(got)
+    assert n > 400
+
+
 @pytest.mark.parametrize("path", ["auto", "planes"])
 def test_constraints_golden_records_bit_exact(pkg, constraints_golden, path):
     """-s / -e / -5 / -3 (exact_start_bases / exact_end_bases) with -N 5 and with the automatic

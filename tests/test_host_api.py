@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(pkg, built_lib):
 def test_struct_layouts_match_header(pkg):
     assert C.sizeof(pkg.Hit) == 8 + 8 + 8 + 4 + 4 + 4 + 4 + pkg.PM_MAX_CODES
     assert C.sizeof(pkg.Candidate) == 16
-    assert C.sizeof(pkg.PcrOptions) == 6 * 4 + 2 * 8 + 2 * 8
+    assert C.sizeof(pkg.PcrOptions) == 6 * 4 + 2 * 8 + 2 * 8 + 8 + 8
     assert C.sizeof(pkg.PcrPair) == 8 + 8 + 8 + 4 + 4
 
 

@@ -93,3 +93,53 @@ def test_oracle_pcr_match_matches_reference_golden(oracle, pcr_golden):
         assert got == oracle.parse_pcr_records(case["stdout_records"]), "case %s" % case["seed"]
         n += len(got)
     assert n > 300
+
+
+def test_oracle_pcr_match_reproduces_the_order_of_simultaneous_hits(oracle, pcr_ties_golden):
+    """Hits of different primers that end at one position: the reference leaves them in the order
+    its two std::sort calls on the position alone leave them (filter_bitvec.cc:91, pcr_match.cc:958),
+    and a hit pairs only with partners that come later.  The oracle restates std::sort
+    (std_sort_by_key); 15 cases of the differential campaign in which any simpler rule prints
+    other records."""
+    import dataclasses
+    n = 0
+    for case in pcr_ties_golden["cases"]:
+        st = oracle.normalize_fasta(case["fasta"].encode("latin-1"))
+        par = dict(case["params"])
+        select = par.pop("select")
+        got = oracle.pcr_match(st, case["primers"], index="auto" if select == 0 else "filter_bitvec", **par)
+        want = oracle.parse_pcr_records(case["stdout_records"])
+        assert [dataclasses.astuple(r) for r in got] == [dataclasses.astuple(r) for r in want], "case %s" % case["seed"]
+        n += len(want)
+    assert n > 400
+
+
+def test_std_sort_restatement_matches_libstdcxx(oracle, tmp_path):
+    """std_sort_by_key against the real std::sort (a 10-line C++ program compiled here) on arrays
+    full of equal keys, 1 to 1000 long."""
+    import random
+    import subprocess
+    src = tmp_path / "s.cc"
+    src.write_text("#include <algorithm>\n#include <cstdio>\n#include <vector>\n"
+                   "struct E { long k; long v; bool operator<(const E &o) const { return k < o.k; } };\n"
+                   "int main() { long n; while (scanf(\"%ld\", &n) == 1) { std::vector<E> a(n);\n"
+                   "  for (long i = 0; i < n; i++) { if (scanf(\"%ld\", &a[i].k) != 1) return 1; a[i].v = i; }\n"
+                   "  std::sort(&a[0], &a[0] + n); for (auto &e : a) printf(\"%ld \", e.v); printf(\"\\n\"); } }\n")
+    exe = tmp_path / "s"
+    subprocess.check_call(["g++", "-O2", "-o", str(exe), str(src)])
+    rng = random.Random(5)
+    cases, lines = [], []
+    for t in range(600):
+        n = rng.choice([1, 2, 5, 16, 17, 18, 30, 33, 61, 100, 257, 1000])
+        ks = [rng.randrange(max(2, n // rng.choice([1, 2, 3, 10]))) for _ in range(n)]
+        if t % 7 == 0:
+            ks = sorted(ks)
+        if t % 11 == 0:
+            ks = [0] * n
+        cases.append(ks)
+        lines.append("%d %s" % (n, " ".join(map(str, ks))))
+    out = subprocess.run([str(exe)], input="\n".join(lines).encode(), capture_output=True, timeout=120).stdout.decode()
+    for ks, line in zip(cases, out.strip().split("\n")):
+        want = [int(x) for x in line.split()]
+        got = [i for i, _ in oracle.std_sort_by_key(list(enumerate(ks)), lambda e: e[1])]
+        assert got == want
