@@ -179,7 +179,7 @@ class PatternMatch {
 class b200_index : public PatternMatch {
  public:
   b200_index(int index, unsigned k, char eos, bool wc, bool tn, bool indels, int device = 0)
-      : ctx_(0), hits_(0), nhits_(0), next_(0), scanned_(false), tolerate_bogus_(false) {
+      : ctx_(0), hits_(0), nhits_(0), next_(0), k_((int)k), scanned_(false), tolerate_bogus_(false) {
     pm_options o;
     std::memset(&o, 0, sizeof o);
     o.device = device; o.index = index; o.k = (int)k; o.indels = indels; o.wildcards = wc; o.text_n = tn;
@@ -207,9 +207,17 @@ class b200_index : public PatternMatch {
         fatal("Bogus hit returned to primer_match main()");  // primer_match.cc:1249
       if (rc != PM_OK && rc != PM_E_BOGUS) fatal(std::string("Fatal error: ") + pm_last_error());
       scanned_ = true;
+      // the order filter_bitvec reports its hits in (hits that begin at one position: pm_hit_order);
+      // primer_match prints them as they come, pcr_match sorts them by position alone
+      const pm_candidate *cands = 0;
+      uint64_t ncands = 0;
+      last_candidates(&cands, &ncands);
+      order_.assign(nhits_, 0);
+      if (nhits_ && pm_hit_order(hits_, nhits_, cands, ncands, k_, order_.data()) != PM_OK)
+        fatal(std::string("Fatal error: ") + pm_last_error());
     }
     while (next_ < nhits_ && pas.size() < minka) {
-      const pm_hit &h = hits_[next_++];
+      const pm_hit &h = hits_[order_[next_++]];
       pattern_hit ph = {h.end, h.pattern_id, (unsigned char)h.value};
       pas.push_back(ph);
       batch_.push_back(&h);
@@ -240,7 +248,9 @@ class b200_index : public PatternMatch {
   pm_ctx *ctx_;
   const pm_hit *hits_;
   uint64_t nhits_, next_;
+  int k_;
   bool scanned_, tolerate_bogus_;
+  std::vector<uint64_t> order_;
   std::vector<const pm_hit *> batch_;
 };
 

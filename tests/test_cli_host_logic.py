@@ -167,7 +167,7 @@ def _blocks(text, n):
     if lines and lines[-1] == "":
         lines.pop()
     assert len(lines) % n == 0
-    return sorted(tuple(lines[i:i + n]) for i in range(0, len(lines), n))
+    return [tuple(lines[i:i + n]) for i in range(0, len(lines), n)]
 
 
 def test_primer_match_host_logic_matches_reference_output(oracle, golden, mock_tools, tmp_path):

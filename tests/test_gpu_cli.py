@@ -1,8 +1,9 @@
 """The drop-in command line tool (bin/primer_match, C++ host code over the C
 ABI) against the text the UNMODIFIED reference printed for the same command
 lines (tests/golden/make_golden.py: default format, a custom -A format, -c and
--C/-a counts).  Hit records are compared as multisets: the reference orders
-simultaneous hits of different primers by an unstable std::sort."""
+-C/-a counts).  The text is compared record by record IN ORDER: primer_match prints
+its hits as the index reports them, and the tool hands them over in that order
+(pm_hit_order: filter_bitvec's std::sort of the candidates, chains in that order)."""
 import importlib
 import os
 import subprocess
@@ -54,7 +55,7 @@ def _blocks(text, n):
     if lines and lines[-1] == "":
         lines.pop()
     assert len(lines) % n == 0
-    return sorted(tuple(lines[i:i + n]) for i in range(0, len(lines), n))
+    return [tuple(lines[i:i + n]) for i in range(0, len(lines), n)]
 
 
 def test_cli_output_matches_reference(cli, golden, tmp_path):
