@@ -109,3 +109,51 @@ def test_pcr_pairs_edge_cases(pkg, built_lib):
     assert got == [(0, 1, 320, 1), (0, 2, 420, 1)]
     got = pkg.pcr_pairs(_hits(pkg, [fwd, rev, (2, 500, 520, 0), (4, 600, 620, 0)]), 2, patlen, keys, allorient=True)
     assert got == [(0, 1, 320, 1), (0, 2, 420, 1), (0, 3, 520, 1)]
+
+
+def test_hit_order_replays_the_reference_sort_and_chain_walk(pkg, built_lib, oracle):
+    """pm_hit_order (host code of the library: the real std::sort on the candidates' positions, then
+    filter_bitvec's chain walk) against the oracle's restatement (std_sort_by_key + the same walk in
+    Python) on candidate lists full of equal positions, 1 to 3 000 long."""
+    import random
+    rng = random.Random(31)
+    for trial in range(120):
+        k = rng.choice([1, 2, 3])
+        npat = rng.choice([1, 2, 5, 16])
+        n = rng.choice([1, 5, 16, 17, 40, 200, 3000])
+        span = max(4, n // rng.choice([1, 2, 4]))
+        cands = sorted({(rng.randrange(1, span + 1), rng.randrange(1, npat + 1)) for _ in range(n)})
+        # the oracle's side: candidates as the scan reports them (position, pattern) -> std::sort on the
+        # position alone -> chains (same pattern, at most 2k+1 apart) in that order
+        srt = oracle.std_sort_by_key(cands, lambda c: c[0])
+        done = [False] * len(srt)
+        heads = []
+        for i, (pos, pid) in enumerate(srt):
+            if done[i]:
+                continue
+            done[i] = True
+            last = pos
+            heads.append((pid, pos))
+            j = i + 1
+            while j < len(srt) and (done[j] or srt[j][0] <= last + 2 * k + 1):
+                if not done[j] and srt[j][1] == pid:
+                    last = srt[j][0]
+                    done[j] = True
+                j += 1
+        # the library's side: one hit per chain (a third of them dropped: chains whose alignment fails
+        # report nothing), given in (first, pattern) order as pm_find_patterns returns them
+        kept = [h for h in heads if rng.random() < 0.67] or heads[:1]
+        given = sorted(kept, key=lambda h: (h[1], h[0]))
+        hits = np.zeros(len(given), pkg.HIT_DTYPE)
+        for i, (pid, first) in enumerate(given):
+            hits[i]["pattern_id"], hits[i]["first"], hits[i]["end"] = pid, first, first + 3
+        ca = np.zeros(len(cands), pkg.CAND_DTYPE)
+        for i, (pos, pid) in enumerate(sorted(cands, key=lambda c: (c[1], c[0]))):   # as pm_last_candidates sorts them
+            ca[i]["pos"], ca[i]["pattern_id"] = pos, pid
+        order = np.zeros(len(given), np.uint64)
+        rc = built_lib.pm_hit_order(C.c_void_p(hits.ctypes.data), len(hits), C.c_void_p(ca.ctypes.data), len(ca), k,
+                                    C.c_void_p(order.ctypes.data))
+        assert rc == pkg.PM_OK
+        got = [given[int(i)] for i in order]
+        want = [h for h in heads if h in set(kept)]
+        assert got == want, "trial %d" % trial

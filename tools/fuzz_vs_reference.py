@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--first", type=int, default=10000)
     ap.add_argument("--count", type=int, default=500)
     ap.add_argument("--seconds", type=float, default=600.0)
+    ap.add_argument("--oracle", action="store_true",
+                    help="compare the CPU oracle (oracle/pm_oracle.py) with the reference instead of the GPU library: "
+                         "no GPU needed (primer mode)")
     ap.add_argument("--mode", default="primer", choices=["primer", "constraints", "pcr"],
                     help="primer_match; primer_match with -s/-e/-5/-3 (exact_bases); pcr_match")
     a = ap.parse_args()
@@ -42,6 +45,7 @@ def main():
     done = skipped = records = 0
     failures = []
     by_kind = {}
+    O_MAX_K = 3   # the oracle's recurrence is written for k <= 3 in one machine word
     for seed in range(a.first, a.first + a.count):
         if time.time() - t0 > a.seconds:
             break
@@ -65,6 +69,20 @@ def main():
                               "-auto" if select == 0 else "")
         index = pkg.PM_INDEX_AUTO if (select == 0 or params["k"] == 0) else pkg.PM_INDEX_FILTER_BITVEC
         st = pkg.normalize_fasta(fasta.encode("latin-1"))
+        if a.oracle:
+            try:
+                got = as_tuples(O.primer_match(O.normalize_fasta(fasta.encode("latin-1")), primers,
+                                               index="auto" if select == 0 else "filter_bitvec", **params))
+                ok = got == as_tuples(want)
+                why = None if ok else "records differ: %d against %d" % (len(got), len(want))
+            except Exception as e:   # noqa: BLE001
+                ok, why = False, "%s: %s" % (type(e).__name__, e)
+            if not ok:
+                failures.append(dict(seed=seed, path="oracle", kind=kind, select=select, why=why))
+            done += 1
+            records += len(want)
+            by_kind[kind] = by_kind.get(kind, 0) + 1
+            continue
         for sp_name, sp in (("auto", pkg.PM_SCAN_AUTO), ("planes", pkg.PM_SCAN_PLANES)):
             try:
                 got = as_tuples(pkg.primer_match(st, primers, scan_path=sp, index=index, **params))
