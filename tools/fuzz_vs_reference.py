@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=600.0)
     ap.add_argument("--oracle", action="store_true",
                     help="compare the CPU oracle (oracle/pm_oracle.py) with the reference instead of the GPU library: "
-                         "no GPU needed (primer mode)")
+                         "no GPU needed")
     ap.add_argument("--mode", default="primer", choices=["primer", "constraints", "pcr"],
                     help="primer_match; primer_match with -s/-e/-5/-3 (exact_bases); pcr_match")
     a = ap.parse_args()
@@ -144,6 +144,9 @@ def other_modes(a):
             index = pkg.PM_INDEX_AUTO if select == 0 else pkg.PM_INDEX_FILTER_BITVEC
 
             def run(sp):
+                if a.oracle:
+                    return as_tuples(O.primer_match(O.normalize_fasta(fasta.encode("latin-1")), primers,
+                                                    index="auto" if select == 0 else "filter_bitvec", **params, **cons))
                 return as_tuples(pkg.primer_match(st, primers, scan_path=sp, index=index, **params, **cons))
             label = dict(params=params, cons=cons, select=select)
         else:
@@ -172,11 +175,14 @@ def other_modes(a):
             index = pkg.PM_INDEX_AUTO if select == 0 else pkg.PM_INDEX_FILTER_BITVEC
 
             def run(sp):
+                if a.oracle:
+                    return [dataclasses.astuple(r) for r in O.pcr_match(O.normalize_fasta(fasta.encode("latin-1")), primers,
+                                                                        index="auto" if select == 0 else "filter_bitvec", **par)]
                 return [dataclasses.astuple(r) for r in pkg.pcr_match(st, primers, index=index, sts_sizes=None, **par)]
             label = dict(params=params)
         for sp_name, sp in (("auto", pkg.PM_SCAN_AUTO), ("planes", pkg.PM_SCAN_PLANES)):
-            if a.mode == "pcr" and sp_name == "planes":
-                continue                       # pcr_match() has no scan-path argument
+            if (a.mode == "pcr" or a.oracle) and sp_name == "planes":
+                continue                       # pcr_match() has no scan-path argument; the oracle has one path
             try:
                 got = run(sp)
                 ok = got == want
