@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--oracle", action="store_true",
                     help="compare the CPU oracle (oracle/pm_oracle.py) with the reference instead of the GPU library: "
                          "no GPU needed")
+    ap.add_argument("--long", action="store_true", help="primers of 33-64 characters (primer mode)")
     ap.add_argument("--mode", default="primer", choices=["primer", "constraints", "pcr"],
                     help="primer_match; primer_match with -s/-e/-5/-3 (exact_bases); pcr_match")
     a = ap.parse_args()
@@ -54,6 +55,8 @@ def main():
         select = rng.choice([None, None, 0])       # -N 5, or the reference's automatic choice
         if rng.random() < 0.1:
             params["k"] = kw["k"] = rng.choice([4, 5])
+        if a.long:
+            kw["plen"] = rng.choice([(33, 40), (33, 64), (48, 64), (64, 64)])
         if rng.random() < 0.3:                       # longer databases: several tiles' worth of rows
             kw["seqlen"] = rng.choice([5000, 20000])
         fasta, primers = casegen.make_case(seed, **kw)
